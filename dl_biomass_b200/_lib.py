@@ -1,0 +1,63 @@
+"""ctypes binding of libb2pn.so (the C ABI declared in include/b2pn.h).
+
+There is deliberately no fallback: if the library is missing or a call fails, the product path
+raises.  Build it with ``python -c "import __graft_entry__ as g; g.build()"`` or
+``make -C dl_biomass_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb2pn.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+_lib = None
+
+_vp, _i32, _i64, _f32, _f64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double
+
+# name -> (restype, argtypes); must list every symbol include/b2pn.h declares (tests check this)
+SIGNATURES = {
+    "b2pn_abi_version": (ctypes.c_int, []),
+    "b2pn_error_string": (ctypes.c_char_p, [ctypes.c_int]),
+    "b2pn_fps_num_samples": (_i64, [_i64, _f32]),
+    "b2pn_fps_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
+    "b2pn_fps_set_variant": (ctypes.c_int, [_i32, _i32]),
+    "b2pn_ball_query_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _f64, _i32, _vp, _vp, _vp]),
+}
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile libb2pn.so in-tree with nvcc for sm_100a (works without a GPU)."""
+    cmd = ["make", "-C", CSRC, "-j8"] + (["-B"] if force else [])
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout[-4000:], res.stderr[-4000:])
+    if res.returncode != 0:
+        raise RuntimeError("building libb2pn.so failed")
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: the B200 path has no fallback. Build it with "
+                f"`make -C {CSRC}` (nvcc, sm_100a).")
+        h = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(h, name)  # AttributeError if the ABI drifted
+            fn.restype, fn.argtypes = res, args
+        if h.b2pn_abi_version() != 1:
+            raise ImportError("libb2pn.so ABI version mismatch; rebuild")
+        _lib = h
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().b2pn_error_string(rc)
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")

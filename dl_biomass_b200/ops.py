@@ -1,0 +1,137 @@
+"""torch.library surface over the C ABI (include/b2pn.h): grouping ops.
+
+``torch.ops.b2pn.fps`` and ``torch.ops.b2pn.ball_query`` stand where
+``torch.ops.torch_cluster.fps`` / ``torch.ops.torch_cluster.radius`` stand in the reference
+(/root/reference/pointnet2_regressor.py:13-15 via torch_geometric).  They only enqueue kernels
+on the current stream of the tensors' device; all sizes come in as host integers, so there is no
+device->host synchronisation anywhere in the forward pass.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+_DEF = torch.library.Library("b2pn", "DEF")
+_DEF.define("fps(Tensor pos, Tensor ptr, Tensor out_ptr, Tensor? start, int max_n, int num_out) "
+            "-> (Tensor, Tensor, Tensor)")
+_DEF.define("ball_query(Tensor src, Tensor qry, Tensor src_ptr, Tensor qry_ptr, int max_src, int max_qry, "
+            "float r, int K) -> (Tensor, Tensor)")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _require_cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("b2pn ops run on a B200 only: got a CPU tensor and there is no CPU fallback")
+
+
+def _fps_cuda(pos, ptr, out_ptr, start, max_n, num_out):
+    _require_cuda(pos, ptr, out_ptr, start)
+    if pos.dtype != torch.float32 or pos.dim() != 2 or pos.size(1) != 3:
+        raise ValueError("fps: pos must be [N,3] float32")
+    pos = pos.contiguous()
+    B = ptr.numel() - 1
+    idx = torch.empty(num_out, dtype=torch.int64, device=pos.device)
+    pos_out = torch.empty(num_out, 3, dtype=torch.float32, device=pos.device)
+    batch_out = torch.empty(num_out, dtype=torch.int64, device=pos.device)
+    with torch.cuda.device(pos.device):
+        rc = _lib.lib().b2pn_fps_f32(pos.data_ptr(), ptr.data_ptr(), out_ptr.data_ptr(), _ptr(start), B, max_n,
+                                     idx.data_ptr(), pos_out.data_ptr(), batch_out.data_ptr(), _stream(pos))
+    _lib.check(rc, "b2pn_fps_f32")
+    return idx, pos_out, batch_out
+
+
+def _ball_query_cuda(src, qry, src_ptr, qry_ptr, max_src, max_qry, r, K):
+    _require_cuda(src, qry, src_ptr, qry_ptr)
+    if src.dtype != torch.float32 or qry.dtype != torch.float32:
+        raise ValueError("ball_query: positions must be float32")
+    src, qry = src.contiguous(), qry.contiguous()
+    B = src_ptr.numel() - 1
+    M = qry.size(0)
+    nbr = torch.empty(M, K, dtype=torch.int32, device=src.device)
+    cnt = torch.empty(M, dtype=torch.int32, device=src.device)
+    with torch.cuda.device(src.device):
+        rc = _lib.lib().b2pn_ball_query_f32(src.data_ptr(), qry.data_ptr(), src_ptr.data_ptr(), qry_ptr.data_ptr(),
+                                            B, max_src, max_qry, float(r), K, nbr.data_ptr(), cnt.data_ptr(),
+                                            _stream(src))
+    _lib.check(rc, "b2pn_ball_query_f32")
+    return nbr, cnt
+
+
+_IMPL = torch.library.Library("b2pn", "IMPL")
+_IMPL.impl("fps", _fps_cuda, "CUDA")
+_IMPL.impl("ball_query", _ball_query_cuda, "CUDA")
+
+
+def _no_cpu(*args, **kwargs):
+    raise RuntimeError("b2pn ops run on a B200 only: there is no CPU fallback (tensors must be CUDA tensors)")
+
+
+_IMPL.impl("fps", _no_cpu, "CPU")
+_IMPL.impl("ball_query", _no_cpu, "CPU")
+
+
+@torch.library.register_fake("b2pn::fps")
+def _fps_fake(pos, ptr, out_ptr, start, max_n, num_out):
+    return (pos.new_empty(num_out, dtype=torch.int64), pos.new_empty(num_out, 3),
+            pos.new_empty(num_out, dtype=torch.int64))
+
+
+@torch.library.register_fake("b2pn::ball_query")
+def _bq_fake(src, qry, src_ptr, qry_ptr, max_src, max_qry, r, K):
+    return qry.new_empty(qry.size(0), K, dtype=torch.int32), qry.new_empty(qry.size(0), dtype=torch.int32)
+
+
+# --------------------------------------------------------------------------------------------------
+#  host-side layout of the hierarchy (cloud offsets at every level, computed without device reads)
+# --------------------------------------------------------------------------------------------------
+def fps_num_samples(n: int, ratio: float) -> int:
+    """ceil(float32(n)*float32(ratio)) -- the sizing rule of torch_cluster.fps."""
+    return int(_lib.lib().b2pn_fps_num_samples(int(n), float(ratio)))
+
+
+@dataclass
+class Level:
+    sizes: List[int]          # points per cloud (host)
+    ptr: torch.Tensor         # [B+1] int64 on the device
+    total: int
+    max_n: int
+
+
+def build_levels(sizes0: Sequence[int], ratios: Sequence[float], device: torch.device) -> List[Level]:
+    """Level 0 = input clouds; level i+1 = after fps with ratios[i].  One pinned H2D copy in total."""
+    all_sizes = [list(int(s) for s in sizes0)]
+    for r in ratios:
+        all_sizes.append([fps_num_samples(n, r) for n in all_sizes[-1]])
+    B = len(all_sizes[0])
+    host = torch.zeros(len(all_sizes), B + 1, dtype=torch.int64)
+    for i, s in enumerate(all_sizes):
+        host[i, 1:] = torch.cumsum(torch.tensor(s, dtype=torch.int64), 0)
+    if device.type == "cuda":
+        dev = host.pin_memory().to(device, non_blocking=True)
+    else:
+        dev = host
+    return [Level(s, dev[i], int(host[i, -1]), max(s) if s else 0) for i, s in enumerate(all_sizes)]
+
+
+def fps(pos: torch.Tensor, src: Level, dst: Level, start: Optional[torch.Tensor] = None
+        ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """idx [M] int64 (global), pos[idx] [M,3], batch[idx] [M] -- pointnet2_regressor.py:13,19."""
+    return torch.ops.b2pn.fps(pos, src.ptr, dst.ptr, start, src.max_n, dst.total)
+
+
+def ball_query(src_pos: torch.Tensor, qry_pos: torch.Tensor, src: Level, qry: Level, r: float, K: int = 64
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fixed-width neighbour slots nbr [M,K] int32 / cnt [M] -- pointnet2_regressor.py:14-16."""
+    return torch.ops.b2pn.ball_query(src_pos, qry_pos, src.ptr, qry.ptr, src.max_n, qry.max_n, float(r), K)

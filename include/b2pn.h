@@ -1,0 +1,78 @@
+/*
+ * b2pn -- C ABI of the B200-native PointNet++ set-abstraction path (libb2pn.so).
+ *
+ * The reference (cczls1991/DL_Biomass) is pure Python and has no FFI of its own; the native
+ * boundary it crosses for this path is the torch.ops surface of torch_cluster / torch_scatter
+ * / ATen that torch_geometric dispatches to.  Each entry point below names the reference call
+ * site (file:line under /root/reference) and the upstream op it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the comment says "host"; the caller owns all
+ *     buffers (inputs, outputs, workspaces); the library never allocates or synchronises, it
+ *     only enqueues work on `stream` (a cudaStream_t passed as void*).
+ *   - `ptr` arrays are CSR-style cloud offsets (int64, B+1 entries), as torch_cluster takes.
+ *   - return value: 0 = ok, <0 = B2PN_E* argument error (nothing enqueued), >0 = cudaError_t
+ *     reported by the launch.  b2pn_error_string() renders either.
+ *   - re-entrant: no global mutable state besides one-time per-device kernel attributes.
+ */
+#ifndef B2PN_H_
+#define B2PN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2PN_ABI_VERSION 1
+#define B2PN_OK 0
+#define B2PN_EINVAL (-1)   /* null pointer / negative size / bad flag            */
+#define B2PN_ENOTSUP (-2)  /* shape outside what the sm_100a kernels are built for */
+
+typedef void *b2pn_stream_t;
+
+int b2pn_abi_version(void);
+const char *b2pn_error_string(int code);
+
+/* samples per cloud: ceil(float32(n) * float32(ratio)) -- torch_cluster.fps sizing
+ * (reached from /root/reference/pointnet2_regressor.py:13).  Host-side helper. */
+int64_t b2pn_fps_num_samples(int64_t n, float ratio);
+
+/*
+ * Farthest-point sampling.  Replaces torch.ops.torch_cluster.fps(src, ptr, ratio, random_start)
+ * called at /root/reference/pointnet2_regressor.py:13 (SAModule.forward: idx = fps(pos, batch, ratio)).
+ *   pos      [N,3] f32 row-major, clouds concatenated
+ *   ptr      [B+1] i64 cloud offsets into pos
+ *   out_ptr  [B+1] i64 offsets into out_idx (caller computes them with b2pn_fps_num_samples)
+ *   start    [B]   i64 cloud-local start index, or NULL for 0 (random_start is drawn by the caller)
+ *   max_n    host scalar: largest cloud in the batch (selects the kernel variant)
+ *   out_idx  [M]   i64 GLOBAL point indices, per cloud in selection order (first = start)
+ *   out_pos  [M,3] f32 pos[out_idx]   (optional, may be NULL; fuses pointnet2_regressor.py:19)
+ *   out_batch[M]   i64 cloud id       (optional, may be NULL; fuses batch[idx] of :19)
+ * Distances are ((dx*dx+dy*dy)+dz*dz) in separately rounded fp32; ties -> lowest index.
+ */
+int b2pn_fps_f32(const float *pos, const int64_t *ptr, const int64_t *out_ptr, const int64_t *start,
+                 int32_t B, int64_t max_n, int64_t *out_idx, float *out_pos, int64_t *out_batch,
+                 b2pn_stream_t stream);
+
+/* Force a kernel variant (benchmark sweeps): cluster size (1,2,4,8,16), threads per CTA; 0 = auto. */
+int b2pn_fps_set_variant(int32_t cluster, int32_t threads);
+
+/*
+ * Segmented radius ball query with a neighbour cap.  Replaces
+ * torch.ops.torch_cluster.radius(x, y, ptr_x, ptr_y, r, max_num_neighbors, num_workers) called at
+ * /root/reference/pointnet2_regressor.py:14-15.  Instead of the compacted [2,E] edge list it
+ * writes fixed-width slots (no data-dependent shape, no host sync):
+ *   nbr [M,K] i32  GLOBAL source indices, ascending, first K with d2 < r*r (strict); pad = -1
+ *   cnt [M]   i32  number of valid slots
+ * edge_index of pointnet2_regressor.py:16 is (col = nbr[m,k], row = m) for k < cnt[m].
+ * max_src / max_qry: host scalars, largest number of sources / queries in one cloud.
+ */
+int b2pn_ball_query_f32(const float *src_pos, const float *qry_pos, const int64_t *src_ptr,
+                        const int64_t *qry_ptr, int32_t B, int64_t max_src, int64_t max_qry, double r,
+                        int32_t K, int32_t *nbr, int32_t *cnt, b2pn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2PN_H_ */

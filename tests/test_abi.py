@@ -1,0 +1,76 @@
+"""CPU: the C-ABI library loads, exports every symbol include/b2pn.h declares, and the grouping
+kernels' SASS keeps the bit-exact arithmetic contract (no fused multiply-add)."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "b2pn.h")
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from dl_biomass_b200 import _lib
+    _lib.build()
+    return _lib
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2pn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported_and_bound(built_lib):
+    names = declared_symbols()
+    assert "b2pn_fps_f32" in names and "b2pn_ball_query_f32" in names
+    nm = subprocess.run(["nm", "-D", "--defined-only", built_lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (b2pn_[a-z0-9_]+)", nm))
+    assert set(names) <= exported, sorted(set(names) - exported)
+    assert set(names) == set(built_lib.SIGNATURES), "ctypes table and header disagree"
+    h = built_lib.lib()
+    assert h.b2pn_abi_version() == 1
+    assert h.b2pn_fps_num_samples(7168, 0.2) == 1434
+    assert b"invalid" in h.b2pn_error_string(-1)
+
+
+def test_argument_errors_need_no_gpu(built_lib):
+    h = built_lib.lib()
+    assert h.b2pn_fps_f32(None, None, None, None, 2, 10, None, None, None, None) == -1
+    assert h.b2pn_fps_f32(None, None, None, None, 0, 0, None, None, None, None) == 0
+    assert h.b2pn_ball_query_f32(None, None, None, None, 1, 5, 5, 2.0, 64, None, None, None) == -1
+    assert h.b2pn_ball_query_f32(None, None, None, None, 1, 5, 5, 2.0, 0, None, None, None) == -1
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "dl_biomass_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "libb2pn_oracle" not in txt, f
+
+
+def test_cpu_tensors_fail_loudly(built_lib):
+    import torch
+    from dl_biomass_b200 import ops
+    lv = ops.build_levels([10], [0.5], torch.device("cpu"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.fps(torch.zeros(10, 3), lv[0], lv[1])
+
+
+def test_grouping_sass_has_no_fma(built_lib):
+    """Distances must be ((dx*dx+dy*dy)+dz*dz) with separate roundings."""
+    sass = subprocess.run(["cuobjdump", "-sass", built_lib.LIB_PATH], capture_output=True, text=True).stdout
+    cur, bad = None, []
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+        elif cur and ("fps_kernel" in cur or "ball_query_kernel" in cur) and re.search(r"\bFFMA2?\b", line):
+            bad.append((cur, line.strip()))
+    assert not bad, bad[:3]
+    assert "FMUL2" in sass and "FADD2" in sass and "REDUX" in sass

@@ -1,0 +1,137 @@
+"""GPU parity (bit-exact) of Kernel 1 (FPS) and Kernel 2 (ball query) against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref
+from dl_biomass_b200 import _lib, ops
+from dl_biomass_b200.data import Batch, synthetic_clouds
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _run_level(pos_cpu, sizes, ratio, r, dev, start=None, K=64):
+    lv = ops.build_levels(sizes, [ratio], dev)
+    pos = pos_cpu.to(dev)
+    st = None if start is None else start.to(dev)
+    idx, pos_out, batch_out = ops.fps(pos, lv[0], lv[1], st)
+    nbr, cnt = ops.ball_query(pos, pos_out, lv[0], lv[1], r, K)
+    torch.cuda.synchronize()
+    return lv, idx.cpu(), pos_out.cpu(), batch_out.cpu(), nbr.cpu(), cnt.cpu()
+
+
+def _check_level(pos_cpu, ptr, ratio, r, dev, start=None, K=64):
+    sizes = (ptr[1:] - ptr[:-1]).tolist()
+    lv, idx, pos_out, batch_out, nbr, cnt = _run_level(pos_cpu, sizes, ratio, r, dev, start, K)
+    want_idx = ref.fps_ref(pos_cpu, ptr, ratio, start)
+    assert torch.equal(idx, want_idx), f"fps mismatch at {int((idx != want_idx).nonzero()[0])}"
+    assert torch.equal(pos_out, pos_cpu[want_idx])
+    qptr = ref.sample_ptr(ptr, ratio)
+    assert torch.equal(batch_out, torch.repeat_interleave(torch.arange(len(sizes)), qptr[1:] - qptr[:-1]))
+    want_nbr, want_cnt = ref.ball_query_ref(pos_cpu, pos_cpu[want_idx], ptr, qptr, r, K)
+    assert torch.equal(cnt, want_cnt)
+    assert torch.equal(nbr, want_nbr)
+    return idx, nbr, cnt
+
+
+@pytest.mark.parametrize("B,n,ragged", [(1, 64, False), (3, 1000, False), (4, 513, True), (2, 4099, True),
+                                        (12, 10000, False)])
+def test_two_levels_match_oracle(cuda_device, B, n, ragged):
+    b = Batch.from_data_list(synthetic_clouds(1234, B, n, 1, ragged))
+    idx1, _, _ = _check_level(b.pos, b.ptr, 0.2, 2.0, cuda_device)
+    ptr1 = ref.sample_ptr(b.ptr, 0.2)
+    _check_level(b.pos[idx1].contiguous(), ptr1, 0.25, 8.0, cuda_device)
+
+
+def test_explicit_start_and_small_k(cuda_device):
+    b = Batch.from_data_list(synthetic_clouds(8, 3, 700, 1, True))
+    _check_level(b.pos, b.ptr, 0.2, 3.0, cuda_device, start=torch.tensor([5, 0, 333]), K=16)
+
+
+def test_ties_and_duplicates(cuda_device):
+    """Dyadic grid clouds are full of exactly tied distances; duplicated points add zero distances."""
+    rng = np.random.default_rng(3)
+    pts = torch.from_numpy(rng.integers(-32, 32, size=(3000, 3)).astype(np.float32) / 4.0)
+    pts = torch.cat([pts, pts[:500]], 0)  # duplicates
+    ptr = torch.tensor([0, 1200, 3500])
+    _check_level(pts, ptr, 0.25, 2.0, cuda_device)
+    _check_level(pts, ptr, 0.9, 1.0, cuda_device)  # nearly exhausts the clouds
+
+
+def test_reference_numpy_fps_golden(cuda_device):
+    """The reference's own FPS (downsampling_point_clouds.py:55-92) on fp32-exact clouds."""
+    g = np.load(os.path.join(GOLD, "fps_reference_numpy.npz"))
+    for i, kind in enumerate(g["kinds"]):
+        if kind != "dyadic":
+            continue
+        pos, want = g[f"pos_{i}"], g[f"idx_{i}"]
+        n, k = pos.shape[0], len(want)
+        lv = ops.build_levels([n], [k / n], cuda_device)
+        assert lv[1].total == k
+        idx, _, _ = ops.fps(torch.from_numpy(pos.astype(np.float32)).to(cuda_device), lv[0], lv[1])
+        assert np.array_equal(idx.cpu().numpy(), want)
+
+
+def test_golden_grouping_fixture(cuda_device):
+    g = np.load(os.path.join(GOLD, "grouping_oracle.npz"))
+    i = 0
+    while f"spec_{i}" in g:
+        seed, B, n, ragged, r1, r2 = g[f"spec_{i}"]
+        b = Batch.from_data_list(synthetic_clouds(int(seed), int(B), int(n), 1, bool(ragged)))
+        sizes = (b.ptr[1:] - b.ptr[:-1]).tolist()
+        lv, idx, pos1, _, nbr, cnt = _run_level(b.pos, sizes, 0.2, float(r1), cuda_device)
+        assert np.array_equal(idx.numpy(), g[f"idx1_{i}"])
+        assert np.array_equal(nbr.numpy(), g[f"nbr1_{i}"]) and np.array_equal(cnt.numpy(), g[f"cnt1_{i}"])
+        lv2, idx2, _, _, nbr2, cnt2 = _run_level(pos1, lv[1].sizes, 0.25, float(r2), cuda_device)
+        assert np.array_equal(idx2.numpy(), g[f"idx2_{i}"])
+        assert np.array_equal(nbr2.numpy(), g[f"nbr2_{i}"]) and np.array_equal(cnt2.numpy(), g[f"cnt2_{i}"])
+        i += 1
+
+
+@pytest.mark.parametrize("cluster,threads", [(1, 256), (1, 512), (1, 1024), (2, 512), (4, 256), (8, 256), (8, 512),
+                                             (16, 256)])
+def test_fps_variants_agree(cuda_device, cluster, threads):
+    b = Batch.from_data_list(synthetic_clouds(77, 5, 6000, 1, True))
+    want = ref.fps_ref(b.pos, b.ptr, 0.2)
+    lv = ops.build_levels((b.ptr[1:] - b.ptr[:-1]).tolist(), [0.2], cuda_device)
+    try:
+        _lib.check(_lib.lib().b2pn_fps_set_variant(cluster, threads), "set_variant")
+        idx, _, _ = ops.fps(b.pos.to(cuda_device), lv[0], lv[1])
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().b2pn_fps_set_variant(0, 0)
+    assert torch.equal(idx.cpu(), want)
+
+
+def test_dense_cloud_properties(cuda_device):
+    """100k-point cloud (BASELINE config 4): too slow for a full oracle pass in CI, so check
+    size-independent properties + an oracle prefix."""
+    b = Batch.from_data_list(synthetic_clouds(11, 2, 100000, 1, False))
+    lv = ops.build_levels([100000, 100000], [0.2], cuda_device)
+    pos = b.pos.to(cuda_device)
+    idx, pos_out, _ = ops.fps(pos, lv[0], lv[1])
+    nbr, cnt = ops.ball_query(pos, pos_out, lv[0], lv[1], 4.0, 64)
+    idx_c = idx.cpu()
+    for c in range(2):
+        seg = idx_c[c * 20000:(c + 1) * 20000]
+        assert seg.unique().numel() == 20000 and int(seg.min()) >= c * 100000 and int(seg.max()) < (c + 1) * 100000
+    # oracle on the first cloud only, first 300 samples (prefix of FPS is independent of the total count)
+    ptr = torch.tensor([0, 100000])
+    want = ref.fps_ref(b.pos[:100000], ptr, 300 / 100000)
+    assert torch.equal(idx_c[:300], want)
+    # neighbour slots: ascending, in range, within radius, and the centroid's own cloud
+    nbr_c, cnt_c = nbr.cpu().long(), cnt.cpu().long()
+    assert int(cnt_c.min()) >= 1
+    q = torch.randint(0, 40000, (200,))
+    for m in q.tolist():
+        k = int(cnt_c[m])
+        row = nbr_c[m, :k]
+        assert bool((row[1:] > row[:-1]).all()) and bool((nbr_c[m, k:] == -1).all())
+        d2 = ((b.pos[row] - b.pos[idx_c[m]]) ** 2).sum(1)
+        assert bool((d2 < 16.0).all())
+        want_n, want_c = ref.ball_query_ref(b.pos, b.pos[idx_c[m]][None], torch.tensor([0, 100000, 200000]),
+                                            torch.tensor([0, 1, 1]) if m < 20000 else torch.tensor([0, 0, 1]), 4.0, 64)
+        assert int(want_c[0]) == k and torch.equal(want_n[0, :k].long(), row)
