@@ -18,14 +18,40 @@ _lib = None
 
 _vp, _i32, _i64, _f32, _f64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double
 
+class Mlp3(ctypes.Structure):
+    _fields_ = [("c", ctypes.c_int32 * 4), ("act", ctypes.c_int32), ("eps", ctypes.c_float),
+                ("momentum", ctypes.c_float), ("w", _vp * 3), ("b", _vp * 3), ("gamma", _vp * 2),
+                ("beta", _vp * 2), ("running_mean", _vp * 2), ("running_var", _vp * 2),
+                ("num_batches_tracked", _vp * 2)]
+
+
+class SaArgs(ctypes.Structure):
+    _fields_ = [("precision", ctypes.c_int32), ("training", ctypes.c_int32), ("seg_mode", ctypes.c_int32),
+                ("K", ctypes.c_int32), ("n_src", ctypes.c_int64), ("n_dst", ctypes.c_int64),
+                ("c_in", ctypes.c_int32), ("reserved", ctypes.c_int32), ("x", _vp), ("pos_src", _vp),
+                ("pos_dst", _vp), ("nbr", _vp), ("cnt", _vp), ("batch", _vp), ("mlp", Mlp3), ("out", _vp),
+                ("arg", _vp), ("h1", _vp), ("h2", _vp), ("bn", _vp), ("workspace", _vp),
+                ("workspace_bytes", ctypes.c_int64)]
+
+
+class SaGrads(ctypes.Structure):
+    _fields_ = [("grad_out", _vp), ("grad_w", _vp * 3), ("grad_b", _vp * 3), ("grad_gamma", _vp * 2),
+                ("grad_beta", _vp * 2), ("grad_x", _vp)]
+
+
+
 # name -> (restype, argtypes); must list every symbol include/b2pn.h declares (tests check this)
 SIGNATURES = {
     "b2pn_abi_version": (ctypes.c_int, []),
     "b2pn_error_string": (ctypes.c_char_p, [ctypes.c_int]),
+    "b2pn_launch_count": (_i64, []),
     "b2pn_fps_num_samples": (_i64, [_i64, _f32]),
     "b2pn_fps_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
     "b2pn_fps_set_variant": (ctypes.c_int, [_i32, _i32]),
     "b2pn_ball_query_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _f64, _i32, _vp, _vp, _vp]),
+    "b2pn_sa_workspace_bytes": (_i64, [ctypes.POINTER(SaArgs), _i32]),
+    "b2pn_sa_forward": (ctypes.c_int, [ctypes.POINTER(SaArgs), _vp]),
+    "b2pn_sa_backward": (ctypes.c_int, [ctypes.POINTER(SaArgs), ctypes.POINTER(SaGrads), _vp]),
 }
 
 

@@ -3,7 +3,13 @@
 
 #include "common.cuh"
 
+namespace b2pn {
+long long g_launches = 0;
+}
+
 extern "C" int b2pn_abi_version(void) { return B2PN_ABI_VERSION; }
+
+extern "C" int64_t b2pn_launch_count(void) { return (int64_t)__atomic_load_n(&b2pn::g_launches, __ATOMIC_RELAXED); }
 
 extern "C" const char *b2pn_error_string(int code)
 {
@@ -19,4 +25,34 @@ extern "C" int64_t b2pn_fps_num_samples(int64_t n, float ratio)
     // torch_cluster: ceil(float32(n) * float32(ratio)); keep the product in fp32
     volatile float prod = (float)n * ratio;
     return (int64_t)ceilf(prod);
+}
+
+// ---- set-abstraction levels: precision dispatch ---------------------------------------------------
+namespace b2pn {
+namespace simt {
+int64_t sa_workspace_bytes_f32(const b2pn_sa_args &a, int backward);
+int sa_forward_f32(const b2pn_sa_args &a, cudaStream_t st);
+int sa_backward_f32(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t st);
+}  // namespace simt
+}  // namespace b2pn
+
+extern "C" int64_t b2pn_sa_workspace_bytes(const b2pn_sa_args *args, int32_t backward)
+{
+    if (!args) return B2PN_EINVAL;
+    if (args->precision == B2PN_PREC_F32) return b2pn::simt::sa_workspace_bytes_f32(*args, backward);
+    return B2PN_ENOTSUP;
+}
+
+extern "C" int b2pn_sa_forward(const b2pn_sa_args *args, b2pn_stream_t stream)
+{
+    if (!args) return B2PN_EINVAL;
+    if (args->precision == B2PN_PREC_F32) return b2pn::simt::sa_forward_f32(*args, (cudaStream_t)stream);
+    return B2PN_ENOTSUP;
+}
+
+extern "C" int b2pn_sa_backward(const b2pn_sa_args *args, const b2pn_sa_grads *grads, b2pn_stream_t stream)
+{
+    if (!args || !grads) return B2PN_EINVAL;
+    if (args->precision == B2PN_PREC_F32) return b2pn::simt::sa_backward_f32(*args, *grads, (cudaStream_t)stream);
+    return B2PN_ENOTSUP;
 }

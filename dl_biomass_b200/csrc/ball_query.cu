@@ -172,6 +172,7 @@ extern "C" int b2pn_ball_query_f32(const float *src_pos, const float *qry_pos, c
     const unsigned gx = (unsigned)((max_qry + QPB - 1) / QPB);
     dim3 grid(gx, (unsigned)B);
     ball_query_kernel<THREADS, QPW, TILE><<<grid, THREADS, 0, (cudaStream_t)stream>>>(p);
+    note_launch();
     B2PN_LAUNCH_CHECK();
     return B2PN_OK;
 }

@@ -25,6 +25,10 @@ namespace b2pn {
 
 typedef unsigned long long u64;
 
+// number of kernels this library has enqueued (bench.py reports it as gpu_launches)
+extern long long g_launches;
+static inline void note_launch(int n = 1) { __atomic_fetch_add(&g_launches, (long long)n, __ATOMIC_RELAXED); }
+
 // ---- packed fp32x2 arithmetic (Blackwell FADD2/FMUL2), each half rounded separately ----------
 // NOTE: ptxas contracts mul.f32x2 + add.f32x2 into FFMA2 even with .rn, which would break the
 // bit-exact distance contract, so only sub and mul are packed; the adds stay scalar __fadd_rn.

@@ -215,6 +215,7 @@ static int launch_fps(const FpsParams &p, int B, cudaStream_t stream)
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+    note_launch();
     return e == cudaSuccess ? 0 : (int)e;
 }
 
@@ -288,8 +289,9 @@ extern "C" int b2pn_fps_f32(const float *pos, const int64_t *ptr, const int64_t 
     int threads = g_force_threads, cluster = g_force_cluster;
     if (threads == 0) threads = 512;
     if (cluster == 0) {
-        // smallest cluster whose register capacity holds the largest cloud, then widen while the
-        // per-thread scan (c points) still dominates the ~cluster-barrier cost and SMs are free
+        // Measured on B200 (profiles/r01_fps_sweep.md): barrier.cluster costs more per iteration than
+        // the scan it saves up to ~12k points, so use the smallest cluster whose registers hold the
+        // largest cloud (512 threads x 24 points per CTA).
         cluster = 16;
         for (int cl = 1; cl <= 16; cl *= 2) {
             if ((int64_t)cl * threads * max_ppt(threads) >= max_n) {
@@ -297,7 +299,6 @@ extern "C" int b2pn_fps_f32(const float *pos, const int64_t *ptr, const int64_t 
                 break;
             }
         }
-        while (cluster < 8 && (int64_t)B * cluster * 2 <= 148 && max_n > (int64_t)cluster * threads * 8) cluster *= 2;
     }
     if ((int64_t)cluster * threads * max_ppt(threads) < max_n) return B2PN_ENOTSUP;
     return dispatch_cluster(p, B, max_n, cluster, threads, (cudaStream_t)stream);

@@ -59,6 +59,7 @@ class Batch(Data):
         out.y = None if data_list[0].y is None else torch.cat([d.y.reshape(-1) for d in data_list], 0)
         out.batch = torch.repeat_interleave(torch.arange(len(data_list), dtype=torch.int64), sizes)
         out.ptr = ptr
+        out.cloud_sizes = sizes.tolist()  # host copy: lets the model size its launches without a device read
         out.num_graphs = len(data_list)
         return out
 

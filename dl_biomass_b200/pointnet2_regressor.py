@@ -1,0 +1,182 @@
+"""B200-native drop-in for /root/reference/pointnet2_regressor.py.
+
+Same classes, constructor arguments and ``forward`` contracts as the reference module
+(``SAModule(ratio, r, nn)``, ``GlobalSAModule(nn)``, ``Net(num_features, activation_function,
+neuron_multiplier, dropout_probability)``; ``forward(data)`` over ``data.x / data.pos / data.batch``),
+and the same ``state_dict`` keys as the PyG-built reference model (``sa1_module.conv.local_nn.lins.0.weight``,
+``...norms.0.running_mean`` ...), so ``main.py`` can ``from pointnet2_regressor import Net`` unchanged.
+Underneath, everything PyG / torch_cluster / torch_scatter did is done by libb2pn's sm_100a kernels:
+
+    fps            -> torch.ops.b2pn.fps          (Kernel 1, csrc/fps.cu)
+    radius         -> torch.ops.b2pn.ball_query   (Kernel 2, csrc/ball_query.cu)
+    PointConv(nn)  -> sa.sa_apply                 (Kernel 3, csrc/sa_*.cu: gather + concat + MLP + max)
+    nn(cat) + global_max_pool -> sa.sa_apply in CLOUDS mode
+
+There is no CPU path: tensors must live on a B200.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+from . import ops, sa
+
+_PRECISIONS = {"fp32": sa.PREC_F32, "f32": sa.PREC_F32, "float32": sa.PREC_F32,
+               "bf16": sa.PREC_BF16, "bfloat16": sa.PREC_BF16}
+
+
+class MLP(torch.nn.Module):
+    """Parameter container shaped like ``torch_geometric.nn.MLP(channel_list, act=..., dropout=...)``
+    (SURVEY.md A.4): ``lins[i]`` Linear, ``norms[i]`` BatchNorm1d after every hidden layer, last layer plain.
+    ``forward`` is the plain layer-by-layer evaluation (used for the tiny regression head); inside the
+    set-abstraction modules the parameters are consumed by the fused kernels instead."""
+
+    def __init__(self, channel_list: Sequence[int], act="relu", dropout: float = 0.0, batch_norm: bool = True,
+                 bias: bool = True):
+        super().__init__()
+        if not batch_norm or not bias:
+            raise NotImplementedError("the reference only builds MLPs with batch_norm=True, bias=True")
+        self.channel_list = list(int(c) for c in channel_list)
+        self.act_name = None if act is None else (act if isinstance(act, str) else type(act).__name__)
+        sa.act_code(self.act_name)  # fail early on an activation the kernels do not implement
+        self.dropout = float(dropout)
+        self.lins = torch.nn.ModuleList(
+            [torch.nn.Linear(a, b) for a, b in zip(self.channel_list[:-1], self.channel_list[1:])])
+        self.norms = torch.nn.ModuleList([torch.nn.BatchNorm1d(c) for c in self.channel_list[1:-1]])
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = self.lins[0](x)
+        for lin, norm in zip(self.lins[1:], self.norms):
+            x = norm(x)
+            if self.act_name is not None:
+                x = F.relu(x)
+            x = F.dropout(x, p=self.dropout, training=self.training)
+            x = lin(x)
+        return x
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # PyG >= 2.1 wraps BatchNorm1d as ``norms.i.module.*``; accept both spellings
+        for k in list(state_dict.keys()):
+            if k.startswith(prefix + "norms.") and ".module." in k[len(prefix):]:
+                state_dict[k.replace(".module.", ".", 1)] = state_dict.pop(k)
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+
+class PointConv(torch.nn.Module):
+    """Holds ``local_nn`` under the same attribute name as PyG's PointNetConv (state_dict parity)."""
+
+    def __init__(self, local_nn: MLP, add_self_loops: bool = False):
+        super().__init__()
+        if add_self_loops:
+            raise NotImplementedError("the reference uses add_self_loops=False")
+        self.local_nn = local_nn
+
+
+def _cloud_sizes(batch: torch.Tensor, ptr=None) -> List[int]:
+    """Points per cloud as host integers.  Free when a host-side ``ptr`` is available (what
+    ``Batch.from_data_list`` builds on the CPU); otherwise one small device->host read, like the
+    ``int(batch.max())`` inside the reference's fps/radius wrappers."""
+    if ptr is not None:
+        p = ptr if not ptr.is_cuda else ptr.cpu()
+        return (p[1:] - p[:-1]).tolist()
+    if batch.numel() == 0:
+        return []
+    return torch.bincount(batch).cpu().tolist()
+
+
+class SAModule(torch.nn.Module):
+    """/root/reference/pointnet2_regressor.py:5-20."""
+
+    def __init__(self, ratio, r, nn, max_num_neighbors: int = 64):
+        super().__init__()
+        self.ratio = ratio
+        self.r = r
+        self.max_num_neighbors = max_num_neighbors
+        self.conv = PointConv(nn, add_self_loops=False)
+        self.precision = "fp32"
+        self.random_start = True  # torch_cluster.fps default
+
+    def _run(self, x, pos, src: ops.Level, dst: ops.Level, start=None):
+        if start is None and self.random_start and src.total > 0:
+            n = torch.tensor(src.sizes, dtype=torch.float32).to(pos.device, non_blocking=True)
+            start = (torch.rand(len(src.sizes), device=pos.device) * n).to(torch.int64)
+        idx, pos_dst, batch_dst = ops.fps(pos, src, dst, start)                        # :13, :19
+        nbr, cnt = ops.ball_query(pos, pos_dst, src, dst, self.r, self.max_num_neighbors)   # :14-16
+        out, _ = sa.sa_apply(self.conv.local_nn, x, pos, pos_dst, nbr, cnt, None, seg_mode=sa.SEG_SLOTS,
+                             K=self.max_num_neighbors, n_dst=dst.total, precision=_PRECISIONS[self.precision])  # :18
+        return out, pos_dst, batch_dst, idx
+
+    def forward(self, x, pos, batch):
+        lv = ops.build_levels(_cloud_sizes(batch), [self.ratio], pos.device)
+        out, pos_dst, batch_dst, _ = self._run(x, pos, lv[0], lv[1])
+        return out, pos_dst, batch_dst
+
+
+class GlobalSAModule(torch.nn.Module):
+    """/root/reference/pointnet2_regressor.py:23-33."""
+
+    def __init__(self, nn):
+        super().__init__()
+        self.nn = nn
+        self.precision = "fp32"
+
+    def _run(self, x, pos, batch, num_clouds: int):
+        out, _ = sa.sa_apply(self.nn, x, pos, None, None, None, batch, seg_mode=sa.SEG_CLOUDS, K=0,
+                             n_dst=num_clouds, precision=_PRECISIONS[self.precision])    # :29-30
+        return out
+
+    def forward(self, x, pos, batch):
+        num_clouds = int(batch.max().item()) + 1 if batch.numel() else 0
+        x = self._run(x, pos, batch, num_clouds)
+        pos = pos.new_zeros((x.size(0), 3))                                              # :31
+        batch = torch.arange(x.size(0), device=batch.device)                             # :32
+        return x, pos, batch
+
+
+class Net(torch.nn.Module):
+    """/root/reference/pointnet2_regressor.py:36-58.
+
+    Extra, optional and keyword-only: ``precision`` ("fp32": CUDA-core FMA, the 1e-4 parity mode; "bf16":
+    tcgen05 tensor-core tiles with fp32 accumulation).  It can also be switched later with
+    ``set_precision``."""
+
+    def __init__(self, num_features, activation_function, neuron_multiplier, dropout_probability, *,
+                 precision: str = "fp32"):
+        super().__init__()
+        if neuron_multiplier == 0:
+            neuron_multiplier = 1  # :40-43
+        nm = neuron_multiplier
+        self.sa1_module = SAModule(0.2, 2, MLP([3 + num_features, 64 * nm, 64 * nm, 128 * nm], act=activation_function))
+        self.sa2_module = SAModule(0.25, 8, MLP([128 * nm + 3, 128 * nm, 128 * nm, 256 * nm], act=activation_function))
+        self.sa3_module = GlobalSAModule(MLP([256 * nm + 3, 256 * nm, 512 * nm, 1024 * nm], act=activation_function))
+        self.mlp = MLP([1024 * nm, 128 * nm, 128 * nm, 4], act=None, dropout=dropout_probability)
+        self.set_precision(precision)
+
+    def set_precision(self, precision: str) -> "Net":
+        if precision not in _PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
+        for m in (self.sa1_module, self.sa2_module, self.sa3_module):
+            m.precision = precision
+        self.precision = precision
+        return self
+
+    def set_random_start(self, flag: bool) -> "Net":
+        self.sa1_module.random_start = self.sa2_module.random_start = bool(flag)
+        return self
+
+    def forward(self, data, start: Optional[torch.Tensor] = None):
+        x, pos, batch = data.x, data.pos, data.batch                                     # :53
+        if not pos.is_cuda:
+            raise RuntimeError("dl_biomass_b200.Net runs on a B200 only: move the batch to the GPU "
+                               "(there is no CPU fallback)")
+        sizes = getattr(data, "cloud_sizes", None)
+        if sizes is None:
+            sizes = _cloud_sizes(batch, getattr(data, "ptr", None))
+        lv = ops.build_levels(sizes, [self.sa1_module.ratio, self.sa2_module.ratio], pos.device)
+        pos = pos.to(torch.float32)
+        x1, pos1, _, _ = self.sa1_module._run(x, pos, lv[0], lv[1], start)               # :54
+        x2, pos2, batch2, _ = self.sa2_module._run(x1, pos1, lv[1], lv[2])                # :55
+        x3 = self.sa3_module._run(x2, pos2, batch2, len(sizes))                          # :56
+        return self.mlp(x3)                                                              # :58

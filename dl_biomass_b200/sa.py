@@ -1,0 +1,169 @@
+"""Set-abstraction level op: ctypes mirror of ``b2pn_sa_args`` + the autograd bridge.
+
+``sa_apply`` is what PyG's ``PointNetConv.propagate`` (message -> local_nn -> max aggregate) and
+``global_max_pool(nn(cat[x,pos]))`` are in the reference (/root/reference/pointnet2_regressor.py:18,
+:29-30): one call into libb2pn for the forward, one for the backward.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+PREC_F32, PREC_BF16 = 0, 1
+SEG_SLOTS, SEG_CLOUDS = 0, 1
+ACT_NONE, ACT_RELU = 0, 1
+
+_vp = ctypes.c_void_p
+
+
+Mlp3, SaArgs, SaGrads = _lib.Mlp3, _lib.SaArgs, _lib.SaGrads
+
+
+def _dp(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def act_code(act) -> int:
+    if act is None:
+        return ACT_NONE
+    name = act if isinstance(act, str) else type(act).__name__
+    if name.lower() == "relu":
+        return ACT_RELU
+    raise NotImplementedError(
+        f"activation {act!r}: the B200 kernels implement ReLU (the only activation the reference trains with, "
+        f"/root/reference/main.py:45) and None")
+
+
+def _fill_args(a: SaArgs, *, precision, training, seg_mode, K, n_src, n_dst, c_in, x, pos_src, pos_dst, nbr, cnt,
+               batch, chans, act, eps, momentum, ws, bs, gammas, betas, rmeans, rvars, nbts, out, arg, h1, h2, bn):
+    a.precision, a.training, a.seg_mode, a.K = precision, int(training), seg_mode, K
+    a.n_src, a.n_dst, a.c_in = n_src, n_dst, c_in
+    a.x, a.pos_src, a.pos_dst = _dp(x), _dp(pos_src), _dp(pos_dst)
+    a.nbr, a.cnt, a.batch = _dp(nbr), _dp(cnt), _dp(batch)
+    m = a.mlp
+    for i in range(4):
+        m.c[i] = chans[i]
+    m.act, m.eps, m.momentum = act, eps, momentum
+    for i in range(3):
+        m.w[i], m.b[i] = _dp(ws[i]), _dp(bs[i])
+    for i in range(2):
+        m.gamma[i], m.beta[i] = _dp(gammas[i]), _dp(betas[i])
+        m.running_mean[i], m.running_var[i] = _dp(rmeans[i]), _dp(rvars[i])
+        m.num_batches_tracked[i] = _dp(nbts[i])
+    a.out, a.arg, a.h1, a.h2, a.bn = _dp(out), _dp(arg), _dp(h1), _dp(h2), _dp(bn)
+
+
+class _SAFunction(torch.autograd.Function):
+    """forward/backward of one set-abstraction level through libb2pn."""
+
+    @staticmethod
+    def forward(ctx, cfg, x, pos_src, pos_dst, nbr, cnt, batch, w1, b1, g1, be1, w2, b2, g2, be2, w3, b3,
+                rm1, rv1, nbt1, rm2, rv2, nbt2):
+        lib = _lib.lib()
+        dev = pos_src.device
+        if not pos_src.is_cuda:
+            raise RuntimeError("b2pn set abstraction runs on a B200 only: there is no CPU fallback")
+        prec, training, seg_mode, K, n_dst, act, eps, momentum = cfg
+        f32 = torch.float32
+        ws = [w.detach().to(f32).contiguous() for w in (w1, w2, w3)]
+        bs = [b.detach().to(f32).contiguous() for b in (b1, b2, b3)]
+        gs = [g.detach().contiguous() for g in (g1, g2)]
+        bes = [b.detach().contiguous() for b in (be1, be2)]
+        chans = [ws[0].shape[1], ws[0].shape[0], ws[1].shape[0], ws[2].shape[0]]
+        c_in = 0 if x is None else x.shape[1]
+        if chans[0] != c_in + 3:
+            raise ValueError(f"MLP expects {chans[0]} input channels, got {c_in} features + 3")
+        xs = None if x is None else x.detach().to(f32).contiguous()
+        pos_src = pos_src.contiguous()
+        n_src = pos_src.shape[0]
+        rows = n_src if seg_mode == SEG_CLOUDS else n_dst * K
+        act_dtype = torch.float32 if prec == PREC_F32 else torch.bfloat16
+        out = torch.empty(n_dst, chans[3], dtype=f32, device=dev)
+        arg = torch.empty(n_dst, chans[3], dtype=torch.int32, device=dev)
+        h1 = torch.empty(rows, chans[1], dtype=act_dtype, device=dev)
+        h2 = torch.empty(rows, chans[2], dtype=act_dtype, device=dev)
+        cmax = max(chans[1], chans[2])
+        bn = torch.empty(2, 4, cmax, dtype=f32, device=dev)
+        a = SaArgs()
+        _fill_args(a, precision=prec, training=training, seg_mode=seg_mode, K=K, n_src=n_src, n_dst=n_dst, c_in=c_in,
+                   x=xs, pos_src=pos_src, pos_dst=pos_dst, nbr=nbr, cnt=cnt, batch=batch, chans=chans, act=act,
+                   eps=eps, momentum=momentum, ws=ws, bs=bs, gammas=gs, betas=bes, rmeans=(rm1, rm2),
+                   rvars=(rv1, rv2), nbts=(nbt1, nbt2), out=out, arg=arg, h1=h1, h2=h2, bn=bn)
+        nbytes = lib.b2pn_sa_workspace_bytes(ctypes.byref(a), 0)
+        if nbytes < 0:
+            _lib.check(int(nbytes), "b2pn_sa_workspace_bytes")
+        wsb = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+        a.workspace, a.workspace_bytes = wsb.data_ptr(), wsb.numel()
+        with torch.cuda.device(dev):
+            rc = lib.b2pn_sa_forward(ctypes.byref(a), torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "b2pn_sa_forward")
+        ctx.cfg = cfg
+        ctx.chans = chans
+        ctx.c_in = c_in
+        ctx.has_x = x is not None
+        ctx.x_needs_grad = x is not None and x.requires_grad
+        ctx.save_for_backward(xs, pos_src, pos_dst, nbr, cnt, batch, *ws, *bs, *gs, *bes, rm1, rv1, rm2, rv2,
+                              arg, h1, h2, bn)
+        ctx.mark_non_differentiable(arg)
+        return out, arg
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out, _grad_arg):
+        lib = _lib.lib()
+        (xs, pos_src, pos_dst, nbr, cnt, batch, w1, w2, w3, b1, b2, b3, g1, g2, be1, be2, rm1, rv1, rm2, rv2,
+         arg, h1, h2, bn) = ctx.saved_tensors
+        prec, training, seg_mode, K, n_dst, act, eps, momentum = ctx.cfg
+        dev = pos_src.device
+        chans = ctx.chans
+        f32 = torch.float32
+        grad_out = grad_out.to(f32).contiguous()
+        gw = [torch.empty_like(w) for w in (w1, w2, w3)]
+        gb = [torch.empty_like(b) for b in (b1, b2, b3)]
+        gg = [torch.empty_like(g) for g in (g1, g2)]
+        gbe = [torch.empty_like(b) for b in (be1, be2)]
+        gx = torch.zeros_like(xs) if ctx.x_needs_grad else None
+        a = SaArgs()
+        _fill_args(a, precision=prec, training=training, seg_mode=seg_mode, K=K, n_src=pos_src.shape[0], n_dst=n_dst,
+                   c_in=ctx.c_in, x=xs, pos_src=pos_src, pos_dst=pos_dst, nbr=nbr, cnt=cnt, batch=batch, chans=chans,
+                   act=act, eps=eps, momentum=momentum, ws=(w1, w2, w3), bs=(b1, b2, b3), gammas=(g1, g2),
+                   betas=(be1, be2), rmeans=(rm1, rm2), rvars=(rv1, rv2), nbts=(None, None), out=grad_out, arg=arg,
+                   h1=h1, h2=h2, bn=bn)
+        nbytes = lib.b2pn_sa_workspace_bytes(ctypes.byref(a), 1)
+        if nbytes < 0:
+            _lib.check(int(nbytes), "b2pn_sa_workspace_bytes")
+        wsb = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+        a.workspace, a.workspace_bytes = wsb.data_ptr(), wsb.numel()
+        g = SaGrads()
+        g.grad_out = grad_out.data_ptr()
+        for i in range(3):
+            g.grad_w[i], g.grad_b[i] = gw[i].data_ptr(), gb[i].data_ptr()
+        for i in range(2):
+            g.grad_gamma[i], g.grad_beta[i] = gg[i].data_ptr(), gbe[i].data_ptr()
+        g.grad_x = _dp(gx)
+        with torch.cuda.device(dev):
+            rc = lib.b2pn_sa_backward(ctypes.byref(a), ctypes.byref(g), torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "b2pn_sa_backward")
+        return (None, gx, None, None, None, None, None, gw[0], gb[0], gg[0], gbe[0], gw[1], gb[1], gg[1], gbe[1],
+                gw[2], gb[2], None, None, None, None, None, None)
+
+
+def sa_apply(mlp, x, pos_src, pos_dst, nbr, cnt, batch, *, seg_mode: int, K: int, n_dst: int, precision: int):
+    """Run one set-abstraction level with the parameters of ``mlp`` (a b2pn ``MLP`` of three Linear layers)."""
+    if len(mlp.lins) != 3 or len(mlp.norms) != 2:
+        raise NotImplementedError("set-abstraction kernels are built for the reference's 3-layer MLPs with BatchNorm")
+    if mlp.dropout != 0.0 and mlp.training:
+        raise NotImplementedError("dropout inside set-abstraction MLPs is not used by the reference")
+    n0, n1 = mlp.norms
+    cfg = (precision, bool(mlp.training), seg_mode, K, n_dst, act_code(mlp.act_name), float(n0.eps),
+           float(n0.momentum if n0.momentum is not None else 0.1))
+    l0, l1, l2 = mlp.lins
+    out, arg = _SAFunction.apply(cfg, x, pos_src, pos_dst, nbr, cnt, batch,
+                                 l0.weight, l0.bias, n0.weight, n0.bias, l1.weight, l1.bias, n1.weight, n1.bias,
+                                 l2.weight, l2.bias, n0.running_mean, n0.running_var, n0.num_batches_tracked,
+                                 n1.running_mean, n1.running_var, n1.num_batches_tracked)
+    return out, arg

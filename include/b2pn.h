@@ -33,6 +33,8 @@ typedef void *b2pn_stream_t;
 
 int b2pn_abi_version(void);
 const char *b2pn_error_string(int code);
+/* kernels enqueued by this library so far in this process (bench.py's gpu_launches) */
+int64_t b2pn_launch_count(void);
 
 /* samples per cloud: ceil(float32(n) * float32(ratio)) -- torch_cluster.fps sizing
  * (reached from /root/reference/pointnet2_regressor.py:13).  Host-side helper. */
@@ -71,6 +73,71 @@ int b2pn_fps_set_variant(int32_t cluster, int32_t threads);
 int b2pn_ball_query_f32(const float *src_pos, const float *qry_pos, const int64_t *src_ptr,
                         const int64_t *qry_ptr, int32_t B, int64_t max_src, int64_t max_qry, double r,
                         int32_t K, int32_t *nbr, int32_t *cnt, b2pn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Set-abstraction levels: fused gather + relative-position concat + shared MLP + max aggregation.
+ *
+ * One b2pn_sa_args describes one SAModule / GlobalSAModule call of
+ * /root/reference/pointnet2_regressor.py:12-20 (PointConv(nn) == PointNetConv: message
+ * nn([x_j || pos_j - pos_i]), aggr max) or :28-33 (nn(cat[x,pos]) + global_max_pool), i.e. the ATen /
+ * cuBLAS / torch_scatter kernels K3..K8 of SURVEY.md 2.2.  `nn` is the PyG MLP of three Linear
+ * layers with BatchNorm1d + activation after the first two.
+ * ---------------------------------------------------------------------------------------------- */
+#define B2PN_PREC_F32 0   /* fp32 FMA on CUDA cores: the 1e-4 parity mode                      */
+#define B2PN_PREC_BF16 1  /* bf16 tcgen05 tensor-core tiles, fp32 accumulation in TMEM          */
+#define B2PN_SEG_SLOTS 0  /* SAModule: targets own K fixed-width neighbour slots (nbr/cnt)      */
+#define B2PN_SEG_CLOUDS 1 /* GlobalSAModule: every source row belongs to cloud batch[row]       */
+#define B2PN_ACT_NONE 0
+#define B2PN_ACT_RELU 1
+
+typedef struct b2pn_mlp3 {
+    int32_t c[4];                /* channel list [c0, c1, c2, c3]; c0 = c_in + 3                     */
+    int32_t act;                 /* B2PN_ACT_*                                                        */
+    float eps, momentum;         /* BatchNorm1d eps (1e-5) and momentum (0.1)                         */
+    const float *w[3];           /* Linear weight [c_{l+1}, c_l] row-major (torch layout)             */
+    const float *b[3];           /* Linear bias   [c_{l+1}]                                           */
+    const float *gamma[2];       /* BN weight [c_{l+1}] for l = 0,1                                   */
+    const float *beta[2];        /* BN bias                                                           */
+    float *running_mean[2];      /* updated in place when training                                    */
+    float *running_var[2];
+    int64_t *num_batches_tracked[2];
+} b2pn_mlp3;
+
+typedef struct b2pn_sa_args {
+    int32_t precision;           /* B2PN_PREC_*                                                       */
+    int32_t training;            /* 1: batch statistics + running-stat update, 0: running statistics  */
+    int32_t seg_mode;            /* B2PN_SEG_*                                                        */
+    int32_t K;                   /* slots per target (SLOTS), multiple of 8 dividing 128              */
+    int64_t n_src, n_dst;        /* source points; targets (centroids or clouds)                      */
+    int32_t c_in;                /* feature channels of x (0: no features, pointnet2_regressor.py:17) */
+    int32_t reserved;
+    const float *x;              /* [n_src, c_in] f32 or NULL                                         */
+    const float *pos_src;        /* [n_src, 3]                                                        */
+    const float *pos_dst;        /* [n_dst, 3] (SLOTS) / NULL (CLOUDS: centre is the origin)          */
+    const int32_t *nbr;          /* [n_dst, K] (SLOTS)                                                */
+    const int32_t *cnt;          /* [n_dst]    (SLOTS)                                                */
+    const int64_t *batch;        /* [n_src] sorted cloud id per row (CLOUDS)                          */
+    b2pn_mlp3 mlp;
+    float *out;                  /* [n_dst, c3]                                                       */
+    int32_t *arg;                /* [n_dst, c3] arg-max slot (SLOTS) or source row (CLOUDS); -1 none  */
+    void *h1, *h2;               /* saved pre-BN activations [rows, c1], [rows, c2]; rows = n_dst*K
+                                    (SLOTS) or n_src (CLOUDS); f32 or bf16 by precision               */
+    float *bn;                   /* [2][4][cmax] per BN layer: mean, rstd, scale, shift; cmax=max(c1,c2) */
+    void *workspace;             /* b2pn_sa_workspace_bytes() bytes, scratch                          */
+    int64_t workspace_bytes;
+} b2pn_sa_args;
+
+typedef struct b2pn_sa_grads {
+    const float *grad_out;       /* [n_dst, c3]                                                       */
+    float *grad_w[3], *grad_b[3];/* overwritten                                                       */
+    float *grad_gamma[2], *grad_beta[2];
+    float *grad_x;               /* [n_src, c_in], ZERO-INITIALISED by the caller (scatter-add); NULL = skip */
+} b2pn_sa_grads;
+
+/* scratch bytes needed by forward (backward=0) or backward (backward=1) for these shapes */
+int64_t b2pn_sa_workspace_bytes(const b2pn_sa_args *args, int32_t backward);
+int b2pn_sa_forward(const b2pn_sa_args *args, b2pn_stream_t stream);
+int b2pn_sa_backward(const b2pn_sa_args *args, const b2pn_sa_grads *grads, b2pn_stream_t stream);
 
 #ifdef __cplusplus
 }
