@@ -52,6 +52,7 @@ SIGNATURES = {
     "b2pn_sa_workspace_bytes": (_i64, [ctypes.POINTER(SaArgs), _i32]),
     "b2pn_sa_forward": (ctypes.c_int, [ctypes.POINTER(SaArgs), _vp]),
     "b2pn_sa_backward": (ctypes.c_int, [ctypes.POINTER(SaArgs), ctypes.POINTER(SaGrads), _vp]),
+    "b2pn_tc_gemm_selftest": (ctypes.c_int, [_vp, _i32, _i32, _vp, _i32, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _vp]),
 }
 
 

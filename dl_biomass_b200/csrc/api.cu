@@ -56,3 +56,19 @@ extern "C" int b2pn_sa_backward(const b2pn_sa_args *args, const b2pn_sa_grads *g
     if (args->precision == B2PN_PREC_F32) return b2pn::simt::sa_backward_f32(*args, *grads, (cudaStream_t)stream);
     return B2PN_ENOTSUP;
 }
+
+// ---- tcgen05 pipeline self-test (debug aid) ---------------------------------------------------------
+namespace b2pn {
+namespace tc {
+int tc_gemm_selftest(const float *w, int m_out, int k, const void *b, int mode, int64_t rows, int64_t ld, const float *zeros3,
+                     float *out, int64_t ld_out, void *workspace, int64_t workspace_bytes, cudaStream_t st);
+}
+}  // namespace b2pn
+
+extern "C" int b2pn_tc_gemm_selftest(const float *w, int32_t m_out, int32_t k, const void *b_bf16, int32_t mode, int64_t rows,
+                                     int64_t ld, const float *zeros3, float *out, int64_t ld_out, void *workspace,
+                                     int64_t workspace_bytes, b2pn_stream_t stream)
+{
+    return b2pn::tc::tc_gemm_selftest(w, m_out, k, b_bf16, mode, rows, ld, zeros3, out, ld_out, workspace, workspace_bytes,
+                                      (cudaStream_t)stream);
+}
