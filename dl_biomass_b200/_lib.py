@@ -28,7 +28,7 @@ class Mlp3(ctypes.Structure):
 class SaArgs(ctypes.Structure):
     _fields_ = [("precision", ctypes.c_int32), ("training", ctypes.c_int32), ("seg_mode", ctypes.c_int32),
                 ("K", ctypes.c_int32), ("n_src", ctypes.c_int64), ("n_dst", ctypes.c_int64),
-                ("c_in", ctypes.c_int32), ("reserved", ctypes.c_int32), ("x", _vp), ("pos_src", _vp),
+                ("c_in", ctypes.c_int32), ("x_dtype", ctypes.c_int32), ("x", _vp), ("pos_src", _vp),
                 ("pos_dst", _vp), ("nbr", _vp), ("cnt", _vp), ("batch", _vp), ("mlp", Mlp3), ("out", _vp),
                 ("arg", _vp), ("h1", _vp), ("h2", _vp), ("bn", _vp), ("workspace", _vp),
                 ("workspace_bytes", ctypes.c_int64)]

@@ -34,12 +34,18 @@ int64_t sa_workspace_bytes_f32(const b2pn_sa_args &a, int backward);
 int sa_forward_f32(const b2pn_sa_args &a, cudaStream_t st);
 int sa_backward_f32(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t st);
 }  // namespace simt
+namespace tc {
+int64_t sa_workspace_bytes_bf16(const b2pn_sa_args &a, int backward);
+int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st);
+int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t st);
+}  // namespace tc
 }  // namespace b2pn
 
 extern "C" int64_t b2pn_sa_workspace_bytes(const b2pn_sa_args *args, int32_t backward)
 {
     if (!args) return B2PN_EINVAL;
     if (args->precision == B2PN_PREC_F32) return b2pn::simt::sa_workspace_bytes_f32(*args, backward);
+    if (args->precision == B2PN_PREC_BF16) return b2pn::tc::sa_workspace_bytes_bf16(*args, backward);
     return B2PN_ENOTSUP;
 }
 
@@ -47,6 +53,7 @@ extern "C" int b2pn_sa_forward(const b2pn_sa_args *args, b2pn_stream_t stream)
 {
     if (!args) return B2PN_EINVAL;
     if (args->precision == B2PN_PREC_F32) return b2pn::simt::sa_forward_f32(*args, (cudaStream_t)stream);
+    if (args->precision == B2PN_PREC_BF16) return b2pn::tc::sa_forward_bf16(*args, (cudaStream_t)stream);
     return B2PN_ENOTSUP;
 }
 
@@ -54,6 +61,7 @@ extern "C" int b2pn_sa_backward(const b2pn_sa_args *args, const b2pn_sa_grads *g
 {
     if (!args || !grads) return B2PN_EINVAL;
     if (args->precision == B2PN_PREC_F32) return b2pn::simt::sa_backward_f32(*args, *grads, (cudaStream_t)stream);
+    if (args->precision == B2PN_PREC_BF16) return b2pn::tc::sa_backward_bf16(*args, *grads, (cudaStream_t)stream);
     return B2PN_ENOTSUP;
 }
 

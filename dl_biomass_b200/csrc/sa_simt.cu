@@ -844,7 +844,7 @@ int sa_forward_f32(const b2pn_sa_args &a, cudaStream_t st)
     }
     if (s.rows > 0) {
         // layer 1: gather + concat + Linear
-        GatherLoader gl = {rm, a.x, a.c_in, a.pos_src, a.pos_dst};
+        GatherLoader gl = {rm, (const float *)a.x, a.c_in, a.pos_src, a.pos_dst};
         StoreStatsEp e1 = {rm, h1, a.mlp.b[0], f.partial};
         launch_rows_gemm(gl, BMat{f.wt[0], s.c1, s.c0, s.c1}, e1, s.tiles, st);
     }
@@ -939,7 +939,7 @@ int sa_backward_f32(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t 
     // ---- layer 1 -------------------------------------------------------------------------------------
     PlainLoader y1 = {rm, b.dz1, s.c1};
     {
-        GatherLoader gl = {rm, a.x, a.c_in, a.pos_src, a.pos_dst};
+        GatherLoader gl = {rm, (const float *)a.x, a.c_in, a.pos_src, a.pos_dst};
         WithOnes<GatherLoader> glo = {gl, s.c0};
         launch_dw(y1, glo, s.c1, s.c0 + 1, s, b.dwp, g.grad_w[0], g.grad_b[0], st);
     }

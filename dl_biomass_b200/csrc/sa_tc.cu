@@ -21,9 +21,11 @@ namespace tc {
 
 constexpr int R = 128;          // rows per tile = UMMA N
 constexpr int KC = 64;          // reduction chunk = one 128-byte line of bf16
-constexpr int NUM_EPI = 128;    // warps 0-3
-constexpr int NUM_LOAD = 128;   // warps 4-7
-constexpr int NT = 288;         // + warp 8: MMA issuer / TMEM owner
+constexpr int NUM_EPI = 256;    // warps 0-7: warp w drains TMEM lanes 32*(w%4).., column half w/4
+constexpr int NUM_LOAD = 128;   // threads per loader group
+constexpr int LOAD_GROUPS = 2;  // warps 8-11 and 12-15 fill alternate pipeline stages (hides global-load latency)
+constexpr int MMA_WARP = (NUM_EPI + LOAD_GROUPS * NUM_LOAD) / 32;  // warp 16: MMA issuer / TMEM owner
+constexpr int NT = NUM_EPI + LOAD_GROUPS * NUM_LOAD + 32;
 constexpr int B_BYTES = R * LINE_BYTES;  // 16 KB: [128 row lines x 64 k] or [2 row blocks][64 k lines x 64 rows]
 
 struct RowMapTC {
@@ -33,21 +35,21 @@ struct RowMapTC {
     const int64_t *batch;
     int64_t rows;    // logical rows
     int64_t n_dst;
+    int kshift;      // log2(K): the tensor-core path takes K in {16, 32, 64, 128}
+    __device__ __forceinline__ int64_t seg_of(int64_t row) const { return row >> kshift; }
+    __device__ __forceinline__ int slot_of(int64_t row) const { return (int)(row & (int64_t)(K - 1)); }
     __device__ __forceinline__ bool valid(int64_t row) const
     {
         if (row >= rows) return false;
         if (seg_mode) return true;
-        const int64_t m = row / K;
-        return (int)(row - m * K) < cnt[m];
+        return slot_of(row) < cnt[seg_of(row)];
     }
     // number of valid rows among the 8 rows starting at row8 (row8 % 8 == 0, K % 8 == 0)
     __device__ __forceinline__ int valid8(int64_t row8) const
     {
         if (row8 >= rows) return 0;
         if (seg_mode) return (int)min((int64_t)8, rows - row8);
-        const int64_t m = row8 / K;
-        const int k0 = (int)(row8 - m * K);
-        return max(0, min(8, cnt[m] - k0));
+        return max(0, min(8, cnt[seg_of(row8)] - slot_of(row8)));
     }
 };
 
@@ -57,23 +59,45 @@ struct GemmParams {
     int64_t num_tiles;
 };
 
+// layer-1 operand columns: [x (c_in) | x_lo (c_in, only when x arrives in fp32) | dpos_hi (3) | dpos_lo (3)].
+// Raw fp32 inputs (intensity, relative positions) are split into bf16 hi + lo parts that meet the SAME
+// weight column, so the tensor cores see them with ~16 mantissa bits at no extra MMA cost (the columns
+// live in the padding of the 64-wide K chunk).
+struct InCols {
+    int c_in;
+    int x_f32;
+    __host__ __device__ int nx() const { return c_in * (x_f32 ? 2 : 1); }
+    __host__ __device__ int k_img() const { return nx() + 6; }
+    __host__ __device__ int src_col(int k) const  // weight column that feeds image column k (-1: padding)
+    {
+        const int n = nx();
+        if (k < n) return k < c_in ? k : k - c_in;
+        const int j = k - n;
+        if (j < 3) return c_in + j;
+        if (j < 6) return c_in + j - 3;
+        return -1;
+    }
+};
+
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16(v)); }
+
 // =================================================================================================
-//  B-tile loaders (128 threads).  produce() fills one 16 KB chunk for reduction chunk kc.
+//  B-tile loaders for the rows GEMM (128 threads).  produce() fills one 16 KB chunk for K chunk kc.
 // =================================================================================================
-struct GatherLoaderTC {  // K-major B: line = row of the tile, 64 k per line: [x_j || pos_j - pos_i || 0]
+struct GatherLoaderTC {  // K-major B: line = row of the tile, 64 k per line
     static constexpr bool B_MN = false;
     RowMapTC rm;
-    const __nv_bfloat16 *x;  // [n_src, c_in] bf16 row-major (may be null when c_in == 0)
-    int c_in;
+    const void *x;  // [n_src, c_in] row-major, fp32 (cols.x_f32) or bf16
+    InCols cols;
     const float *pos_src;
     const float *pos_dst;
-    // per-thread, per-tile state
+    int ones_col;  // image column that carries 1 for valid rows (dW bias column), -1: none
+    // per-thread state for the current row
     bool ok;
     int64_t src;
     float d0, d1, d2;
-    __device__ __forceinline__ void begin_tile(int64_t tile, int lt)
+    __device__ __forceinline__ void set_row(int64_t row)
     {
-        const int64_t row = tile * R + lt;
         ok = rm.valid(row);
         src = 0;
         d0 = d1 = d2 = 0.f;
@@ -83,104 +107,190 @@ struct GatherLoaderTC {  // K-major B: line = row of the tile, 64 k per line: [x
             d1 = pos_src[3 * src + 1];
             d2 = pos_src[3 * src + 2];
             if (!rm.seg_mode) {
-                const int64_t m = row / rm.K;
+                const int64_t m = rm.seg_of(row);
                 d0 = __fsub_rn(d0, pos_dst[3 * m + 0]);
                 d1 = __fsub_rn(d1, pos_dst[3 * m + 1]);
                 d2 = __fsub_rn(d2, pos_dst[3 * m + 2]);
             }
         }
     }
+    __device__ __forceinline__ void begin_tile(int64_t tile, int lt) { set_row(tile * R + lt); }
     __device__ __forceinline__ float elem(int k) const
     {
-        if (k < c_in) return __bfloat162float(x[src * c_in + k]);
-        const int j = k - c_in;
-        return j == 0 ? d0 : (j == 1 ? d1 : (j == 2 ? d2 : 0.f));
+        if (k == ones_col) return 1.f;
+        const int c_in = cols.c_in, nx = cols.nx();
+        if (k < c_in) {
+            return cols.x_f32 ? reinterpret_cast<const float *>(x)[src * c_in + k]
+                              : __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(x)[src * c_in + k]);
+        }
+        if (k < nx) {
+            const float v = reinterpret_cast<const float *>(x)[src * c_in + (k - c_in)];
+            return v - bf16_round(v);
+        }
+        const int j = k - nx;
+        if (j >= 6) return 0.f;
+        const int a = j < 3 ? j : j - 3;
+        const float v = a == 0 ? d0 : (a == 1 ? d1 : d2);
+        return j < 3 ? v : v - bf16_round(v);
+    }
+    // 16-byte chunk holding image columns kk .. kk+7 of the current row
+    __device__ __forceinline__ uint4 chunk(int kk) const
+    {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (!ok) return v;
+        if (!cols.x_f32 && (cols.c_in & 7) == 0 && kk + 8 <= cols.c_in)
+            return __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(x) + src * cols.c_in + kk));
+        if (kk < cols.k_img() + (ones_col >= 0 ? 1 : 0)) {
+            v.x = pack_bf16x2(elem(kk + 0), elem(kk + 1));
+            v.y = pack_bf16x2(elem(kk + 2), elem(kk + 3));
+            v.z = pack_bf16x2(elem(kk + 4), elem(kk + 5));
+            v.w = pack_bf16x2(elem(kk + 6), elem(kk + 7));
+        }
+        return v;
     }
     __device__ __forceinline__ void produce(uint8_t *B, int kc, int lt) const
     {
-        const int k0 = kc * KC;
-        const bool vec_ok = (c_in & 7) == 0;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const int kk = k0 + c * 8;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (ok) {
-                if (vec_ok && kk + 8 <= c_in) {
-                    v = __ldg(reinterpret_cast<const uint4 *>(x + src * c_in + kk));
-                } else if (kk < c_in + 3) {
-                    v.x = pack_bf16x2(elem(kk + 0), elem(kk + 1));
-                    v.y = pack_bf16x2(elem(kk + 2), elem(kk + 3));
-                    v.z = pack_bf16x2(elem(kk + 4), elem(kk + 5));
-                    v.w = pack_bf16x2(elem(kk + 6), elem(kk + 7));
-                }
-            }
-            *reinterpret_cast<uint4 *>(B + line_chunk_off(lt, c)) = v;
-        }
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4 *>(B + line_chunk_off(lt, c)) = chunk(kc * KC + c * 8);
     }
-    // descriptor of the 16-wide k step ks inside the chunk: K-major, SBO = 8 lines
     static __device__ __forceinline__ uint64_t b_desc(uint32_t b_saddr, int ks) { return smem_desc_sw128(b_saddr + ks * 32, 16, ATOM_BYTES); }
 };
 
-// feature-major source [C][ld] -> MN-major B tile: [2 row blocks of 64][64 channel lines]
-// thread lt handles channel line (lt >> 1) of the chunk and row block (lt & 1)
-template <int MODE>  // 0: plain (masked), 1: BN + act (masked with 0), 2: BN + act, invalid slots duplicate slot 0
-struct FeatLoaderTC {
-    static constexpr bool B_MN = true;
+__device__ __forceinline__ void unpack8(const uint4 &raw, float (&f)[8])
+{
+    f[0] = bf16_lo(raw.x); f[1] = bf16_hi(raw.x); f[2] = bf16_lo(raw.y); f[3] = bf16_hi(raw.y);
+    f[4] = bf16_lo(raw.z); f[5] = bf16_hi(raw.z); f[6] = bf16_lo(raw.w); f[7] = bf16_hi(raw.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8])
+{
+    uint4 o;
+    o.x = pack_bf16x2(f[0], f[1]);
+    o.y = pack_bf16x2(f[2], f[3]);
+    o.z = pack_bf16x2(f[4], f[5]);
+    o.w = pack_bf16x2(f[6], f[7]);
+    return o;
+}
+
+// 8 consecutive rows (r8 .. r8+7) of channel ch of a feature-major tensor, as the B/A operand wants them:
+//   MODE 0: plain, invalid rows -> 0      MODE 1: activation on load, invalid rows -> 0
+//   MODE 2: activation on load, invalid slots duplicate slot 0 of their centroid (so a plain max over
+//           all K slots equals the max over the valid ones and the first-max rule still picks a valid slot)
+template <int MODE>
+struct FeatSource {
     RowMapTC rm;
-    const __nv_bfloat16 *h;  // [C][ld]
+    const __nv_bfloat16 *t;  // [C][ld]; MODE 1/2: the normalised value zhat, activation input is gamma*zhat+beta
     int C;
     int64_t ld;
-    const float *scale;
-    const float *shift;
     int act;
+    int ones_line;  // channel index that carries 1 for valid rows (dW bias column), -1: none
+    const float *gamma;
+    const float *beta;
+    __device__ __forceinline__ uint4 chunk(int ch, int64_t r8) const { return chunk_nv(ch, r8, rm.valid8(r8)); }
+    __device__ __forceinline__ uint4 chunk_nv(int ch, int64_t r8, int nv) const
+    {
+        float f[8];
+        if (ch == ones_line) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = e < nv ? 1.f : 0.f;
+            return pack8(f);
+        }
+        const bool live = ch < C && (nv > 0 || (MODE == 2 && r8 < rm.rows));
+        uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+        if (live) raw = __ldg(reinterpret_cast<const uint4 *>(t + (int64_t)ch * ld + r8));
+        if (MODE == 0) {
+            if (nv == 8 || !live) return raw;
+        } else if (!live) {
+            return raw;
+        }
+        unpack8(raw, f);
+        float ga = 1.f, be = 0.f;
+        if (MODE != 0) {
+            ga = gamma[ch];
+            be = beta[ch];
+        }
+        float fill = 0.f;
+        if (MODE == 2 && nv < 8 && !rm.seg_mode) {
+            fill = fmaf(__bfloat162float(t[(int64_t)ch * ld + (rm.seg_of(r8) << rm.kshift)]), ga, be);
+            if (act == B2PN_ACT_RELU) fill = fmaxf(fill, 0.f);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float v = f[e];
+            if (MODE != 0) {
+                v = fmaf(v, ga, be);
+                if (act == B2PN_ACT_RELU) v = fmaxf(v, 0.f);
+            }
+            f[e] = e < nv ? v : fill;
+        }
+        return pack8(f);
+    }
+};
+
+// routed gradient of the max aggregation, dh3^T[ch][row] = dout[seg][ch] if arg[seg][ch] names this row
+struct ArgGradSource {
+    RowMapTC rm;
+    const float *dout;
+    const int32_t *arg;
+    int C;
+    __device__ __forceinline__ uint4 chunk_nv(int ch, int64_t r8, int nv) const { return nv > 0 ? chunk(ch, r8) : make_uint4(0u, 0u, 0u, 0u); }
+    __device__ __forceinline__ uint4 chunk(int ch, int64_t r8) const
+    {
+        if (ch >= C || r8 >= rm.rows) return make_uint4(0u, 0u, 0u, 0u);
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = 0.f;
+        if (!rm.seg_mode) {
+            const int64_t m = rm.seg_of(r8);
+            const int k0 = rm.slot_of(r8);
+            const int a = arg[m * C + ch] - k0;
+            if (a < 0 || a >= 8) return make_uint4(0u, 0u, 0u, 0u);
+            const float g = dout[m * C + ch];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = e == a ? g : 0.f;
+        } else {
+            bool any = false;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int64_t row = r8 + e;
+                if (row < rm.rows) {
+                    const int64_t sg = rm.batch[row];
+                    if ((int64_t)arg[sg * C + ch] == row) {
+                        f[e] = dout[sg * C + ch];
+                        any = true;
+                    }
+                }
+            }
+            if (!any) return make_uint4(0u, 0u, 0u, 0u);
+        }
+        return pack8(f);
+    }
+};
+
+// MN-major B tile of the rows GEMM from a feature-major source: [2 row blocks of 64][64 channel lines];
+// thread lt fills channel line (lt >> 1) of the chunk for row block (lt & 1)
+template <class SRC>
+struct FeatLoaderTC {
+    static constexpr bool B_MN = true;
+    SRC src;
     int64_t row0;
-    __device__ __forceinline__ void begin_tile(int64_t tile, int lt) { row0 = tile * R + (lt & 1) * 64; }
+    unsigned nvp;  // valid-row counts of the 8 row groups of my row block, 4 bits each
+    __device__ __forceinline__ void begin_tile(int64_t tile, int lt)
+    {
+        row0 = tile * R + (lt & 1) * 64;
+        nvp = 0u;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) nvp |= (unsigned)src.rm.valid8(row0 + g * 8) << (4 * g);
+    }
     __device__ __forceinline__ void produce(uint8_t *B, int kc, int lt) const
     {
         const int cl = lt >> 1, nb = lt & 1;
-        const int ch = kc * KC + cl;
         uint8_t *dst = B + nb * (64 * LINE_BYTES);
-        if (ch >= C) {
+        const int ch = kc * KC + cl;
+        uint4 v[8];
 #pragma unroll
-            for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4 *>(dst + line_chunk_off(cl, g)) = make_uint4(0u, 0u, 0u, 0u);
-            return;
-        }
-        const __nv_bfloat16 *srcp = h + (int64_t)ch * ld + row0;
-        float sc = 1.f, sh = 0.f;
-        if (MODE != 0) {
-            sc = scale[ch];
-            sh = shift[ch];
-        }
+        for (int g = 0; g < 8; ++g) v[g] = src.chunk_nv(ch, row0 + g * 8, (int)((nvp >> (4 * g)) & 15u));
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            const int64_t r8 = row0 + g * 8;
-            const int nv = rm.valid8(r8);
-            uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-            if (nv > 0 || MODE == 2) raw = __ldg(reinterpret_cast<const uint4 *>(srcp + g * 8));
-            float f[8] = {bf16_lo(raw.x), bf16_hi(raw.x), bf16_lo(raw.y), bf16_hi(raw.y),
-                          bf16_lo(raw.z), bf16_hi(raw.z), bf16_lo(raw.w), bf16_hi(raw.w)};
-            float fill = 0.f;
-            if (MODE == 2 && nv < 8 && !rm.seg_mode && r8 < rm.rows) {  // value of slot 0 of this centroid
-                const int64_t m = r8 / rm.K;
-                fill = fmaf(__bfloat162float(h[(int64_t)ch * ld + m * rm.K]), sc, sh);
-                if (act == B2PN_ACT_RELU) fill = fmaxf(fill, 0.f);
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                float v = f[e];
-                if (MODE != 0) {
-                    v = fmaf(v, sc, sh);
-                    if (act == B2PN_ACT_RELU) v = fmaxf(v, 0.f);
-                }
-                f[e] = e < nv ? v : fill;
-            }
-            uint4 o;
-            o.x = pack_bf16x2(f[0], f[1]);
-            o.y = pack_bf16x2(f[2], f[3]);
-            o.z = pack_bf16x2(f[4], f[5]);
-            o.w = pack_bf16x2(f[6], f[7]);
-            *reinterpret_cast<uint4 *>(dst + line_chunk_off(cl, g)) = o;
-        }
+        for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4 *>(dst + line_chunk_off(cl, g)) = v[g];
     }
     // MN-major: 16 k lines per step; LBO = stride between the two 64-row blocks, SBO = 8 lines
     static __device__ __forceinline__ uint64_t b_desc(uint32_t b_saddr, int ks)
@@ -190,17 +300,17 @@ struct FeatLoaderTC {
 };
 
 // =================================================================================================
-//  Epilogues (128 threads, thread et owns TMEM lane et = output channel within the M tile)
+//  Epilogues of the rows GEMM (128 threads; thread tid owns TMEM lane tid = channel within the M tile)
 // =================================================================================================
 struct StoreF32Ep {  // self-test: out[ch][row] = acc
     float *out;
     int C;
     int64_t ld;
     __device__ __forceinline__ void begin() {}
-    __device__ __forceinline__ void tile(uint32_t taddr, int64_t tile, int ch)
+    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half)
     {
 #pragma unroll 1
-        for (int cc = 0; cc < R / 32; ++cc) {
+        for (int cc = half * 2; cc < half * 2 + 2; ++cc) {
             float v[32];
             tmem_ld32(taddr + cc * 32, v);
             if (ch < C) {
@@ -210,15 +320,12 @@ struct StoreF32Ep {  // self-test: out[ch][row] = acc
             }
         }
     }
-    __device__ __forceinline__ void finish(int mt_count, int ch_base) {}
+    __device__ __forceinline__ void finish_mt(int ch, int mt, int half) {}
 };
 
 template <int MT>
-struct StoreStatsEpTC {  // hT[ch][row] = bf16(acc + bias); per-channel sum / sum of squares of acc
-    __nv_bfloat16 *h;
+struct StatsEpTC {  // pass A of a BatchNorm layer: per-channel sum and sum of squares of the bias-free accumulators
     int C;
-    int64_t ld;
-    const float *bias;
     double *partial;  // [gridDim.x][2][cpad]
     int cpad;
     double S[MT], Q[MT];
@@ -227,62 +334,85 @@ struct StoreStatsEpTC {  // hT[ch][row] = bf16(acc + bias); per-channel sum / su
 #pragma unroll
         for (int i = 0; i < MT; ++i) S[i] = Q[i] = 0.0;
     }
-    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt)
+    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half)
     {
-        const float b = ch < C ? bias[ch] : 0.f;
         float s = 0.f, q = 0.f;
 #pragma unroll 1
-        for (int cc = 0; cc < R / 32; ++cc) {
+        for (int cc = half * 2; cc < half * 2 + 2; ++cc) {
             float v[32];
             tmem_ld32(taddr + cc * 32, v);
-            if (ch < C) {
-                uint4 *dst = reinterpret_cast<uint4 *>(h + (int64_t)ch * ld + tile * R + cc * 32);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint4 o;
-                    const float *p = v + 8 * j;
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        s += p[e];
-                        q = fmaf(p[e], p[e], q);
-                    }
-                    o.x = pack_bf16x2(p[0] + b, p[1] + b);
-                    o.y = pack_bf16x2(p[2] + b, p[3] + b);
-                    o.z = pack_bf16x2(p[4] + b, p[5] + b);
-                    o.w = pack_bf16x2(p[6] + b, p[7] + b);
-                    dst[j] = o;
-                }
+            for (int j = 0; j < 32; ++j) {
+                s += v[j];
+                q = fmaf(v[j], v[j], q);
             }
         }
         S[mt] += (double)s;
         Q[mt] += (double)q;
     }
-    __device__ __forceinline__ void finish_mt(int ch, int mt)
+    __device__ __forceinline__ void finish_mt(int ch, int mt, int half)
     {
         if (ch < C) {
-            double *pt = partial + (int64_t)blockIdx.x * 2 * cpad;
+            double *pt = partial + ((int64_t)blockIdx.x * 2 + half) * 2 * cpad;
             pt[ch] = S[mt];
             pt[cpad + ch] = Q[mt];
         }
     }
 };
 
+struct NormStoreEpTC {  // pass B: zT[ch][row] = bf16((acc + bias - mean) * rstd), the NORMALISED value zhat (the affine
+                        // gamma*zhat+beta and the activation are applied when the next layer / backward load it)
+    __nv_bfloat16 *z;
+    int C;
+    int64_t ld;
+    const float *bias;
+    const float *mean;
+    const float *rstd;
+    __device__ __forceinline__ void begin() {}
+    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half)
+    {
+        float sc = 0.f, sh = 0.f;
+        if (ch < C) {
+            sc = rstd[ch];
+            sh = (bias[ch] - mean[ch]) * sc;
+        }
+#pragma unroll 1
+        for (int cc = half * 2; cc < half * 2 + 2; ++cc) {
+            float v[32];
+            tmem_ld32(taddr + cc * 32, v);
+            if (ch < C) {
+                uint4 *dst = reinterpret_cast<uint4 *>(z + (int64_t)ch * ld + tile * R + cc * 32);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = fmaf(v[8 * j + e], sc, sh);
+                    dst[j] = pack8(f);
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void finish_mt(int ch, int mt, int half) {}
+};
+
 template <int KS>  // slots per centroid: 16, 32, 64 or 128
-struct SlotMaxEpTC {  // out[m][ch] = max over the K slots (invalid slots were filled with slot 0), arg = first max slot
-    __nv_bfloat16 *out;  // [n_dst][C] bf16 row-major
+struct SlotMaxEpTC {  // out[m][ch] = max over the K slots (invalid slots duplicate slot 0), arg = first max slot
+    float *out;  // [n_dst][C] fp32 row-major
     int32_t *arg;
     int C;
     const float *bias;
     const int32_t *cnt;
     int64_t n_dst;
     __device__ __forceinline__ void begin() {}
-    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt)
+    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half)
     {
         const float b = ch < C ? bias[ch] : 0.f;
         float best = -INFINITY;
         int bk = 0;
+        if (KS == 128 && half) return;  // a 128-slot centroid spans both column halves: the half-0 warps scan all of it
+        const int cc0 = KS == 128 ? 0 : half * 2, cc1 = KS == 128 ? 4 : half * 2 + 2;
 #pragma unroll 1
-        for (int cc = 0; cc < R / 32; ++cc) {
+        for (int cc = cc0; cc < cc1; ++cc) {
             float v[32];
             tmem_ld32(taddr + cc * 32, v);
 #pragma unroll
@@ -302,14 +432,14 @@ struct SlotMaxEpTC {  // out[m][ch] = max over the K slots (invalid slots were f
                     const int64_t m = tile * (R / KS) + col / KS;
                     if (ch < C && m < n_dst) {
                         const bool any = cnt[m] > 0;
-                        out[m * C + ch] = __float2bfloat16(any ? best : 0.f);
+                        out[m * C + ch] = any ? best : 0.f;
                         arg[m * C + ch] = any ? bk : -1;
                     }
                 }
             }
         }
     }
-    __device__ __forceinline__ void finish_mt(int ch, int mt) {}
+    __device__ __forceinline__ void finish_mt(int ch, int mt, int half) {}
 };
 
 __device__ __forceinline__ unsigned f32_orderable_tc(float f)
@@ -325,13 +455,13 @@ struct CloudMaxEpTC {  // global_max_pool over sorted cloud ids: 64-bit atomicMa
     const int64_t *batch;
     int64_t rows;
     __device__ __forceinline__ void begin() {}
-    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt)
+    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half)
     {
         const float b = ch < C ? bias[ch] : 0.f;
         int64_t curseg = -1;
         unsigned long long best = 0ull;
 #pragma unroll 1
-        for (int cc = 0; cc < R / 32; ++cc) {
+        for (int cc = half * 2; cc < half * 2 + 2; ++cc) {
             float v[32];
             tmem_ld32(taddr + cc * 32, v);
             if (ch < C) {
@@ -354,18 +484,105 @@ struct CloudMaxEpTC {  // global_max_pool over sorted cloud ids: 64-bit atomicMa
         }
         if (ch < C && curseg >= 0) atomicMax(keys + curseg * C + ch, best);
     }
-    __device__ __forceinline__ void finish_mt(int ch, int mt) {}
+    __device__ __forceinline__ void finish_mt(int ch, int mt, int half) {}
 };
 
-struct StoreF32EpW {  // adapter giving StoreF32Ep the tile_mt / finish_mt interface
-    StoreF32Ep e;
+template <int MT>
+struct MaskSumsStoreEpTC {  // backward through activation + sums for the BatchNorm backward (thread = channel of the
+                            // layer being differentiated through): dz = da * [z > 0];  S1 = sum dz, S2 = sum dz * zhat
+    __nv_bfloat16 *dz;       // [C][ld] out
+    const __nv_bfloat16 *z;  // [C][ld] saved normalised value zhat of that layer
+    int C;
+    int64_t ld;
+    const float *gamma;
+    const float *beta;
+    int act;
+    double *partial;
+    int cpad;
+    double S[MT], Q[MT];
+    __device__ __forceinline__ void begin()
+    {
+#pragma unroll
+        for (int i = 0; i < MT; ++i) S[i] = Q[i] = 0.0;
+    }
+    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half)
+    {
+        float be = 0.f, ga = 0.f;
+        if (ch < C) {
+            be = beta[ch];
+            ga = gamma[ch];
+        }
+        float s = 0.f, q = 0.f;
+#pragma unroll 1
+        for (int cc = half * 2; cc < half * 2 + 2; ++cc) {
+            float v[32];
+            tmem_ld32(taddr + cc * 32, v);
+            if (ch < C) {
+                const int64_t off = (int64_t)ch * ld + tile * R + cc * 32;
+                const uint4 *zs = reinterpret_cast<const uint4 *>(z + off);
+                uint4 *dst = reinterpret_cast<uint4 *>(dz + off);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float zf[8], o[8];
+                    unpack8(__ldg(zs + j), zf);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float da = v[8 * j + e];
+                        const bool pass = da != 0.f && (act != B2PN_ACT_RELU || fmaf(zf[e], ga, be) > 0.f);
+                        const float g = pass ? da : 0.f;
+                        s += g;
+                        q += pass ? g * zf[e] : 0.f;
+                        o[e] = g;
+                    }
+                    dst[j] = pack8(o);
+                }
+            }
+        }
+        S[mt] += (double)s;
+        Q[mt] += (double)q;
+    }
+    __device__ __forceinline__ void finish_mt(int ch, int mt, int half)
+    {
+        if (ch < C) {
+            double *pt = partial + ((int64_t)blockIdx.x * 2 + half) * 2 * cpad;
+            pt[ch] = S[mt];
+            pt[cpad + ch] = Q[mt];
+        }
+    }
+};
+
+struct ScatterEpTC {  // gradient w.r.t. the gathered source features (thread = feature channel)
+    RowMapTC rm;
+    float *dx;  // [n_src][C] fp32, zero-initialised by the caller in SLOTS mode
+    int C;
     __device__ __forceinline__ void begin() {}
-    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt) { e.tile(taddr, tile, ch); }
-    __device__ __forceinline__ void finish_mt(int ch, int mt) {}
+    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half)
+    {
+#pragma unroll 1
+        for (int cc = half * 2; cc < half * 2 + 2; ++cc) {
+            float v[32];
+            tmem_ld32(taddr + cc * 32, v);
+            if (ch < C) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int64_t row = tile * R + cc * 32 + j;
+                    if (row < rm.rows) {
+                        if (rm.seg_mode) {
+                            dx[row * C + ch] = v[j];
+                        } else {
+                            const int s = rm.nbr[row];
+                            if (s >= 0 && v[j] != 0.f) atomicAdd(dx + (int64_t)s * C + ch, v[j]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void finish_mt(int ch, int mt, int half) {}
 };
 
 // =================================================================================================
-//  The kernel
+//  The rows GEMM kernel:  D^T[channel, row] = A[channel, k] * B[k, row]
 // =================================================================================================
 template <int MT>
 struct SmemPlan {
@@ -403,19 +620,26 @@ __global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp
         }
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc<TCOLS>(tmem_holder);
+    if (warp == MMA_WARP) tmem_alloc<TCOLS>(tmem_holder);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
-    if (warp >= 4 && warp < 8) {
-        // ------------------------------------------------------------------ loaders
-        const int lt = tid - NUM_EPI;
+    if (warp >= NUM_EPI / 32 && warp < MMA_WARP) {
+        // ------------------------------------------------------------------ loaders: group g takes every
+        // LOAD_GROUPS-th (tile, k-chunk) item, so the groups' global-load latencies overlap
+        const int g = (tid - NUM_EPI) / NUM_LOAD;
+        const int lt = (tid - NUM_EPI) % NUM_LOAD;
         uint32_t it = 0;
+        int64_t cur_tile = -1;
         for (int64_t tile = blockIdx.x; tile < gp.num_tiles; tile += gridDim.x) {
-            bl.begin_tile(tile, lt);
             for (int kc = 0; kc < gp.num_kc; ++kc, ++it) {
+                if ((int)(it % LOAD_GROUPS) != g) continue;
+                if (tile != cur_tile) {
+                    bl.begin_tile(tile, lt);
+                    cur_tile = tile;
+                }
                 const int s = it % P::STAGES;
                 const uint32_t ph = (it / P::STAGES) & 1u;
                 mbar_wait(&empty[s], ph ^ 1u);
@@ -430,7 +654,7 @@ __global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp
                 mbar_arrive(&full[s]);
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == MMA_WARP) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             constexpr uint32_t IDESC = idesc_bf16(128, R, false, BL::B_MN);
@@ -461,37 +685,224 @@ __global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 0-3)
+        // ------------------------------------------------------------------ epilogue (warps 0-7)
         ep.begin();
         uint32_t tl = 0;
-        const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+        const int half = warp >> 2;
+        const int chl = tid & 127;
+        const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
         for (int64_t tile = blockIdx.x; tile < gp.num_tiles; tile += gridDim.x, ++tl) {
             const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
             mbar_wait(&tfull[acc], aph);
             tc_fence_after();
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
-                const int ch = (mg * MT + mt) * 128 + tid;
-                ep.tile_mt(tmem_base + lane_base + acc * (MT * R) + mt * R, tile, ch, mt);
+                const int ch = (mg * MT + mt) * 128 + chl;
+                ep.tile_mt(tmem_base + lane_base + acc * (MT * R) + mt * R, tile, ch, mt, half);
             }
             tc_fence_before();
             mbar_arrive(&tempty[acc]);
         }
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) ep.finish_mt((mg * MT + mt) * 128 + tid, mt);
+        for (int mt = 0; mt < MT; ++mt) ep.finish_mt((mg * MT + mt) * 128 + chl, mt, half);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc<TCOLS>(tmem_base);
+    if (warp == MMA_WARP) tmem_dealloc<TCOLS>(tmem_base);
+}
+
+// =================================================================================================
+//  The dW kernel:  dW[n, k] = sum over rows of Y^T[n, row] * X^T[k, row]
+//  Both operands are K-major with K = rows: line = channel, 64 rows per line and per stage.  For layer 1 the
+//  X side is the gathered concat tile (line = row, elements = input columns), i.e. an MN-major B operand.
+//  Accumulators stay in TMEM over the CTA's whole row range; one epilogue at the end writes the partial.
+// =================================================================================================
+struct DwParams {
+    int64_t chunks;            // 64-row chunks in total
+    int64_t chunks_per_split;
+    int n_out;                 // Y channels (rows of dW)
+    int nb_lines;              // UMMA N: X lines handled by this launch group, multiple of 16, <= 256
+    int k_total;               // columns of the partial (all N groups)
+    float *partial;            // [splits][n_out][k_total]
+};
+
+template <class SRC>
+struct LineFillK {  // K-major X side from a feature-major source
+    static constexpr bool B_MN = false;
+    SRC src;
+    static __host__ __device__ int bytes(int nb_lines) { return nb_lines * LINE_BYTES; }
+    __device__ __forceinline__ void fill(uint8_t *B, int lt, int64_t r0, int ng, int nb_lines, unsigned nvp)
+    {
+        for (int line = lt; line < nb_lines; line += NUM_LOAD) {
+            const int ch = ng * 256 + line;
+            uint4 v[8];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) v[g] = src.chunk_nv(ch, r0 + g * 8, (int)((nvp >> (4 * g)) & 15u));
+#pragma unroll
+            for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4 *>(B + line_chunk_off(line, g)) = v[g];
+        }
+    }
+    static __device__ __forceinline__ uint64_t b_desc(uint32_t b_saddr, int ks) { return smem_desc_sw128(b_saddr + ks * 32, 16, ATOM_BYTES); }
+};
+
+struct LineFillGather {  // MN-major X side: [column blocks of 64][64 row lines]; thread lt: row line lt>>1, half of the chunks
+    static constexpr bool B_MN = true;
+    GatherLoaderTC g;
+    static __host__ __device__ int bytes(int nb_lines) { return ((nb_lines + 63) / 64) * 64 * LINE_BYTES; }
+    __device__ __forceinline__ void fill(uint8_t *B, int lt, int64_t r0, int ng, int nb_lines, unsigned nvp)
+    {
+        const int rl = lt >> 1, half = lt & 1;
+        g.set_row(r0 + rl);
+        const int nblk = (nb_lines + 63) / 64;
+        for (int blk = 0; blk < nblk; ++blk) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int cc = half * 4 + c;
+                *reinterpret_cast<uint4 *>(B + blk * (64 * LINE_BYTES) + line_chunk_off(rl, cc)) =
+                    g.chunk(ng * 256 + blk * 64 + cc * 8);
+            }
+        }
+    }
+    // K = row lines: 16 lines per step; LBO = stride between 64-column blocks, SBO = 8 lines
+    static __device__ __forceinline__ uint64_t b_desc(uint32_t b_saddr, int ks)
+    {
+        return smem_desc_sw128(b_saddr + ks * (16 * LINE_BYTES), 64 * LINE_BYTES, ATOM_BYTES);
+    }
+};
+
+template <int MTA>
+struct DwPlan {
+    static constexpr int A_BYTES = MTA * 128 * LINE_BYTES;
+    static constexpr int B_MAX = 256 * LINE_BYTES;
+    static constexpr int STAGE_BYTES = A_BYTES + B_MAX;
+    static constexpr int STAGES = 3;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+template <int MTA, class YS, class XF>
+__global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, XF xf, const int ng)
+{
+    using P = DwPlan<MTA>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + P::BAR_OFF);
+    uint64_t *empty = full + P::STAGES;
+    uint64_t *done = empty + P::STAGES;
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(done + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int split = blockIdx.x, mg = blockIdx.y;
+    constexpr int TCOLS = MTA * 256;
+    const int64_t c_beg = (int64_t)split * p.chunks_per_split;
+    const int64_t c_end = min(p.chunks, c_beg + p.chunks_per_split);
+    const int64_t nchunks = c_end > c_beg ? c_end - c_beg : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < P::STAGES; ++s) {
+            mbar_init(&full[s], NUM_LOAD);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(done, 1);
+        fence_barrier_init();
+    }
+    if (warp == MMA_WARP) tmem_alloc<TCOLS>(tmem_holder);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp >= NUM_EPI / 32 && warp < MMA_WARP) {
+        const int grp = (tid - NUM_EPI) / NUM_LOAD;
+        const int lt = (tid - NUM_EPI) % NUM_LOAD;
+        for (int64_t i = grp; i < nchunks; i += LOAD_GROUPS) {
+            const int s = (int)(i % P::STAGES);
+            const uint32_t ph = (uint32_t)(i / P::STAGES) & 1u;
+            mbar_wait(&empty[s], ph ^ 1u);
+            uint8_t *A = smem + s * P::STAGE_BYTES;
+            uint8_t *B = A + P::A_BYTES;
+            const int64_t r0 = (c_beg + i) * 64;
+            unsigned nvp = 0u;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) nvp |= (unsigned)ys.rm.valid8(r0 + g * 8) << (4 * g);
+#pragma unroll
+            for (int m = 0; m < MTA; ++m) {
+                const int line = m * 128 + lt;
+                const int ch = mg * (MTA * 128) + line;
+                uint4 v[8];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) v[g] = ys.chunk_nv(ch, r0 + g * 8, (int)((nvp >> (4 * g)) & 15u));
+#pragma unroll
+                for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4 *>(A + line_chunk_off(line, g)) = v[g];
+            }
+            xf.fill(B, lt, r0, ng, p.nb_lines, nvp);
+            fence_proxy_async_smem();
+            mbar_arrive(&full[s]);
+        }
+    } else if (warp == MMA_WARP) {
+        if (lane == 0 && nchunks > 0) {
+            const uint32_t idesc = idesc_bf16(128, p.nb_lines, false, XF::B_MN);
+            for (int64_t i = 0; i < nchunks; ++i) {
+                const int s = (int)(i % P::STAGES);
+                const uint32_t ph = (uint32_t)(i / P::STAGES) & 1u;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t a_s = smem_u32(smem + s * P::STAGE_BYTES);
+                const uint32_t b_s = a_s + P::A_BYTES;
+#pragma unroll
+                for (int mt = 0; mt < MTA; ++mt) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t ad = smem_desc_sw128(a_s + mt * (128 * LINE_BYTES) + ks * 32, 16, ATOM_BYTES);
+                        const uint64_t bd = XF::b_desc(b_s, ks);
+                        umma_bf16(tmem_base + mt * 256, ad, bd, idesc, (i | ks) != 0);
+                    }
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(done);
+        }
+    } else if (warp < 4) {
+        if (nchunks > 0) {
+            mbar_wait(done, 0);
+            tc_fence_after();
+        }
+        const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+#pragma unroll
+        for (int mt = 0; mt < MTA; ++mt) {
+            const int ch = (mg * MTA + mt) * 128 + tid;
+            float *dst = p.partial + ((int64_t)split * p.n_out + ch) * p.k_total + ng * 256;
+            for (int cc = 0; cc * 32 < p.nb_lines; ++cc) {
+                float v[32];
+                if (nchunks > 0) {
+                    tmem_ld32(tmem_base + lane_base + mt * 256 + cc * 32, v);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                }
+                if (ch < p.n_out) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = cc * 32 + j;
+                        if (col < p.nb_lines && ng * 256 + col < p.k_total) dst[col] = v[j];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc<TCOLS>(tmem_base);
 }
 
 // =================================================================================================
 //  small kernels
 // =================================================================================================
-// bf16 operand image of a weight matrix: element (m, k) = w[m*sm + k*sk] for m < M, k < Kd, else 0.
+// bf16 operand image of a weight matrix: element (m, k) = w[m*sm + col(k)*sk] for m < M, k < Kimg (col(k) is the
+// identity, or InCols::src_col for the layer-1 operand), else 0.
 // Layout: [m_group][k_chunk][MT*128 lines][128 B] with the 128B swizzle applied per line.
-__global__ void pack_weights_kernel(const float *w, int M, int Kd, int64_t sm, int64_t sk, int MT, int num_mg, int num_kc,
-                                    uint8_t *img)
+__global__ void pack_weights_kernel(const float *w, int M, int Kimg, int64_t sm, int64_t sk, int use_map, InCols cols, int MT,
+                                    int num_mg, int num_kc, uint8_t *img)
 {
     const int lines = MT * 128;
     const int64_t total = (int64_t)num_mg * num_kc * lines * 8;  // one thread per 16-byte chunk
@@ -508,15 +919,12 @@ __global__ void pack_weights_kernel(const float *w, int M, int Kd, int64_t sm, i
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int k = kc * KC + c * 8 + e;
-        f[e] = (m < M && k < Kd) ? w[(int64_t)m * sm + (int64_t)k * sk] : 0.f;
+        int col = k < Kimg ? k : -1;
+        if (use_map && col >= 0) col = cols.src_col(k);
+        f[e] = (m < M && col >= 0) ? w[(int64_t)m * sm + (int64_t)col * sk] : 0.f;
     }
-    uint4 o;
-    o.x = pack_bf16x2(f[0], f[1]);
-    o.y = pack_bf16x2(f[2], f[3]);
-    o.z = pack_bf16x2(f[4], f[5]);
-    o.w = pack_bf16x2(f[6], f[7]);
     uint8_t *dst = img + (((int64_t)mgi * num_kc + kc) * lines) * LINE_BYTES + line_chunk_off(line, c);
-    *reinterpret_cast<uint4 *>(dst) = o;
+    *reinterpret_cast<uint4 *>(dst) = pack8(f);
 }
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
@@ -526,23 +934,46 @@ struct Packed {
     int MT, num_mg, num_kc;
     int64_t bytes;
 };
-static Packed plan_pack(int M, int Kd)
+static Packed plan_pack(int M, int Kimg)
 {
     Packed p;
     const int mpad = (int)align_up(M, 128);
     p.MT = mpad >= 256 ? 2 : 1;
-    p.num_mg = mpad / (p.MT * 128);
-    if (p.num_mg * p.MT * 128 < mpad) p.num_mg += 1;
-    p.num_kc = (Kd + KC - 1) / KC;
+    p.num_mg = (mpad + p.MT * 128 - 1) / (p.MT * 128);
+    p.num_kc = (Kimg + KC - 1) / KC;
     p.bytes = (int64_t)p.num_mg * p.num_kc * p.MT * 128 * LINE_BYTES;
     p.img = nullptr;
     return p;
 }
-static void launch_pack(const float *w, int M, int Kd, int64_t sm, int64_t sk, const Packed &p, cudaStream_t st)
+static void launch_pack(const float *w, int M, int Kimg, int64_t sm, int64_t sk, const InCols *map, const Packed &p,
+                        cudaStream_t st)
 {
     const int64_t total = p.bytes / 16;
-    pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, M, Kd, sm, sk, p.MT, p.num_mg, p.num_kc, p.img);
+    InCols cols = map ? *map : InCols{0, 0};
+    pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, M, Kimg, sm, sk, map ? 1 : 0, cols, p.MT, p.num_mg,
+                                                                         p.num_kc, p.img);
     note_launch();
+}
+
+static int sm_count()
+{
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+// grid.x of a rows-GEMM launch (the per-CTA statistics partials are indexed by blockIdx.x)
+static int grid_x_for(const Packed &pk, int64_t tiles)
+{
+    int gx = sm_count() / pk.num_mg;
+    if (gx < 1) gx = 1;
+    if ((int64_t)gx > tiles) gx = (int)tiles;
+    return gx;
 }
 
 template <int MT, class BL, class EP>
@@ -552,35 +983,204 @@ static int launch_gemm(const Packed &pk, int64_t tiles, const BL &bl, const EP &
     auto kern = tc_rows_gemm_kernel<MT, BL, EP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
     if (e != cudaSuccess) return (int)e;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int gx = sms / pk.num_mg;
-    if (gx < 1) gx = 1;
-    if ((int64_t)gx > tiles) gx = (int)tiles;
     GemmParams gp = {pk.img, pk.num_kc, tiles};
-    dim3 grid((unsigned)gx, (unsigned)pk.num_mg);
+    dim3 grid((unsigned)grid_x_for(pk, tiles), (unsigned)pk.num_mg);
     kern<<<grid, NT, P::TOTAL, st>>>(gp, bl, ep);
     note_launch();
     e = cudaPeekAtLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
 
-// grid.x used by launch_gemm (the statistics partials are indexed by blockIdx.x)
-static int grid_x_for(const Packed &pk, int64_t tiles)
+template <class BL, class EP1, class EP2>
+static int launch_by_mt(const Packed &pk, int64_t tiles, const BL &bl, const EP1 &e1, const EP2 &e2, cudaStream_t st)
 {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int gx = sms / pk.num_mg;
-    if (gx < 1) gx = 1;
-    if ((int64_t)gx > tiles) gx = (int)tiles;
-    return gx;
+    return pk.MT == 1 ? launch_gemm<1>(pk, tiles, bl, e1, st) : launch_gemm<2>(pk, tiles, bl, e2, st);
+}
+
+__global__ void count_valid_tc_kernel(const int32_t *cnt, int64_t n, double fixed, double *out)
+{
+    __shared__ double red[32];
+    if (cnt == nullptr) {
+        if (threadIdx.x == 0) *out = fixed;
+        return;
+    }
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += (double)cnt[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        *out = t;
+    }
+}
+
+// partial[g][2][cpad]: per-CTA sums of the bias-free accumulators over ALL rows (invalid rows are exact zeros):
+//   mean(h) = S/E + bias,  var(h) = Q/E - (S/E)^2.   bn = [mean, rstd, scale, shift] x cmax
+__device__ __forceinline__ void warp_sum_partials(const double *partial, int gx, int cpad, int c, double &S, double &Q)
+{
+    const int lane = threadIdx.x & 31;
+    double s = 0.0, q = 0.0;
+    for (int g = lane; g < gx; g += 32) {
+        s += partial[(int64_t)g * 2 * cpad + c];
+        q += partial[(int64_t)g * 2 * cpad + cpad + c];
+    }
+    // fixed-order butterfly: deterministic
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    S = s;
+    Q = q;
+}
+
+// one warp per channel
+__global__ void bn_fwd_finalize_tc_kernel(const double *partial, int gx, int C, int cpad, const double *count, int training,
+                                          const float *bias, const float *gamma, const float *beta, float *running_mean,
+                                          float *running_var, int64_t *nbt, float eps, float momentum, float *bn, int cmax)
+{
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= C) return;
+    double mean, var;
+    if (training) {
+        double S, Q;
+        warp_sum_partials(partial, gx, cpad, c, S, Q);
+        const double E = *count;
+        const double ma = E > 0 ? S / E : 0.0;
+        mean = ma + (double)bias[c];
+        var = E > 0 ? Q / E - ma * ma : 0.0;
+        if (var < 0.0) var = 0.0;
+        if ((threadIdx.x & 31) == 0) {
+            const double unbiased = E > 1.0 ? var * E / (E - 1.0) : var;
+            running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+            running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+            if (c == 0 && nbt) *nbt += 1;
+        }
+    } else {
+        mean = running_mean[c];
+        var = running_var[c];
+    }
+    if ((threadIdx.x & 31) == 0) {
+        const double rstd = 1.0 / sqrt(var + (double)eps);
+        const double scale = (double)gamma[c] * rstd;
+        bn[c] = (float)mean;
+        bn[cmax + c] = (float)rstd;
+        bn[2 * cmax + c] = (float)scale;
+        bn[3 * cmax + c] = (float)((double)beta[c] - mean * scale);
+    }
+}
+
+// S1 = sum dz, S2 = sum dz*zhat -> dbeta, dgamma, and the per-channel means the BN backward needs
+__global__ void bn_bwd_finalize_tc_kernel(const double *partial, int gx, int C, int cpad, const double *count, int training,
+                                          float *grad_gamma, float *grad_beta, float *sbar)
+{
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= C) return;
+    double S, Q;
+    warp_sum_partials(partial, gx, cpad, c, S, Q);
+    if ((threadIdx.x & 31) == 0) {
+        const double E = *count;
+        if (grad_beta) grad_beta[c] = (float)S;
+        if (grad_gamma) grad_gamma[c] = (float)Q;
+        sbar[c] = (training && E > 0) ? (float)(S / E) : 0.f;
+        sbar[C + c] = (training && E > 0) ? (float)(Q / E) : 0.f;
+    }
+}
+
+// dh = scale * (dz - mean(dz) - zhat * mean(dz*zhat)) on valid rows, 0 elsewhere; in place, feature-major bf16
+__global__ void bn_bwd_apply_tc_kernel(RowMapTC rm, __nv_bfloat16 *dz, const __nv_bfloat16 *z, int C, int64_t ld,
+                                       const float *scale, const float *sbar)
+{
+    const int64_t groups = ld / 8;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= groups * C) return;
+    const int ch = (int)(i / groups);
+    const int64_t r8 = (i - (int64_t)ch * groups) * 8;
+    const int nv = rm.valid8(r8);
+    uint4 *p = reinterpret_cast<uint4 *>(dz + (int64_t)ch * ld + r8);
+    if (nv == 0) {
+        *p = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    float d[8], zf[8];
+    unpack8(*p, d);
+    unpack8(__ldg(reinterpret_cast<const uint4 *>(z + (int64_t)ch * ld + r8)), zf);
+    const float sc = scale[ch];
+    const float s1 = sbar[ch], s2 = sbar[C + ch];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) d[e] = e < nv ? sc * (d[e] - s1 - zf[e] * s2) : 0.f;
+    *p = pack8(d);
+}
+
+// dW = sum over the split partials; image columns that share a weight column (hi/lo parts) are added up;
+// the "ones" image column is the bias gradient.
+__global__ void dw_reduce_tc_kernel(const float *partial, int splits, int n_out, int k_total, int use_map, InCols cols,
+                                    int k_true, int ones_idx, float *grad_w, float *grad_b)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per output element (coalesced)
+    if (i >= (int64_t)n_out * (k_true + 1)) return;
+    const int n = (int)(i / (k_true + 1));
+    const int k = (int)(i - (int64_t)n * (k_true + 1));
+    int c0 = -1, c1 = -1;
+    if (k == k_true) {
+        c0 = ones_idx;
+    } else if (!use_map) {
+        c0 = k;
+    } else {
+        const int nx = cols.nx();
+        if (k < cols.c_in) {
+            c0 = k;
+            c1 = cols.x_f32 ? k + cols.c_in : -1;
+        } else {
+            c0 = nx + (k - cols.c_in);
+            c1 = c0 + 3;
+        }
+    }
+    const int64_t stride = (int64_t)n_out * k_total;
+    const float *base = partial + (int64_t)n * k_total;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};  // four independent chains keep several loads in flight; fixed order
+    int p = 0;
+    for (; p + 4 <= splits; p += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float *row = base + (int64_t)(p + u) * stride;
+            float v = row[c0];
+            if (c1 >= 0) v += row[c1];
+            acc[u] += (double)v;
+        }
+    }
+    for (; p < splits; ++p) {
+        const float *row = base + (int64_t)p * stride;
+        acc[0] += (double)row[c0];
+        if (c1 >= 0) acc[0] += (double)row[c1];
+    }
+    const double s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    if (k == k_true) {
+        if (grad_b) grad_b[n] = (float)s;
+    } else if (grad_w) {
+        grad_w[(int64_t)n * k_true + k] = (float)s;
+    }
+}
+
+__global__ void unpack_keys_tc_kernel(const unsigned long long *keys, float *out, int32_t *arg, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = keys[i];
+    if (k == 0ull) {
+        out[i] = 0.f;
+        arg[i] = -1;
+    } else {
+        const unsigned o = (unsigned)(k >> 32);
+        out[i] = __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+        arg[i] = (int32_t)(0xffffffffu - (unsigned)(k & 0xffffffffu));
+    }
 }
 
 // -------------------------------------------------------------------------------------------------
 //  self-test: out[m][row] = sum_k w[m][k] * b(row, k) with b given row-major [rows][k] bf16 (mode 0, K-major
-//  B tiles through the gather loader without positions) or feature-major [k][ld] bf16 (mode 1, MN-major)
+//  B tiles through the gather loader) or feature-major [k][ld] bf16 (mode 1, MN-major B tiles)
 // -------------------------------------------------------------------------------------------------
 int tc_gemm_selftest(const float *w, int m_out, int k, const void *b, int mode, int64_t rows, int64_t ld, const float *zeros3,
                      float *out, int64_t ld_out, void *workspace, int64_t workspace_bytes, cudaStream_t st)
@@ -589,17 +1189,371 @@ int tc_gemm_selftest(const float *w, int m_out, int k, const void *b, int mode, 
     Packed pk = plan_pack(m_out, k);
     if (workspace_bytes < pk.bytes + 1024) return B2PN_EINVAL;
     pk.img = (uint8_t *)align_up((int64_t)(uintptr_t)workspace, 1024);
-    launch_pack(w, m_out, k, k, 1, pk, st);
+    launch_pack(w, m_out, k, k, 1, nullptr, pk, st);
     const int64_t tiles = (rows + R - 1) / R;
-    RowMapTC rm = {B2PN_SEG_CLOUDS, 1, nullptr, nullptr, nullptr, rows, 0};
-    StoreF32EpW ep = {{out, m_out, ld_out}};
+    RowMapTC rm = {B2PN_SEG_CLOUDS, 1, nullptr, nullptr, nullptr, rows, 0, 0};
+    StoreF32Ep ep = {out, m_out, ld_out};
     if (mode == 0) {
-        // all k columns are features (c_in = k); the appended pos_j - 0 columns multiply zero weights
-        GatherLoaderTC gl = {rm, (const __nv_bfloat16 *)b, k, zeros3, nullptr};
-        return pk.MT == 1 ? launch_gemm<1>(pk, tiles, gl, ep, st) : launch_gemm<2>(pk, tiles, gl, ep, st);
+        // all k columns are bf16 features (c_in = k); the appended dpos columns multiply zero weights
+        GatherLoaderTC gl = {rm, b, InCols{k, 0}, zeros3, nullptr, -1};
+        return launch_by_mt(pk, tiles, gl, ep, ep, st);
     }
-    FeatLoaderTC<0> fl = {rm, (const __nv_bfloat16 *)b, k, ld, nullptr, nullptr, 0};
-    return pk.MT == 1 ? launch_gemm<1>(pk, tiles, fl, ep, st) : launch_gemm<2>(pk, tiles, fl, ep, st);
+    FeatLoaderTC<FeatSource<0>> fl = {{rm, (const __nv_bfloat16 *)b, k, ld, 0, -1, nullptr, nullptr}};
+    return launch_by_mt(pk, tiles, fl, ep, ep, st);
+}
+
+// =================================================================================================
+//  host orchestration
+// =================================================================================================
+struct WsTC {
+    char *base;
+    int64_t off;
+    explicit WsTC(void *p) : base((char *)p), off(0)
+    {
+        if (base) off = align_up((int64_t)(uintptr_t)base, 1024) - (int64_t)(uintptr_t)base;
+    }
+    template <class T>
+    T *take(int64_t n)
+    {
+        T *r = base ? (T *)(base + off) : nullptr;
+        off = align_up(off + n * (int64_t)sizeof(T), 1024);
+        return r;
+    }
+};
+
+struct ShapesTC {
+    int64_t rows, tiles, ld;
+    int c0, c1, c2, c3, cmax, cpad, k1;
+    InCols cols;
+};
+static ShapesTC shapes_tc(const b2pn_sa_args &a)
+{
+    ShapesTC s;
+    s.rows = a.seg_mode == B2PN_SEG_CLOUDS ? a.n_src : a.n_dst * (int64_t)a.K;
+    s.tiles = (s.rows + R - 1) / R;
+    s.ld = s.tiles * R;
+    s.c0 = a.mlp.c[0];
+    s.c1 = a.mlp.c[1];
+    s.c2 = a.mlp.c[2];
+    s.c3 = a.mlp.c[3];
+    s.cmax = s.c1 > s.c2 ? s.c1 : s.c2;
+    s.cols = InCols{a.c_in, a.x_dtype == B2PN_X_F32 ? 1 : 0};
+    s.k1 = s.cols.k_img();
+    int mx = s.cmax > s.c3 ? s.cmax : s.c3;
+    mx = mx > s.k1 + 1 ? mx : s.k1 + 1;
+    s.cpad = (int)align_up(mx, 128);
+    return s;
+}
+
+constexpr int MAX_GX = 160;  // >= SM count: rows of the per-CTA partial buffers
+
+static int check_args_tc(const b2pn_sa_args &a)
+{
+    if (a.n_src < 0 || a.n_dst < 0 || a.c_in < 0) return B2PN_EINVAL;
+    if (a.mlp.c[0] != a.c_in + 3 || a.mlp.c[1] <= 0 || a.mlp.c[2] <= 0 || a.mlp.c[3] <= 0) return B2PN_EINVAL;
+    if (a.mlp.act != B2PN_ACT_NONE && a.mlp.act != B2PN_ACT_RELU) return B2PN_ENOTSUP;
+    if (a.x_dtype != B2PN_X_F32 && a.x_dtype != B2PN_X_BF16) return B2PN_EINVAL;
+    if (a.seg_mode == B2PN_SEG_SLOTS) {
+        if (!(a.K == 16 || a.K == 32 || a.K == 64 || a.K == 128)) return B2PN_ENOTSUP;
+        if (a.n_dst > 0 && (!a.nbr || !a.cnt || !a.pos_dst)) return B2PN_EINVAL;
+    } else if (a.seg_mode == B2PN_SEG_CLOUDS) {
+        if (a.n_src > 0 && !a.batch) return B2PN_EINVAL;
+    } else {
+        return B2PN_EINVAL;
+    }
+    if (a.n_src > 0 && (!a.pos_src || (a.c_in > 0 && !a.x))) return B2PN_EINVAL;
+    for (int l = 0; l < 3; ++l)
+        if (!a.mlp.w[l] || !a.mlp.b[l]) return B2PN_EINVAL;
+    for (int l = 0; l < 2; ++l)
+        if (!a.mlp.gamma[l] || !a.mlp.beta[l] || !a.mlp.running_mean[l] || !a.mlp.running_var[l]) return B2PN_EINVAL;
+    if (!a.out || !a.arg || !a.h1 || !a.h2 || !a.bn) return B2PN_EINVAL;
+    return B2PN_OK;
+}
+
+static RowMapTC rowmap_tc(const b2pn_sa_args &a, const ShapesTC &s)
+{
+    RowMapTC rm;
+    rm.seg_mode = a.seg_mode;
+    rm.K = a.seg_mode == B2PN_SEG_CLOUDS ? 1 : a.K;
+    rm.nbr = a.nbr;
+    rm.cnt = a.cnt;
+    rm.batch = a.batch;
+    rm.rows = s.rows;
+    rm.n_dst = a.n_dst;
+    rm.kshift = 0;
+    while ((1 << rm.kshift) < rm.K) ++rm.kshift;
+    return rm;
+}
+
+struct FwdWsTC {
+    Packed pk[3];
+    double *count;
+    double *partial;
+    unsigned long long *keys;
+};
+static FwdWsTC carve_fwd_tc(const b2pn_sa_args &a, const ShapesTC &s, WsTC &ws)
+{
+    FwdWsTC f;
+    f.pk[0] = plan_pack(s.c1, s.k1);
+    f.pk[1] = plan_pack(s.c2, s.c1);
+    f.pk[2] = plan_pack(s.c3, s.c2);
+    for (int l = 0; l < 3; ++l) f.pk[l].img = ws.take<uint8_t>(f.pk[l].bytes);
+    f.count = ws.take<double>(1);
+    f.partial = ws.take<double>((int64_t)MAX_GX * 2 * 2 * s.cpad);
+    f.keys = a.seg_mode == B2PN_SEG_CLOUDS ? ws.take<unsigned long long>(a.n_dst * (int64_t)s.c3) : nullptr;
+    return f;
+}
+
+struct DwPlanHost {
+    int MTA, num_mg, splits, nbl_total;
+    int64_t chunks, cps, floats;
+};
+static DwPlanHost plan_dw(int n_out, int k_total, int64_t ld)
+{
+    DwPlanHost d;
+    const int mpad = (int)align_up(n_out, 128);
+    d.MTA = mpad >= 256 ? 2 : 1;
+    d.num_mg = (mpad + d.MTA * 128 - 1) / (d.MTA * 128);
+    d.nbl_total = (int)align_up(k_total, 16);
+    d.chunks = ld / 64;
+    int sp = sm_count() / d.num_mg;
+    if (sp < 1) sp = 1;
+    if ((int64_t)sp > d.chunks) sp = (int)(d.chunks > 0 ? d.chunks : 1);
+    d.splits = sp;
+    d.cps = (d.chunks + sp - 1) / sp;
+    d.floats = (int64_t)sp * n_out * k_total;
+    return d;
+}
+
+struct BwdWsTC {
+    Packed pkT[3];
+    double *count;
+    double *partial;
+    __nv_bfloat16 *dz1, *dz2;
+    float *sbar;
+    float *dwp;
+};
+static BwdWsTC carve_bwd_tc(const b2pn_sa_args &a, const ShapesTC &s, WsTC &ws)
+{
+    BwdWsTC b;
+    b.pkT[2] = plan_pack(s.c2, s.c3);               // W3^T
+    b.pkT[1] = plan_pack(s.c1, s.c2);               // W2^T
+    b.pkT[0] = plan_pack(a.c_in > 0 ? a.c_in : 1, s.c1);  // feature rows of W1^T
+    for (int l = 0; l < 3; ++l) b.pkT[l].img = ws.take<uint8_t>(b.pkT[l].bytes);
+    b.count = ws.take<double>(1);
+    b.partial = ws.take<double>((int64_t)MAX_GX * 2 * 2 * s.cpad);
+    b.dz1 = ws.take<__nv_bfloat16>((int64_t)s.c1 * s.ld);
+    b.dz2 = ws.take<__nv_bfloat16>((int64_t)s.c2 * s.ld);
+    b.sbar = ws.take<float>(2 * s.cmax);
+    int64_t mx = plan_dw(s.c3, s.c2 + 1, s.ld).floats;
+    const int64_t m2 = plan_dw(s.c2, s.c1 + 1, s.ld).floats, m1 = plan_dw(s.c1, s.k1 + 1, s.ld).floats;
+    mx = mx > m2 ? mx : m2;
+    mx = mx > m1 ? mx : m1;
+    b.dwp = ws.take<float>(mx);
+    return b;
+}
+
+int64_t sa_workspace_bytes_bf16(const b2pn_sa_args &a, int backward)
+{
+    const ShapesTC s = shapes_tc(a);
+    WsTC ws(nullptr);
+    if (backward) carve_bwd_tc(a, s, ws);
+    else carve_fwd_tc(a, s, ws);
+    return ws.off + 2048;
+}
+
+int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
+{
+    int rc = check_args_tc(a);
+    if (rc) return rc;
+    const ShapesTC s = shapes_tc(a);
+    if (a.n_dst == 0) return B2PN_OK;
+    if (a.workspace_bytes < sa_workspace_bytes_bf16(a, 0) || !a.workspace) return B2PN_EINVAL;
+    WsTC ws(a.workspace);
+    FwdWsTC f = carve_fwd_tc(a, s, ws);
+    const RowMapTC rm = rowmap_tc(a, s);
+    __nv_bfloat16 *z1 = (__nv_bfloat16 *)a.h1, *z2 = (__nv_bfloat16 *)a.h2;
+    float *bn1 = a.bn, *bn2 = a.bn + 4 * s.cmax;
+    const int train = a.training;
+
+    launch_pack(a.mlp.w[0], s.c1, s.k1, s.c0, 1, &s.cols, f.pk[0], st);
+    launch_pack(a.mlp.w[1], s.c2, s.c1, s.c1, 1, nullptr, f.pk[1], st);
+    launch_pack(a.mlp.w[2], s.c3, s.c2, s.c2, 1, nullptr, f.pk[2], st);
+    count_valid_tc_kernel<<<1, 1024, 0, st>>>(a.seg_mode == B2PN_SEG_SLOTS ? a.cnt : nullptr, a.n_dst, (double)s.rows, f.count);
+    note_launch();
+
+    // ---- layer 1: gather + concat + Linear; pass A = batch statistics, pass B = normalise + store z1
+    GatherLoaderTC gl = {rm, a.x, s.cols, a.pos_src, a.pos_dst, -1};
+    if (train && s.rows > 0) {
+        StatsEpTC<1> e1 = {s.c1, f.partial, s.cpad};
+        StatsEpTC<2> e2 = {s.c1, f.partial, s.cpad};
+        if ((rc = launch_by_mt(f.pk[0], s.tiles, gl, e1, e2, st))) return rc;
+    }
+    bn_fwd_finalize_tc_kernel<<<(s.c1 + 3) / 4, 128, 0, st>>>(f.partial, 2 * grid_x_for(f.pk[0], s.tiles), s.c1, s.cpad, f.count, train,
+                                                                 a.mlp.b[0], a.mlp.gamma[0], a.mlp.beta[0], a.mlp.running_mean[0],
+                                                                 a.mlp.running_var[0], a.mlp.num_batches_tracked[0], a.mlp.eps,
+                                                                 a.mlp.momentum, bn1, s.cmax);
+    note_launch();
+    if (s.rows > 0) {
+        NormStoreEpTC e = {z1, s.c1, s.ld, a.mlp.b[0], bn1, bn1 + s.cmax};
+        if ((rc = launch_by_mt(f.pk[0], s.tiles, gl, e, e, st))) return rc;
+    }
+    // ---- layer 2
+    FeatLoaderTC<FeatSource<1>> l2 = {{rm, z1, s.c1, s.ld, a.mlp.act, -1, a.mlp.gamma[0], a.mlp.beta[0]}};
+    if (train && s.rows > 0) {
+        StatsEpTC<1> e1 = {s.c2, f.partial, s.cpad};
+        StatsEpTC<2> e2 = {s.c2, f.partial, s.cpad};
+        if ((rc = launch_by_mt(f.pk[1], s.tiles, l2, e1, e2, st))) return rc;
+    }
+    bn_fwd_finalize_tc_kernel<<<(s.c2 + 3) / 4, 128, 0, st>>>(f.partial, 2 * grid_x_for(f.pk[1], s.tiles), s.c2, s.cpad, f.count, train,
+                                                                 a.mlp.b[1], a.mlp.gamma[1], a.mlp.beta[1], a.mlp.running_mean[1],
+                                                                 a.mlp.running_var[1], a.mlp.num_batches_tracked[1], a.mlp.eps,
+                                                                 a.mlp.momentum, bn2, s.cmax);
+    note_launch();
+    if (s.rows > 0) {
+        NormStoreEpTC e = {z2, s.c2, s.ld, a.mlp.b[1], bn2, bn2 + s.cmax};
+        if ((rc = launch_by_mt(f.pk[1], s.tiles, l2, e, e, st))) return rc;
+    }
+    // ---- layer 3 + max aggregation
+    if (a.seg_mode == B2PN_SEG_SLOTS) {
+        FeatLoaderTC<FeatSource<2>> l3 = {{rm, z2, s.c2, s.ld, a.mlp.act, -1, a.mlp.gamma[1], a.mlp.beta[1]}};
+#define B2PN_SLOTMAX(KS)                                                        \
+    {                                                                           \
+        SlotMaxEpTC<KS> e = {a.out, a.arg, s.c3, a.mlp.b[2], a.cnt, a.n_dst};   \
+        rc = launch_by_mt(f.pk[2], s.tiles, l3, e, e, st);                      \
+    }
+        if (a.K == 16) B2PN_SLOTMAX(16)
+        else if (a.K == 32) B2PN_SLOTMAX(32)
+        else if (a.K == 64) B2PN_SLOTMAX(64)
+        else B2PN_SLOTMAX(128)
+#undef B2PN_SLOTMAX
+        if (rc) return rc;
+    } else {
+        const int64_t n = a.n_dst * (int64_t)s.c3;
+        B2PN_CUDA(cudaMemsetAsync(f.keys, 0, n * sizeof(unsigned long long), st));
+        if (s.rows > 0) {
+            FeatLoaderTC<FeatSource<1>> l3 = {{rm, z2, s.c2, s.ld, a.mlp.act, -1, a.mlp.gamma[1], a.mlp.beta[1]}};
+            CloudMaxEpTC e = {f.keys, s.c3, a.mlp.b[2], a.batch, s.rows};
+            if ((rc = launch_by_mt(f.pk[2], s.tiles, l3, e, e, st))) return rc;
+        }
+        unpack_keys_tc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(f.keys, a.out, a.arg, n);
+        note_launch();
+    }
+    B2PN_LAUNCH_CHECK();
+    return B2PN_OK;
+}
+
+template <class YS, class XF>
+static int launch_dw(const YS &ys, const XF &xf, int n_out, int k_total, const ShapesTC &s, float *dwp, cudaStream_t st)
+{
+    const DwPlanHost d = plan_dw(n_out, k_total, s.ld);
+    for (int ng = 0; ng * 256 < d.nbl_total; ++ng) {
+        const int nb = d.nbl_total - ng * 256 < 256 ? d.nbl_total - ng * 256 : 256;
+        DwParams p = {d.chunks, d.cps, n_out, nb, k_total, dwp};
+        dim3 grid((unsigned)d.splits, (unsigned)d.num_mg, 1);
+        cudaError_t e;
+        if (d.MTA == 1) {
+            auto kern = tc_dw_kernel<1, YS, XF>;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DwPlan<1>::TOTAL);
+            if (e != cudaSuccess) return (int)e;
+            kern<<<grid, NT, DwPlan<1>::TOTAL, st>>>(p, ys, xf, ng);
+        } else {
+            auto kern = tc_dw_kernel<2, YS, XF>;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DwPlan<2>::TOTAL);
+            if (e != cudaSuccess) return (int)e;
+            kern<<<grid, NT, DwPlan<2>::TOTAL, st>>>(p, ys, xf, ng);
+        }
+        note_launch();
+        e = cudaPeekAtLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
+}
+
+static void launch_dw_reduce(const float *dwp, int n_out, int k_total, const InCols *map, int k_true, int ones_idx,
+                             const ShapesTC &s, float *gw, float *gb, cudaStream_t st)
+{
+    const DwPlanHost d = plan_dw(n_out, k_total, s.ld);
+    const int64_t tot = (int64_t)n_out * (k_true + 1);
+    InCols cols = map ? *map : InCols{0, 0};
+    dw_reduce_tc_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(dwp, d.splits, n_out, k_total, map ? 1 : 0, cols, k_true,
+                                                                       ones_idx, gw, gb);
+    note_launch();
+}
+
+int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t st)
+{
+    int rc = check_args_tc(a);
+    if (rc) return rc;
+    if (!g.grad_out) return B2PN_EINVAL;
+    const ShapesTC s = shapes_tc(a);
+    if (a.n_dst == 0 || s.rows == 0) return B2PN_OK;
+    if (a.workspace_bytes < sa_workspace_bytes_bf16(a, 1) || !a.workspace) return B2PN_EINVAL;
+    WsTC ws(a.workspace);
+    BwdWsTC b = carve_bwd_tc(a, s, ws);
+    const RowMapTC rm = rowmap_tc(a, s);
+    const __nv_bfloat16 *z1 = (const __nv_bfloat16 *)a.h1, *z2 = (const __nv_bfloat16 *)a.h2;
+    float *bn1 = a.bn, *bn2 = a.bn + 4 * s.cmax;
+    const bool need_dx = g.grad_x != nullptr && a.c_in > 0;
+
+    launch_pack(a.mlp.w[2], s.c2, s.c3, 1, s.c2, nullptr, b.pkT[2], st);  // (m, k) = W3[k][m]
+    launch_pack(a.mlp.w[1], s.c1, s.c2, 1, s.c1, nullptr, b.pkT[1], st);
+    if (need_dx) launch_pack(a.mlp.w[0], a.c_in, s.c1, 1, s.c0, nullptr, b.pkT[0], st);
+    count_valid_tc_kernel<<<1, 1024, 0, st>>>(a.seg_mode == B2PN_SEG_SLOTS ? a.cnt : nullptr, a.n_dst, (double)s.rows, b.count);
+    note_launch();
+
+    // ---- layer 3 ---------------------------------------------------------------------------------------
+    ArgGradSource y3 = {rm, g.grad_out, a.arg, s.c3};
+    {
+        FeatLoaderTC<ArgGradSource> bl = {y3};
+        MaskSumsStoreEpTC<1> e1 = {b.dz2, z2, s.c2, s.ld, a.mlp.gamma[1], a.mlp.beta[1], a.mlp.act, b.partial, s.cpad};
+        MaskSumsStoreEpTC<2> e2 = {b.dz2, z2, s.c2, s.ld, a.mlp.gamma[1], a.mlp.beta[1], a.mlp.act, b.partial, s.cpad};
+        if ((rc = launch_by_mt(b.pkT[2], s.tiles, bl, e1, e2, st))) return rc;          // da2 = W3^T dh3
+        LineFillK<FeatSource<1>> xa2 = {{rm, z2, s.c2, s.ld, a.mlp.act, s.c2, a.mlp.gamma[1], a.mlp.beta[1]}};
+        if ((rc = launch_dw(y3, xa2, s.c3, s.c2 + 1, s, b.dwp, st))) return rc;         // dW3 = dh3^T a2
+        launch_dw_reduce(b.dwp, s.c3, s.c2 + 1, nullptr, s.c2, s.c2, s, g.grad_w[2], g.grad_b[2], st);
+    }
+    bn_bwd_finalize_tc_kernel<<<(s.c2 + 3) / 4, 128, 0, st>>>(b.partial, 2 * grid_x_for(b.pkT[2], s.tiles), s.c2, s.cpad, b.count,
+                                                                 a.training, g.grad_gamma[1], g.grad_beta[1], b.sbar);
+    note_launch();
+    {
+        const int64_t n = (s.ld / 8) * s.c2;
+        bn_bwd_apply_tc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rm, b.dz2, z2, s.c2, s.ld, bn2 + 2 * s.cmax, b.sbar);
+        note_launch();
+    }
+    // ---- layer 2 ---------------------------------------------------------------------------------------
+    FeatSource<0> y2 = {rm, b.dz2, s.c2, s.ld, 0, -1, nullptr, nullptr};
+    {
+        FeatLoaderTC<FeatSource<0>> bl = {y2};
+        MaskSumsStoreEpTC<1> e1 = {b.dz1, z1, s.c1, s.ld, a.mlp.gamma[0], a.mlp.beta[0], a.mlp.act, b.partial, s.cpad};
+        MaskSumsStoreEpTC<2> e2 = {b.dz1, z1, s.c1, s.ld, a.mlp.gamma[0], a.mlp.beta[0], a.mlp.act, b.partial, s.cpad};
+        if ((rc = launch_by_mt(b.pkT[1], s.tiles, bl, e1, e2, st))) return rc;
+        LineFillK<FeatSource<1>> xa1 = {{rm, z1, s.c1, s.ld, a.mlp.act, s.c1, a.mlp.gamma[0], a.mlp.beta[0]}};
+        if ((rc = launch_dw(y2, xa1, s.c2, s.c1 + 1, s, b.dwp, st))) return rc;
+        launch_dw_reduce(b.dwp, s.c2, s.c1 + 1, nullptr, s.c1, s.c1, s, g.grad_w[1], g.grad_b[1], st);
+    }
+    bn_bwd_finalize_tc_kernel<<<(s.c1 + 3) / 4, 128, 0, st>>>(b.partial, 2 * grid_x_for(b.pkT[1], s.tiles), s.c1, s.cpad, b.count,
+                                                                 a.training, g.grad_gamma[0], g.grad_beta[0], b.sbar);
+    note_launch();
+    {
+        const int64_t n = (s.ld / 8) * s.c1;
+        bn_bwd_apply_tc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rm, b.dz1, z1, s.c1, s.ld, bn1 + 2 * s.cmax, b.sbar);
+        note_launch();
+    }
+    // ---- layer 1 ---------------------------------------------------------------------------------------
+    FeatSource<0> y1 = {rm, b.dz1, s.c1, s.ld, 0, -1, nullptr, nullptr};
+    {
+        LineFillGather xg = {{rm, a.x, s.cols, a.pos_src, a.pos_dst, s.k1}};
+        if ((rc = launch_dw(y1, xg, s.c1, s.k1 + 1, s, b.dwp, st))) return rc;
+        launch_dw_reduce(b.dwp, s.c1, s.k1 + 1, &s.cols, s.c0, s.k1, s, g.grad_w[0], g.grad_b[0], st);
+    }
+    if (need_dx) {
+        FeatLoaderTC<FeatSource<0>> bl = {y1};
+        ScatterEpTC e = {rm, g.grad_x, a.c_in};
+        if ((rc = launch_by_mt(b.pkT[0], s.tiles, bl, e, e, st))) return rc;
+    }
+    B2PN_LAUNCH_CHECK();
+    return B2PN_OK;
 }
 
 }  // namespace tc

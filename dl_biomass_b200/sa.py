@@ -42,6 +42,7 @@ def _fill_args(a: SaArgs, *, precision, training, seg_mode, K, n_src, n_dst, c_i
                batch, chans, act, eps, momentum, ws, bs, gammas, betas, rmeans, rvars, nbts, out, arg, h1, h2, bn):
     a.precision, a.training, a.seg_mode, a.K = precision, int(training), seg_mode, K
     a.n_src, a.n_dst, a.c_in = n_src, n_dst, c_in
+    a.x_dtype = 1 if (x is not None and x.dtype == torch.bfloat16) else 0
     a.x, a.pos_src, a.pos_dst = _dp(x), _dp(pos_src), _dp(pos_dst)
     a.nbr, a.cnt, a.batch = _dp(nbr), _dp(cnt), _dp(batch)
     m = a.mlp
@@ -77,15 +78,23 @@ class _SAFunction(torch.autograd.Function):
         c_in = 0 if x is None else x.shape[1]
         if chans[0] != c_in + 3:
             raise ValueError(f"MLP expects {chans[0]} input channels, got {c_in} features + 3")
-        xs = None if x is None else x.detach().to(f32).contiguous()
         pos_src = pos_src.contiguous()
         n_src = pos_src.shape[0]
         rows = n_src if seg_mode == SEG_CLOUDS else n_dst * K
-        act_dtype = torch.float32 if prec == PREC_F32 else torch.bfloat16
         out = torch.empty(n_dst, chans[3], dtype=f32, device=dev)
         arg = torch.empty(n_dst, chans[3], dtype=torch.int32, device=dev)
-        h1 = torch.empty(rows, chans[1], dtype=act_dtype, device=dev)
-        h2 = torch.empty(rows, chans[2], dtype=act_dtype, device=dev)
+        if prec == PREC_F32:   # row-major fp32 activations [rows, c]
+            xs = None if x is None else x.detach().to(f32).contiguous()
+            h1 = torch.empty(rows, chans[1], dtype=f32, device=dev)
+            h2 = torch.empty(rows, chans[2], dtype=f32, device=dev)
+        else:                  # feature-major bf16 activations [c, ld], ld = rows rounded up to whole 128-row tiles
+            # raw low-dimensional inputs (e.g. lidar intensity) stay fp32: the kernel feeds them to the tensor
+            # cores as bf16 hi+lo column pairs; wide feature maps from the previous level go in as bf16
+            split = x is not None and x.dtype == f32 and c_in <= 16
+            xs = None if x is None else x.detach().to(f32 if split else torch.bfloat16).contiguous()
+            ld = (rows + 127) // 128 * 128
+            h1 = torch.empty(chans[1], ld, dtype=torch.bfloat16, device=dev)
+            h2 = torch.empty(chans[2], ld, dtype=torch.bfloat16, device=dev)
         cmax = max(chans[1], chans[2])
         bn = torch.empty(2, 4, cmax, dtype=f32, device=dev)
         a = SaArgs()
@@ -126,7 +135,7 @@ class _SAFunction(torch.autograd.Function):
         gb = [torch.empty_like(b) for b in (b1, b2, b3)]
         gg = [torch.empty_like(g) for g in (g1, g2)]
         gbe = [torch.empty_like(b) for b in (be1, be2)]
-        gx = torch.zeros_like(xs) if ctx.x_needs_grad else None
+        gx = torch.zeros(xs.shape, dtype=f32, device=dev) if ctx.x_needs_grad else None
         a = SaArgs()
         _fill_args(a, precision=prec, training=training, seg_mode=seg_mode, K=K, n_src=pos_src.shape[0], n_dst=n_dst,
                    c_in=ctx.c_in, x=xs, pos_src=pos_src, pos_dst=pos_dst, nbr=nbr, cnt=cnt, batch=batch, chans=chans,
@@ -167,3 +176,16 @@ def sa_apply(mlp, x, pos_src, pos_dst, nbr, cnt, batch, *, seg_mode: int, K: int
                                  l2.weight, l2.bias, n0.running_mean, n0.running_var, n0.num_batches_tracked,
                                  n1.running_mean, n1.running_var, n1.num_batches_tracked)
     return out, arg
+
+
+def bf16_available() -> bool:
+    """True once libb2pn implements forward AND backward of the set-abstraction levels on tcgen05."""
+    a = SaArgs()
+    a.precision = PREC_BF16
+    a.seg_mode = SEG_SLOTS
+    a.K = 64
+    a.n_src = a.n_dst = 1
+    a.c_in = 1
+    for i, c in enumerate((4, 64, 64, 128)):
+        a.mlp.c[i] = c
+    return _lib.lib().b2pn_sa_workspace_bytes(ctypes.byref(a), 1) > 0

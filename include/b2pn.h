@@ -87,6 +87,8 @@ int b2pn_ball_query_f32(const float *src_pos, const float *qry_pos, const int64_
 #define B2PN_PREC_BF16 1  /* bf16 tcgen05 tensor-core tiles, fp32 accumulation in TMEM          */
 #define B2PN_SEG_SLOTS 0  /* SAModule: targets own K fixed-width neighbour slots (nbr/cnt)      */
 #define B2PN_SEG_CLOUDS 1 /* GlobalSAModule: every source row belongs to cloud batch[row]       */
+#define B2PN_X_F32 0
+#define B2PN_X_BF16 1
 #define B2PN_ACT_NONE 0
 #define B2PN_ACT_RELU 1
 
@@ -110,8 +112,8 @@ typedef struct b2pn_sa_args {
     int32_t K;                   /* slots per target (SLOTS), multiple of 8 dividing 128              */
     int64_t n_src, n_dst;        /* source points; targets (centroids or clouds)                      */
     int32_t c_in;                /* feature channels of x (0: no features, pointnet2_regressor.py:17) */
-    int32_t reserved;
-    const float *x;              /* [n_src, c_in] f32 or NULL                                         */
+    int32_t x_dtype;             /* B2PN_X_F32 / B2PN_X_BF16 (bf16 only with B2PN_PREC_BF16)          */
+    const void *x;               /* [n_src, c_in] row-major or NULL                                   */
     const float *pos_src;        /* [n_src, 3]                                                        */
     const float *pos_dst;        /* [n_dst, 3] (SLOTS) / NULL (CLOUDS: centre is the origin)          */
     const int32_t *nbr;          /* [n_dst, K] (SLOTS)                                                */
@@ -120,8 +122,10 @@ typedef struct b2pn_sa_args {
     b2pn_mlp3 mlp;
     float *out;                  /* [n_dst, c3]                                                       */
     int32_t *arg;                /* [n_dst, c3] arg-max slot (SLOTS) or source row (CLOUDS); -1 none  */
-    void *h1, *h2;               /* saved pre-BN activations [rows, c1], [rows, c2]; rows = n_dst*K
-                                    (SLOTS) or n_src (CLOUDS); f32 or bf16 by precision               */
+    void *h1, *h2;               /* saved activations of the two hidden layers, rows = n_dst*K (SLOTS) or
+                                    n_src (CLOUDS).  PREC_F32: pre-BN values, f32 row-major [rows, c].
+                                    PREC_BF16: normalised values (h-mean)*rstd, bf16 FEATURE-major [c, ld],
+                                    ld = rows rounded up to a multiple of 128                          */
     float *bn;                   /* [2][4][cmax] per BN layer: mean, rstd, scale, shift; cmax=max(c1,c2) */
     void *workspace;             /* b2pn_sa_workspace_bytes() bytes, scratch                          */
     int64_t workspace_bytes;

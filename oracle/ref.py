@@ -153,8 +153,26 @@ def _resolve_act(act):
     return table[name]()
 
 
+class _RoundBF16(torch.autograd.Function):
+    """Round to bf16 in forward, identity in backward (models where the B200 bf16 mode rounds)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
 class MLPRef(torch.nn.Module):
-    """PyG ``MLP(channel_list, act=..., dropout=..., batch_norm=True)``."""
+    """PyG ``MLP(channel_list, act=..., dropout=..., batch_norm=True)``.
+
+    ``emulate_bf16 = True`` rounds weights and the post-BatchNorm values to bf16 exactly where the bf16
+    tensor-core mode does (fp32 accumulation and statistics), so tests can separate kernel bugs from the
+    arg-max / ReLU-mask flips that bf16 rounding legitimately causes in the gradients."""
+
+    emulate_bf16 = False
 
     def __init__(self, channel_list: Sequence[int], act="relu", dropout: float = 0.0):
         super().__init__()
@@ -166,6 +184,20 @@ class MLPRef(torch.nn.Module):
         self.norms = torch.nn.ModuleList([torch.nn.BatchNorm1d(c) for c in channel_list[1:-1]])
 
     def forward(self, x):
+        if self.emulate_bf16:
+            q = _RoundBF16.apply
+            x = F.linear(x, q(self.lins[0].weight), self.lins[0].bias)
+            for lin, norm in zip(self.lins[1:], self.norms):
+                # the kernels store the NORMALISED value in bf16 and apply gamma/beta afterwards
+                xhat = F.batch_norm(x, norm.running_mean, norm.running_var, None, None, self.training, norm.momentum,
+                                    norm.eps)
+                if self.training and norm.num_batches_tracked is not None:
+                    norm.num_batches_tracked += 1
+                x = q(q(xhat) * norm.weight + norm.bias)   # second rounding: the MMA operand itself is bf16
+                if self.act is not None:
+                    x = self.act(x)
+                x = F.linear(x, q(lin.weight), lin.bias)
+            return x
         x = self.lins[0](x)
         for lin, norm in zip(self.lins[1:], self.norms):
             x = norm(x)
@@ -289,7 +321,7 @@ def seeded_init_(model: torch.nn.Module, seed: int = 7) -> torch.nn.Module:
     g = torch.Generator(device="cpu").manual_seed(seed)
     with torch.no_grad():
         for name, p in sorted(model.named_parameters(), key=lambda kv: kv[0]):
-            if ".norms." in name:
+            if "norms." in name:
                 lo, hi = (0.5, 1.5) if name.endswith("weight") else (-0.2, 0.2)
             else:
                 fan_in = p.shape[1] if p.dim() == 2 else p.shape[0]
