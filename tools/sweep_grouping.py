@@ -30,14 +30,16 @@ def timeit(fn, iters=5, warm=2):
 def main():
     dev = torch.device("cuda:0")
     out = {"gpu": torch.cuda.get_device_name(0), "fps": [], "bq": []}
-    for (B, n, ratio, tag) in [(12, 10000, 0.2, "sa1_10k"), (12, 2000, 0.25, "sa2_10k"), (8, 100000, 0.2, "sa1_100k"),
-                               (64, 10000, 0.2, "sa1_10k_b64")]:
+    quick = os.environ.get("QUICK") == "1"
+    cfgs = [(12, 10000, 0.2, "sa1_10k"), (12, 2000, 0.25, "sa2_10k"), (8, 100000, 0.2, "sa1_100k"),
+            (64, 10000, 0.2, "sa1_10k_b64")]
+    for (B, n, ratio, tag) in (cfgs[:2] if quick else cfgs):
         b = Batch.from_data_list(synthetic_clouds(1234, B, n, 1, False))
         pos = b.pos.to(dev)
         lv = ops.build_levels([n] * B, [ratio], dev)
         m = lv[1].sizes[0]
         ref_idx = None
-        for cluster in (1, 2, 4, 8, 16):
+        for cluster in ((1,) if quick else (1, 2, 4, 8, 16)):
             for threads in (256, 512, 1024):
                 rc = _lib.lib().b2pn_fps_set_variant(cluster, threads)
                 try:
