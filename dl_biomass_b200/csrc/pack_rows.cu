@@ -1,0 +1,159 @@
+// Edge compaction for the tensor-core set-abstraction path.
+//
+// torch_cluster.radius (reached from /root/reference/pointnet2_regressor.py:14-15) returns a COMPACT
+// edge list; Kernel 2 writes fixed-width slots instead (no host sync).  At the reference's level-1
+// radius only ~1/3 of the 64 slots are filled, so before the MLP runs the filled slots are packed into
+// ROWS on the device, still without a host round trip: the number of rows stays in device memory and
+// every consumer kernel reads it there.
+//
+// Row layout: centroid m owns c8 = max(8, round_up(cnt[m], 8)) consecutive rows (slot s of the centroid is its row s);
+// a centroid never crosses a 64-row boundary (one epilogue thread scans 64 accumulator columns), chunks
+// of PACK_G consecutive centroids start on a 64-row boundary so the offsets can be computed in parallel.
+// Per 8-row group g the kernels get one descriptor word rgrp[g]:
+//   bits 0..23 centroid (0xFFFFFF: none)   24..26 first slot / 8   27..30 valid rows (0..8)   31 last group
+#include "common.cuh"
+
+namespace b2pn {
+
+constexpr int PACK_G = 64;        // centroids per sequential chunk
+constexpr int PACK_THREADS = 1024;
+
+__device__ __forceinline__ int c8_of(int c, int K)
+{
+    c = c < 0 ? 0 : (c > K ? K : c);
+    const int r = (c + 7) & ~7;
+    return r < 8 ? 8 : r;
+}
+
+// one CTA: local offsets per chunk, exclusive scan of the chunk sizes, total -> num_rows
+__global__ void __launch_bounds__(PACK_THREADS) pack_rows_scan_kernel(const int32_t *cnt, int64_t n_dst, int K, int32_t *row_off,
+                                                                      int32_t *chunk_base, int64_t *num_rows)
+{
+    __shared__ int s_warp[PACK_THREADS / 32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t chunks = (n_dst + PACK_G - 1) / PACK_G;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t c0 = 0; c0 < chunks; c0 += PACK_THREADS) {
+        const int64_t ch = c0 + tid;
+        int blocks = 0;  // 64-row blocks used by my chunk
+        if (ch < chunks) {
+            const int64_t m0 = ch * PACK_G;
+            const int64_t m1 = m0 + PACK_G < n_dst ? m0 + PACK_G : n_dst;
+            int off = 0;
+            for (int64_t m = m0; m < m1; ++m) {
+                const int c8 = c8_of(cnt[m], K);
+                if ((off & 63) + c8 > 64) off = (off + 63) & ~63;
+                row_off[m] = off;
+                off += c8;
+            }
+            blocks = (off + 63) >> 6;
+        }
+        // block-wide exclusive scan of `blocks`
+        int v = blocks;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        if (lane == 31) s_warp[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            s_warp[lane] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        const int excl = carry + (warp > 0 ? s_warp[warp - 1] : 0) + v - blocks;
+        if (ch < chunks) chunk_base[ch] = excl * 64;
+        __syncthreads();
+        if (tid == PACK_THREADS - 1) s_carry = carry + s_warp[PACK_THREADS / 32 - 1];
+        __syncthreads();
+    }
+    if (tid == 0) *num_rows = (int64_t)s_carry * 64;
+}
+
+// one thread per (centroid, 8-row group): group descriptors and per-row source index
+__global__ void pack_rows_fill_kernel(const int32_t *cnt, const int32_t *nbr, int64_t n_dst, int K, const int32_t *chunk_base,
+                                      const int32_t *row_off, uint32_t *rgrp, int32_t *row_src)
+{
+    const int G8 = (K + 7) >> 3;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_dst * G8) return;
+    const int64_t m = i / G8;
+    const int g = (int)(i - m * G8);
+    int c = cnt[m];
+    c = c < 0 ? 0 : (c > K ? K : c);
+    const int c8 = c8_of(c, K);
+    if (g * 8 >= c8) return;
+    const int64_t r0 = (int64_t)chunk_base[m / PACK_G] + row_off[m] + g * 8;
+    const int nv = c - g * 8 < 0 ? 0 : (c - g * 8 > 8 ? 8 : c - g * 8);
+    const unsigned last = (g * 8 + 8 >= c8) ? 1u : 0u;
+    rgrp[r0 >> 3] = ((unsigned)m & 0xffffffu) | ((unsigned)g << 24) | ((unsigned)nv << 27) | (last << 31);
+    int32_t v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = e < nv ? nbr[m * K + g * 8 + e] : -1;
+    int4 *dst = reinterpret_cast<int4 *>(row_src + r0);
+    dst[0] = make_int4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_int4(v[4], v[5], v[6], v[7]);
+}
+
+}  // namespace b2pn
+
+extern "C" int64_t b2pn_pack_rows_capacity(int64_t n_dst, int32_t K)
+{
+    if (n_dst < 0 || K <= 0) return B2PN_EINVAL;
+    if (K > 64) return B2PN_ENOTSUP;
+    const int64_t k8 = (K + 7) / 8 * 8;
+    const int64_t cpb = 64 / k8;  // a closed 64-row block holds at least this many centroids
+    // blocks <= sum over chunks of ceil(G_chunk / cpb) <= n_dst / cpb + chunks
+    const int64_t chunks = (n_dst + b2pn::PACK_G - 1) / b2pn::PACK_G;
+    const int64_t rows = (n_dst / cpb + chunks + 2) * 64;
+    return (rows + 127) / 128 * 128;
+}
+
+extern "C" int64_t b2pn_pack_rows_workspace_bytes(int64_t n_dst)
+{
+    if (n_dst < 0) return B2PN_EINVAL;
+    const int64_t chunks = (n_dst + b2pn::PACK_G - 1) / b2pn::PACK_G;
+    return (chunks + n_dst) * (int64_t)sizeof(int32_t) + 256;
+}
+
+extern "C" int b2pn_pack_rows(const int32_t *cnt, const int32_t *nbr, int64_t n_dst, int32_t K, uint32_t *rgrp,
+                              int32_t *row_src, int64_t *num_rows, void *workspace, int64_t workspace_bytes,
+                              b2pn_stream_t stream)
+{
+    using namespace b2pn;
+    if (n_dst < 0 || K <= 0) return B2PN_EINVAL;
+    if (K > 64 || n_dst >= (1 << 24) - 1) return B2PN_ENOTSUP;
+    if (!num_rows) return B2PN_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_dst == 0) {
+        B2PN_CUDA(cudaMemsetAsync(num_rows, 0, sizeof(int64_t), st));
+        return B2PN_OK;
+    }
+    if (!cnt || !nbr || !rgrp || !row_src || !workspace) return B2PN_EINVAL;
+    if (workspace_bytes < b2pn_pack_rows_workspace_bytes(n_dst)) return B2PN_EINVAL;
+    const int64_t chunks = (n_dst + PACK_G - 1) / PACK_G;
+    const int64_t cap = b2pn_pack_rows_capacity(n_dst, K);
+    int32_t *chunk_base = (int32_t *)workspace;
+    int32_t *row_off = chunk_base + chunks;
+    // rows / groups no centroid owns: source -1, descriptor 0xFFFFFFFF ("centroid none"; consumers ignore the
+    // other fields of such a group)
+    B2PN_CUDA(cudaMemsetAsync(row_src, 0xff, cap * sizeof(int32_t), st));
+    B2PN_CUDA(cudaMemsetAsync(rgrp, 0xff, (cap / 8) * sizeof(uint32_t), st));
+    pack_rows_scan_kernel<<<1, PACK_THREADS, 0, st>>>(cnt, n_dst, K, row_off, chunk_base, num_rows);
+    note_launch();
+    const int G8 = (K + 7) >> 3;
+    const int64_t tot = n_dst * G8;
+    pack_rows_fill_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cnt, nbr, n_dst, K, chunk_base, row_off, rgrp, row_src);
+    note_launch();
+    B2PN_LAUNCH_CHECK();
+    return B2PN_OK;
+}

@@ -28,35 +28,43 @@ constexpr int MMA_WARP = (NUM_EPI + LOAD_GROUPS * NUM_LOAD) / 32;  // warp 16: M
 constexpr int NT = NUM_EPI + LOAD_GROUPS * NUM_LOAD + 32;
 constexpr int B_BYTES = R * LINE_BYTES;  // 16 KB: [128 row lines x 64 k] or [2 row blocks][64 k lines x 64 rows]
 
+// Row structure of a level.
+//   CLOUDS: row = source point, all rows < rows are valid.
+//   SLOTS:  rows are the COMPACTED neighbour slots built by b2pn_pack_rows (pack_rows.cu): per 8-row group one
+//           descriptor word (centroid, first slot, valid rows, last-group flag), per row the gathered source index.
+//           The number of rows is only known on the device (rows_dev); kernels call resolve() first.
+constexpr unsigned GI_NONE = 0x00ffffffu;  // no centroid, 0 valid rows
+__device__ __forceinline__ int gi_seg(unsigned b) { return (int)(b & 0xffffffu); }
+__device__ __forceinline__ bool gi_none(unsigned b) { return (b & 0xffffffu) == 0xffffffu; }
+__device__ __forceinline__ int gi_slot0(unsigned b) { return (int)((b >> 24) & 7u) << 3; }
+__device__ __forceinline__ int gi_nv(unsigned b) { return (int)((b >> 27) & 15u); }
+__device__ __forceinline__ bool gi_last(unsigned b) { return (b >> 31) != 0u; }
+
 struct RowMapTC {
-    int seg_mode, K;
-    const int32_t *nbr;
-    const int32_t *cnt;
-    const int64_t *batch;
-    int64_t rows;    // logical rows
+    int seg_mode;
+    const uint32_t *rgrp;     // SLOTS: [rows/8] group descriptors
+    const int32_t *row_src;   // SLOTS: [rows] source point of the row, -1 = padding
+    const int32_t *cnt;       // SLOTS: [n_dst]
+    const int64_t *batch;     // CLOUDS: [rows] sorted cloud id
+    int64_t rows;             // logical rows; SLOTS: filled in on the device (resolve) from b2pn_pack_rows' scalar
     int64_t n_dst;
-    int kshift;      // log2(K): the tensor-core path takes K in {16, 32, 64, 128}
-    __device__ __forceinline__ int64_t seg_of(int64_t row) const { return row >> kshift; }
-    __device__ __forceinline__ int slot_of(int64_t row) const { return (int)(row & (int64_t)(K - 1)); }
-    __device__ __forceinline__ bool valid(int64_t row) const
+    __device__ __forceinline__ void resolve(int64_t r) { rows = r; }
+    // descriptor of the 8 rows starting at r8 (r8 % 8 == 0), normalised: nv == 0 wherever nothing is valid
+    __device__ __forceinline__ unsigned info(int64_t r8) const
     {
-        if (row >= rows) return false;
-        if (seg_mode) return true;
-        return slot_of(row) < cnt[seg_of(row)];
+        if (r8 >= rows) return GI_NONE;
+        if (seg_mode) return GI_NONE | ((unsigned)min((int64_t)8, rows - r8) << 27);
+        const unsigned b = __ldg(rgrp + (r8 >> 3));
+        return gi_none(b) ? GI_NONE : b;
     }
-    // number of valid rows among the 8 rows starting at row8 (row8 % 8 == 0, K % 8 == 0)
-    __device__ __forceinline__ int valid8(int64_t row8) const
-    {
-        if (row8 >= rows) return 0;
-        if (seg_mode) return (int)min((int64_t)8, rows - row8);
-        return max(0, min(8, cnt[seg_of(row8)] - slot_of(row8)));
-    }
+    __device__ __forceinline__ int valid8(int64_t r8) const { return gi_nv(info(r8)); }
 };
 
 struct GemmParams {
     const uint8_t *a_packed;  // [m_group][k_chunk][MT*128 lines][128 B], swizzled bf16
     int num_kc;
-    int64_t num_tiles;
+    int64_t rows;             // host value (CLOUDS, self-test) ...
+    const int64_t *rows_dev;  // ... or the device scalar of the compacted SLOTS layout (wins when non-NULL)
 };
 
 // layer-1 operand columns: [x (c_in) | x_lo (c_in, only when x arrives in fp32) | dpos_hi (3) | dpos_lo (3)].
@@ -96,18 +104,25 @@ struct GatherLoaderTC {  // K-major B: line = row of the tile, 64 k per line
     bool ok;
     int64_t src;
     float d0, d1, d2;
+    __device__ __forceinline__ void resolve(int64_t r) { rm.resolve(r); }
     __device__ __forceinline__ void set_row(int64_t row)
     {
-        ok = rm.valid(row);
+        ok = row < rm.rows;
         src = 0;
         d0 = d1 = d2 = 0.f;
+        if (ok && !rm.seg_mode) {
+            const int sidx = __ldg(rm.row_src + row);
+            ok = sidx >= 0;
+            src = ok ? sidx : 0;
+        } else if (ok) {
+            src = row;
+        }
         if (ok) {
-            src = rm.seg_mode ? row : (int64_t)rm.nbr[row];
             d0 = pos_src[3 * src + 0];
             d1 = pos_src[3 * src + 1];
             d2 = pos_src[3 * src + 2];
             if (!rm.seg_mode) {
-                const int64_t m = rm.seg_of(row);
+                const int64_t m = gi_seg(__ldg(rm.rgrp + (row >> 3)));
                 d0 = __fsub_rn(d0, pos_dst[3 * m + 0]);
                 d1 = __fsub_rn(d1, pos_dst[3 * m + 1]);
                 d2 = __fsub_rn(d2, pos_dst[3 * m + 2]);
@@ -172,46 +187,38 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8])
 }
 
 // 8 consecutive rows (r8 .. r8+7) of channel ch of a feature-major tensor, as the B/A operand wants them:
-//   MODE 0: plain, invalid rows -> 0      MODE 1: activation on load, invalid rows -> 0
-//   MODE 2: activation on load, invalid slots duplicate slot 0 of their centroid (so a plain max over
-//           all K slots equals the max over the valid ones and the first-max rule still picks a valid slot)
+//   MODE 0: plain, invalid rows -> 0      MODE 1: affine + activation on load, invalid rows -> 0
+// `inf` is the group descriptor RowMapTC::info(r8) (the caller caches it per tile).
 template <int MODE>
 struct FeatSource {
     RowMapTC rm;
-    const __nv_bfloat16 *t;  // [C][ld]; MODE 1/2: the normalised value zhat, activation input is gamma*zhat+beta
+    const __nv_bfloat16 *t;  // [C][ld]; MODE 1: the normalised value zhat, activation input is gamma*zhat+beta
     int C;
     int64_t ld;
     int act;
     int ones_line;  // channel index that carries 1 for valid rows (dW bias column), -1: none
     const float *gamma;
     const float *beta;
-    __device__ __forceinline__ uint4 chunk(int ch, int64_t r8) const { return chunk_nv(ch, r8, rm.valid8(r8)); }
-    __device__ __forceinline__ uint4 chunk_nv(int ch, int64_t r8, int nv) const
+    __device__ __forceinline__ void resolve(int64_t r) { rm.resolve(r); }
+    __device__ __forceinline__ uint4 chunk_i(int ch, int64_t r8, unsigned inf) const
     {
+        const int nv = gi_nv(inf);
         float f[8];
         if (ch == ones_line) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = e < nv ? 1.f : 0.f;
             return pack8(f);
         }
-        const bool live = ch < C && (nv > 0 || (MODE == 2 && r8 < rm.rows));
+        const bool live = ch < C && nv > 0;
         uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-        if (live) raw = __ldg(reinterpret_cast<const uint4 *>(t + (int64_t)ch * ld + r8));
-        if (MODE == 0) {
-            if (nv == 8 || !live) return raw;
-        } else if (!live) {
-            return raw;
-        }
+        if (!live) return raw;
+        raw = __ldg(reinterpret_cast<const uint4 *>(t + (int64_t)ch * ld + r8));
+        if (MODE == 0 && nv == 8) return raw;
         unpack8(raw, f);
         float ga = 1.f, be = 0.f;
         if (MODE != 0) {
             ga = gamma[ch];
             be = beta[ch];
-        }
-        float fill = 0.f;
-        if (MODE == 2 && nv < 8 && !rm.seg_mode) {
-            fill = fmaf(__bfloat162float(t[(int64_t)ch * ld + (rm.seg_of(r8) << rm.kshift)]), ga, be);
-            if (act == B2PN_ACT_RELU) fill = fmaxf(fill, 0.f);
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -220,7 +227,7 @@ struct FeatSource {
                 v = fmaf(v, ga, be);
                 if (act == B2PN_ACT_RELU) v = fmaxf(v, 0.f);
             }
-            f[e] = e < nv ? v : fill;
+            f[e] = e < nv ? v : 0.f;
         }
         return pack8(f);
     }
@@ -230,21 +237,20 @@ struct FeatSource {
 struct ArgGradSource {
     RowMapTC rm;
     const float *dout;
-    const int32_t *arg;
+    const int32_t *arg;  // SLOTS: arg-max SLOT of the centroid; CLOUDS: arg-max source row
     int C;
-    __device__ __forceinline__ uint4 chunk_nv(int ch, int64_t r8, int nv) const { return nv > 0 ? chunk(ch, r8) : make_uint4(0u, 0u, 0u, 0u); }
-    __device__ __forceinline__ uint4 chunk(int ch, int64_t r8) const
+    __device__ __forceinline__ void resolve(int64_t r) { rm.resolve(r); }
+    __device__ __forceinline__ uint4 chunk_i(int ch, int64_t r8, unsigned inf) const
     {
-        if (ch >= C || r8 >= rm.rows) return make_uint4(0u, 0u, 0u, 0u);
+        if (ch >= C || gi_nv(inf) == 0) return make_uint4(0u, 0u, 0u, 0u);
         float f[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) f[e] = 0.f;
         if (!rm.seg_mode) {
-            const int64_t m = rm.seg_of(r8);
-            const int k0 = rm.slot_of(r8);
-            const int a = arg[m * C + ch] - k0;
+            const int64_t m = gi_seg(inf);
+            const int a = __ldg(arg + m * C + ch) - gi_slot0(inf);
             if (a < 0 || a >= 8) return make_uint4(0u, 0u, 0u, 0u);
-            const float g = dout[m * C + ch];
+            const float g = __ldg(dout + m * C + ch);
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = e == a ? g : 0.f;
         } else {
@@ -273,13 +279,13 @@ struct FeatLoaderTC {
     static constexpr bool B_MN = true;
     SRC src;
     int64_t row0;
-    unsigned nvp;  // valid-row counts of the 8 row groups of my row block, 4 bits each
+    unsigned inf[8];  // descriptors of the 8 row groups of my row block
+    __device__ __forceinline__ void resolve(int64_t r) { src.resolve(r); }
     __device__ __forceinline__ void begin_tile(int64_t tile, int lt)
     {
         row0 = tile * R + (lt & 1) * 64;
-        nvp = 0u;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) nvp |= (unsigned)src.rm.valid8(row0 + g * 8) << (4 * g);
+        for (int g = 0; g < 8; ++g) inf[g] = src.rm.info(row0 + g * 8);
     }
     __device__ __forceinline__ void produce(uint8_t *B, int kc, int lt) const
     {
@@ -288,7 +294,7 @@ struct FeatLoaderTC {
         const int ch = kc * KC + cl;
         uint4 v[8];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) v[g] = src.chunk_nv(ch, row0 + g * 8, (int)((nvp >> (4 * g)) & 15u));
+        for (int g = 0; g < 8; ++g) v[g] = src.chunk_i(ch, row0 + g * 8, inf[g]);
 #pragma unroll
         for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4 *>(dst + line_chunk_off(cl, g)) = v[g];
     }
@@ -306,6 +312,7 @@ struct StoreF32Ep {  // self-test: out[ch][row] = acc
     float *out;
     int C;
     int64_t ld;
+    __device__ __forceinline__ void resolve(int64_t) {}
     __device__ __forceinline__ void begin() {}
     __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half)
     {
@@ -329,6 +336,7 @@ struct StatsEpTC {  // pass A of a BatchNorm layer: per-channel sum and sum of s
     double *partial;  // [gridDim.x][2][cpad]
     int cpad;
     double S[MT], Q[MT];
+    __device__ __forceinline__ void resolve(int64_t) {}
     __device__ __forceinline__ void begin()
     {
 #pragma unroll
@@ -368,6 +376,7 @@ struct NormStoreEpTC {  // pass B: zT[ch][row] = bf16((acc + bias - mean) * rstd
     const float *bias;
     const float *mean;
     const float *rstd;
+    __device__ __forceinline__ void resolve(int64_t) {}
     __device__ __forceinline__ void begin() {}
     __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half)
     {
@@ -395,46 +404,48 @@ struct NormStoreEpTC {  // pass B: zT[ch][row] = bf16((acc + bias - mean) * rstd
     __device__ __forceinline__ void finish_mt(int ch, int mt, int half) {}
 };
 
-template <int KS>  // slots per centroid: 16, 32, 64 or 128
-struct SlotMaxEpTC {  // out[m][ch] = max over the K slots (invalid slots duplicate slot 0), arg = first max slot
+struct SlotMaxEpTC {  // out[m][ch] = max over the valid rows of centroid m, arg = first max SLOT (compacted rows:
+                      // a centroid is a run of 8-row groups that never crosses a 64-row boundary)
     float *out;  // [n_dst][C] fp32 row-major
     int32_t *arg;
     int C;
     const float *bias;
-    const int32_t *cnt;
-    int64_t n_dst;
+    const uint32_t *rgrp;
+    int64_t rows;
+    __device__ __forceinline__ void resolve(int64_t r) { rows = r; }
     __device__ __forceinline__ void begin() {}
     __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half)
     {
         const float b = ch < C ? bias[ch] : 0.f;
         float best = -INFINITY;
-        int bk = 0;
-        if (KS == 128 && half) return;  // a 128-slot centroid spans both column halves: the half-0 warps scan all of it
-        const int cc0 = KS == 128 ? 0 : half * 2, cc1 = KS == 128 ? 4 : half * 2 + 2;
+        int bk = -1;
 #pragma unroll 1
-        for (int cc = cc0; cc < cc1; ++cc) {
+        for (int cc = half * 2; cc < half * 2 + 2; ++cc) {
             float v[32];
             tmem_ld32(taddr + cc * 32, v);
+            const int64_t g0 = tile * (R / 8) + cc * 4;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int col = cc * 32 + j;
-                const int slot = col % KS;
-                if (slot == 0) {
+            for (int gg = 0; gg < 4; ++gg) {
+                unsigned inf = GI_NONE;
+                if ((g0 + gg) * 8 < rows) inf = __ldg(rgrp + g0 + gg);  // warp-uniform
+                if (gi_none(inf)) continue;
+                const int s0 = gi_slot0(inf), nv = gi_nv(inf);
+                if (s0 == 0) {
                     best = -INFINITY;
-                    bk = 0;
+                    bk = -1;
                 }
-                const float x = v[j] + b;
-                if (x > best) {
-                    best = x;
-                    bk = slot;
-                }
-                if (slot == KS - 1) {
-                    const int64_t m = tile * (R / KS) + col / KS;
-                    if (ch < C && m < n_dst) {
-                        const bool any = cnt[m] > 0;
-                        out[m * C + ch] = any ? best : 0.f;
-                        arg[m * C + ch] = any ? bk : -1;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float x = v[gg * 8 + e] + b;
+                    if (e < nv && x > best) {
+                        best = x;
+                        bk = s0 + e;
                     }
+                }
+                if (gi_last(inf) && ch < C) {
+                    const int64_t m = gi_seg(inf);
+                    out[m * C + ch] = bk >= 0 ? best : 0.f;
+                    arg[m * C + ch] = bk;
                 }
             }
         }
@@ -454,6 +465,7 @@ struct CloudMaxEpTC {  // global_max_pool over sorted cloud ids: 64-bit atomicMa
     const float *bias;
     const int64_t *batch;
     int64_t rows;
+    __device__ __forceinline__ void resolve(int64_t) {}
     __device__ __forceinline__ void begin() {}
     __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half)
     {
@@ -500,6 +512,7 @@ struct MaskSumsStoreEpTC {  // backward through activation + sums for the BatchN
     double *partial;
     int cpad;
     double S[MT], Q[MT];
+    __device__ __forceinline__ void resolve(int64_t) {}
     __device__ __forceinline__ void begin()
     {
 #pragma unroll
@@ -555,6 +568,7 @@ struct ScatterEpTC {  // gradient w.r.t. the gathered source features (thread = 
     RowMapTC rm;
     float *dx;  // [n_src][C] fp32, zero-initialised by the caller in SLOTS mode
     int C;
+    __device__ __forceinline__ void resolve(int64_t rows) { rm.rows = rows; }
     __device__ __forceinline__ void begin() {}
     __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half)
     {
@@ -570,7 +584,7 @@ struct ScatterEpTC {  // gradient w.r.t. the gathered source features (thread = 
                         if (rm.seg_mode) {
                             dx[row * C + ch] = v[j];
                         } else {
-                            const int s = rm.nbr[row];
+                            const int s = __ldg(rm.row_src + row);
                             if (s >= 0 && v[j] != 0.f) atomicAdd(dx + (int64_t)s * C + ch, v[j]);
                         }
                     }
@@ -608,6 +622,10 @@ __global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int mg = blockIdx.y;
     constexpr int TCOLS = MT * R * 2;  // two accumulator buffers
+    const int64_t rows = gp.rows_dev ? *gp.rows_dev : gp.rows;
+    const int64_t num_tiles = (rows + R - 1) / R;
+    bl.resolve(rows);
+    ep.resolve(rows);
 
     if (tid == 0) {
         for (int s = 0; s < P::STAGES; ++s) {
@@ -633,7 +651,7 @@ __global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp
         const int lt = (tid - NUM_EPI) % NUM_LOAD;
         uint32_t it = 0;
         int64_t cur_tile = -1;
-        for (int64_t tile = blockIdx.x; tile < gp.num_tiles; tile += gridDim.x) {
+        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             for (int kc = 0; kc < gp.num_kc; ++kc, ++it) {
                 if ((int)(it % LOAD_GROUPS) != g) continue;
                 if (tile != cur_tile) {
@@ -659,7 +677,7 @@ __global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp
         if (lane == 0) {
             constexpr uint32_t IDESC = idesc_bf16(128, R, false, BL::B_MN);
             uint32_t it = 0, tl = 0;
-            for (int64_t tile = blockIdx.x; tile < gp.num_tiles; tile += gridDim.x, ++tl) {
+            for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
                 const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
                 mbar_wait(&tempty[acc], aph ^ 1u);
                 tc_fence_after();
@@ -691,7 +709,7 @@ __global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp
         const int half = warp >> 2;
         const int chl = tid & 127;
         const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
-        for (int64_t tile = blockIdx.x; tile < gp.num_tiles; tile += gridDim.x, ++tl) {
+        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
             const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
             mbar_wait(&tfull[acc], aph);
             tc_fence_after();
@@ -718,12 +736,12 @@ __global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp
 //  Accumulators stay in TMEM over the CTA's whole row range; one epilogue at the end writes the partial.
 // =================================================================================================
 struct DwParams {
-    int64_t chunks;            // 64-row chunks in total
-    int64_t chunks_per_split;
+    int64_t rows;              // host value, or ...
+    const int64_t *rows_dev;   // ... the device scalar of the compacted SLOTS layout (wins when non-NULL)
     int n_out;                 // Y channels (rows of dW)
-    int nb_lines;              // UMMA N: X lines handled by this launch group, multiple of 16, <= 256
+    int nbl_total;             // X lines over all N groups (blockIdx.z), multiple of 16; a group handles <= 256
     int k_total;               // columns of the partial (all N groups)
-    float *partial;            // [splits][n_out][k_total]
+    float *partial;            // [splits = gridDim.x][n_out][k_total]
 };
 
 template <class SRC>
@@ -731,13 +749,14 @@ struct LineFillK {  // K-major X side from a feature-major source
     static constexpr bool B_MN = false;
     SRC src;
     static __host__ __device__ int bytes(int nb_lines) { return nb_lines * LINE_BYTES; }
-    __device__ __forceinline__ void fill(uint8_t *B, int lt, int64_t r0, int ng, int nb_lines, unsigned nvp)
+    __device__ __forceinline__ void resolve(int64_t r) { src.resolve(r); }
+    __device__ __forceinline__ void fill(uint8_t *B, int lt, int64_t r0, int ng, int nb_lines, const unsigned (&inf)[8])
     {
         for (int line = lt; line < nb_lines; line += NUM_LOAD) {
             const int ch = ng * 256 + line;
             uint4 v[8];
 #pragma unroll
-            for (int g = 0; g < 8; ++g) v[g] = src.chunk_nv(ch, r0 + g * 8, (int)((nvp >> (4 * g)) & 15u));
+            for (int g = 0; g < 8; ++g) v[g] = src.chunk_i(ch, r0 + g * 8, inf[g]);
 #pragma unroll
             for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4 *>(B + line_chunk_off(line, g)) = v[g];
         }
@@ -749,7 +768,8 @@ struct LineFillGather {  // MN-major X side: [column blocks of 64][64 row lines]
     static constexpr bool B_MN = true;
     GatherLoaderTC g;
     static __host__ __device__ int bytes(int nb_lines) { return ((nb_lines + 63) / 64) * 64 * LINE_BYTES; }
-    __device__ __forceinline__ void fill(uint8_t *B, int lt, int64_t r0, int ng, int nb_lines, unsigned nvp)
+    __device__ __forceinline__ void resolve(int64_t r) { g.resolve(r); }
+    __device__ __forceinline__ void fill(uint8_t *B, int lt, int64_t r0, int ng, int nb_lines, const unsigned (&inf)[8])
     {
         const int rl = lt >> 1, half = lt & 1;
         g.set_row(r0 + rl);
@@ -781,7 +801,7 @@ struct DwPlan {
 };
 
 template <int MTA, class YS, class XF>
-__global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, XF xf, const int ng)
+__global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, XF xf)
 {
     using P = DwPlan<MTA>;
     extern __shared__ uint8_t smem_raw[];
@@ -792,11 +812,17 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(done + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int split = blockIdx.x, mg = blockIdx.y;
+    const int split = blockIdx.x, mg = blockIdx.y, ng = blockIdx.z;
     constexpr int TCOLS = MTA * 256;
-    const int64_t c_beg = (int64_t)split * p.chunks_per_split;
-    const int64_t c_end = min(p.chunks, c_beg + p.chunks_per_split);
+    const int64_t rows = p.rows_dev ? *p.rows_dev : p.rows;
+    ys.resolve(rows);
+    xf.resolve(rows);
+    const int64_t chunks = (rows + 63) / 64;
+    const int64_t cps = (chunks + gridDim.x - 1) / gridDim.x;
+    const int64_t c_beg = (int64_t)split * cps;
+    const int64_t c_end = min(chunks, c_beg + cps);
     const int64_t nchunks = c_end > c_beg ? c_end - c_beg : 0;
+    const int nb_lines = min(256, p.nbl_total - ng * 256);
 
     if (tid == 0) {
         for (int s = 0; s < P::STAGES; ++s) {
@@ -822,26 +848,26 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
             uint8_t *A = smem + s * P::STAGE_BYTES;
             uint8_t *B = A + P::A_BYTES;
             const int64_t r0 = (c_beg + i) * 64;
-            unsigned nvp = 0u;
+            unsigned inf[8];
 #pragma unroll
-            for (int g = 0; g < 8; ++g) nvp |= (unsigned)ys.rm.valid8(r0 + g * 8) << (4 * g);
+            for (int g = 0; g < 8; ++g) inf[g] = ys.rm.info(r0 + g * 8);
 #pragma unroll
             for (int m = 0; m < MTA; ++m) {
                 const int line = m * 128 + lt;
                 const int ch = mg * (MTA * 128) + line;
                 uint4 v[8];
 #pragma unroll
-                for (int g = 0; g < 8; ++g) v[g] = ys.chunk_nv(ch, r0 + g * 8, (int)((nvp >> (4 * g)) & 15u));
+                for (int g = 0; g < 8; ++g) v[g] = ys.chunk_i(ch, r0 + g * 8, inf[g]);
 #pragma unroll
                 for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4 *>(A + line_chunk_off(line, g)) = v[g];
             }
-            xf.fill(B, lt, r0, ng, p.nb_lines, nvp);
+            xf.fill(B, lt, r0, ng, nb_lines, inf);
             fence_proxy_async_smem();
             mbar_arrive(&full[s]);
         }
     } else if (warp == MMA_WARP) {
         if (lane == 0 && nchunks > 0) {
-            const uint32_t idesc = idesc_bf16(128, p.nb_lines, false, XF::B_MN);
+            const uint32_t idesc = idesc_bf16(128, nb_lines, false, XF::B_MN);
             for (int64_t i = 0; i < nchunks; ++i) {
                 const int s = (int)(i % P::STAGES);
                 const uint32_t ph = (uint32_t)(i / P::STAGES) & 1u;
@@ -872,7 +898,7 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
         for (int mt = 0; mt < MTA; ++mt) {
             const int ch = (mg * MTA + mt) * 128 + tid;
             float *dst = p.partial + ((int64_t)split * p.n_out + ch) * p.k_total + ng * 256;
-            for (int cc = 0; cc * 32 < p.nb_lines; ++cc) {
+            for (int cc = 0; cc * 32 < nb_lines; ++cc) {
                 float v[32];
                 if (nchunks > 0) {
                     tmem_ld32(tmem_base + lane_base + mt * 256 + cc * 32, v);
@@ -884,7 +910,7 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int col = cc * 32 + j;
-                        if (col < p.nb_lines && ng * 256 + col < p.k_total) dst[col] = v[j];
+                        if (col < nb_lines && ng * 256 + col < p.k_total) dst[col] = v[j];
                     }
                 }
             }
@@ -976,15 +1002,23 @@ static int grid_x_for(const Packed &pk, int64_t tiles)
     return gx;
 }
 
+// rows of a launch: an upper bound known on the host (sizes the grid) and, for the compacted SLOTS layout, the
+// device scalar holding the real count
+struct RowsArg {
+    int64_t cap;
+    const int64_t *dev;
+    int64_t tiles() const { return (cap + R - 1) / R; }
+};
+
 template <int MT, class BL, class EP>
-static int launch_gemm(const Packed &pk, int64_t tiles, const BL &bl, const EP &ep, cudaStream_t st)
+static int launch_gemm(const Packed &pk, const RowsArg &ra, const BL &bl, const EP &ep, cudaStream_t st)
 {
     using P = SmemPlan<MT>;
     auto kern = tc_rows_gemm_kernel<MT, BL, EP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
     if (e != cudaSuccess) return (int)e;
-    GemmParams gp = {pk.img, pk.num_kc, tiles};
-    dim3 grid((unsigned)grid_x_for(pk, tiles), (unsigned)pk.num_mg);
+    GemmParams gp = {pk.img, pk.num_kc, ra.cap, ra.dev};
+    dim3 grid((unsigned)grid_x_for(pk, ra.tiles()), (unsigned)pk.num_mg);
     kern<<<grid, NT, P::TOTAL, st>>>(gp, bl, ep);
     note_launch();
     e = cudaPeekAtLastError();
@@ -992,9 +1026,9 @@ static int launch_gemm(const Packed &pk, int64_t tiles, const BL &bl, const EP &
 }
 
 template <class BL, class EP1, class EP2>
-static int launch_by_mt(const Packed &pk, int64_t tiles, const BL &bl, const EP1 &e1, const EP2 &e2, cudaStream_t st)
+static int launch_by_mt(const Packed &pk, const RowsArg &ra, const BL &bl, const EP1 &e1, const EP2 &e2, cudaStream_t st)
 {
-    return pk.MT == 1 ? launch_gemm<1>(pk, tiles, bl, e1, st) : launch_gemm<2>(pk, tiles, bl, e2, st);
+    return pk.MT == 1 ? launch_gemm<1>(pk, ra, bl, e1, st) : launch_gemm<2>(pk, ra, bl, e2, st);
 }
 
 __global__ void count_valid_tc_kernel(const int32_t *cnt, int64_t n, double fixed, double *out)
@@ -1089,28 +1123,30 @@ __global__ void bn_bwd_finalize_tc_kernel(const double *partial, int gx, int C, 
 }
 
 // dh = scale * (dz - mean(dz) - zhat * mean(dz*zhat)) on valid rows, 0 elsewhere; in place, feature-major bf16
-__global__ void bn_bwd_apply_tc_kernel(RowMapTC rm, __nv_bfloat16 *dz, const __nv_bfloat16 *z, int C, int64_t ld,
-                                       const float *scale, const float *sbar)
+__global__ void bn_bwd_apply_tc_kernel(RowMapTC rm, const int64_t *rows_dev, __nv_bfloat16 *dz, const __nv_bfloat16 *z, int C,
+                                       int64_t ld, const float *scale, const float *sbar)
 {
-    const int64_t groups = ld / 8;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= groups * C) return;
-    const int ch = (int)(i / groups);
-    const int64_t r8 = (i - (int64_t)ch * groups) * 8;
-    const int nv = rm.valid8(r8);
-    uint4 *p = reinterpret_cast<uint4 *>(dz + (int64_t)ch * ld + r8);
-    if (nv == 0) {
-        *p = make_uint4(0u, 0u, 0u, 0u);
-        return;
-    }
-    float d[8], zf[8];
-    unpack8(*p, d);
-    unpack8(__ldg(reinterpret_cast<const uint4 *>(z + (int64_t)ch * ld + r8)), zf);
-    const float sc = scale[ch];
-    const float s1 = sbar[ch], s2 = sbar[C + ch];
+    if (rows_dev) rm.rows = *rows_dev;
+    const int64_t groups = (rm.rows + 127) / 128 * 16;  // whole tiles: the pad rows of the last tile are zeroed too
+    const int64_t total = groups * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i / groups);
+        const int64_t r8 = (i - (int64_t)ch * groups) * 8;
+        const int nv = rm.valid8(r8);
+        uint4 *p = reinterpret_cast<uint4 *>(dz + (int64_t)ch * ld + r8);
+        if (nv == 0) {
+            *p = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+        }
+        float d[8], zf[8];
+        unpack8(*p, d);
+        unpack8(__ldg(reinterpret_cast<const uint4 *>(z + (int64_t)ch * ld + r8)), zf);
+        const float sc = scale[ch];
+        const float s1 = sbar[ch], s2 = sbar[C + ch];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) d[e] = e < nv ? sc * (d[e] - s1 - zf[e] * s2) : 0.f;
-    *p = pack8(d);
+        for (int e = 0; e < 8; ++e) d[e] = e < nv ? sc * (d[e] - s1 - zf[e] * s2) : 0.f;
+        *p = pack8(d);
+    }
 }
 
 // dW = sum over the split partials; image columns that share a weight column (hi/lo parts) are added up;
@@ -1190,16 +1226,16 @@ int tc_gemm_selftest(const float *w, int m_out, int k, const void *b, int mode, 
     if (workspace_bytes < pk.bytes + 1024) return B2PN_EINVAL;
     pk.img = (uint8_t *)align_up((int64_t)(uintptr_t)workspace, 1024);
     launch_pack(w, m_out, k, k, 1, nullptr, pk, st);
-    const int64_t tiles = (rows + R - 1) / R;
-    RowMapTC rm = {B2PN_SEG_CLOUDS, 1, nullptr, nullptr, nullptr, rows, 0, 0};
+    const RowsArg ra = {rows, nullptr};
+    RowMapTC rm = {B2PN_SEG_CLOUDS, nullptr, nullptr, nullptr, nullptr, rows, 0};
     StoreF32Ep ep = {out, m_out, ld_out};
     if (mode == 0) {
         // all k columns are bf16 features (c_in = k); the appended dpos columns multiply zero weights
         GatherLoaderTC gl = {rm, b, InCols{k, 0}, zeros3, nullptr, -1};
-        return launch_by_mt(pk, tiles, gl, ep, ep, st);
+        return launch_by_mt(pk, ra, gl, ep, ep, st);
     }
     FeatLoaderTC<FeatSource<0>> fl = {{rm, (const __nv_bfloat16 *)b, k, ld, 0, -1, nullptr, nullptr}};
-    return launch_by_mt(pk, tiles, fl, ep, ep, st);
+    return launch_by_mt(pk, ra, fl, ep, ep, st);
 }
 
 // =================================================================================================
@@ -1229,7 +1265,8 @@ struct ShapesTC {
 static ShapesTC shapes_tc(const b2pn_sa_args &a)
 {
     ShapesTC s;
-    s.rows = a.seg_mode == B2PN_SEG_CLOUDS ? a.n_src : a.n_dst * (int64_t)a.K;
+    // SLOTS: capacity of the compacted row layout (upper bound; the real count lives in *a.num_rows)
+    s.rows = a.seg_mode == B2PN_SEG_CLOUDS ? a.n_src : a.row_capacity;
     s.tiles = (s.rows + R - 1) / R;
     s.ld = s.tiles * R;
     s.c0 = a.mlp.c[0];
@@ -1254,8 +1291,12 @@ static int check_args_tc(const b2pn_sa_args &a)
     if (a.mlp.act != B2PN_ACT_NONE && a.mlp.act != B2PN_ACT_RELU) return B2PN_ENOTSUP;
     if (a.x_dtype != B2PN_X_F32 && a.x_dtype != B2PN_X_BF16) return B2PN_EINVAL;
     if (a.seg_mode == B2PN_SEG_SLOTS) {
-        if (!(a.K == 16 || a.K == 32 || a.K == 64 || a.K == 128)) return B2PN_ENOTSUP;
+        if (a.K <= 0) return B2PN_EINVAL;
+        if (a.K > 64) return B2PN_ENOTSUP;  // a centroid's rows must fit one 64-column epilogue scan
         if (a.n_dst > 0 && (!a.nbr || !a.cnt || !a.pos_dst)) return B2PN_EINVAL;
+        // compacted rows from b2pn_pack_rows
+        if (a.n_dst > 0 && (!a.rgrp || !a.row_src || !a.num_rows)) return B2PN_EINVAL;
+        if (a.n_dst > 0 && a.row_capacity < b2pn_pack_rows_capacity(a.n_dst, a.K)) return B2PN_EINVAL;
     } else if (a.seg_mode == B2PN_SEG_CLOUDS) {
         if (a.n_src > 0 && !a.batch) return B2PN_EINVAL;
     } else {
@@ -1274,15 +1315,17 @@ static RowMapTC rowmap_tc(const b2pn_sa_args &a, const ShapesTC &s)
 {
     RowMapTC rm;
     rm.seg_mode = a.seg_mode;
-    rm.K = a.seg_mode == B2PN_SEG_CLOUDS ? 1 : a.K;
-    rm.nbr = a.nbr;
+    rm.rgrp = a.rgrp;
+    rm.row_src = a.row_src;
     rm.cnt = a.cnt;
     rm.batch = a.batch;
     rm.rows = s.rows;
     rm.n_dst = a.n_dst;
-    rm.kshift = 0;
-    while ((1 << rm.kshift) < rm.K) ++rm.kshift;
     return rm;
+}
+static RowsArg rowsarg_tc(const b2pn_sa_args &a, const ShapesTC &s)
+{
+    return RowsArg{s.rows, a.seg_mode == B2PN_SEG_SLOTS ? a.num_rows : nullptr};
 }
 
 struct FwdWsTC {
@@ -1305,9 +1348,11 @@ static FwdWsTC carve_fwd_tc(const b2pn_sa_args &a, const ShapesTC &s, WsTC &ws)
 }
 
 struct DwPlanHost {
-    int MTA, num_mg, splits, nbl_total;
-    int64_t chunks, cps, floats;
+    int MTA, num_mg, num_ng, splits, nbl_total;
+    int64_t floats;
 };
+// one launch covers all (row split, M group, N group) blocks; the row range is split so that the launch fills
+// the GPU about once -- the partials the reduction has to read shrink with the size of dW
 static DwPlanHost plan_dw(int n_out, int k_total, int64_t ld)
 {
     DwPlanHost d;
@@ -1315,12 +1360,12 @@ static DwPlanHost plan_dw(int n_out, int k_total, int64_t ld)
     d.MTA = mpad >= 256 ? 2 : 1;
     d.num_mg = (mpad + d.MTA * 128 - 1) / (d.MTA * 128);
     d.nbl_total = (int)align_up(k_total, 16);
-    d.chunks = ld / 64;
-    int sp = sm_count() / d.num_mg;
+    d.num_ng = (d.nbl_total + 255) / 256;
+    const int64_t chunks = ld / 64;
+    int sp = sm_count() / (d.num_mg * d.num_ng);
     if (sp < 1) sp = 1;
-    if ((int64_t)sp > d.chunks) sp = (int)(d.chunks > 0 ? d.chunks : 1);
+    if ((int64_t)sp > chunks) sp = (int)(chunks > 0 ? chunks : 1);
     d.splits = sp;
-    d.cps = (d.chunks + sp - 1) / sp;
     d.floats = (int64_t)sp * n_out * k_total;
     return d;
 }
@@ -1372,6 +1417,7 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
     WsTC ws(a.workspace);
     FwdWsTC f = carve_fwd_tc(a, s, ws);
     const RowMapTC rm = rowmap_tc(a, s);
+    const RowsArg ra = rowsarg_tc(a, s);
     __nv_bfloat16 *z1 = (__nv_bfloat16 *)a.h1, *z2 = (__nv_bfloat16 *)a.h2;
     float *bn1 = a.bn, *bn2 = a.bn + 4 * s.cmax;
     const int train = a.training;
@@ -1387,7 +1433,7 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
     if (train && s.rows > 0) {
         StatsEpTC<1> e1 = {s.c1, f.partial, s.cpad};
         StatsEpTC<2> e2 = {s.c1, f.partial, s.cpad};
-        if ((rc = launch_by_mt(f.pk[0], s.tiles, gl, e1, e2, st))) return rc;
+        if ((rc = launch_by_mt(f.pk[0], ra, gl, e1, e2, st))) return rc;
     }
     bn_fwd_finalize_tc_kernel<<<(s.c1 + 3) / 4, 128, 0, st>>>(f.partial, 2 * grid_x_for(f.pk[0], s.tiles), s.c1, s.cpad, f.count, train,
                                                                  a.mlp.b[0], a.mlp.gamma[0], a.mlp.beta[0], a.mlp.running_mean[0],
@@ -1396,14 +1442,14 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
     note_launch();
     if (s.rows > 0) {
         NormStoreEpTC e = {z1, s.c1, s.ld, a.mlp.b[0], bn1, bn1 + s.cmax};
-        if ((rc = launch_by_mt(f.pk[0], s.tiles, gl, e, e, st))) return rc;
+        if ((rc = launch_by_mt(f.pk[0], ra, gl, e, e, st))) return rc;
     }
     // ---- layer 2
     FeatLoaderTC<FeatSource<1>> l2 = {{rm, z1, s.c1, s.ld, a.mlp.act, -1, a.mlp.gamma[0], a.mlp.beta[0]}};
     if (train && s.rows > 0) {
         StatsEpTC<1> e1 = {s.c2, f.partial, s.cpad};
         StatsEpTC<2> e2 = {s.c2, f.partial, s.cpad};
-        if ((rc = launch_by_mt(f.pk[1], s.tiles, l2, e1, e2, st))) return rc;
+        if ((rc = launch_by_mt(f.pk[1], ra, l2, e1, e2, st))) return rc;
     }
     bn_fwd_finalize_tc_kernel<<<(s.c2 + 3) / 4, 128, 0, st>>>(f.partial, 2 * grid_x_for(f.pk[1], s.tiles), s.c2, s.cpad, f.count, train,
                                                                  a.mlp.b[1], a.mlp.gamma[1], a.mlp.beta[1], a.mlp.running_mean[1],
@@ -1412,29 +1458,20 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
     note_launch();
     if (s.rows > 0) {
         NormStoreEpTC e = {z2, s.c2, s.ld, a.mlp.b[1], bn2, bn2 + s.cmax};
-        if ((rc = launch_by_mt(f.pk[1], s.tiles, l2, e, e, st))) return rc;
+        if ((rc = launch_by_mt(f.pk[1], ra, l2, e, e, st))) return rc;
     }
     // ---- layer 3 + max aggregation
     if (a.seg_mode == B2PN_SEG_SLOTS) {
-        FeatLoaderTC<FeatSource<2>> l3 = {{rm, z2, s.c2, s.ld, a.mlp.act, -1, a.mlp.gamma[1], a.mlp.beta[1]}};
-#define B2PN_SLOTMAX(KS)                                                        \
-    {                                                                           \
-        SlotMaxEpTC<KS> e = {a.out, a.arg, s.c3, a.mlp.b[2], a.cnt, a.n_dst};   \
-        rc = launch_by_mt(f.pk[2], s.tiles, l3, e, e, st);                      \
-    }
-        if (a.K == 16) B2PN_SLOTMAX(16)
-        else if (a.K == 32) B2PN_SLOTMAX(32)
-        else if (a.K == 64) B2PN_SLOTMAX(64)
-        else B2PN_SLOTMAX(128)
-#undef B2PN_SLOTMAX
-        if (rc) return rc;
+        FeatLoaderTC<FeatSource<1>> l3 = {{rm, z2, s.c2, s.ld, a.mlp.act, -1, a.mlp.gamma[1], a.mlp.beta[1]}};
+        SlotMaxEpTC e = {a.out, a.arg, s.c3, a.mlp.b[2], a.rgrp, s.rows};
+        if ((rc = launch_by_mt(f.pk[2], ra, l3, e, e, st))) return rc;
     } else {
         const int64_t n = a.n_dst * (int64_t)s.c3;
         B2PN_CUDA(cudaMemsetAsync(f.keys, 0, n * sizeof(unsigned long long), st));
         if (s.rows > 0) {
             FeatLoaderTC<FeatSource<1>> l3 = {{rm, z2, s.c2, s.ld, a.mlp.act, -1, a.mlp.gamma[1], a.mlp.beta[1]}};
             CloudMaxEpTC e = {f.keys, s.c3, a.mlp.b[2], a.batch, s.rows};
-            if ((rc = launch_by_mt(f.pk[2], s.tiles, l3, e, e, st))) return rc;
+            if ((rc = launch_by_mt(f.pk[2], ra, l3, e, e, st))) return rc;
         }
         unpack_keys_tc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(f.keys, a.out, a.arg, n);
         note_launch();
@@ -1444,30 +1481,37 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
 }
 
 template <class YS, class XF>
-static int launch_dw(const YS &ys, const XF &xf, int n_out, int k_total, const ShapesTC &s, float *dwp, cudaStream_t st)
+static int launch_dw(const YS &ys, const XF &xf, int n_out, int k_total, const ShapesTC &s, const RowsArg &ra, float *dwp,
+                     cudaStream_t st)
 {
     const DwPlanHost d = plan_dw(n_out, k_total, s.ld);
-    for (int ng = 0; ng * 256 < d.nbl_total; ++ng) {
-        const int nb = d.nbl_total - ng * 256 < 256 ? d.nbl_total - ng * 256 : 256;
-        DwParams p = {d.chunks, d.cps, n_out, nb, k_total, dwp};
-        dim3 grid((unsigned)d.splits, (unsigned)d.num_mg, 1);
-        cudaError_t e;
-        if (d.MTA == 1) {
-            auto kern = tc_dw_kernel<1, YS, XF>;
-            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DwPlan<1>::TOTAL);
-            if (e != cudaSuccess) return (int)e;
-            kern<<<grid, NT, DwPlan<1>::TOTAL, st>>>(p, ys, xf, ng);
-        } else {
-            auto kern = tc_dw_kernel<2, YS, XF>;
-            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DwPlan<2>::TOTAL);
-            if (e != cudaSuccess) return (int)e;
-            kern<<<grid, NT, DwPlan<2>::TOTAL, st>>>(p, ys, xf, ng);
-        }
-        note_launch();
-        e = cudaPeekAtLastError();
+    DwParams p = {ra.cap, ra.dev, n_out, d.nbl_total, k_total, dwp};
+    dim3 grid((unsigned)d.splits, (unsigned)d.num_mg, (unsigned)d.num_ng);
+    cudaError_t e;
+    if (d.MTA == 1) {
+        auto kern = tc_dw_kernel<1, YS, XF>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DwPlan<1>::TOTAL);
         if (e != cudaSuccess) return (int)e;
+        kern<<<grid, NT, DwPlan<1>::TOTAL, st>>>(p, ys, xf);
+    } else {
+        auto kern = tc_dw_kernel<2, YS, XF>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DwPlan<2>::TOTAL);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<grid, NT, DwPlan<2>::TOTAL, st>>>(p, ys, xf);
     }
-    return 0;
+    note_launch();
+    e = cudaPeekAtLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+// grid of the element-wise BN-backward pass: grid-stride, at most 8 blocks of 256 threads per SM
+static unsigned apply_grid(int64_t ld, int C)
+{
+    const int64_t n = (ld / 8) * C;
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    return (unsigned)(blocks > 0 ? blocks : 1);
 }
 
 static void launch_dw_reduce(const float *dwp, int n_out, int k_total, const InCols *map, int k_true, int ones_idx,
@@ -1492,6 +1536,7 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
     WsTC ws(a.workspace);
     BwdWsTC b = carve_bwd_tc(a, s, ws);
     const RowMapTC rm = rowmap_tc(a, s);
+    const RowsArg ra = rowsarg_tc(a, s);
     const __nv_bfloat16 *z1 = (const __nv_bfloat16 *)a.h1, *z2 = (const __nv_bfloat16 *)a.h2;
     float *bn1 = a.bn, *bn2 = a.bn + 4 * s.cmax;
     const bool need_dx = g.grad_x != nullptr && a.c_in > 0;
@@ -1508,17 +1553,16 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
         FeatLoaderTC<ArgGradSource> bl = {y3};
         MaskSumsStoreEpTC<1> e1 = {b.dz2, z2, s.c2, s.ld, a.mlp.gamma[1], a.mlp.beta[1], a.mlp.act, b.partial, s.cpad};
         MaskSumsStoreEpTC<2> e2 = {b.dz2, z2, s.c2, s.ld, a.mlp.gamma[1], a.mlp.beta[1], a.mlp.act, b.partial, s.cpad};
-        if ((rc = launch_by_mt(b.pkT[2], s.tiles, bl, e1, e2, st))) return rc;          // da2 = W3^T dh3
+        if ((rc = launch_by_mt(b.pkT[2], ra, bl, e1, e2, st))) return rc;          // da2 = W3^T dh3
         LineFillK<FeatSource<1>> xa2 = {{rm, z2, s.c2, s.ld, a.mlp.act, s.c2, a.mlp.gamma[1], a.mlp.beta[1]}};
-        if ((rc = launch_dw(y3, xa2, s.c3, s.c2 + 1, s, b.dwp, st))) return rc;         // dW3 = dh3^T a2
+        if ((rc = launch_dw(y3, xa2, s.c3, s.c2 + 1, s, ra, b.dwp, st))) return rc;         // dW3 = dh3^T a2
         launch_dw_reduce(b.dwp, s.c3, s.c2 + 1, nullptr, s.c2, s.c2, s, g.grad_w[2], g.grad_b[2], st);
     }
     bn_bwd_finalize_tc_kernel<<<(s.c2 + 3) / 4, 128, 0, st>>>(b.partial, 2 * grid_x_for(b.pkT[2], s.tiles), s.c2, s.cpad, b.count,
                                                                  a.training, g.grad_gamma[1], g.grad_beta[1], b.sbar);
     note_launch();
     {
-        const int64_t n = (s.ld / 8) * s.c2;
-        bn_bwd_apply_tc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rm, b.dz2, z2, s.c2, s.ld, bn2 + 2 * s.cmax, b.sbar);
+        bn_bwd_apply_tc_kernel<<<apply_grid(s.ld, s.c2), 256, 0, st>>>(rm, ra.dev, b.dz2, z2, s.c2, s.ld, bn2 + 2 * s.cmax, b.sbar);
         note_launch();
     }
     // ---- layer 2 ---------------------------------------------------------------------------------------
@@ -1527,30 +1571,29 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
         FeatLoaderTC<FeatSource<0>> bl = {y2};
         MaskSumsStoreEpTC<1> e1 = {b.dz1, z1, s.c1, s.ld, a.mlp.gamma[0], a.mlp.beta[0], a.mlp.act, b.partial, s.cpad};
         MaskSumsStoreEpTC<2> e2 = {b.dz1, z1, s.c1, s.ld, a.mlp.gamma[0], a.mlp.beta[0], a.mlp.act, b.partial, s.cpad};
-        if ((rc = launch_by_mt(b.pkT[1], s.tiles, bl, e1, e2, st))) return rc;
+        if ((rc = launch_by_mt(b.pkT[1], ra, bl, e1, e2, st))) return rc;
         LineFillK<FeatSource<1>> xa1 = {{rm, z1, s.c1, s.ld, a.mlp.act, s.c1, a.mlp.gamma[0], a.mlp.beta[0]}};
-        if ((rc = launch_dw(y2, xa1, s.c2, s.c1 + 1, s, b.dwp, st))) return rc;
+        if ((rc = launch_dw(y2, xa1, s.c2, s.c1 + 1, s, ra, b.dwp, st))) return rc;
         launch_dw_reduce(b.dwp, s.c2, s.c1 + 1, nullptr, s.c1, s.c1, s, g.grad_w[1], g.grad_b[1], st);
     }
     bn_bwd_finalize_tc_kernel<<<(s.c1 + 3) / 4, 128, 0, st>>>(b.partial, 2 * grid_x_for(b.pkT[1], s.tiles), s.c1, s.cpad, b.count,
                                                                  a.training, g.grad_gamma[0], g.grad_beta[0], b.sbar);
     note_launch();
     {
-        const int64_t n = (s.ld / 8) * s.c1;
-        bn_bwd_apply_tc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rm, b.dz1, z1, s.c1, s.ld, bn1 + 2 * s.cmax, b.sbar);
+        bn_bwd_apply_tc_kernel<<<apply_grid(s.ld, s.c1), 256, 0, st>>>(rm, ra.dev, b.dz1, z1, s.c1, s.ld, bn1 + 2 * s.cmax, b.sbar);
         note_launch();
     }
     // ---- layer 1 ---------------------------------------------------------------------------------------
     FeatSource<0> y1 = {rm, b.dz1, s.c1, s.ld, 0, -1, nullptr, nullptr};
     {
         LineFillGather xg = {{rm, a.x, s.cols, a.pos_src, a.pos_dst, s.k1}};
-        if ((rc = launch_dw(y1, xg, s.c1, s.k1 + 1, s, b.dwp, st))) return rc;
+        if ((rc = launch_dw(y1, xg, s.c1, s.k1 + 1, s, ra, b.dwp, st))) return rc;
         launch_dw_reduce(b.dwp, s.c1, s.k1 + 1, &s.cols, s.c0, s.k1, s, g.grad_w[0], g.grad_b[0], st);
     }
     if (need_dx) {
         FeatLoaderTC<FeatSource<0>> bl = {y1};
         ScatterEpTC e = {rm, g.grad_x, a.c_in};
-        if ((rc = launch_by_mt(b.pkT[0], s.tiles, bl, e, e, st))) return rc;
+        if ((rc = launch_by_mt(b.pkT[0], ra, bl, e, e, st))) return rc;
     }
     B2PN_LAUNCH_CHECK();
     return B2PN_OK;

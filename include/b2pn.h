@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B2PN_ABI_VERSION 1
+#define B2PN_ABI_VERSION 2
 #define B2PN_OK 0
 #define B2PN_EINVAL (-1)   /* null pointer / negative size / bad flag            */
 #define B2PN_ENOTSUP (-2)  /* shape outside what the sm_100a kernels are built for */
@@ -74,6 +74,25 @@ int b2pn_ball_query_f32(const float *src_pos, const float *qry_pos, const int64_
                         const int64_t *qry_ptr, int32_t B, int64_t max_src, int64_t max_qry, double r,
                         int32_t K, int32_t *nbr, int32_t *cnt, b2pn_stream_t stream);
 
+/*
+ * Edge compaction (tensor-core path).  torch_cluster.radius returns a compact [2,E] edge list
+ * (/root/reference/pointnet2_regressor.py:14-16); b2pn_ball_query_f32 writes fixed-width slots instead, and
+ * this call packs the FILLED slots into rows for the bf16 set-abstraction kernels -- on the device, without
+ * the masked_select host round trip: the row count stays in device memory (*num_rows).
+ *   cnt [n_dst], nbr [n_dst,K]    output of b2pn_ball_query_f32, K <= 64
+ *   rgrp    [capacity/8] u32      one descriptor per 8-row group: bits 0..23 centroid (0xFFFFFF none),
+ *                                 24..26 first slot/8, 27..30 valid rows, 31 last group of the centroid
+ *   row_src [capacity]   i32      gathered source point of the row, -1 = padding
+ *   num_rows [1]         i64      rows in use (multiple of 64)
+ * Centroid m owns max(8, round_up(cnt[m], 8)) consecutive rows that never cross a 64-row boundary.
+ * capacity = b2pn_pack_rows_capacity(n_dst, K) rows (host-side upper bound used to size every buffer).
+ */
+int64_t b2pn_pack_rows_capacity(int64_t n_dst, int32_t K);
+int64_t b2pn_pack_rows_workspace_bytes(int64_t n_dst);
+int b2pn_pack_rows(const int32_t *cnt, const int32_t *nbr, int64_t n_dst, int32_t K, uint32_t *rgrp,
+                   int32_t *row_src, int64_t *num_rows, void *workspace, int64_t workspace_bytes,
+                   b2pn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Set-abstraction levels: fused gather + relative-position concat + shared MLP + max aggregation.
  *
@@ -109,7 +128,7 @@ typedef struct b2pn_sa_args {
     int32_t precision;           /* B2PN_PREC_*                                                       */
     int32_t training;            /* 1: batch statistics + running-stat update, 0: running statistics  */
     int32_t seg_mode;            /* B2PN_SEG_*                                                        */
-    int32_t K;                   /* slots per target (SLOTS), multiple of 8 dividing 128              */
+    int32_t K;                   /* slots per target (SLOTS); PREC_BF16: K <= 64                      */
     int64_t n_src, n_dst;        /* source points; targets (centroids or clouds)                      */
     int32_t c_in;                /* feature channels of x (0: no features, pointnet2_regressor.py:17) */
     int32_t x_dtype;             /* B2PN_X_F32 / B2PN_X_BF16 (bf16 only with B2PN_PREC_BF16)          */
@@ -122,13 +141,19 @@ typedef struct b2pn_sa_args {
     b2pn_mlp3 mlp;
     float *out;                  /* [n_dst, c3]                                                       */
     int32_t *arg;                /* [n_dst, c3] arg-max slot (SLOTS) or source row (CLOUDS); -1 none  */
-    void *h1, *h2;               /* saved activations of the two hidden layers, rows = n_dst*K (SLOTS) or
-                                    n_src (CLOUDS).  PREC_F32: pre-BN values, f32 row-major [rows, c].
-                                    PREC_BF16: normalised values (h-mean)*rstd, bf16 FEATURE-major [c, ld],
-                                    ld = rows rounded up to a multiple of 128                          */
+    void *h1, *h2;               /* saved activations of the two hidden layers.
+                                    PREC_F32: pre-BN values, f32 row-major [rows, c], rows = n_dst*K (SLOTS) or
+                                    n_src (CLOUDS).  PREC_BF16: normalised values (h-mean)*rstd, bf16
+                                    FEATURE-major [c, ld], ld = row_capacity (SLOTS) or n_src rounded up to a
+                                    multiple of 128 (CLOUDS)                                            */
     float *bn;                   /* [2][4][cmax] per BN layer: mean, rstd, scale, shift; cmax=max(c1,c2) */
     void *workspace;             /* b2pn_sa_workspace_bytes() bytes, scratch                          */
     int64_t workspace_bytes;
+    /* PREC_BF16 + SEG_SLOTS: compacted rows from b2pn_pack_rows (ignored otherwise)                    */
+    const uint32_t *rgrp;
+    const int32_t *row_src;
+    const int64_t *num_rows;
+    int64_t row_capacity;        /* b2pn_pack_rows_capacity(n_dst, K)                                   */
 } b2pn_sa_args;
 
 typedef struct b2pn_sa_grads {

@@ -31,7 +31,7 @@ def test_header_symbols_exported_and_bound(built_lib):
     assert set(names) <= exported, sorted(set(names) - exported)
     assert set(names) == set(built_lib.SIGNATURES), "ctypes table and header disagree"
     h = built_lib.lib()
-    assert h.b2pn_abi_version() == 1
+    assert h.b2pn_abi_version() == built_lib.ABI_VERSION
     assert h.b2pn_fps_num_samples(7168, 0.2) == 1434
     assert b"invalid" in h.b2pn_error_string(-1)
 

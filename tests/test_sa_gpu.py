@@ -159,7 +159,8 @@ def test_training_steps_track_oracle(cuda_device):
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("c_in,chans,K,train", [(1, [4, 64, 64, 128], 64, True), (1, [4, 64, 64, 128], 64, False),
                                                 (16, [19, 32, 48, 40], 16, True), (0, [3, 64, 64, 128], 32, True),
-                                                (128, [131, 128, 128, 256], 64, True), (8, [11, 64, 128, 256], 128, True)])
+                                                (128, [131, 128, 128, 256], 64, True), (8, [11, 64, 128, 256], 40, True),
+                                                (2, [5, 64, 64, 64], 8, True)])
 def test_sa_slots_level_bf16_forward(cuda_device, c_in, chans, K, train):
     b = Batch.from_data_list(synthetic_clouds(21, 3, 600, max(c_in, 1), True))
     x = None if c_in == 0 else (torch.randn(b.pos.size(0), c_in, generator=torch.Generator().manual_seed(1)))
@@ -185,6 +186,65 @@ def test_sa_slots_level_bf16_forward(cuda_device, c_in, chans, K, train):
     if train:
         for (k, v), (_, vr) in zip(m.named_buffers(), mref.named_buffers()):
             assert rel_err(v.float(), vr.float()) < 2e-2, k
+
+
+@pytest.mark.parametrize("K,n,r", [(64, 600, 2.5), (64, 3000, 1.0), (40, 600, 2.5), (8, 600, 9.0), (16, 50, 0.01)])
+def test_pack_rows_structure(cuda_device, K, n, r):
+    """b2pn_pack_rows: every centroid owns max(8, round_up(cnt, 8)) consecutive rows inside one 64-row block,
+    rows carry the neighbour slots in order, the device-side row count covers exactly the rows in use."""
+    b = Batch.from_data_list(synthetic_clouds(77, 4, n, 1, True))
+    idx = ref.fps_ref(b.pos, b.ptr, 0.2)
+    qptr = ref.sample_ptr(b.ptr, 0.2)
+    nbr, cnt = ref.ball_query_ref(b.pos, b.pos[idx], b.ptr, qptr, r, K)
+    rgrp, row_src, num_rows, cap = sa.pack_rows(nbr.to(cuda_device), cnt.to(cuda_device), K)
+    torch.cuda.synchronize()
+    rows = int(num_rows.item())
+    assert rows % 64 == 0 and 0 < rows <= cap
+    g = rgrp.cpu().numpy().astype("uint32")
+    src = row_src.cpu().numpy()
+    seg = (g & 0xFFFFFF).astype("int64")
+    slot0 = ((g >> 24) & 7).astype("int64") * 8
+    nv = ((g >> 27) & 15).astype("int64")
+    last = (g >> 31).astype("int64")
+    none = seg == 0xFFFFFF
+    assert none[rows // 8:].all() and (src[rows:] == -1).all()
+    import numpy as np
+    used = np.nonzero(~none[: rows // 8])[0]
+    cntn, nbrn = cnt.numpy(), nbr.numpy()
+    seen = np.zeros(cnt.numel(), dtype=bool)
+    # walk the groups centroid by centroid
+    i = 0
+    while i < len(used):
+        gi = used[i]
+        m = seg[gi]
+        assert slot0[gi] == 0 and not seen[m]
+        seen[m] = True
+        c8 = max(8, (int(cntn[m]) + 7) // 8 * 8)
+        ng = c8 // 8
+        assert (gi * 8) // 64 == (gi * 8 + c8 - 1) // 64, "centroid crosses a 64-row boundary"
+        for j in range(ng):
+            assert used[i + j] == gi + j and seg[gi + j] == m and slot0[gi + j] == 8 * j
+            want_nv = min(8, max(0, int(cntn[m]) - 8 * j))
+            assert nv[gi + j] == want_nv and last[gi + j] == (1 if j == ng - 1 else 0)
+            want_src = np.full(8, -1, dtype=np.int64)
+            want_src[:want_nv] = nbrn[m, 8 * j: 8 * j + want_nv]
+            assert (src[(gi + j) * 8: (gi + j) * 8 + 8] == want_src).all()
+        i += ng
+    assert seen.all()
+    # centroids keep their order
+    firsts = used[slot0[used] == 0]
+    assert (np.diff(seg[firsts]) > 0).all()
+
+
+def test_bf16_rejects_wide_slots(cuda_device):
+    m = MLP([4, 64, 64, 128], act="ReLU").to(cuda_device)
+    pos = torch.randn(200, 3, device=cuda_device)
+    x = torch.randn(200, 1, device=cuda_device)
+    nbr = torch.zeros(10, 128, dtype=torch.int32, device=cuda_device)
+    cnt = torch.ones(10, dtype=torch.int32, device=cuda_device)
+    with pytest.raises(RuntimeError):
+        sa.sa_apply(m, x, pos, pos[:10].contiguous(), nbr, cnt, None, seg_mode=sa.SEG_SLOTS, K=128, n_dst=10,
+                    precision=sa.PREC_BF16)
 
 
 def test_global_sa_level_bf16_forward(cuda_device):
@@ -232,7 +292,8 @@ def _grad_errs(m, mref, skip_bn_biases=True):
 
 
 @pytest.mark.parametrize("c_in,chans,K", [(1, [4, 64, 64, 128], 64), (16, [19, 32, 48, 40], 16),
-                                          (128, [131, 128, 128, 256], 64), (0, [3, 64, 64, 128], 32)])
+                                          (128, [131, 128, 128, 256], 64), (0, [3, 64, 64, 128], 32),
+                                          (8, [11, 64, 128, 256], 40)])
 def test_sa_slots_level_bf16_backward(cuda_device, c_in, chans, K):
     """bf16 gradients against the oracle run with bf16 rounding emulated at the same points (weights, post-BN
     values).  Against the un-rounded oracle they differ by ~10 % because rounding flips a few arg-max / ReLU
