@@ -191,6 +191,315 @@ __global__ void __launch_bounds__(THREADS, 1) fps_kernel(const FpsParams p)
     }
 }
 
+// =================================================================================================
+//  Kernel 1b -- the same sampling with SPATIAL PRUNING (one CTA per cloud).
+//
+//  The points are sorted along a Morton curve inside the kernel (bitonic sort in shared memory), so
+//  every warp owns a spatially compact bucket and keeps its bounding box.  A new sample c can only
+//  lower the running distance of a point p if d2(p,c) < D[p] <= max D of p's bucket, and for every p of
+//  a bucket d2(p,c) >= d2(box,c) IN THE SAME fp32 ARITHMETIC (sub/mul/add are monotone under
+//  round-to-nearest and the box distance is built from the same operations), so a bucket with
+//  d2(box,c) >= its current max is skipped without changing a single bit of the result.  Late in the
+//  sampling a new point touches 2-4 buckets of 32, so the scan shrinks by ~8x and an iteration costs
+//  one block barrier: every warp publishes {max, index, xyz} (from registers; recomputed only when
+//  the bucket was touched), then every warp reduces the 32 records redundantly.
+//  Ties go to the lowest ORIGINAL index at every level (perm[] maps sorted position -> original).
+// =================================================================================================
+__device__ __forceinline__ unsigned morton_spread10(unsigned v)
+{
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+template <int THREADS, int MAXS>
+__global__ void __launch_bounds__(THREADS, 1) fps_pruned_kernel(const FpsParams p, const int npad)
+{
+    constexpr int NW = THREADS / 32;
+    extern __shared__ __align__(16) unsigned char fps_dyn[];
+    u64 *keys = reinterpret_cast<u64 *>(fps_dyn);  // [npad] during the sort
+    __shared__ float s_red[6][NW];
+    __shared__ int s_rec[2][5][32];  // per warp {max distance bits, original index, x, y, z}, double-buffered
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t p0 = p.ptr[b];
+    const int n = (int)(p.ptr[b + 1] - p0);
+    const int64_t o0 = p.out_ptr[b];
+    const int m = (int)(p.out_ptr[b + 1] - o0);
+    if (n <= 0 || m <= 0) return;
+    const float *gpos = p.pos + 3 * p0;
+
+    // ---- 1. cloud bounding box -> 10-bit quantisation per axis ----------------------------------------------
+    {
+        float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int i = tid; i < n; i += THREADS) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float v = __ldg(gpos + 3 * i + a);
+                mn[a] = fminf(mn[a], v);
+                mx[a] = fmaxf(mx[a], v);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+                mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+            }
+            if (lane == 0) {
+                s_red[a][warp] = mn[a];
+                s_red[3 + a][warp] = mx[a];
+            }
+        }
+    }
+    __syncthreads();
+    float qlo[3], qsc[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float mn = INFINITY, mx = -INFINITY;
+        for (int w = 0; w < NW; ++w) {
+            mn = fminf(mn, s_red[a][w]);
+            mx = fmaxf(mx, s_red[3 + a][w]);
+        }
+        qlo[a] = mn;
+        const float ext = mx - mn;
+        qsc[a] = ext > 0.f ? 1023.f / ext : 0.f;
+    }
+    // ---- 2. Morton keys (the sort order only decides the bucketing, never the result) -----------------------
+    for (int i = tid; i < npad; i += THREADS) {
+        u64 k = ~0ull;
+        if (i < n) {
+            unsigned code = 0u;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float v = __ldg(gpos + 3 * i + a);
+                float q = (v - qlo[a]) * qsc[a];
+                q = fminf(fmaxf(q, 0.f), 1023.f);
+                code |= morton_spread10((unsigned)q) << a;
+            }
+            k = ((u64)code << 32) | (u64)(unsigned)i;
+        }
+        keys[i] = k;
+    }
+    __syncthreads();
+    // ---- 3. bitonic sort of the 64-bit keys (unique, so the order is deterministic) --------------------------
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (npad >> 1); t += THREADS) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const u64 a = keys[i], c = keys[l];
+                const bool up = (i & k) == 0;
+                if ((a > c) == up) {
+                    keys[i] = c;
+                    keys[l] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- 4. buckets: warp w owns S buckets of 32 consecutive points of the Morton order; point (bucket k, lane l)
+    //         sits at q = (w*S + k)*32 + l of the SoA arrays below.  Lane k keeps bucket k's box and running max. ---
+    const int S = (n + THREADS - 1) / THREADS;  // buckets per warp in use (<= MAXS <= 32)
+    const int NP = THREADS * S;
+    unsigned myidx[MAXS];
+#pragma unroll
+    for (int k = 0; k < MAXS; ++k) {
+        const int q = (warp * S + k) * 32 + lane;
+        myidx[k] = (k < S && q < n) ? (unsigned)(keys[q] & 0xffffffffull) : 0xffffffffu;
+    }
+    __syncthreads();  // everybody has read its keys: the buffer becomes the point arrays
+    float *sx = reinterpret_cast<float *>(fps_dyn);
+    float *sy = sx + NP, *sz = sy + NP, *sD = sz + NP;
+    unsigned short *sperm = reinterpret_cast<unsigned short *>(sD + NP);  // original index (n <= 65535)
+    float blx = INFINITY, bly = INFINITY, blz = INFINITY, bhx = -INFINITY, bhy = -INFINITY, bhz = -INFINITY;
+    float bmax = -1.f;
+#pragma unroll
+    for (int k = 0; k < MAXS; ++k) {
+        if (k < S) {
+            const bool ok = myidx[k] != 0xffffffffu;
+            const float *g = gpos + 3 * (int64_t)(ok ? myidx[k] : 0u);
+            const float x = ok ? __ldg(g + 0) : 0.f, y = ok ? __ldg(g + 1) : 0.f, z = ok ? __ldg(g + 2) : 0.f;
+            const int q = (warp * S + k) * 32 + lane;
+            sx[q] = x;
+            sy[q] = y;
+            sz[q] = z;
+            sD[q] = ok ? __int_as_float(0x7f800000) : -1.f;  // +inf: the first update sets dist-to-start
+            sperm[q] = (unsigned short)(ok ? myidx[k] : 0xffffu);
+            float lx = ok ? x : INFINITY, ly = ok ? y : INFINITY, lz = ok ? z : INFINITY;
+            float hx = ok ? x : -INFINITY, hy = ok ? y : -INFINITY, hz = ok ? z : -INFINITY;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o)); hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o));
+                ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o)); hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o));
+                lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+            }
+            if (lane == k) {
+                blx = lx; bly = ly; blz = lz; bhx = hx; bhy = hy; bhz = hz;
+                bmax = (lx <= hx) ? __int_as_float(0x7f800000) : -1.f;  // empty bucket: never touched
+            }
+        }
+    }
+
+    // ---- start point ---------------------------------------------------------------------------------------------
+    int cur = 0;
+    if (p.start != nullptr) {
+        const int64_t s = p.start[b];
+        cur = (s >= 0 && s < n) ? (int)s : 0;
+    }
+    float cx = __ldg(gpos + 3 * cur + 0), cy = __ldg(gpos + 3 * cur + 1), cz = __ldg(gpos + 3 * cur + 2);
+    if (tid == 0) {
+        p.out_idx[o0] = p0 + cur;
+        if (p.out_pos) {
+            p.out_pos[3 * o0 + 0] = cx;
+            p.out_pos[3 * o0 + 1] = cy;
+            p.out_pos[3 * o0 + 2] = cz;
+        }
+    }
+    if (p.out_batch) {
+#pragma unroll 1
+        for (int i = tid; i < m; i += THREADS) p.out_batch[o0 + i] = b;
+    }
+    if (lane < 5) s_rec[0][lane][warp] = lane == 0 ? __float_as_int(-1.f) : (lane == 1 ? 0x7fffffff : 0);
+    __syncwarp();
+
+    const int qw = warp * S * 32 + lane;
+    for (int it = 1; it < m; ++it) {
+        const int par = it & 1;
+        // lane k: distance from the new sample to the box of bucket k, in the arithmetic of the point distances
+        const float ex = fmaxf(fmaxf(__fsub_rn(blx, cx), __fsub_rn(cx, bhx)), 0.f);
+        const float ey = fmaxf(fmaxf(__fsub_rn(bly, cy), __fsub_rn(cy, bhy)), 0.f);
+        const float ez = fmaxf(fmaxf(__fsub_rn(blz, cz), __fsub_rn(cz, bhz)), 0.f);
+        const float bd = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+        unsigned hits = __ballot_sync(0xffffffffu, bd < bmax);  // empty buckets: bmax = -1
+        if (hits != 0u) {                                       // warp-uniform
+            // touched buckets, two at a time so that their shared-memory round trips overlap
+            while (hits != 0u) {
+                const int k0 = __ffs(hits) - 1;
+                hits &= hits - 1u;
+                const bool two = hits != 0u;
+                const int k1 = two ? __ffs(hits) - 1 : k0;
+                hits &= hits - 1u;  // 0 - 1 & 0 = 0: harmless when already empty
+                const int q0 = qw + k0 * 32, q1 = qw + k1 * 32;
+                const float x0 = sx[q0], y0 = sy[q0], z0 = sz[q0], D0 = sD[q0];
+                const float x1 = sx[q1], y1 = sy[q1], z1 = sz[q1], D1 = sD[q1];
+                const float n0 = fminf(D0, dist2_scalar(x0, y0, z0, cx, cy, cz));
+                const float n1 = fminf(D1, dist2_scalar(x1, y1, z1, cx, cy, cz));
+                sD[q0] = n0;
+                if (two) sD[q1] = n1;
+                const int m0 = __reduce_max_sync(0xffffffffu, __float_as_int(n0));
+                const int m1 = __reduce_max_sync(0xffffffffu, __float_as_int(n1));
+                if (lane == k0) bmax = __int_as_float(m0);
+                if (lane == k1) bmax = __int_as_float(m1);
+            }
+            __syncwarp();
+            // new warp record: max over my buckets, lowest original index among the points at the max
+            const int wmax = __reduce_max_sync(0xffffffffu, __float_as_int(bmax));
+            unsigned tb = __ballot_sync(0xffffffffu, __float_as_int(bmax) == wmax);
+            unsigned best = 0xffffffffu;
+            int bq = 0;
+            do {  // one bucket unless distances tie across buckets
+                const int k = __ffs(tb) - 1;
+                tb &= tb - 1u;
+                const int q = qw + k * 32;
+                const unsigned cand = (__float_as_int(sD[q]) == wmax) ? (unsigned)sperm[q] : 0xffffffffu;
+                if (cand < best) {
+                    best = cand;
+                    bq = q;
+                }
+            } while (tb != 0u);
+            const unsigned widx = __reduce_min_sync(0xffffffffu, best);
+            if (best == widx) {  // exactly one lane (original indices are unique); an empty warp never gets here
+                s_rec[par][0][warp] = wmax;
+                s_rec[par][1][warp] = (int)widx;
+                s_rec[par][2][warp] = __float_as_int(sx[bq]);
+                s_rec[par][3][warp] = __float_as_int(sy[bq]);
+                s_rec[par][4][warp] = __float_as_int(sz[bq]);
+            }
+        } else if (lane < 5) {
+            s_rec[par][lane][warp] = s_rec[par ^ 1][lane][warp];  // unchanged bucket set: republish
+        }
+        __syncthreads();
+        const bool live = lane < NW;
+        const int key = live ? s_rec[par][0][lane] : INT_MIN;
+        const unsigned ki = live ? (unsigned)s_rec[par][1][lane] : 0xffffffffu;
+        const float rx = live ? __int_as_float(s_rec[par][2][lane]) : 0.f;
+        const float ry = live ? __int_as_float(s_rec[par][3][lane]) : 0.f;
+        const float rz = live ? __int_as_float(s_rec[par][4][lane]) : 0.f;
+        const int gmax = __reduce_max_sync(0xffffffffu, key);
+        const unsigned sel = key == gmax ? ki : 0xffffffffu;
+        const unsigned gidx = __reduce_min_sync(0xffffffffu, sel);
+        const int ww = __ffs(__ballot_sync(0xffffffffu, sel == gidx)) - 1;
+        cx = __shfl_sync(0xffffffffu, rx, ww);
+        cy = __shfl_sync(0xffffffffu, ry, ww);
+        cz = __shfl_sync(0xffffffffu, rz, ww);
+        if (tid == 0) {
+            p.out_idx[o0 + it] = p0 + (int64_t)gidx;
+            if (p.out_pos) {
+                p.out_pos[3 * (o0 + it) + 0] = cx;
+                p.out_pos[3 * (o0 + it) + 1] = cy;
+                p.out_pos[3 * (o0 + it) + 2] = cz;
+            }
+        }
+    }
+}
+
+static int next_pow2(int v)
+{
+    int r = 1;
+    while (r < v) r <<= 1;
+    return r;
+}
+
+template <int THREADS, int MAXS>
+static int launch_fps_pruned(const FpsParams &p, int B, int64_t max_n, cudaStream_t stream)
+{
+    auto kern = fps_pruned_kernel<THREADS, MAXS>;
+    const int npad = next_pow2((int)max_n);
+    const int S = (int)((max_n + THREADS - 1) / THREADS);
+    const int after = THREADS * S * 18;  // x, y, z, D (fp32) + original index (u16) per slot
+    const int smem = npad * 8 > after ? npad * 8 : after;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<(unsigned)B, THREADS, smem, stream>>>(p, npad);
+    note_launch();
+    e = cudaPeekAtLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+// capacity of the pruned variant: 18 B of shared memory per point
+constexpr int64_t PRUNED_MAX_N = 12288;
+
+template <int THREADS>
+static int dispatch_pruned_s(const FpsParams &p, int B, int64_t max_n, cudaStream_t stream)
+{
+    const int S = (int)((max_n + THREADS - 1) / THREADS);
+    if (S <= 4) return launch_fps_pruned<THREADS, 4>(p, B, max_n, stream);
+    if (S <= 8) return launch_fps_pruned<THREADS, 8>(p, B, max_n, stream);
+    if (S <= 12) return launch_fps_pruned<THREADS, 12>(p, B, max_n, stream);
+    if (S <= 24) return launch_fps_pruned<THREADS, 24>(p, B, max_n, stream);
+    if (S <= 32) return launch_fps_pruned<THREADS, 32>(p, B, max_n, stream);
+    return B2PN_ENOTSUP;
+}
+
+static int dispatch_pruned(const FpsParams &p, int B, int64_t max_n, int threads, cudaStream_t stream)
+{
+    if (max_n > PRUNED_MAX_N || max_n > 65535) return B2PN_ENOTSUP;
+    if (threads == 0) threads = max_n <= 2048 ? 256 : (max_n <= 4096 ? 512 : 1024);
+    if ((int64_t)threads * 32 < max_n) return B2PN_ENOTSUP;
+    switch (threads) {
+        case 256: return dispatch_pruned_s<256>(p, B, max_n, stream);
+        case 512: return dispatch_pruned_s<512>(p, B, max_n, stream);
+        case 1024: return dispatch_pruned_s<1024>(p, B, max_n, stream);
+    }
+    return B2PN_EINVAL;
+}
+
 static int g_force_cluster = 0;
 static int g_force_threads = 0;
 
@@ -268,7 +577,7 @@ static int dispatch_cluster(const FpsParams &p, int B, int64_t max_n, int cluste
 
 extern "C" int b2pn_fps_set_variant(int32_t cluster, int32_t threads)
 {
-    if (!(cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8 || cluster == 16))
+    if (!(cluster == -1 || cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8 || cluster == 16))
         return B2PN_EINVAL;
     if (!(threads == 0 || threads == 256 || threads == 512 || threads == 1024)) return B2PN_EINVAL;
     b2pn::g_force_cluster = cluster;
@@ -287,6 +596,11 @@ extern "C" int b2pn_fps_f32(const float *pos, const int64_t *ptr, const int64_t 
     FpsParams p = {pos, ptr, out_ptr, start, out_idx, out_pos, out_batch};
 
     int threads = g_force_threads, cluster = g_force_cluster;
+    // cluster == -1: the spatially pruned kernel (bit-identical results).  Measured on B200
+    // (profiles/r01_fps_experiments.md) it prunes ~75 % of the scan but its serial chain of uniform-datapath
+    // reductions (CREDUX / VOTE / FLO at 50-70 cycles each) makes an iteration SLOWER than the plain register scan
+    // at 10k points, so it is opt-in and the register scan below stays the default.
+    if (cluster == -1) return dispatch_pruned(p, B, max_n, threads, (cudaStream_t)stream);
     if (threads == 0) threads = 512;
     if (cluster == 0) {
         // Measured on B200 (profiles/r01_fps_sweep.md): barrier.cluster costs more per iteration than

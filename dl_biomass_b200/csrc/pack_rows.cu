@@ -16,7 +16,7 @@
 namespace b2pn {
 
 constexpr int PACK_G = 64;        // centroids per sequential chunk
-constexpr int PACK_THREADS = 1024;
+constexpr int PACK_THREADS = 256;   // 64 registers of counts + 64 of offsets per thread
 
 __device__ __forceinline__ int c8_of(int c, int K)
 {
@@ -41,12 +41,38 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_rows_scan_kernel(const int3
         if (ch < chunks) {
             const int64_t m0 = ch * PACK_G;
             const int64_t m1 = m0 + PACK_G < n_dst ? m0 + PACK_G : n_dst;
+            // all loads first (one memory latency), then the sequential greedy packing out of registers
+            int c8[PACK_G];
+            if (m1 - m0 == PACK_G && ((uintptr_t)(cnt + m0) & 15u) == 0) {
+                const int4 *src = reinterpret_cast<const int4 *>(cnt + m0);
+#pragma unroll
+                for (int i = 0; i < PACK_G / 4; ++i) {
+                    const int4 v = __ldg(src + i);
+                    c8[4 * i + 0] = c8_of(v.x, K);
+                    c8[4 * i + 1] = c8_of(v.y, K);
+                    c8[4 * i + 2] = c8_of(v.z, K);
+                    c8[4 * i + 3] = c8_of(v.w, K);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < PACK_G; ++i) c8[i] = m0 + i < m1 ? c8_of(__ldg(cnt + m0 + i), K) : 0;
+            }
             int off = 0;
-            for (int64_t m = m0; m < m1; ++m) {
-                const int c8 = c8_of(cnt[m], K);
-                if ((off & 63) + c8 > 64) off = (off + 63) & ~63;
-                row_off[m] = off;
-                off += c8;
+            int lo[PACK_G];
+#pragma unroll
+            for (int i = 0; i < PACK_G; ++i) {
+                if ((off & 63) + c8[i] > 64) off = (off + 63) & ~63;
+                lo[i] = off;
+                off += c8[i];
+            }
+            if (m1 - m0 == PACK_G && ((uintptr_t)(row_off + m0) & 15u) == 0) {
+                int4 *dst = reinterpret_cast<int4 *>(row_off + m0);
+#pragma unroll
+                for (int i = 0; i < PACK_G / 4; ++i) dst[i] = make_int4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < PACK_G; ++i)
+                    if (m0 + i < m1) row_off[m0 + i] = lo[i];
             }
             blocks = (off + 63) >> 6;
         }
@@ -60,13 +86,13 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_rows_scan_kernel(const int3
         if (lane == 31) s_warp[warp] = v;
         __syncthreads();
         if (warp == 0) {
-            int w = s_warp[lane];
+            int w = lane < PACK_THREADS / 32 ? s_warp[lane] : 0;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int t = __shfl_up_sync(0xffffffffu, w, o);
                 if (lane >= o) w += t;
             }
-            s_warp[lane] = w;  // inclusive over warps
+            if (lane < PACK_THREADS / 32) s_warp[lane] = w;  // inclusive over warps
         }
         __syncthreads();
         const int carry = s_carry;

@@ -91,7 +91,7 @@ def test_golden_grouping_fixture(cuda_device):
         i += 1
 
 
-@pytest.mark.parametrize("cluster,threads", [(1, 256), (1, 512), (1, 1024), (2, 512), (4, 256), (8, 256), (8, 512),
+@pytest.mark.parametrize("cluster,threads", [(-1, 256), (-1, 512), (-1, 1024), (1, 256), (1, 512), (1, 1024), (2, 512), (4, 256), (8, 256), (8, 512),
                                              (16, 256)])
 def test_fps_variants_agree(cuda_device, cluster, threads):
     b = Batch.from_data_list(synthetic_clouds(77, 5, 6000, 1, True))

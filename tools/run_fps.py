@@ -1,16 +1,24 @@
-"""Kernel 1 alone on BASELINE configs[1] shapes (for ncu captures)."""
-import os, sys
+"""Run Kernel 1 (FPS) alone on the bench shape -- the target of `ncu --set full` captures.
+usage: run_fps.py [cluster threads [n [ratio]]]   (cluster -1 = spatially pruned kernel, 0 = auto)"""
+import os
+import sys
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import torch
-from dl_biomass_b200 import ops
-from dl_biomass_b200.data import Batch, synthetic_clouds
+import torch  # noqa: E402
+from dl_biomass_b200 import _lib, ops  # noqa: E402
+from dl_biomass_b200.data import Batch, synthetic_clouds  # noqa: E402
+
+cluster = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+threads = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 10000
+ratio = float(sys.argv[4]) if len(sys.argv) > 4 else 0.2
 dev = torch.device("cuda:0")
-b = Batch.from_data_list(synthetic_clouds(1234, 12, 10000, 1, False))
+b = Batch.from_data_list(synthetic_clouds(1234, 12, n, 1, False))
 pos = b.pos.to(dev)
-lv = ops.build_levels(b.cloud_sizes, [0.2], dev)
+lv = ops.build_levels([n] * 12, [ratio], dev)
+_lib.check(_lib.lib().b2pn_fps_set_variant(cluster, threads), "set_variant")
 for _ in range(3):
-    idx, p1, _ = ops.fps(pos, lv[0], lv[1])
-nbr, cnt = ops.ball_query(pos, p1, lv[0], lv[1], 2.0, 64)
+    idx, _, _ = ops.fps(pos, lv[0], lv[1])
 torch.cuda.synchronize()
-print("ok", int(idx[1]), float(cnt.float().mean()))
+print("ok", idx[:4].tolist())
