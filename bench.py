@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--points", type=int, default=10000)
     ap.add_argument("--pool", type=int, default=4, help="distinct batches rotated through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     return ap.parse_args()
 
 
@@ -113,8 +114,9 @@ def make_pool(args, rank, pin):
     return pool
 
 
-def batch_h2d_bytes(b):
-    return sum(t.numel() * t.element_size() for t in (b.x, b.pos, b.batch, b.y) if t is not None)
+def batch_h2d_bytes(b, with_batch_vector=True):
+    ts = (b.x, b.pos, b.batch, b.y) if with_batch_vector else (b.x, b.pos, b.y)
+    return sum(t.numel() * t.element_size() for t in ts if t is not None)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -177,7 +179,7 @@ def run_b200(args):
     from dl_biomass_b200 import _lib, ops
     from dl_biomass_b200.parallel import GradReducer
     from dl_biomass_b200.pointnet2_regressor import Net
-    from dl_biomass_b200.train import make_optimizer, train_step
+    from dl_biomass_b200.train import GraphedTrainStep, make_optimizer, train_step
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a B200: no CUDA device (the product path has no CPU fallback)")
@@ -199,7 +201,8 @@ def run_b200(args):
     torch.manual_seed(7)
     net = Net(1, "ReLU", 0, 0.5, precision=precision).to(dev)
     net.train()
-    opt = make_optimizer(net.parameters())
+    use_graph = not args.no_graph
+    opt = make_optimizer(net.parameters(), capturable=use_graph)
     reducer = GradReducer(net) if world > 1 else None
 
     pool_host = make_pool(args, rank, pin=True)
@@ -229,9 +232,16 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # the whole step (forward, loss, backward, all-reduce, Adam) is captured once and replayed: same kernels, one
+    # launch.  Batches whose cloud sizes differ from the captured layout would run eagerly (none here).
+    graphed = GraphedTrainStep(net, opt, pool_dev[0], reducer) if use_graph else None
+
+    def run_step(batch):
+        return graphed(batch) if graphed is not None else train_step(net, opt, batch, reducer)
+
     # ---- resident-input arm ("value") ------------------------------------------------------------
     def step_resident(i):
-        train_step(net, opt, pool_dev[i % len(pool_dev)], reducer)
+        run_step(pool_dev[i % len(pool_dev)])
 
     for i in range(max(args.warmup, 3)):
         step_resident(i)
@@ -239,6 +249,8 @@ def run_b200(args):
     l0 = lib.b2pn_launch_count()
     total_ms = timed(step_resident, args.steps)
     launches = lib.b2pn_launch_count() - l0
+    if graphed is not None:  # replayed kernels do not pass through the library's launch counter
+        launches = graphed.launches_per_replay * args.steps
     clocks = sampler.stop() if sampler else None
     value = world * args.batch * args.steps / (total_ms * 1e-3)
 
@@ -246,8 +258,11 @@ def run_b200(args):
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
     def step_e2e(i):
-        b = pool_host[i % len(pool_host)].to(dev, non_blocking=True)
-        loss = train_step(net, opt, b, reducer)
+        hb = pool_host[i % len(pool_host)]
+        if graphed is not None:
+            loss = graphed(hb)  # pinned host tensors are copied straight into the graph's input buffers
+        else:
+            loss = train_step(net, opt, hb.to(dev, non_blocking=True), reducer)
         loss_host.copy_(loss, non_blocking=True)
 
     for i in range(3):
@@ -307,10 +322,12 @@ def run_b200(args):
                                    f"F=1, {precision} MLPs (BASELINE configs[1])",
                        "global_batch": world * args.batch, "points_per_cloud": args.points,
                        "parallelism": f"dp{world}", "l2": "256 MB buffer rewritten before every timed step",
-                       "timing": "per-step CUDA events on the launching stream, summed; max over ranks"},
+                       "timing": "per-step CUDA events on the launching stream, summed; max over ranks",
+                       "launch": "one CUDA graph replay per step" if use_graph else "eager kernel launches"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(e2e_ms / args.steps, 4),
-                    "h2d_bytes_per_step": batch_h2d_bytes(pool_host[0]), "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": batch_h2d_bytes(pool_host[0], with_batch_vector=graphed is None),
+                    "d2h_bytes_per_step": 4},
             "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:

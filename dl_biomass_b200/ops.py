@@ -107,10 +107,29 @@ class Level:
     ptr: torch.Tensor         # [B+1] int64 on the device
     total: int
     max_n: int
+    sizes_f32: Optional[torch.Tensor] = None  # [B] float32 on the device (scales the random FPS start)
+
+
+_LEVEL_CACHE: dict = {}
+_LEVEL_CACHE_MAX = 64
 
 
 def build_levels(sizes0: Sequence[int], ratios: Sequence[float], device: torch.device) -> List[Level]:
-    """Level 0 = input clouds; level i+1 = after fps with ratios[i].  One pinned H2D copy in total."""
+    """Level 0 = input clouds; level i+1 = after fps with ratios[i].  One pinned H2D copy in total, and none at
+    all when the same batch layout was seen before (the offsets only depend on the cloud sizes): a training
+    loop with fixed-size clouds builds them once, which also keeps the forward pass capturable in a CUDA graph."""
+    key = (tuple(int(s) for s in sizes0), tuple(float(r) for r in ratios), str(device))
+    hit = _LEVEL_CACHE.get(key)
+    if hit is not None:
+        return hit
+    lv = _build_levels(sizes0, ratios, device)
+    if len(_LEVEL_CACHE) >= _LEVEL_CACHE_MAX:
+        _LEVEL_CACHE.pop(next(iter(_LEVEL_CACHE)))
+    _LEVEL_CACHE[key] = lv
+    return lv
+
+
+def _build_levels(sizes0: Sequence[int], ratios: Sequence[float], device: torch.device) -> List[Level]:
     all_sizes = [list(int(s) for s in sizes0)]
     for r in ratios:
         all_sizes.append([fps_num_samples(n, r) for n in all_sizes[-1]])
@@ -118,11 +137,14 @@ def build_levels(sizes0: Sequence[int], ratios: Sequence[float], device: torch.d
     host = torch.zeros(len(all_sizes), B + 1, dtype=torch.int64)
     for i, s in enumerate(all_sizes):
         host[i, 1:] = torch.cumsum(torch.tensor(s, dtype=torch.int64), 0)
+    hostf = torch.tensor(all_sizes, dtype=torch.float32).reshape(len(all_sizes), B)
     if device.type == "cuda":
         dev = host.pin_memory().to(device, non_blocking=True)
+        devf = hostf.pin_memory().to(device, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()  # the pinned staging buffers die here; cached result is final
     else:
-        dev = host
-    return [Level(s, dev[i], int(host[i, -1]), max(s) if s else 0) for i, s in enumerate(all_sizes)]
+        dev, devf = host, hostf
+    return [Level(s, dev[i], int(host[i, -1]), max(s) if s else 0, devf[i]) for i, s in enumerate(all_sizes)]
 
 
 def fps(pos: torch.Tensor, src: Level, dst: Level, start: Optional[torch.Tensor] = None

@@ -100,7 +100,9 @@ class SAModule(torch.nn.Module):
 
     def _run(self, x, pos, src: ops.Level, dst: ops.Level, start=None):
         if start is None and self.random_start and src.total > 0:
-            n = torch.tensor(src.sizes, dtype=torch.float32).to(pos.device, non_blocking=True)
+            n = src.sizes_f32
+            if n is None:
+                n = torch.tensor(src.sizes, dtype=torch.float32).to(pos.device, non_blocking=True)
             start = (torch.rand(len(src.sizes), device=pos.device) * n).to(torch.int64)
         idx, pos_dst, batch_dst = ops.fps(pos, src, dst, start)                        # :13, :19
         nbr, cnt = ops.ball_query(pos, pos_dst, src, dst, self.r, self.max_num_neighbors)   # :14-16

@@ -376,3 +376,30 @@ def test_net_train_step_bf16_vs_oracle(cuda_device):
         assert torch.isfinite(a).all()
     print("bf16 net grad cosine min/mean", min(cos), sum(cos) / len(cos))
     assert min(cos) > 0.7 and sum(cos) / len(cos) > 0.95, cos
+
+
+def test_graphed_train_step_matches_eager(cuda_device):
+    """train.GraphedTrainStep (one CUDA-graph replay per iteration) walks the same trajectory as eager launches."""
+    from dl_biomass_b200.train import GraphedTrainStep, make_optimizer, train_step
+    batches = [Batch.from_data_list(synthetic_clouds(900 + 7 * i, 4, 512, 1, False)).to(cuda_device) for i in range(3)]
+    losses = {}
+    for mode in ("eager", "graph"):
+        torch.manual_seed(3)
+        net = Net(1, "ReLU", 0, 0.0, precision="bf16").to(cuda_device).set_random_start(False)
+        net.train()
+        opt = make_optimizer(net.parameters(), capturable=(mode == "graph"))
+        if mode == "graph":
+            state = {k: v.clone() for k, v in net.state_dict().items()}
+            step = GraphedTrainStep(net, opt, batches[0], warmup=1)   # warm-up + capture already trained a little:
+            net.load_state_dict(state)                                # rewind the weights and the optimiser state
+            for st in opt.state.values():
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+            assert step.launches_per_replay > 20
+            losses[mode] = [float(step(b)) for b in batches]
+        else:
+            losses[mode] = [float(train_step(net, opt, b)) for b in batches]
+    print(losses)
+    for a, b in zip(losses["eager"], losses["graph"]):
+        assert abs(a - b) <= 2e-3 * max(abs(a), 1e-6)
