@@ -500,6 +500,316 @@ static int dispatch_pruned(const FpsParams &p, int B, int64_t max_n, int threads
     return B2PN_EINVAL;
 }
 
+// =================================================================================================
+//  Kernel 1c -- the register scan of Kernel 1 with a per-THREAD spatial test in front of it.
+//
+//  Same layout and arg-max chain as fps_kernel (points and running distances in registers, REDUX per warp,
+//  two block barriers), but the points are Morton-sorted first, so the PPT points a thread owns are neighbours in
+//  space and a warp's 32 x PPT points form one compact region.  Before the update a thread tests the new sample
+//  against the bounding box of its own points with the distance arithmetic of the points themselves (monotone
+//  under round-to-nearest, see Kernel 1b); if NO thread of the warp can be affected, the warp skips its whole
+//  update and keeps its cached maximum.  Results are bit-identical; ties go to the lowest ORIGINAL index: slots of
+//  a thread are ordered by original index, lanes and warps that tie are resolved through perm[].
+// =================================================================================================
+template <int THREADS, int PPT>
+__global__ void __launch_bounds__(THREADS, 1) fps_sorted_kernel(const FpsParams p, const int npad)
+{
+    static_assert(PPT % 2 == 0, "points per thread must be even (packed f32x2)");
+    constexpr int NW = THREADS / 32;
+    extern __shared__ __align__(16) unsigned char fps_dyn[];
+    u64 *keys = reinterpret_cast<u64 *>(fps_dyn);  // [npad] during the sort
+    __shared__ float s_red[6][NW];
+    __shared__ int s_wmax[32];
+    __shared__ unsigned s_cand[32];
+    __shared__ __align__(16) unsigned s_rec[2][8];  // {key, original index, x, y, z}
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t p0 = p.ptr[b];
+    const int n = (int)(p.ptr[b + 1] - p0);
+    const int64_t o0 = p.out_ptr[b];
+    const int m = (int)(p.out_ptr[b + 1] - o0);
+    if (n <= 0 || m <= 0) return;
+    const float *gpos = p.pos + 3 * p0;
+
+    // ---- Morton sort (decides the ownership of points only, never the result) -------------------------------
+    {
+        float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int i = tid; i < n; i += THREADS) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float v = __ldg(gpos + 3 * i + a);
+                mn[a] = fminf(mn[a], v);
+                mx[a] = fmaxf(mx[a], v);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+                mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+            }
+            if (lane == 0) {
+                s_red[a][warp] = mn[a];
+                s_red[3 + a][warp] = mx[a];
+            }
+        }
+    }
+    __syncthreads();
+    {
+        float qlo[3], qsc[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float mn = INFINITY, mx = -INFINITY;
+            for (int w = 0; w < NW; ++w) {
+                mn = fminf(mn, s_red[a][w]);
+                mx = fmaxf(mx, s_red[3 + a][w]);
+            }
+            qlo[a] = mn;
+            const float ext = mx - mn;
+            qsc[a] = ext > 0.f ? 1023.f / ext : 0.f;
+        }
+        for (int i = tid; i < npad; i += THREADS) {
+            u64 k = ~0ull;
+            if (i < n) {
+                unsigned code = 0u;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const float v = __ldg(gpos + 3 * i + a);
+                    float q = (v - qlo[a]) * qsc[a];
+                    q = fminf(fmaxf(q, 0.f), 1023.f);
+                    code |= morton_spread10((unsigned)q) << a;
+                }
+                k = ((u64)code << 32) | (u64)(unsigned)i;
+            }
+            keys[i] = k;
+        }
+    }
+    __syncthreads();
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (npad >> 1); t += THREADS) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const u64 a = keys[i], c = keys[l];
+                const bool up = (i & k) == 0;
+                if ((a > c) == up) {
+                    keys[i] = c;
+                    keys[l] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- my points: sorted positions [tid*c, tid*c + c), slots in ascending ORIGINAL index -----------------------
+    const int c = (n + THREADS - 1) / THREADS;
+    const int base = tid * c;
+    const int lim = min(c, n - base);  // may be <= 0
+    unsigned myidx[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) myidx[k] = (k < lim) ? (unsigned)(keys[base + k] & 0xffffffffull) : 0xffffffffu;
+#pragma unroll
+    for (int pass = 0; pass < PPT; ++pass) {  // odd-even transposition sort, static indices only
+#pragma unroll
+        for (int k = pass & 1; k + 1 < PPT; k += 2) {
+            const unsigned lo = min(myidx[k], myidx[k + 1]), hi = max(myidx[k], myidx[k + 1]);
+            myidx[k] = lo;
+            myidx[k + 1] = hi;
+        }
+    }
+    __syncthreads();  // everybody has read its keys: the buffer becomes perm[]
+    unsigned *perm = reinterpret_cast<unsigned *>(fps_dyn);
+    u64 X[PPT / 2], Y[PPT / 2], Z[PPT / 2];
+    float D[PPT];
+    float lox = INFINITY, loy = INFINITY, loz = INFINITY, hix = -INFINITY, hiy = -INFINITY, hiz = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < PPT / 2; ++j) {
+        float xs[2], ys[2], zs[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = 2 * j + h;
+            const bool ok = myidx[k] != 0xffffffffu;
+            const float *q = gpos + 3 * (int64_t)(ok ? myidx[k] : 0u);
+            xs[h] = ok ? __ldg(q + 0) : 0.f;
+            ys[h] = ok ? __ldg(q + 1) : 0.f;
+            zs[h] = ok ? __ldg(q + 2) : 0.f;
+            D[k] = ok ? __int_as_float(0x7f800000) : -1.f;  // +inf: the first update sets dist-to-start
+            if (k < c && base + k < THREADS * c) perm[base + k] = myidx[k];
+            if (ok) {
+                lox = fminf(lox, xs[h]); hix = fmaxf(hix, xs[h]);
+                loy = fminf(loy, ys[h]); hiy = fmaxf(hiy, ys[h]);
+                loz = fminf(loz, zs[h]); hiz = fmaxf(hiz, zs[h]);
+            }
+        }
+        X[j] = pack2(xs[0], xs[1]);
+        Y[j] = pack2(ys[0], ys[1]);
+        Z[j] = pack2(zs[0], zs[1]);
+    }
+    __syncthreads();  // perm[] complete
+
+    // ---- start point ---------------------------------------------------------------------------------------------
+    int cur = 0;
+    if (p.start != nullptr) {
+        const int64_t s = p.start[b];
+        cur = (s >= 0 && s < n) ? (int)s : 0;
+    }
+    float cx = __ldg(gpos + 3 * cur + 0), cy = __ldg(gpos + 3 * cur + 1), cz = __ldg(gpos + 3 * cur + 2);
+    if (tid == 0) {
+        p.out_idx[o0] = p0 + cur;
+        if (p.out_pos) {
+            p.out_pos[3 * o0 + 0] = cx;
+            p.out_pos[3 * o0 + 1] = cy;
+            p.out_pos[3 * o0 + 2] = cz;
+        }
+    }
+    if (p.out_batch) {
+#pragma unroll 1
+        for (int i = tid; i < m; i += THREADS) p.out_batch[o0 + i] = b;
+    }
+
+    float lmax = lim > 0 ? __int_as_float(0x7f800000) : -1.f;  // my running maximum (cached while the warp skips)
+    int wmax = __float_as_int(-1.f);                           // the warp's (cached)
+    int wlane = 0;                                             // lane holding it, ties resolved by original index
+    bool first = true;
+
+    for (int it = 1; it < m; ++it) {
+        // 1. can the new sample lower any of my distances?  box distance in the arithmetic of the point distances
+        const float ex = fmaxf(fmaxf(__fsub_rn(lox, cx), __fsub_rn(cx, hix)), 0.f);
+        const float ey = fmaxf(fmaxf(__fsub_rn(loy, cy), __fsub_rn(cy, hiy)), 0.f);
+        const float ez = fmaxf(fmaxf(__fsub_rn(loz, cz), __fsub_rn(cz, hiz)), 0.f);
+        const float bd = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+        if (__any_sync(0xffffffffu, bd < lmax) || first) {  // warp-uniform; empty threads: box = (+inf,-inf) -> NaN/inf
+            first = false;
+            const u64 px = pack2(cx, cx), py = pack2(cy, cy), pz = pack2(cz, cz);
+            float lm = -1.f;
+#pragma unroll
+            for (int j = 0; j < PPT / 2; ++j) {
+                float d0, d1;
+                dist2_pair(X[j], Y[j], Z[j], px, py, pz, d0, d1);
+                D[2 * j] = fminf(D[2 * j], d0);
+                D[2 * j + 1] = fminf(D[2 * j + 1], d1);
+                lm = fmaxf(lm, fmaxf(D[2 * j], D[2 * j + 1]));
+            }
+            lmax = lm;
+            const int lb = __float_as_int(lm);
+            wmax = __reduce_max_sync(0xffffffffu, lb);
+            const unsigned cand = __ballot_sync(0xffffffffu, lb == wmax);
+            wlane = __ffs(cand) - 1;
+            if (cand & (cand - 1u)) {  // several lanes tie: lowest original index wins (rare)
+                unsigned oi = 0xffffffffu;
+                if (lb == wmax) {
+#pragma unroll
+                    for (int k = PPT - 1; k >= 0; --k)
+                        if (__float_as_int(D[k]) == wmax) oi = perm[base + k];  // ends at the lowest k = lowest index
+                }
+                const unsigned best = __reduce_min_sync(0xffffffffu, oi);
+                wlane = __ffs(__ballot_sync(0xffffffffu, oi == best)) - 1;
+            }
+            if (lane == 0) s_wmax[warp] = wmax;
+        }
+        __syncthreads();
+        // 2. block arg-max, computed redundantly by every warp
+        const int v = (lane < NW) ? s_wmax[lane] : INT_MIN;
+        const int cmax = __reduce_max_sync(0xffffffffu, v);
+        const unsigned cw = __ballot_sync(0xffffffffu, v == cmax);
+        int wwarp = __ffs(cw) - 1;
+        if (cw & (cw - 1u)) {  // several warps tie (block-uniform, rare): compare their candidates' original indices
+            if ((cw >> warp) & 1u) {
+                if (lane == wlane) {
+                    unsigned oi = 0xffffffffu;
+#pragma unroll
+                    for (int k = PPT - 1; k >= 0; --k)
+                        if (__float_as_int(D[k]) == cmax) oi = perm[base + k];
+                    s_cand[warp] = oi;
+                }
+            }
+            __syncthreads();
+            const unsigned oi = (lane < NW && ((cw >> lane) & 1u)) ? s_cand[lane] : 0xffffffffu;
+            const unsigned best = __reduce_min_sync(0xffffffffu, oi);
+            wwarp = __ffs(__ballot_sync(0xffffffffu, oi == best)) - 1;
+        }
+        const int par = it & 1;
+        if (warp == wwarp && lane == wlane) {
+            int ksel = 0;
+            float wx = 0.f, wy = 0.f, wz = 0.f;
+#pragma unroll
+            for (int k = PPT - 1; k >= 0; --k) {
+                if (__float_as_int(D[k]) == cmax) {
+                    ksel = k;
+                    wx = (k & 1) ? hi32(X[k >> 1]) : lo32(X[k >> 1]);
+                    wy = (k & 1) ? hi32(Y[k >> 1]) : lo32(Y[k >> 1]);
+                    wz = (k & 1) ? hi32(Z[k >> 1]) : lo32(Z[k >> 1]);
+                }
+            }
+            const unsigned widx = perm[base + ksel];
+            *reinterpret_cast<uint4 *>(&s_rec[par][0]) =
+                make_uint4((unsigned)cmax, widx, __float_as_uint(wx), __float_as_uint(wy));
+            s_rec[par][4] = __float_as_uint(wz);
+            p.out_idx[o0 + it] = p0 + (int64_t)widx;
+            if (p.out_pos) {
+                p.out_pos[3 * (o0 + it) + 0] = wx;
+                p.out_pos[3 * (o0 + it) + 1] = wy;
+                p.out_pos[3 * (o0 + it) + 2] = wz;
+            }
+        }
+        __syncthreads();
+        const uint4 r = *reinterpret_cast<const uint4 *>(&s_rec[par][0]);
+        cx = __uint_as_float(r.z);
+        cy = __uint_as_float(r.w);
+        cz = __uint_as_float(s_rec[par][4]);
+    }
+}
+
+template <int THREADS, int PPT>
+static int launch_fps_sorted(const FpsParams &p, int B, int64_t max_n, cudaStream_t stream)
+{
+    auto kern = fps_sorted_kernel<THREADS, PPT>;
+    const int npad = next_pow2((int)max_n);
+    const int c = (int)((max_n + THREADS - 1) / THREADS);
+    const int smem = npad * 8 > THREADS * c * 4 ? npad * 8 : THREADS * c * 4;  // sort keys, then perm[] in the same bytes
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<(unsigned)B, THREADS, smem, stream>>>(p, npad);
+    note_launch();
+    e = cudaPeekAtLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+// capacity: 16384 sort keys of 8 B in shared memory
+constexpr int64_t SORTED_MAX_N = 16384;
+
+template <int THREADS>
+static int dispatch_sorted_ppt(const FpsParams &p, int B, int64_t max_n, cudaStream_t stream)
+{
+    constexpr int MAXP = THREADS >= 1024 ? 8 : (THREADS >= 768 ? 14 : (THREADS >= 640 ? 18 : (THREADS >= 512 ? 20 : 32)));
+    const int c = (int)((max_n + THREADS - 1) / THREADS);
+    if (c <= 2) return launch_fps_sorted<THREADS, 2>(p, B, max_n, stream);
+    if (c <= 4) return launch_fps_sorted<THREADS, 4>(p, B, max_n, stream);
+    if (c <= 8) return launch_fps_sorted<THREADS, 8>(p, B, max_n, stream);
+    if (MAXP >= 12 && c <= 12) return launch_fps_sorted<THREADS, (MAXP >= 12 ? 12 : 2)>(p, B, max_n, stream);
+    if (MAXP >= 14 && c <= 14) return launch_fps_sorted<THREADS, (MAXP >= 14 ? 14 : 2)>(p, B, max_n, stream);
+    if (MAXP >= 16 && c <= 16) return launch_fps_sorted<THREADS, (MAXP >= 16 ? 16 : 2)>(p, B, max_n, stream);
+    if (MAXP >= 18 && c <= 18) return launch_fps_sorted<THREADS, (MAXP >= 18 ? 18 : 2)>(p, B, max_n, stream);
+    if (MAXP >= 20 && c <= 20) return launch_fps_sorted<THREADS, (MAXP >= 20 ? 20 : 2)>(p, B, max_n, stream);
+    if (MAXP >= 32 && c <= 32) return launch_fps_sorted<THREADS, (MAXP >= 32 ? 32 : 2)>(p, B, max_n, stream);
+    return B2PN_ENOTSUP;
+}
+
+static int dispatch_sorted(const FpsParams &p, int B, int64_t max_n, int threads, cudaStream_t stream)
+{
+    if (max_n > SORTED_MAX_N) return B2PN_ENOTSUP;
+    if (threads == 0) threads = max_n <= 2048 ? 256 : (max_n <= 8192 ? 512 : 640);
+    switch (threads) {
+        case 256: return dispatch_sorted_ppt<256>(p, B, max_n, stream);
+        case 512: return dispatch_sorted_ppt<512>(p, B, max_n, stream);
+        case 640: return dispatch_sorted_ppt<640>(p, B, max_n, stream);
+        case 768: return dispatch_sorted_ppt<768>(p, B, max_n, stream);
+        case 1024: return dispatch_sorted_ppt<1024>(p, B, max_n, stream);
+    }
+    return B2PN_EINVAL;
+}
+
 static int g_force_cluster = 0;
 static int g_force_threads = 0;
 
@@ -577,9 +887,10 @@ static int dispatch_cluster(const FpsParams &p, int B, int64_t max_n, int cluste
 
 extern "C" int b2pn_fps_set_variant(int32_t cluster, int32_t threads)
 {
-    if (!(cluster == -1 || cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8 || cluster == 16))
+    if (!(cluster == -2 || cluster == -1 || cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8 || cluster == 16))
         return B2PN_EINVAL;
-    if (!(threads == 0 || threads == 256 || threads == 512 || threads == 1024)) return B2PN_EINVAL;
+    if (!(threads == 0 || threads == 256 || threads == 512 || threads == 640 || threads == 768 || threads == 1024))
+        return B2PN_EINVAL;
     b2pn::g_force_cluster = cluster;
     b2pn::g_force_threads = threads;
     return B2PN_OK;
@@ -601,6 +912,7 @@ extern "C" int b2pn_fps_f32(const float *pos, const int64_t *ptr, const int64_t 
     // reductions (CREDUX / VOTE / FLO at 50-70 cycles each) makes an iteration SLOWER than the plain register scan
     // at 10k points, so it is opt-in and the register scan below stays the default.
     if (cluster == -1) return dispatch_pruned(p, B, max_n, threads, (cudaStream_t)stream);
+    if (cluster == -2) return dispatch_sorted(p, B, max_n, threads, (cudaStream_t)stream);
     if (threads == 0) threads = 512;
     if (cluster == 0) {
         // Measured on B200 (profiles/r01_fps_sweep.md): barrier.cluster costs more per iteration than

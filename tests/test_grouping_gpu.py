@@ -61,6 +61,22 @@ def test_ties_and_duplicates(cuda_device):
     _check_level(pts, ptr, 0.9, 1.0, cuda_device)  # nearly exhausts the clouds
 
 
+@pytest.mark.parametrize("cluster,threads", [(-2, 256), (-2, 512), (-2, 640), (-1, 512), (1, 512), (2, 256)])
+def test_ties_and_duplicates_all_variants(cuda_device, cluster, threads):
+    """Every FPS variant (plain register scan, Morton-sorted scans, cluster kernels) breaks ties towards the lowest
+    ORIGINAL index, whatever order it keeps the points in."""
+    rng = np.random.default_rng(5)
+    pts = torch.from_numpy(rng.integers(-16, 16, size=(4000, 3)).astype(np.float32) / 2.0)
+    pts = torch.cat([pts, pts[:700]], 0)  # duplicates
+    ptr = torch.tensor([0, 1700, 4700])
+    try:
+        _lib.check(_lib.lib().b2pn_fps_set_variant(cluster, threads), "set_variant")
+        _check_level(pts, ptr, 0.3, 2.0, cuda_device)
+        _check_level(pts, ptr, 0.95, 1.0, cuda_device)
+    finally:
+        _lib.lib().b2pn_fps_set_variant(0, 0)
+
+
 def test_reference_numpy_fps_golden(cuda_device):
     """The reference's own FPS (downsampling_point_clouds.py:55-92) on fp32-exact clouds."""
     g = np.load(os.path.join(GOLD, "fps_reference_numpy.npz"))
@@ -91,7 +107,7 @@ def test_golden_grouping_fixture(cuda_device):
         i += 1
 
 
-@pytest.mark.parametrize("cluster,threads", [(-1, 256), (-1, 512), (-1, 1024), (1, 256), (1, 512), (1, 1024), (2, 512), (4, 256), (8, 256), (8, 512),
+@pytest.mark.parametrize("cluster,threads", [(-2, 512), (-2, 640), (-2, 768), (-1, 256), (-1, 512), (-1, 1024), (1, 256), (1, 512), (1, 1024), (2, 512), (4, 256), (8, 256), (8, 512),
                                              (16, 256)])
 def test_fps_variants_agree(cuda_device, cluster, threads):
     b = Batch.from_data_list(synthetic_clouds(77, 5, 6000, 1, True))

@@ -39,8 +39,8 @@ def main():
         lv = ops.build_levels([n] * B, [ratio], dev)
         m = lv[1].sizes[0]
         ref_idx = None
-        for cluster in ((1, -1) if quick else (1, -1, 2, 4, 8, 16)):
-            for threads in (256, 512, 1024):
+        for cluster in ((1, -2) if quick else (1, -2, -1, 2, 4, 8, 16)):
+            for threads in ((256, 512, 640, 768, 1024) if cluster == -2 else (256, 512, 1024)):
                 rc = _lib.lib().b2pn_fps_set_variant(cluster, threads)
                 try:
                     idx, _, _ = ops.fps(pos, lv[0], lv[1])
