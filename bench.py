@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--pool", type=int, default=4, help="distinct batches rotated through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="sample (FPS) every batch inside its own step instead of one step ahead on a second stream")
     return ap.parse_args()
 
 
@@ -179,7 +181,7 @@ def run_b200(args):
     from dl_biomass_b200 import _lib, ops
     from dl_biomass_b200.parallel import GradReducer
     from dl_biomass_b200.pointnet2_regressor import Net
-    from dl_biomass_b200.train import GraphedTrainStep, make_optimizer, train_step
+    from dl_biomass_b200.train import GraphedTrainStep, PipelinedTrainStep, make_optimizer, train_step
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a B200: no CUDA device (the product path has no CPU fallback)")
@@ -234,16 +236,24 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # the whole step (forward, loss, backward, all-reduce, Adam) is captured once and replayed: same kernels, one
-    # launch.  Batches whose cloud sizes differ from the captured layout would run eagerly (none here).
-    graphed = GraphedTrainStep(net, opt, pool_dev[0], reducer) if use_graph else None
+    # The step (forward, loss, backward, all-reduce, Adam) is captured once and replayed (single GPU), and the
+    # farthest-point sampling of batch i+1 runs on a second stream while batch i trains (train.PipelinedTrainStep):
+    # every timed step still contains one full sampling and one full training pass, only overlapped.
+    pipeline = not args.no_pipeline
+    graphed = stepper = None
+    if pipeline:
+        stepper = PipelinedTrainStep(net, opt, pool_dev[0], reducer, graph=use_graph)
+    elif use_graph:
+        graphed = GraphedTrainStep(net, opt, pool_dev[0], reducer)
 
     def run_step(batch):
+        if stepper is not None:
+            return stepper.step(batch)
         return graphed(batch) if graphed is not None else train_step(net, opt, batch, reducer)
 
     # ---- resident-input arm ("value") ------------------------------------------------------------
     def step_resident(i):
-        run_step(pool_dev[i % len(pool_dev)])
+        run_step(pool_dev[(i + 1) % len(pool_dev)])
 
     for i in range(max(args.warmup, 3)):
         step_resident(i)
@@ -251,18 +261,20 @@ def run_b200(args):
     l0 = lib.b2pn_launch_count()
     total_ms = timed(step_resident, args.steps)
     launches = lib.b2pn_launch_count() - l0
-    if graphed is not None:  # replayed kernels do not pass through the library's launch counter
-        launches = graphed.launches_per_replay * args.steps
     clocks = sampler.stop() if sampler else None
+    if stepper is not None and use_graph:  # replayed kernels do not pass through the library's launch counter
+        launches = stepper.launches_per_step * args.steps
+    elif graphed is not None:
+        launches = graphed.launches_per_replay * args.steps
     value = world * args.batch * args.steps / (total_ms * 1e-3)
 
     # ---- end-to-end arm: host buffers in, loss out ---------------------------------------------------
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
     def step_e2e(i):
-        hb = pool_host[i % len(pool_host)]
-        if graphed is not None:
-            loss = graphed(hb)  # pinned host tensors are copied straight into the graph's input buffers
+        hb = pool_host[(i + 1) % len(pool_host)]
+        if stepper is not None or graphed is not None:
+            loss = run_step(hb)  # pinned host tensors are copied straight into the step's input buffers
         else:
             loss = train_step(net, opt, hb.to(dev, non_blocking=True), reducer)
         loss_host.copy_(loss, non_blocking=True)
@@ -271,6 +283,9 @@ def run_b200(args):
         step_e2e(i)
     e2e_ms = timed(step_e2e, args.steps)
     e2e_value = world * args.batch * args.steps / (e2e_ms * 1e-3)
+    sm_limit_note = stepper.sm_limit if stepper is not None else 0
+    if stepper is not None:
+        stepper.close()
 
     # ---- roofline of the dominant grouping kernel: FPS level 1, timed alone -----------------------------
     hbm_peak, _, peak_kind = measured_peaks()
@@ -325,10 +340,12 @@ def run_b200(args):
                        "global_batch": world * args.batch, "points_per_cloud": args.points,
                        "parallelism": f"dp{world}", "l2": "256 MB buffer rewritten before every timed step",
                        "timing": "per-step CUDA events on the launching stream, summed; max over ranks",
-                       "launch": "one CUDA graph replay per step" if use_graph else "eager kernel launches"},
+                       "launch": "one CUDA graph replay per step" if use_graph else "eager kernel launches",
+                       "pipeline": ("FPS of batch i+1 on a second stream during step i; persistent kernels capped at "
+                                    f"{sm_limit_note} CTAs") if stepper is not None else "none"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(e2e_ms / args.steps, 4),
-                    "h2d_bytes_per_step": batch_h2d_bytes(pool_host[0], with_batch_vector=graphed is None),
+                    "h2d_bytes_per_step": batch_h2d_bytes(pool_host[0], with_batch_vector=not use_graph),
                     "d2h_bytes_per_step": 4},
             "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)

@@ -5,6 +5,14 @@
 
 namespace b2pn {
 long long g_launches = 0;
+int g_sm_limit = 0;
+}
+
+extern "C" int b2pn_set_sm_limit(int32_t n)
+{
+    if (n < 0) return B2PN_EINVAL;
+    b2pn::g_sm_limit = n;
+    return B2PN_OK;
 }
 
 extern "C" int b2pn_abi_version(void) { return B2PN_ABI_VERSION; }

@@ -27,6 +27,8 @@ typedef unsigned long long u64;
 
 // number of kernels this library has enqueued (bench.py reports it as gpu_launches)
 extern long long g_launches;
+// upper bound on the CTAs of the persistent tcgen05 kernels (0 = every SM), see b2pn_set_sm_limit
+extern int g_sm_limit;
 static inline void note_launch(int n = 1) { __atomic_fetch_add(&g_launches, (long long)n, __ATOMIC_RELAXED); }
 
 // ---- packed fp32x2 arithmetic (Blackwell FADD2/FMUL2), each half rounded separately ----------

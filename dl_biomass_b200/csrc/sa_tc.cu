@@ -990,7 +990,10 @@ static int sm_count()
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
     }
-    return sms;
+    // b2pn_set_sm_limit: leave SMs free for kernels of a concurrent stream (the persistent kernels below take one
+    // CTA per SM and stride over tiles by gridDim.x, so a CTA that cannot become resident would double their time)
+    const int lim = g_sm_limit;
+    return (lim > 0 && lim < sms) ? lim : sms;
 }
 
 // grid.x of a rows-GEMM launch (the per-CTA statistics partials are indexed by blockIdx.x)

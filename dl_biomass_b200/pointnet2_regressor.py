@@ -98,13 +98,17 @@ class SAModule(torch.nn.Module):
         self.precision = "fp32"
         self.random_start = True  # torch_cluster.fps default
 
-    def _run(self, x, pos, src: ops.Level, dst: ops.Level, start=None):
+    def _sample(self, pos, src: ops.Level, dst: ops.Level, start=None):
+        """fps + pos[idx] + batch[idx] (:13, :19): depends on the positions only, never on the weights."""
         if start is None and self.random_start and src.total > 0:
             n = src.sizes_f32
             if n is None:
                 n = torch.tensor(src.sizes, dtype=torch.float32).to(pos.device, non_blocking=True)
             start = (torch.rand(len(src.sizes), device=pos.device) * n).to(torch.int64)
-        idx, pos_dst, batch_dst = ops.fps(pos, src, dst, start)                        # :13, :19
+        return ops.fps(pos, src, dst, start)
+
+    def _run(self, x, pos, src: ops.Level, dst: ops.Level, start=None, sampled=None):
+        idx, pos_dst, batch_dst = sampled if sampled is not None else self._sample(pos, src, dst, start)
         nbr, cnt = ops.ball_query(pos, pos_dst, src, dst, self.r, self.max_num_neighbors)   # :14-16
         out, _ = sa.sa_apply(self.conv.local_nn, x, pos, pos_dst, nbr, cnt, None, seg_mode=sa.SEG_SLOTS,
                              K=self.max_num_neighbors, n_dst=dst.total, precision=_PRECISIONS[self.precision])  # :18
@@ -135,6 +139,18 @@ class GlobalSAModule(torch.nn.Module):
         pos = pos.new_zeros((x.size(0), 3))                                              # :31
         batch = torch.arange(x.size(0), device=batch.device)                             # :32
         return x, pos, batch
+
+
+class Sampling:
+    """Farthest-point samples of both set-abstraction levels of one batch (``Net.sample``): (idx, pos, batch) per
+    level.  They depend on the point positions only, so a training loop can compute them for the NEXT batch on a
+    second stream while the current batch trains (``train.PipelinedTrainStep``)."""
+
+    def __init__(self, sizes, level1, level2):
+        self.sizes, self.level1, self.level2 = tuple(sizes), tuple(level1), tuple(level2)
+
+    def tensors(self):
+        return list(self.level1) + list(self.level2)
 
 
 class Net(torch.nn.Module):
@@ -168,17 +184,34 @@ class Net(torch.nn.Module):
         self.sa1_module.random_start = self.sa2_module.random_start = bool(flag)
         return self
 
-    def forward(self, data, start: Optional[torch.Tensor] = None):
-        x, pos, batch = data.x, data.pos, data.batch                                     # :53
+    def _levels(self, data):
+        pos = data.pos
         if not pos.is_cuda:
             raise RuntimeError("dl_biomass_b200.Net runs on a B200 only: move the batch to the GPU "
                                "(there is no CPU fallback)")
         sizes = getattr(data, "cloud_sizes", None)
         if sizes is None:
-            sizes = _cloud_sizes(batch, getattr(data, "ptr", None))
-        lv = ops.build_levels(sizes, [self.sa1_module.ratio, self.sa2_module.ratio], pos.device)
+            sizes = _cloud_sizes(data.batch, getattr(data, "ptr", None))
+        return sizes, ops.build_levels(sizes, [self.sa1_module.ratio, self.sa2_module.ratio], pos.device)
+
+    def sample(self, data, start: Optional[torch.Tensor] = None) -> Sampling:
+        """Farthest-point sampling of both levels for ``data`` (no weights involved); pass the result to
+        ``forward(data, sampling=...)``."""
+        sizes, lv = self._levels(data)
+        pos = data.pos.to(torch.float32)
+        l1 = self.sa1_module._sample(pos, lv[0], lv[1], start)
+        l2 = self.sa2_module._sample(l1[1], lv[1], lv[2])
+        return Sampling(sizes, l1, l2)
+
+    def forward(self, data, start: Optional[torch.Tensor] = None, sampling: Optional[Sampling] = None):
+        x, pos, batch = data.x, data.pos, data.batch                                     # :53
+        sizes, lv = self._levels(data)
+        if sampling is not None and tuple(sampling.sizes) != tuple(sizes):
+            raise ValueError("sampling was computed for a batch with different cloud sizes")
         pos = pos.to(torch.float32)
-        x1, pos1, _, _ = self.sa1_module._run(x, pos, lv[0], lv[1], start)               # :54
-        x2, pos2, batch2, _ = self.sa2_module._run(x1, pos1, lv[1], lv[2])                # :55
+        s1 = None if sampling is None else sampling.level1
+        s2 = None if sampling is None else sampling.level2
+        x1, pos1, _, _ = self.sa1_module._run(x, pos, lv[0], lv[1], start, s1)           # :54
+        x2, pos2, batch2, _ = self.sa2_module._run(x1, pos1, lv[1], lv[2], None, s2)      # :55
         x3 = self.sa3_module._run(x2, pos2, batch2, len(sizes))                          # :56
         return self.mlp(x3)                                                              # :58

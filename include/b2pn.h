@@ -36,6 +36,14 @@ const char *b2pn_error_string(int code);
 /* kernels enqueued by this library so far in this process (bench.py's gpu_launches) */
 int64_t b2pn_launch_count(void);
 
+/*
+ * Cap the grid of the persistent tensor-core kernels at n CTAs (0 = one per SM, the default).  Used when
+ * the grouping kernels of the NEXT batch run on a second stream: farthest-point sampling occupies one SM per
+ * cloud for its whole (latency-bound) duration, and a persistent kernel must not wait for those SMs.
+ * Process-wide setting; change it only between steps.
+ */
+int b2pn_set_sm_limit(int32_t n);
+
 /* samples per cloud: ceil(float32(n) * float32(ratio)) -- torch_cluster.fps sizing
  * (reached from /root/reference/pointnet2_regressor.py:13).  Host-side helper. */
 int64_t b2pn_fps_num_samples(int64_t n, float ratio);

@@ -403,3 +403,42 @@ def test_graphed_train_step_matches_eager(cuda_device):
     print(losses)
     for a, b in zip(losses["eager"], losses["graph"]):
         assert abs(a - b) <= 2e-3 * max(abs(a), 1e-6)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_pipelined_train_step_matches_eager(cuda_device, graph):
+    """train.PipelinedTrainStep (FPS of the next batch on a second stream, optionally one CUDA graph per step)
+    trains exactly like the plain loop, one call later."""
+    from dl_biomass_b200 import _lib
+    from dl_biomass_b200.train import PipelinedTrainStep, make_optimizer, train_step
+    batches = [Batch.from_data_list(synthetic_clouds(500 + 11 * i, 4, 512, 1, False)).to(cuda_device) for i in range(4)]
+
+    def fresh():
+        torch.manual_seed(5)
+        net = Net(1, "ReLU", 0, 0.0, precision="bf16").to(cuda_device).set_random_start(False)
+        net.train()
+        return net
+
+    net = fresh()
+    opt = make_optimizer(net.parameters())
+    want = [float(train_step(net, opt, b)) for b in batches[:3]]
+
+    net = fresh()
+    opt = make_optimizer(net.parameters(), capturable=graph)
+    state = {k: v.clone() for k, v in net.state_dict().items()}
+    stepper = PipelinedTrainStep(net, opt, batches[0], graph=graph, warmup=1)
+    try:
+        if graph:  # warm-up and capture trained a little: rewind weights and optimiser state
+            net.load_state_dict(state)
+            for st in opt.state.values():
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+        got = [float(stepper.step(b)) for b in batches[1:4]]
+        assert stepper.launches_per_step > 20
+    finally:
+        stepper.close()
+    print(want, got)
+    for a, b in zip(want, got):
+        assert abs(a - b) <= 2e-3 * max(abs(a), 1e-6)
+    assert _lib.lib().b2pn_set_sm_limit(0) == 0
