@@ -27,10 +27,15 @@ class GradReducer:
     """Flat gradient buckets + async all-reduce.  Backend-agnostic: NCCL on GPUs, gloo in the CPU tests."""
 
     def __init__(self, module: torch.nn.Module, buckets: Sequence[Sequence[str]] = DEFAULT_BUCKETS,
-                 process_group=None, broadcast_params: bool = True):
+                 process_group=None, broadcast_params: bool = True, overlap: bool = True):
         if not dist.is_initialized():
             raise RuntimeError("GradReducer needs torch.distributed to be initialised")
         self.group = process_group
+        # overlap=True: a bucket is reduced as soon as backward has filled it (NCCL runs beside the remaining
+        # backward kernels).  overlap=False: all buckets are reduced in finish(), after backward -- used when another
+        # stream already shares the GPU with backward (train.PipelinedTrainStep): NCCL's CTAs would otherwise queue
+        # behind the persistent kernels and the sampling kernels and stall both ranks.
+        self.overlap = overlap
         self.world_size = dist.get_world_size(process_group)
         self.module = module
         named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
@@ -84,7 +89,7 @@ class GradReducer:
             self.views[p].copy_(p.grad)
             p.grad = self.views[p]
         self.pending[i] -= 1
-        if self.pending[i] == 0:
+        if self.pending[i] == 0 and self.overlap:
             self._launch(i)
 
     def _launch(self, i: int) -> None:

@@ -128,6 +128,8 @@ class PipelinedTrainStep:
         ncl = len(self.sizes)
         self.sm_limit = sms - ncl if ncl * 4 <= sms else 0
         self.lib.b2pn_set_sm_limit(self.sm_limit)
+        if reducer is not None:
+            reducer.overlap = False  # see GradReducer: reduce after backward, the side stream already shares the GPU
         self.graph = None
         self.launches_per_step = 0
         if graph:
