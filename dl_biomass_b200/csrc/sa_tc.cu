@@ -1178,11 +1178,14 @@ __global__ void dw_reduce_tc_kernel(const float *partial, int splits, int n_out,
     }
     const int64_t stride = (int64_t)n_out * k_total;
     const float *base = partial + (int64_t)n * k_total;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};  // four independent chains keep several loads in flight; fixed order
-    int p = 0;
-    for (; p + 4 <= splits; p += 4) {
+    constexpr int U = 16;  // independent chains: the loop is a string of L2 round trips, keep 16 in flight; fixed order
+    double acc[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) acc[u] = 0.0;
+    int p = 0;
+    for (; p + U <= splits; p += U) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
             const float *row = base + (int64_t)(p + u) * stride;
             float v = row[c0];
             if (c1 >= 0) v += row[c1];
@@ -1194,7 +1197,11 @@ __global__ void dw_reduce_tc_kernel(const float *partial, int splits, int n_out,
         acc[0] += (double)row[c0];
         if (c1 >= 0) acc[0] += (double)row[c1];
     }
-    const double s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+#pragma unroll
+    for (int w = U / 2; w > 0; w >>= 1)
+#pragma unroll
+        for (int u = 0; u < w; ++u) acc[u] += acc[u + w];
+    const double s = acc[0];
     if (k == k_true) {
         if (grad_b) grad_b[n] = (float)s;
     } else if (grad_w) {

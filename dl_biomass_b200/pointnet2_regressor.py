@@ -203,7 +203,10 @@ class Net(torch.nn.Module):
         l2 = self.sa2_module._sample(l1[1], lv[1], lv[2])
         return Sampling(sizes, l1, l2)
 
-    def forward(self, data, start: Optional[torch.Tensor] = None, sampling: Optional[Sampling] = None):
+    def forward(self, data, start: Optional[torch.Tensor] = None, sampling: Optional[Sampling] = None,
+                after_grouping=None):
+        """``after_grouping``: optional callable invoked once both set-abstraction levels have been enqueued
+        (train.PipelinedTrainStep joins its sampling stream there and gives the remaining kernels every SM)."""
         x, pos, batch = data.x, data.pos, data.batch                                     # :53
         sizes, lv = self._levels(data)
         if sampling is not None and tuple(sampling.sizes) != tuple(sizes):
@@ -213,5 +216,7 @@ class Net(torch.nn.Module):
         s2 = None if sampling is None else sampling.level2
         x1, pos1, _, _ = self.sa1_module._run(x, pos, lv[0], lv[1], start, s1)           # :54
         x2, pos2, batch2, _ = self.sa2_module._run(x1, pos1, lv[1], lv[2], None, s2)      # :55
+        if after_grouping is not None:
+            after_grouping()
         x3 = self.sa3_module._run(x2, pos2, batch2, len(sizes))                          # :56
         return self.mlp(x3)                                                              # :58

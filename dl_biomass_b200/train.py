@@ -36,13 +36,16 @@ def make_optimizer(params, lr: float = ADAM_LR, weight_decay: float = ADAM_WEIGH
     return torch.optim.Adam(params, lr=lr, weight_decay=weight_decay, fused=fused, capturable=capturable and fused)
 
 
-def train_step(model, optimizer, batch, reducer=None, sampling=None) -> torch.Tensor:
+def train_step(model, optimizer, batch, reducer=None, sampling=None, after_grouping=None) -> torch.Tensor:
     """One iteration of main.py:150-172.  ``reducer`` is the data-parallel gradient reducer (parallel.py);
     ``sampling`` an optional ``Net.sample(batch)`` computed ahead of time."""
     optimizer.zero_grad(set_to_none=reducer is None)
     if reducer is not None:
         reducer.prepare()
-    outs = model(batch) if sampling is None else model(batch, sampling=sampling)
+    if sampling is None and after_grouping is None:
+        outs = model(batch)
+    else:
+        outs = model(batch, sampling=sampling, after_grouping=after_grouping)
     loss = weighted_mse_loss(outs, batch.y)
     loss.backward()
     if reducer is not None:
@@ -127,7 +130,6 @@ class PipelinedTrainStep:
         sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
         ncl = len(self.sizes)
         self.sm_limit = sms - ncl if ncl * 4 <= sms else 0
-        self.lib.b2pn_set_sm_limit(self.sm_limit)
         if reducer is not None:
             reducer.overlap = False  # see GradReducer: reduce after backward, the side stream already shares the GPU
         self.graph = None
@@ -147,8 +149,16 @@ class PipelinedTrainStep:
         self.side.wait_stream(main)                       # nxt's tensors (an H2D copy, say) are ordered before this
         with torch.cuda.stream(self.side):
             nxt_sampling = self.model.sample(nxt)
-        loss = train_step(self.model, self.optimizer, cur, self.reducer, sampling=cur_sampling)
-        main.wait_stream(self.side)
+        # The sampling branch (~1.4 ms) is about as long as the forward pass of the two set-abstraction levels, so
+        # those kernels leave its SMs alone (grid cap); the join sits right behind them and everything after
+        # (global level, head, the whole backward pass, Adam) is launched with one CTA per SM again.
+        self.lib.b2pn_set_sm_limit(self.sm_limit)
+
+        def join():
+            main.wait_stream(self.side)
+            self.lib.b2pn_set_sm_limit(0)
+
+        loss = train_step(self.model, self.optimizer, cur, self.reducer, sampling=cur_sampling, after_grouping=join)
         return loss, nxt_sampling
 
     # ---- graph ---------------------------------------------------------------------------------------------------
