@@ -12,6 +12,7 @@
 // or BatchNorm + ReLU on load) and fetch the pre-packed weight chunk with a bulk copy (TMA unit);
 // warp 8 issues tcgen05.mma; warps 0-3 drain TMEM and run the epilogue.  K is streamed in chunks of
 // 64 through a ring of shared-memory stages; two TMEM accumulator buffers overlap epilogue and MMA.
+#include <cuda.h>  // CUtensorMap types only; the encoder is fetched through the runtime (no libcuda link)
 #include <math.h>
 
 #include "tc_common.cuh"
@@ -60,6 +61,39 @@ struct RowMapTC {
     __device__ __forceinline__ int valid8(int64_t r8) const { return gi_nv(info(r8)); }
 };
 
+// ---- TMA tensor maps ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+// box = 64 rows (128 bytes, the swizzle span) x 64 channels; channels past `channels` read as zeros
+int make_tma_feature_major(TmaMap *out, const void *base, int64_t channels, int64_t ld)
+{
+    static_assert(sizeof(CUtensorMap) == sizeof(TmaMap), "CUtensorMap is 128 bytes");
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return B2PN_ENOTSUP;
+    if (!base || channels <= 0 || ld <= 0 || (ld & 7) || ((uintptr_t)base & 15u)) return B2PN_EINVAL;
+    const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)channels};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2u};
+    const cuuint32_t box[2] = {64u, 64u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = fn(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims,
+                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? B2PN_OK : B2PN_EINVAL;
+}
+
 struct GemmParams {
     const uint8_t *a_packed;  // [m_group][k_chunk][MT*128 lines][128 B], swizzled bf16
     int num_kc;
@@ -94,6 +128,7 @@ __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(_
 // =================================================================================================
 struct GatherLoaderTC {  // K-major B: line = row of the tile, 64 k per line
     static constexpr bool B_MN = false;
+    static constexpr bool USES_TMA = false;
     RowMapTC rm;
     const void *x;  // [n_src, c_in] row-major, fp32 (cols.x_f32) or bf16
     InCols cols;
@@ -191,6 +226,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8])
 // `inf` is the group descriptor RowMapTC::info(r8) (the caller caches it per tile).
 template <int MODE>
 struct FeatSource {
+    static constexpr bool USES_TMA = false;
     RowMapTC rm;
     const __nv_bfloat16 *t;  // [C][ld]; MODE 1: the normalised value zhat, activation input is gamma*zhat+beta
     int C;
@@ -235,6 +271,7 @@ struct FeatSource {
 
 // routed gradient of the max aggregation, dh3^T[ch][row] = dout[seg][ch] if arg[seg][ch] names this row
 struct ArgGradSource {
+    static constexpr bool USES_TMA = false;
     RowMapTC rm;
     const float *dout;
     const int32_t *arg;  // SLOTS: arg-max SLOT of the centroid; CLOUDS: arg-max source row
@@ -272,11 +309,21 @@ struct ArgGradSource {
     }
 };
 
+// Y side of the dW GEMM fetched by TMA (a stored feature-major tensor whose invalid rows are already zero, e.g. dh after
+// the BatchNorm-backward pass): the kernel issues the tensor-map copies itself, this only carries the row structure.
+struct TmaSource {
+    static constexpr bool USES_TMA = true;
+    RowMapTC rm;
+    __device__ __forceinline__ void resolve(int64_t r) { rm.resolve(r); }
+    __device__ __forceinline__ uint4 chunk_i(int, int64_t, unsigned) const { return make_uint4(0u, 0u, 0u, 0u); }
+};
+
 // MN-major B tile of the rows GEMM from a feature-major source: [2 row blocks of 64][64 channel lines];
 // thread lt fills channel line (lt >> 1) of the chunk for row block (lt & 1)
 template <class SRC>
 struct FeatLoaderTC {
     static constexpr bool B_MN = true;
+    static constexpr bool USES_TMA = false;
     SRC src;
     int64_t row0;
     unsigned inf[8];  // descriptors of the 8 row groups of my row block
@@ -299,6 +346,26 @@ struct FeatLoaderTC {
         for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4 *>(dst + line_chunk_off(cl, g)) = v[g];
     }
     // MN-major: 16 k lines per step; LBO = stride between the two 64-row blocks, SBO = 8 lines
+    static __device__ __forceinline__ uint64_t b_desc(uint32_t b_saddr, int ks)
+    {
+        return smem_desc_sw128(b_saddr + ks * (16 * LINE_BYTES), 64 * LINE_BYTES, ATOM_BYTES);
+    }
+};
+
+// The same MN-major B tile fetched by the TMA unit: for a stored feature-major tensor that needs no arithmetic on
+// the way in (invalid rows already zero) the whole tile is two tensor-map copies issued by one thread -- no loader
+// instructions, no registers, any prefetch depth the stage ring allows.
+struct TmaFeatLoader {
+    static constexpr bool B_MN = true;
+    static constexpr bool USES_TMA = true;
+    __device__ __forceinline__ void resolve(int64_t) {}
+    __device__ __forceinline__ void begin_tile(int64_t, int) {}
+    __device__ __forceinline__ void produce_tma(uint8_t *B, int64_t tile, int kc, const TmaMap *map, uint64_t *bar) const
+    {
+        mbar_expect_tx(bar, B_BYTES);
+        tma_load_2d(B, map, (int)(tile * R), kc * KC, bar);
+        tma_load_2d(B + 64 * LINE_BYTES, map, (int)(tile * R + 64), kc * KC, bar);
+    }
     static __device__ __forceinline__ uint64_t b_desc(uint32_t b_saddr, int ks)
     {
         return smem_desc_sw128(b_saddr + ks * (16 * LINE_BYTES), 64 * LINE_BYTES, ATOM_BYTES);
@@ -608,7 +675,7 @@ struct SmemPlan {
 };
 
 template <int MT, class BL, class EP>
-__global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp, BL bl, EP ep)
+__global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp, BL bl, EP ep, const __grid_constant__ TmaMap tmap)
 {
     using P = SmemPlan<MT>;
     extern __shared__ uint8_t smem_raw[];
@@ -667,8 +734,12 @@ __global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp
                     mbar_expect_tx(&full[s], P::A_BYTES);
                     bulk_g2s(A, gp.a_packed + ((int64_t)mg * gp.num_kc + kc) * P::A_BYTES, P::A_BYTES, &full[s]);
                 }
-                bl.produce(B, kc, lt);
-                fence_proxy_async_smem();
+                if constexpr (BL::USES_TMA) {
+                    if (lt == 0) bl.produce_tma(B, tile, kc, &tmap, &full[s]);
+                } else {
+                    bl.produce(B, kc, lt);
+                    fence_proxy_async_smem();
+                }
                 mbar_arrive(&full[s]);
             }
         }
@@ -801,7 +872,7 @@ struct DwPlan {
 };
 
 template <int MTA, class YS, class XF>
-__global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, XF xf)
+__global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, XF xf, const __grid_constant__ TmaMap tmap_y)
 {
     using P = DwPlan<MTA>;
     extern __shared__ uint8_t smem_raw[];
@@ -851,15 +922,24 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
             unsigned inf[8];
 #pragma unroll
             for (int g = 0; g < 8; ++g) inf[g] = ys.rm.info(r0 + g * 8);
+            if constexpr (YS::USES_TMA) {
+                if (lt == 0) {  // MTA*128 lines x 64 rows straight from the feature-major tensor, 64 lines per copy
+                    mbar_expect_tx(&full[s], P::A_BYTES);
 #pragma unroll
-            for (int m = 0; m < MTA; ++m) {
-                const int line = m * 128 + lt;
-                const int ch = mg * (MTA * 128) + line;
-                uint4 v[8];
+                    for (int m = 0; m < MTA * 2; ++m)
+                        tma_load_2d(A + m * (64 * LINE_BYTES), &tmap_y, (int)r0, mg * (MTA * 128) + m * 64, &full[s]);
+                }
+            } else {
 #pragma unroll
-                for (int g = 0; g < 8; ++g) v[g] = ys.chunk_i(ch, r0 + g * 8, inf[g]);
+                for (int m = 0; m < MTA; ++m) {
+                    const int line = m * 128 + lt;
+                    const int ch = mg * (MTA * 128) + line;
+                    uint4 v[8];
 #pragma unroll
-                for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4 *>(A + line_chunk_off(line, g)) = v[g];
+                    for (int g = 0; g < 8; ++g) v[g] = ys.chunk_i(ch, r0 + g * 8, inf[g]);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4 *>(A + line_chunk_off(line, g)) = v[g];
+                }
             }
             xf.fill(B, lt, r0, ng, nb_lines, inf);
             fence_proxy_async_smem();
@@ -1013,8 +1093,11 @@ struct RowsArg {
     int64_t tiles() const { return (cap + R - 1) / R; }
 };
 
+static const TmaMap kNoMap = {};
+
 template <int MT, class BL, class EP>
-static int launch_gemm(const Packed &pk, const RowsArg &ra, const BL &bl, const EP &ep, cudaStream_t st)
+static int launch_gemm(const Packed &pk, const RowsArg &ra, const BL &bl, const EP &ep, cudaStream_t st,
+                       const TmaMap &map = kNoMap)
 {
     using P = SmemPlan<MT>;
     auto kern = tc_rows_gemm_kernel<MT, BL, EP>;
@@ -1022,16 +1105,17 @@ static int launch_gemm(const Packed &pk, const RowsArg &ra, const BL &bl, const 
     if (e != cudaSuccess) return (int)e;
     GemmParams gp = {pk.img, pk.num_kc, ra.cap, ra.dev};
     dim3 grid((unsigned)grid_x_for(pk, ra.tiles()), (unsigned)pk.num_mg);
-    kern<<<grid, NT, P::TOTAL, st>>>(gp, bl, ep);
+    kern<<<grid, NT, P::TOTAL, st>>>(gp, bl, ep, map);
     note_launch();
     e = cudaPeekAtLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
 
 template <class BL, class EP1, class EP2>
-static int launch_by_mt(const Packed &pk, const RowsArg &ra, const BL &bl, const EP1 &e1, const EP2 &e2, cudaStream_t st)
+static int launch_by_mt(const Packed &pk, const RowsArg &ra, const BL &bl, const EP1 &e1, const EP2 &e2, cudaStream_t st,
+                        const TmaMap &map = kNoMap)
 {
-    return pk.MT == 1 ? launch_gemm<1>(pk, ra, bl, e1, st) : launch_gemm<2>(pk, ra, bl, e2, st);
+    return pk.MT == 1 ? launch_gemm<1>(pk, ra, bl, e1, st, map) : launch_gemm<2>(pk, ra, bl, e2, st, map);
 }
 
 __global__ void count_valid_tc_kernel(const int32_t *cnt, int64_t n, double fixed, double *out)
@@ -1243,6 +1327,13 @@ int tc_gemm_selftest(const float *w, int m_out, int k, const void *b, int mode, 
         // all k columns are bf16 features (c_in = k); the appended dpos columns multiply zero weights
         GatherLoaderTC gl = {rm, b, InCols{k, 0}, zeros3, nullptr, -1};
         return launch_by_mt(pk, ra, gl, ep, ep, st);
+    }
+    if (mode == 2) {  // the same feature-major operand through the TMA unit
+        TmaMap map;
+        const int rc = make_tma_feature_major(&map, b, k, ld);
+        if (rc) return rc;
+        TmaFeatLoader tl;
+        return launch_by_mt(pk, ra, tl, ep, ep, st, map);
     }
     FeatLoaderTC<FeatSource<0>> fl = {{rm, (const __nv_bfloat16 *)b, k, ld, 0, -1, nullptr, nullptr}};
     return launch_by_mt(pk, ra, fl, ep, ep, st);
@@ -1492,7 +1583,7 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
 
 template <class YS, class XF>
 static int launch_dw(const YS &ys, const XF &xf, int n_out, int k_total, const ShapesTC &s, const RowsArg &ra, float *dwp,
-                     cudaStream_t st)
+                     cudaStream_t st, const TmaMap &map_y = kNoMap)
 {
     const DwPlanHost d = plan_dw(n_out, k_total, s.ld);
     DwParams p = {ra.cap, ra.dev, n_out, d.nbl_total, k_total, dwp};
@@ -1502,12 +1593,12 @@ static int launch_dw(const YS &ys, const XF &xf, int n_out, int k_total, const S
         auto kern = tc_dw_kernel<1, YS, XF>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DwPlan<1>::TOTAL);
         if (e != cudaSuccess) return (int)e;
-        kern<<<grid, NT, DwPlan<1>::TOTAL, st>>>(p, ys, xf);
+        kern<<<grid, NT, DwPlan<1>::TOTAL, st>>>(p, ys, xf, map_y);
     } else {
         auto kern = tc_dw_kernel<2, YS, XF>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DwPlan<2>::TOTAL);
         if (e != cudaSuccess) return (int)e;
-        kern<<<grid, NT, DwPlan<2>::TOTAL, st>>>(p, ys, xf);
+        kern<<<grid, NT, DwPlan<2>::TOTAL, st>>>(p, ys, xf, map_y);
     }
     note_launch();
     e = cudaPeekAtLastError();
@@ -1576,14 +1667,18 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
         note_launch();
     }
     // ---- layer 2 ---------------------------------------------------------------------------------------
-    FeatSource<0> y2 = {rm, b.dz2, s.c2, s.ld, 0, -1, nullptr, nullptr};
+    // dh2 / dh1 are plain stored tensors by now (invalid rows zeroed by the BN-backward pass): the TMA unit feeds them
+    TmaMap map2, map1;
+    if ((rc = make_tma_feature_major(&map2, b.dz2, s.c2, s.ld))) return rc;
+    if ((rc = make_tma_feature_major(&map1, b.dz1, s.c1, s.ld))) return rc;
+    TmaSource y2 = {rm};
     {
-        FeatLoaderTC<FeatSource<0>> bl = {y2};
+        TmaFeatLoader bl;
         MaskSumsStoreEpTC<1> e1 = {b.dz1, z1, s.c1, s.ld, a.mlp.gamma[0], a.mlp.beta[0], a.mlp.act, b.partial, s.cpad};
         MaskSumsStoreEpTC<2> e2 = {b.dz1, z1, s.c1, s.ld, a.mlp.gamma[0], a.mlp.beta[0], a.mlp.act, b.partial, s.cpad};
-        if ((rc = launch_by_mt(b.pkT[1], ra, bl, e1, e2, st))) return rc;
+        if ((rc = launch_by_mt(b.pkT[1], ra, bl, e1, e2, st, map2))) return rc;
         LineFillK<FeatSource<1>> xa1 = {{rm, z1, s.c1, s.ld, a.mlp.act, s.c1, a.mlp.gamma[0], a.mlp.beta[0]}};
-        if ((rc = launch_dw(y2, xa1, s.c2, s.c1 + 1, s, ra, b.dwp, st))) return rc;
+        if ((rc = launch_dw(y2, xa1, s.c2, s.c1 + 1, s, ra, b.dwp, st, map2))) return rc;
         launch_dw_reduce(b.dwp, s.c2, s.c1 + 1, nullptr, s.c1, s.c1, s, g.grad_w[1], g.grad_b[1], st);
     }
     bn_bwd_finalize_tc_kernel<<<(s.c1 + 3) / 4, 128, 0, st>>>(b.partial, 2 * grid_x_for(b.pkT[1], s.tiles), s.c1, s.cpad, b.count,
@@ -1594,16 +1689,16 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
         note_launch();
     }
     // ---- layer 1 ---------------------------------------------------------------------------------------
-    FeatSource<0> y1 = {rm, b.dz1, s.c1, s.ld, 0, -1, nullptr, nullptr};
+    TmaSource y1 = {rm};
     {
         LineFillGather xg = {{rm, a.x, s.cols, a.pos_src, a.pos_dst, s.k1}};
-        if ((rc = launch_dw(y1, xg, s.c1, s.k1 + 1, s, ra, b.dwp, st))) return rc;
+        if ((rc = launch_dw(y1, xg, s.c1, s.k1 + 1, s, ra, b.dwp, st, map1))) return rc;
         launch_dw_reduce(b.dwp, s.c1, s.k1 + 1, &s.cols, s.c0, s.k1, s, g.grad_w[0], g.grad_b[0], st);
     }
     if (need_dx) {
-        FeatLoaderTC<FeatSource<0>> bl = {y1};
+        TmaFeatLoader bl;
         ScatterEpTC e = {rm, g.grad_x, a.c_in};
-        if ((rc = launch_by_mt(b.pkT[0], ra, bl, e, e, st))) return rc;
+        if ((rc = launch_by_mt(b.pkT[0], ra, bl, e, e, st, map1))) return rc;
     }
     B2PN_LAUNCH_CHECK();
     return B2PN_OK;

@@ -73,6 +73,24 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
                  : "memory");
 }
 
+// ---- TMA tensor-map copy global -> shared (2-D tile, SWIZZLE_128B), completion on an mbarrier -----------
+// A feature-major bf16 tensor [C][ld] is a 2-D tensor with inner dimension = rows; a box of 64 rows x 64 channels
+// lands in shared memory as 64 lines of 128 bytes with the hardware's 128-byte swizzle -- byte for byte the line tile
+// the SIMT loaders build with line_chunk_off(), so the same UMMA descriptors read it.
+struct alignas(64) TmaMap {
+    unsigned char bytes[128];  // CUtensorMap
+};
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const TmaMap *map, int x_inner, int y_outer, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(x_inner), "r"(y_outer), "r"(smem_u32(bar))
+        : "memory");
+}
+// host: encode a map over a feature-major bf16 tensor (sa_tc.cu); returns 0 or a B2PN_E* / cudaError_t code
+int make_tma_feature_major(TmaMap *out, const void *base, int64_t channels, int64_t ld);
+
 // ---- TMEM --------------------------------------------------------------------------------------------
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_holder)  // whole warp

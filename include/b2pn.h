@@ -180,7 +180,7 @@ int b2pn_sa_backward(const b2pn_sa_args *args, const b2pn_sa_grads *grads, b2pn_
  * Hardware self-test of the tcgen05 GEMM pipeline (debug aid used by tests/test_tc_gpu.py; not part of
  * the reference's surface).  out[m][row] (fp32, leading dimension ld_out) = sum_k w[m][k] * b(row, k) with
  * b in bf16, row-major [rows][k] (mode 0: K-major B tiles) or feature-major [k][ld] (mode 1: MN-major B
- * tiles).  zeros3: [rows,3] fp32 zeros.  workspace >= packed weight image + 1 KB.
+ * tiles; mode 2: the same operand fetched by TMA tensor-map copies).  zeros3: [rows,3] fp32 zeros.  workspace >= packed weight image + 1 KB.
  */
 int b2pn_tc_gemm_selftest(const float *w, int32_t m_out, int32_t k, const void *b_bf16, int32_t mode, int64_t rows,
                           int64_t ld, const float *zeros3, float *out, int64_t ld_out, void *workspace,

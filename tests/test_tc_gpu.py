@@ -1,5 +1,6 @@
 """GPU: the tcgen05/TMEM GEMM pipeline of the bf16 mode against a plain torch matmul on the same
-bf16-rounded operands (both B-tile layouts: K-major gather tiles and MN-major feature-major tiles)."""
+bf16-rounded operands (K-major gather tiles, MN-major feature-major tiles built by the SIMT loaders (mode 1) and
+the same tiles fetched by TMA tensor-map copies (mode 2))."""
 import pytest
 import torch
 
@@ -38,7 +39,7 @@ def _run(m_out, k, rows, mode, dev):
     return err, got, want
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("m_out,k,rows", [(64, 64, 128), (128, 128, 1024), (128, 131, 1000), (256, 128, 5000),
                                           (200, 259, 777), (1024, 512, 6000), (64, 8, 300)])
 def test_tc_gemm_selftest(cuda_device, m_out, k, rows, mode):
