@@ -1209,6 +1209,39 @@ __global__ void bn_bwd_finalize_tc_kernel(const double *partial, int gx, int C, 
     }
 }
 
+// Routed gradient of the max aggregation as a dense feature-major bf16 tensor (SLOTS levels):
+//   dh3[ch][row] = dout[m][ch] if row is the arg-max slot of (centroid m, ch), else 0.
+// Written once so that both consumers (dX of the last layer and dW3) take it through the TMA unit instead of
+// re-deriving it per (channel, row group) in their loader warps.  Thread = (channel, 8-row group), groups fastest:
+// 16-byte stores coalesce along the rows, the (arg, dout) reads stay L2-resident.
+__global__ void route_grad_tc_kernel(RowMapTC rm, const int64_t *rows_dev, const float *dout, const int32_t *arg, int C, int64_t ld,
+                                     __nv_bfloat16 *dh)
+{
+    if (rows_dev) rm.rows = *rows_dev;
+    const int64_t groups = (rm.rows + 127) / 128 * 16;  // whole tiles
+    const int64_t total = groups * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i / groups);
+        const int64_t g = i - (int64_t)ch * groups;
+        const unsigned inf = rm.info(g * 8);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (gi_nv(inf) > 0) {
+            const int64_t m = gi_seg(inf);
+            const int a = __ldg(arg + m * C + ch) - gi_slot0(inf);
+            if (a >= 0 && a < 8) {
+                const unsigned short gb = __bfloat16_as_ushort(__float2bfloat16(__ldg(dout + m * C + ch)));
+                const unsigned w = (a & 1) ? ((unsigned)gb << 16) : (unsigned)gb;
+                const int q = a >> 1;
+                v.x = q == 0 ? w : 0u;
+                v.y = q == 1 ? w : 0u;
+                v.z = q == 2 ? w : 0u;
+                v.w = q == 3 ? w : 0u;
+            }
+        }
+        *reinterpret_cast<uint4 *>(dh + (int64_t)ch * ld + g * 8) = v;
+    }
+}
+
 // dh = scale * (dz - mean(dz) - zhat * mean(dz*zhat)) on valid rows, 0 elsewhere; in place, feature-major bf16
 __global__ void bn_bwd_apply_tc_kernel(RowMapTC rm, const int64_t *rows_dev, __nv_bfloat16 *dz, const __nv_bfloat16 *z, int C,
                                        int64_t ld, const float *scale, const float *sbar)
@@ -1476,6 +1509,7 @@ struct BwdWsTC {
     double *count;
     double *partial;
     __nv_bfloat16 *dz1, *dz2;
+    __nv_bfloat16 *dh3;  // SLOTS: materialised routed gradient [c3][ld]
     float *sbar;
     float *dwp;
 };
@@ -1490,6 +1524,7 @@ static BwdWsTC carve_bwd_tc(const b2pn_sa_args &a, const ShapesTC &s, WsTC &ws)
     b.partial = ws.take<double>((int64_t)MAX_GX * 2 * 2 * s.cpad);
     b.dz1 = ws.take<__nv_bfloat16>((int64_t)s.c1 * s.ld);
     b.dz2 = ws.take<__nv_bfloat16>((int64_t)s.c2 * s.ld);
+    b.dh3 = a.seg_mode == B2PN_SEG_SLOTS ? ws.take<__nv_bfloat16>((int64_t)s.c3 * s.ld) : nullptr;
     b.sbar = ws.take<float>(2 * s.cmax);
     int64_t mx = plan_dw(s.c3, s.c2 + 1, s.ld).floats;
     const int64_t m2 = plan_dw(s.c2, s.c1 + 1, s.ld).floats, m1 = plan_dw(s.c1, s.k1 + 1, s.ld).floats;
@@ -1649,16 +1684,26 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
     note_launch();
 
     // ---- layer 3 ---------------------------------------------------------------------------------------
-    ArgGradSource y3 = {rm, g.grad_out, a.arg, s.c3};
-    {
+    MaskSumsStoreEpTC<1> e31 = {b.dz2, z2, s.c2, s.ld, a.mlp.gamma[1], a.mlp.beta[1], a.mlp.act, b.partial, s.cpad};
+    MaskSumsStoreEpTC<2> e32 = {b.dz2, z2, s.c2, s.ld, a.mlp.gamma[1], a.mlp.beta[1], a.mlp.act, b.partial, s.cpad};
+    LineFillK<FeatSource<1>> xa2 = {{rm, z2, s.c2, s.ld, a.mlp.act, s.c2, a.mlp.gamma[1], a.mlp.beta[1]}};
+    if (a.seg_mode == B2PN_SEG_SLOTS) {
+        // materialise dh3 once, then both consumers read it through TMA
+        route_grad_tc_kernel<<<apply_grid(s.ld, s.c3), 256, 0, st>>>(rm, ra.dev, g.grad_out, a.arg, s.c3, s.ld, b.dh3);
+        note_launch();
+        TmaMap map3;
+        if ((rc = make_tma_feature_major(&map3, b.dh3, s.c3, s.ld))) return rc;
+        TmaFeatLoader bl;
+        if ((rc = launch_by_mt(b.pkT[2], ra, bl, e31, e32, st, map3))) return rc;          // da2 = W3^T dh3
+        TmaSource y3 = {rm};
+        if ((rc = launch_dw(y3, xa2, s.c3, s.c2 + 1, s, ra, b.dwp, st, map3))) return rc;   // dW3 = dh3^T a2
+    } else {
+        ArgGradSource y3 = {rm, g.grad_out, a.arg, s.c3};
         FeatLoaderTC<ArgGradSource> bl = {y3};
-        MaskSumsStoreEpTC<1> e1 = {b.dz2, z2, s.c2, s.ld, a.mlp.gamma[1], a.mlp.beta[1], a.mlp.act, b.partial, s.cpad};
-        MaskSumsStoreEpTC<2> e2 = {b.dz2, z2, s.c2, s.ld, a.mlp.gamma[1], a.mlp.beta[1], a.mlp.act, b.partial, s.cpad};
-        if ((rc = launch_by_mt(b.pkT[2], ra, bl, e1, e2, st))) return rc;          // da2 = W3^T dh3
-        LineFillK<FeatSource<1>> xa2 = {{rm, z2, s.c2, s.ld, a.mlp.act, s.c2, a.mlp.gamma[1], a.mlp.beta[1]}};
-        if ((rc = launch_dw(y3, xa2, s.c3, s.c2 + 1, s, ra, b.dwp, st))) return rc;         // dW3 = dh3^T a2
-        launch_dw_reduce(b.dwp, s.c3, s.c2 + 1, nullptr, s.c2, s.c2, s, g.grad_w[2], g.grad_b[2], st);
+        if ((rc = launch_by_mt(b.pkT[2], ra, bl, e31, e32, st))) return rc;
+        if ((rc = launch_dw(y3, xa2, s.c3, s.c2 + 1, s, ra, b.dwp, st))) return rc;
     }
+    launch_dw_reduce(b.dwp, s.c3, s.c2 + 1, nullptr, s.c2, s.c2, s, g.grad_w[2], g.grad_b[2], st);
     bn_bwd_finalize_tc_kernel<<<(s.c2 + 3) / 4, 128, 0, st>>>(b.partial, 2 * grid_x_for(b.pkT[2], s.tiles), s.c2, s.cpad, b.count,
                                                                  a.training, g.grad_gamma[1], g.grad_beta[1], b.sbar);
     note_launch();
