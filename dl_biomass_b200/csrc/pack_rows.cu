@@ -11,6 +11,8 @@
 // of PACK_G consecutive centroids start on a 64-row boundary so the offsets can be computed in parallel.
 // Per 8-row group g the kernels get one descriptor word rgrp[g]:
 //   bits 0..23 centroid (0xFFFFFF: none)   24..26 first slot / 8   27..30 valid rows (0..8)   31 last group
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace b2pn {
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_rows_scan_kernel(const int3
 
 // one thread per (centroid, 8-row group): group descriptors and per-row source index
 __global__ void pack_rows_fill_kernel(const int32_t *cnt, const int32_t *nbr, int64_t n_dst, int K, const int32_t *chunk_base,
-                                      const int32_t *row_off, uint32_t *rgrp, int32_t *row_src)
+                                      const int32_t *row_off, uint32_t *rgrp, int32_t *row_src, uint16_t *row_valid)
 {
     const int G8 = (K + 7) >> 3;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -128,6 +130,12 @@ __global__ void pack_rows_fill_kernel(const int32_t *cnt, const int32_t *nbr, in
     int4 *dst = reinterpret_cast<int4 *>(row_src + r0);
     dst[0] = make_int4(v[0], v[1], v[2], v[3]);
     dst[1] = make_int4(v[4], v[5], v[6], v[7]);
+    if (row_valid) {  // bf16 1.0 = 0x3F80 for valid rows: the "ones" line of the dW GEMMs (bias gradients)
+        unsigned w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[q] = (2 * q < nv ? 0x3F80u : 0u) | (2 * q + 1 < nv ? 0x3F800000u : 0u);
+        *reinterpret_cast<uint4 *>(row_valid + r0) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
 }
 
 }  // namespace b2pn
@@ -152,8 +160,8 @@ extern "C" int64_t b2pn_pack_rows_workspace_bytes(int64_t n_dst)
 }
 
 extern "C" int b2pn_pack_rows(const int32_t *cnt, const int32_t *nbr, int64_t n_dst, int32_t K, uint32_t *rgrp,
-                              int32_t *row_src, int64_t *num_rows, void *workspace, int64_t workspace_bytes,
-                              b2pn_stream_t stream)
+                              int32_t *row_src, void *row_valid, int64_t *num_rows, void *workspace,
+                              int64_t workspace_bytes, b2pn_stream_t stream)
 {
     using namespace b2pn;
     if (n_dst < 0 || K <= 0) return B2PN_EINVAL;
@@ -174,11 +182,13 @@ extern "C" int b2pn_pack_rows(const int32_t *cnt, const int32_t *nbr, int64_t n_
     // other fields of such a group)
     B2PN_CUDA(cudaMemsetAsync(row_src, 0xff, cap * sizeof(int32_t), st));
     B2PN_CUDA(cudaMemsetAsync(rgrp, 0xff, (cap / 8) * sizeof(uint32_t), st));
+    if (row_valid) B2PN_CUDA(cudaMemsetAsync(row_valid, 0, cap * sizeof(uint16_t), st));
     pack_rows_scan_kernel<<<1, PACK_THREADS, 0, st>>>(cnt, n_dst, K, row_off, chunk_base, num_rows);
     note_launch();
     const int G8 = (K + 7) >> 3;
     const int64_t tot = n_dst * G8;
-    pack_rows_fill_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cnt, nbr, n_dst, K, chunk_base, row_off, rgrp, row_src);
+    pack_rows_fill_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cnt, nbr, n_dst, K, chunk_base, row_off, rgrp, row_src,
+                                                                          (uint16_t *)row_valid);
     note_launch();
     B2PN_LAUNCH_CHECK();
     return B2PN_OK;

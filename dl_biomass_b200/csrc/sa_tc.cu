@@ -94,6 +94,22 @@ int make_tma_feature_major(TmaMap *out, const void *base, int64_t channels, int6
     return r == CUDA_SUCCESS ? B2PN_OK : B2PN_EINVAL;
 }
 
+// the row-valid vector as a [1][ld] tensor: a 64-row x 16-line box whose first line is the vector, the rest zeros
+int make_tma_row_valid(TmaMap *out, const void *base, int64_t ld)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return B2PN_ENOTSUP;
+    if (!base || ld <= 0 || (ld & 7) || ((uintptr_t)base & 15u)) return B2PN_EINVAL;
+    const cuuint64_t dims[2] = {(cuuint64_t)ld, 1u};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2u};
+    const cuuint32_t box[2] = {64u, 16u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = fn(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims,
+                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? B2PN_OK : B2PN_EINVAL;
+}
+
 struct GemmParams {
     const uint8_t *a_packed;  // [m_group][k_chunk][MT*128 lines][128 B], swizzled bf16
     int num_kc;
@@ -435,35 +451,58 @@ struct StatsEpTC {  // pass A of a BatchNorm layer: per-channel sum and sum of s
     }
 };
 
-struct NormStoreEpTC {  // pass B: zT[ch][row] = bf16((acc + bias - mean) * rstd), the NORMALISED value zhat (the affine
-                        // gamma*zhat+beta and the activation are applied when the next layer / backward load it)
+struct NormStoreEpTC {  // pass B: zT[ch][row] = bf16((acc + bias - mean) * rstd), the NORMALISED value zhat (what backward
+                        // needs), and aT[ch][row] = bf16(act(gamma*zhat + beta)) with invalid rows zeroed: the operand
+                        // of the next layer and of the dW GEMMs, stored so that they can take it through the TMA unit
     __nv_bfloat16 *z;
+    __nv_bfloat16 *a;
     int C;
     int64_t ld;
     const float *bias;
     const float *mean;
     const float *rstd;
-    __device__ __forceinline__ void resolve(int64_t) {}
+    const float *gamma;
+    const float *beta;
+    int act;
+    RowMapTC rm;
+    __device__ __forceinline__ void resolve(int64_t r) { rm.resolve(r); }
     __device__ __forceinline__ void begin() {}
     __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half)
     {
-        float sc = 0.f, sh = 0.f;
+        float sc = 0.f, sh = 0.f, ga = 0.f, be = 0.f;
         if (ch < C) {
             sc = rstd[ch];
             sh = (bias[ch] - mean[ch]) * sc;
+            ga = gamma[ch];
+            be = beta[ch];
         }
 #pragma unroll 1
         for (int cc = half * 2; cc < half * 2 + 2; ++cc) {
             float v[32];
             tmem_ld32(taddr + cc * 32, v);
+            const int64_t r0 = tile * R + cc * 32;
+            unsigned nvs = 0u;  // valid rows of my four 8-row groups (warp-uniform loads)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) nvs |= (unsigned)gi_nv(rm.info(r0 + 8 * j)) << (4 * j);
             if (ch < C) {
-                uint4 *dst = reinterpret_cast<uint4 *>(z + (int64_t)ch * ld + tile * R + cc * 32);
+                uint4 *dz = reinterpret_cast<uint4 *>(z + (int64_t)ch * ld + r0);
+                uint4 *da = reinterpret_cast<uint4 *>(a + (int64_t)ch * ld + r0);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float f[8];
+                    const int nv = (int)((nvs >> (4 * j)) & 15u);
+                    float f[8], g[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) f[e] = fmaf(v[8 * j + e], sc, sh);
-                    dst[j] = pack8(f);
+                    const uint4 zp = pack8(f);
+                    dz[j] = zp;
+                    unpack8(zp, f);  // the activation is defined on the STORED (bf16) zhat, as backward recomputes it
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        float y = fmaf(f[e], ga, be);
+                        if (act == B2PN_ACT_RELU) y = fmaxf(y, 0.f);
+                        g[e] = e < nv ? y : 0.f;
+                    }
+                    da[j] = pack8(g);
                 }
             }
         }
@@ -818,6 +857,7 @@ struct DwParams {
 template <class SRC>
 struct LineFillK {  // K-major X side from a feature-major source
     static constexpr bool B_MN = false;
+    static constexpr bool USES_TMA = false;
     SRC src;
     static __host__ __device__ int bytes(int nb_lines) { return nb_lines * LINE_BYTES; }
     __device__ __forceinline__ void resolve(int64_t r) { src.resolve(r); }
@@ -835,8 +875,27 @@ struct LineFillK {  // K-major X side from a feature-major source
     static __device__ __forceinline__ uint64_t b_desc(uint32_t b_saddr, int ks) { return smem_desc_sw128(b_saddr + ks * 32, 16, ATOM_BYTES); }
 };
 
+// K-major X side fetched by TMA: the stored activation tensor a[c][ld] (c a multiple of 64) in 64-line boxes, then the
+// 16-line box of the row-valid vector whose first line is the "ones" line (bias gradient).  No loader arithmetic.
+struct TmaFill {
+    static constexpr bool B_MN = false;
+    static constexpr bool USES_TMA = true;
+    int c;  // channels of a (multiple of 64, c + 16 <= 256)
+    static __host__ __device__ int bytes(int nb_lines) { return nb_lines * LINE_BYTES; }
+    __device__ __forceinline__ void resolve(int64_t) {}
+    __device__ __forceinline__ void fill(uint8_t *, int, int64_t, int, int, const unsigned (&)[8]) {}
+    __device__ __forceinline__ void fill_tma(uint8_t *B, int64_t r0, const TmaMap *map_x, const TmaMap *map_v, uint64_t *bar) const
+    {
+        mbar_expect_tx(bar, (unsigned)((c + 16) * LINE_BYTES));
+        for (int blk = 0; blk * 64 < c; ++blk) tma_load_2d(B + blk * (64 * LINE_BYTES), map_x, (int)r0, blk * 64, bar);
+        tma_load_2d(B + c * LINE_BYTES, map_v, (int)r0, 0, bar);
+    }
+    static __device__ __forceinline__ uint64_t b_desc(uint32_t b_saddr, int ks) { return smem_desc_sw128(b_saddr + ks * 32, 16, ATOM_BYTES); }
+};
+
 struct LineFillGather {  // MN-major X side: [column blocks of 64][64 row lines]; thread lt: row line lt>>1, half of the chunks
     static constexpr bool B_MN = true;
+    static constexpr bool USES_TMA = false;
     GatherLoaderTC g;
     static __host__ __device__ int bytes(int nb_lines) { return ((nb_lines + 63) / 64) * 64 * LINE_BYTES; }
     __device__ __forceinline__ void resolve(int64_t r) { g.resolve(r); }
@@ -872,7 +931,8 @@ struct DwPlan {
 };
 
 template <int MTA, class YS, class XF>
-__global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, XF xf, const __grid_constant__ TmaMap tmap_y)
+__global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, XF xf, const __grid_constant__ TmaMap tmap_y,
+                                                       const __grid_constant__ TmaMap tmap_x, const __grid_constant__ TmaMap tmap_v)
 {
     using P = DwPlan<MTA>;
     extern __shared__ uint8_t smem_raw[];
@@ -941,8 +1001,12 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
                     for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4 *>(A + line_chunk_off(line, g)) = v[g];
                 }
             }
-            xf.fill(B, lt, r0, ng, nb_lines, inf);
-            fence_proxy_async_smem();
+            if constexpr (XF::USES_TMA) {
+                if (lt == 0) xf.fill_tma(B, r0, &tmap_x, &tmap_v, &full[s]);
+            } else {
+                xf.fill(B, lt, r0, ng, nb_lines, inf);
+            }
+            if constexpr (!(YS::USES_TMA && XF::USES_TMA)) fence_proxy_async_smem();
             mbar_arrive(&full[s]);
         }
     } else if (warp == MMA_WARP) {
@@ -1441,7 +1505,7 @@ static int check_args_tc(const b2pn_sa_args &a)
         if (!a.mlp.w[l] || !a.mlp.b[l]) return B2PN_EINVAL;
     for (int l = 0; l < 2; ++l)
         if (!a.mlp.gamma[l] || !a.mlp.beta[l] || !a.mlp.running_mean[l] || !a.mlp.running_var[l]) return B2PN_EINVAL;
-    if (!a.out || !a.arg || !a.h1 || !a.h2 || !a.bn) return B2PN_EINVAL;
+    if (!a.out || !a.arg || !a.h1 || !a.h2 || !a.bn || !a.a1 || !a.a2) return B2PN_EINVAL;
     return B2PN_OK;
 }
 
@@ -1577,15 +1641,20 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
                                                                  a.mlp.momentum, bn1, s.cmax);
     note_launch();
     if (s.rows > 0) {
-        NormStoreEpTC e = {z1, s.c1, s.ld, a.mlp.b[0], bn1, bn1 + s.cmax};
+        NormStoreEpTC e = {z1, (__nv_bfloat16 *)a.a1, s.c1, s.ld, a.mlp.b[0], bn1, bn1 + s.cmax, a.mlp.gamma[0], a.mlp.beta[0],
+                           a.mlp.act, rm};
         if ((rc = launch_by_mt(f.pk[0], ra, gl, e, e, st))) return rc;
     }
     // ---- layer 2
-    FeatLoaderTC<FeatSource<1>> l2 = {{rm, z1, s.c1, s.ld, a.mlp.act, -1, a.mlp.gamma[0], a.mlp.beta[0]}};
+    // layers 2 and 3 read the stored activations a1 / a2 through the TMA unit (no loader arithmetic)
+    TmaFeatLoader l2, l3;
+    TmaMap map_a1, map_a2;
+    if ((rc = make_tma_feature_major(&map_a1, a.a1, s.c1, s.ld))) return rc;
+    if ((rc = make_tma_feature_major(&map_a2, a.a2, s.c2, s.ld))) return rc;
     if (train && s.rows > 0) {
         StatsEpTC<1> e1 = {s.c2, f.partial, s.cpad};
         StatsEpTC<2> e2 = {s.c2, f.partial, s.cpad};
-        if ((rc = launch_by_mt(f.pk[1], ra, l2, e1, e2, st))) return rc;
+        if ((rc = launch_by_mt(f.pk[1], ra, l2, e1, e2, st, map_a1))) return rc;
     }
     bn_fwd_finalize_tc_kernel<<<(s.c2 + 3) / 4, 128, 0, st>>>(f.partial, 2 * grid_x_for(f.pk[1], s.tiles), s.c2, s.cpad, f.count, train,
                                                                  a.mlp.b[1], a.mlp.gamma[1], a.mlp.beta[1], a.mlp.running_mean[1],
@@ -1593,21 +1662,20 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
                                                                  a.mlp.momentum, bn2, s.cmax);
     note_launch();
     if (s.rows > 0) {
-        NormStoreEpTC e = {z2, s.c2, s.ld, a.mlp.b[1], bn2, bn2 + s.cmax};
-        if ((rc = launch_by_mt(f.pk[1], ra, l2, e, e, st))) return rc;
+        NormStoreEpTC e = {z2, (__nv_bfloat16 *)a.a2, s.c2, s.ld, a.mlp.b[1], bn2, bn2 + s.cmax, a.mlp.gamma[1], a.mlp.beta[1],
+                           a.mlp.act, rm};
+        if ((rc = launch_by_mt(f.pk[1], ra, l2, e, e, st, map_a1))) return rc;
     }
     // ---- layer 3 + max aggregation
     if (a.seg_mode == B2PN_SEG_SLOTS) {
-        FeatLoaderTC<FeatSource<1>> l3 = {{rm, z2, s.c2, s.ld, a.mlp.act, -1, a.mlp.gamma[1], a.mlp.beta[1]}};
         SlotMaxEpTC e = {a.out, a.arg, s.c3, a.mlp.b[2], a.rgrp, s.rows};
-        if ((rc = launch_by_mt(f.pk[2], ra, l3, e, e, st))) return rc;
+        if ((rc = launch_by_mt(f.pk[2], ra, l3, e, e, st, map_a2))) return rc;
     } else {
         const int64_t n = a.n_dst * (int64_t)s.c3;
         B2PN_CUDA(cudaMemsetAsync(f.keys, 0, n * sizeof(unsigned long long), st));
         if (s.rows > 0) {
-            FeatLoaderTC<FeatSource<1>> l3 = {{rm, z2, s.c2, s.ld, a.mlp.act, -1, a.mlp.gamma[1], a.mlp.beta[1]}};
             CloudMaxEpTC e = {f.keys, s.c3, a.mlp.b[2], a.batch, s.rows};
-            if ((rc = launch_by_mt(f.pk[2], ra, l3, e, e, st))) return rc;
+            if ((rc = launch_by_mt(f.pk[2], ra, l3, e, e, st, map_a2))) return rc;
         }
         unpack_keys_tc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(f.keys, a.out, a.arg, n);
         note_launch();
@@ -1618,7 +1686,7 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
 
 template <class YS, class XF>
 static int launch_dw(const YS &ys, const XF &xf, int n_out, int k_total, const ShapesTC &s, const RowsArg &ra, float *dwp,
-                     cudaStream_t st, const TmaMap &map_y = kNoMap)
+                     cudaStream_t st, const TmaMap &map_y = kNoMap, const TmaMap &map_x = kNoMap, const TmaMap &map_v = kNoMap)
 {
     const DwPlanHost d = plan_dw(n_out, k_total, s.ld);
     DwParams p = {ra.cap, ra.dev, n_out, d.nbl_total, k_total, dwp};
@@ -1628,12 +1696,12 @@ static int launch_dw(const YS &ys, const XF &xf, int n_out, int k_total, const S
         auto kern = tc_dw_kernel<1, YS, XF>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DwPlan<1>::TOTAL);
         if (e != cudaSuccess) return (int)e;
-        kern<<<grid, NT, DwPlan<1>::TOTAL, st>>>(p, ys, xf, map_y);
+        kern<<<grid, NT, DwPlan<1>::TOTAL, st>>>(p, ys, xf, map_y, map_x, map_v);
     } else {
         auto kern = tc_dw_kernel<2, YS, XF>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DwPlan<2>::TOTAL);
         if (e != cudaSuccess) return (int)e;
-        kern<<<grid, NT, DwPlan<2>::TOTAL, st>>>(p, ys, xf, map_y);
+        kern<<<grid, NT, DwPlan<2>::TOTAL, st>>>(p, ys, xf, map_y, map_x, map_v);
     }
     note_launch();
     e = cudaPeekAtLastError();
@@ -1687,6 +1755,15 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
     MaskSumsStoreEpTC<1> e31 = {b.dz2, z2, s.c2, s.ld, a.mlp.gamma[1], a.mlp.beta[1], a.mlp.act, b.partial, s.cpad};
     MaskSumsStoreEpTC<2> e32 = {b.dz2, z2, s.c2, s.ld, a.mlp.gamma[1], a.mlp.beta[1], a.mlp.act, b.partial, s.cpad};
     LineFillK<FeatSource<1>> xa2 = {{rm, z2, s.c2, s.ld, a.mlp.act, s.c2, a.mlp.gamma[1], a.mlp.beta[1]}};
+    // X sides through TMA: stored activations + the row-valid "ones" line (64-channel boxes, so c % 64 == 0)
+    TmaMap map_v = kNoMap, map_a1 = kNoMap, map_a2 = kNoMap;
+    const bool tma_x = a.seg_mode == B2PN_SEG_SLOTS && a.row_valid != nullptr;
+    const bool tma_x2 = tma_x && s.c2 % 64 == 0 && s.c2 + 16 <= 256, tma_x1 = tma_x && s.c1 % 64 == 0 && s.c1 + 16 <= 256;
+    if (tma_x2 || tma_x1) {
+        if ((rc = make_tma_row_valid(&map_v, a.row_valid, s.ld))) return rc;
+    }
+    if (tma_x2 && (rc = make_tma_feature_major(&map_a2, a.a2, s.c2, s.ld))) return rc;
+    if (tma_x1 && (rc = make_tma_feature_major(&map_a1, a.a1, s.c1, s.ld))) return rc;
     if (a.seg_mode == B2PN_SEG_SLOTS) {
         // materialise dh3 once, then both consumers read it through TMA
         route_grad_tc_kernel<<<apply_grid(s.ld, s.c3), 256, 0, st>>>(rm, ra.dev, g.grad_out, a.arg, s.c3, s.ld, b.dh3);
@@ -1696,7 +1773,13 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
         TmaFeatLoader bl;
         if ((rc = launch_by_mt(b.pkT[2], ra, bl, e31, e32, st, map3))) return rc;          // da2 = W3^T dh3
         TmaSource y3 = {rm};
-        if ((rc = launch_dw(y3, xa2, s.c3, s.c2 + 1, s, ra, b.dwp, st, map3))) return rc;   // dW3 = dh3^T a2
+        if (tma_x2) {
+            TmaFill xt = {s.c2};
+            rc = launch_dw(y3, xt, s.c3, s.c2 + 1, s, ra, b.dwp, st, map3, map_a2, map_v);   // dW3 = dh3^T a2
+        } else {
+            rc = launch_dw(y3, xa2, s.c3, s.c2 + 1, s, ra, b.dwp, st, map3);
+        }
+        if (rc) return rc;
     } else {
         ArgGradSource y3 = {rm, g.grad_out, a.arg, s.c3};
         FeatLoaderTC<ArgGradSource> bl = {y3};
@@ -1722,8 +1805,14 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
         MaskSumsStoreEpTC<1> e1 = {b.dz1, z1, s.c1, s.ld, a.mlp.gamma[0], a.mlp.beta[0], a.mlp.act, b.partial, s.cpad};
         MaskSumsStoreEpTC<2> e2 = {b.dz1, z1, s.c1, s.ld, a.mlp.gamma[0], a.mlp.beta[0], a.mlp.act, b.partial, s.cpad};
         if ((rc = launch_by_mt(b.pkT[1], ra, bl, e1, e2, st, map2))) return rc;
-        LineFillK<FeatSource<1>> xa1 = {{rm, z1, s.c1, s.ld, a.mlp.act, s.c1, a.mlp.gamma[0], a.mlp.beta[0]}};
-        if ((rc = launch_dw(y2, xa1, s.c2, s.c1 + 1, s, ra, b.dwp, st, map2))) return rc;
+        if (tma_x1) {
+            TmaFill xt = {s.c1};
+            rc = launch_dw(y2, xt, s.c2, s.c1 + 1, s, ra, b.dwp, st, map2, map_a1, map_v);
+        } else {
+            LineFillK<FeatSource<1>> xa1 = {{rm, z1, s.c1, s.ld, a.mlp.act, s.c1, a.mlp.gamma[0], a.mlp.beta[0]}};
+            rc = launch_dw(y2, xa1, s.c2, s.c1 + 1, s, ra, b.dwp, st, map2);
+        }
+        if (rc) return rc;
         launch_dw_reduce(b.dwp, s.c2, s.c1 + 1, nullptr, s.c1, s.c1, s, g.grad_w[1], g.grad_b[1], st);
     }
     bn_bwd_finalize_tc_kernel<<<(s.c1 + 3) / 4, 128, 0, st>>>(b.partial, 2 * grid_x_for(b.pkT[1], s.tiles), s.c1, s.cpad, b.count,

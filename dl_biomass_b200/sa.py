@@ -40,7 +40,7 @@ def act_code(act) -> int:
 
 def _fill_args(a: SaArgs, *, precision, training, seg_mode, K, n_src, n_dst, c_in, x, pos_src, pos_dst, nbr, cnt,
                batch, chans, act, eps, momentum, ws, bs, gammas, betas, rmeans, rvars, nbts, out, arg, h1, h2, bn,
-               rowmap=None):
+               rowmap=None, acts=None):
     a.precision, a.training, a.seg_mode, a.K = precision, int(training), seg_mode, K
     a.n_src, a.n_dst, a.c_in = n_src, n_dst, c_in
     a.x_dtype = 1 if (x is not None and x.dtype == torch.bfloat16) else 0
@@ -58,15 +58,18 @@ def _fill_args(a: SaArgs, *, precision, training, seg_mode, K, n_src, n_dst, c_i
         m.num_batches_tracked[i] = _dp(nbts[i])
     a.out, a.arg, a.h1, a.h2, a.bn = _dp(out), _dp(arg), _dp(h1), _dp(h2), _dp(bn)
     if rowmap is not None:
-        rgrp, row_src, num_rows, cap = rowmap
+        rgrp, row_src, num_rows, cap, row_valid = rowmap
         a.rgrp, a.row_src, a.num_rows, a.row_capacity = _dp(rgrp), _dp(row_src), _dp(num_rows), cap
+        a.row_valid = _dp(row_valid)
+    if acts is not None:
+        a.a1, a.a2 = _dp(acts[0]), _dp(acts[1])
 
 
 def pack_rows(nbr: torch.Tensor, cnt: torch.Tensor, K: int):
     """Compact the filled neighbour slots into rows for the tensor-core kernels (include/b2pn.h,
     b2pn_pack_rows): what ``radius`` returning a compact edge list is in the reference
     (/root/reference/pointnet2_regressor.py:14-16), minus the host round trip -- the row count stays on the
-    device.  Returns (rgrp, row_src, num_rows, capacity)."""
+    device.  Returns (rgrp, row_src, num_rows, capacity, row_valid)."""
     lib = _lib.lib()
     dev = nbr.device
     n_dst = cnt.numel()
@@ -76,13 +79,14 @@ def pack_rows(nbr: torch.Tensor, cnt: torch.Tensor, K: int):
     rgrp = torch.empty(cap // 8, dtype=torch.int32, device=dev)
     row_src = torch.empty(cap, dtype=torch.int32, device=dev)
     num_rows = torch.empty(1, dtype=torch.int64, device=dev)
+    row_valid = torch.empty(cap, dtype=torch.bfloat16, device=dev)
     wsb = torch.empty(int(lib.b2pn_pack_rows_workspace_bytes(n_dst)), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         rc = lib.b2pn_pack_rows(cnt.data_ptr(), nbr.data_ptr(), n_dst, K, rgrp.data_ptr(), row_src.data_ptr(),
-                                num_rows.data_ptr(), wsb.data_ptr(), wsb.numel(),
+                                row_valid.data_ptr(), num_rows.data_ptr(), wsb.data_ptr(), wsb.numel(),
                                 torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "b2pn_pack_rows")
-    return rgrp, row_src, num_rows, cap
+    return rgrp, row_src, num_rows, cap, row_valid
 
 
 class _SAFunction(torch.autograd.Function):
@@ -114,6 +118,7 @@ class _SAFunction(torch.autograd.Function):
             rows = rowmap[3]
         out = torch.empty(n_dst, chans[3], dtype=f32, device=dev)
         arg = torch.empty(n_dst, chans[3], dtype=torch.int32, device=dev)
+        acts = None
         if prec == PREC_F32:   # row-major fp32 activations [rows, c]
             xs = None if x is None else x.detach().to(f32).contiguous()
             h1 = torch.empty(rows, chans[1], dtype=f32, device=dev)
@@ -126,13 +131,15 @@ class _SAFunction(torch.autograd.Function):
             ld = (rows + 127) // 128 * 128
             h1 = torch.empty(chans[1], ld, dtype=torch.bfloat16, device=dev)
             h2 = torch.empty(chans[2], ld, dtype=torch.bfloat16, device=dev)
+            acts = (torch.empty_like(h1), torch.empty_like(h2))  # post-activation copies (TMA operands)
         cmax = max(chans[1], chans[2])
         bn = torch.empty(2, 4, cmax, dtype=f32, device=dev)
         a = SaArgs()
         _fill_args(a, precision=prec, training=training, seg_mode=seg_mode, K=K, n_src=n_src, n_dst=n_dst, c_in=c_in,
                    x=xs, pos_src=pos_src, pos_dst=pos_dst, nbr=nbr, cnt=cnt, batch=batch, chans=chans, act=act,
                    eps=eps, momentum=momentum, ws=ws, bs=bs, gammas=gs, betas=bes, rmeans=(rm1, rm2),
-                   rvars=(rv1, rv2), nbts=(nbt1, nbt2), out=out, arg=arg, h1=h1, h2=h2, bn=bn, rowmap=rowmap)
+                   rvars=(rv1, rv2), nbts=(nbt1, nbt2), out=out, arg=arg, h1=h1, h2=h2, bn=bn, rowmap=rowmap,
+                   acts=acts)
         nbytes = lib.b2pn_sa_workspace_bytes(ctypes.byref(a), 0)
         if nbytes < 0:
             _lib.check(int(nbytes), "b2pn_sa_workspace_bytes")
@@ -147,9 +154,10 @@ class _SAFunction(torch.autograd.Function):
         ctx.has_x = x is not None
         ctx.x_needs_grad = x is not None and x.requires_grad
         ctx.row_capacity = None if rowmap is None else rowmap[3]
-        rmt = (None, None, None) if rowmap is None else rowmap[:3]
+        rmt = (None, None, None, None) if rowmap is None else (rowmap[0], rowmap[1], rowmap[2], rowmap[4])
+        at = (None, None) if acts is None else acts
         ctx.save_for_backward(xs, pos_src, pos_dst, nbr, cnt, batch, *ws, *bs, *gs, *bes, rm1, rv1, rm2, rv2,
-                              arg, h1, h2, bn, *rmt)
+                              arg, h1, h2, bn, *rmt, *at)
         ctx.mark_non_differentiable(arg)
         return out, arg
 
@@ -158,8 +166,9 @@ class _SAFunction(torch.autograd.Function):
     def backward(ctx, grad_out, _grad_arg):
         lib = _lib.lib()
         (xs, pos_src, pos_dst, nbr, cnt, batch, w1, w2, w3, b1, b2, b3, g1, g2, be1, be2, rm1, rv1, rm2, rv2,
-         arg, h1, h2, bn, rgrp, row_src, num_rows) = ctx.saved_tensors
-        rowmap = None if rgrp is None else (rgrp, row_src, num_rows, ctx.row_capacity)
+         arg, h1, h2, bn, rgrp, row_src, num_rows, row_valid, a1, a2) = ctx.saved_tensors
+        rowmap = None if rgrp is None else (rgrp, row_src, num_rows, ctx.row_capacity, row_valid)
+        acts = None if a1 is None else (a1, a2)
         prec, training, seg_mode, K, n_dst, act, eps, momentum = ctx.cfg
         dev = pos_src.device
         chans = ctx.chans
@@ -175,7 +184,7 @@ class _SAFunction(torch.autograd.Function):
                    c_in=ctx.c_in, x=xs, pos_src=pos_src, pos_dst=pos_dst, nbr=nbr, cnt=cnt, batch=batch, chans=chans,
                    act=act, eps=eps, momentum=momentum, ws=(w1, w2, w3), bs=(b1, b2, b3), gammas=(g1, g2),
                    betas=(be1, be2), rmeans=(rm1, rm2), rvars=(rv1, rv2), nbts=(None, None), out=grad_out, arg=arg,
-                   h1=h1, h2=h2, bn=bn, rowmap=rowmap)
+                   h1=h1, h2=h2, bn=bn, rowmap=rowmap, acts=acts)
         nbytes = lib.b2pn_sa_workspace_bytes(ctypes.byref(a), 1)
         if nbytes < 0:
             _lib.check(int(nbytes), "b2pn_sa_workspace_bytes")

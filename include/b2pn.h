@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B2PN_ABI_VERSION 2
+#define B2PN_ABI_VERSION 3
 #define B2PN_OK 0
 #define B2PN_EINVAL (-1)   /* null pointer / negative size / bad flag            */
 #define B2PN_ENOTSUP (-2)  /* shape outside what the sm_100a kernels are built for */
@@ -91,6 +91,8 @@ int b2pn_ball_query_f32(const float *src_pos, const float *qry_pos, const int64_
  *   rgrp    [capacity/8] u32      one descriptor per 8-row group: bits 0..23 centroid (0xFFFFFF none),
  *                                 24..26 first slot/8, 27..30 valid rows, 31 last group of the centroid
  *   row_src [capacity]   i32      gathered source point of the row, -1 = padding
+ *   row_valid [capacity] bf16     1.0 for valid rows, 0 elsewhere (optional, may be NULL): the "ones" operand
+ *                                 line that yields the bias gradients in the dW GEMMs
  *   num_rows [1]         i64      rows in use (multiple of 64)
  * Centroid m owns max(8, round_up(cnt[m], 8)) consecutive rows that never cross a 64-row boundary.
  * capacity = b2pn_pack_rows_capacity(n_dst, K) rows (host-side upper bound used to size every buffer).
@@ -98,8 +100,8 @@ int b2pn_ball_query_f32(const float *src_pos, const float *qry_pos, const int64_
 int64_t b2pn_pack_rows_capacity(int64_t n_dst, int32_t K);
 int64_t b2pn_pack_rows_workspace_bytes(int64_t n_dst);
 int b2pn_pack_rows(const int32_t *cnt, const int32_t *nbr, int64_t n_dst, int32_t K, uint32_t *rgrp,
-                   int32_t *row_src, int64_t *num_rows, void *workspace, int64_t workspace_bytes,
-                   b2pn_stream_t stream);
+                   int32_t *row_src, void *row_valid, int64_t *num_rows, void *workspace,
+                   int64_t workspace_bytes, b2pn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Set-abstraction levels: fused gather + relative-position concat + shared MLP + max aggregation.
@@ -162,6 +164,11 @@ typedef struct b2pn_sa_args {
     const int32_t *row_src;
     const int64_t *num_rows;
     int64_t row_capacity;        /* b2pn_pack_rows_capacity(n_dst, K)                                   */
+    const void *row_valid;       /* bf16 [row_capacity] from b2pn_pack_rows, or NULL                    */
+    /* PREC_BF16: activations of the two hidden layers AFTER BatchNorm affine + activation, bf16 feature-major
+     * [c, ld] like h1/h2, invalid rows zero.  Written by forward, read by backward: stored next to the
+     * normalised values so that every later consumer is a plain tensor-map (TMA) copy.                  */
+    void *a1, *a2;
 } b2pn_sa_args;
 
 typedef struct b2pn_sa_grads {

@@ -196,7 +196,7 @@ def test_pack_rows_structure(cuda_device, K, n, r):
     idx = ref.fps_ref(b.pos, b.ptr, 0.2)
     qptr = ref.sample_ptr(b.ptr, 0.2)
     nbr, cnt = ref.ball_query_ref(b.pos, b.pos[idx], b.ptr, qptr, r, K)
-    rgrp, row_src, num_rows, cap = sa.pack_rows(nbr.to(cuda_device), cnt.to(cuda_device), K)
+    rgrp, row_src, num_rows, cap, row_valid = sa.pack_rows(nbr.to(cuda_device), cnt.to(cuda_device), K)
     torch.cuda.synchronize()
     rows = int(num_rows.item())
     assert rows % 64 == 0 and 0 < rows <= cap
@@ -231,6 +231,8 @@ def test_pack_rows_structure(cuda_device, K, n, r):
             assert (src[(gi + j) * 8: (gi + j) * 8 + 8] == want_src).all()
         i += ng
     assert seen.all()
+    rv = row_valid.float().cpu().numpy()
+    assert ((rv == 1.0) == (src >= 0)).all() and ((rv == 0.0) | (rv == 1.0)).all()
     # centroids keep their order
     firsts = used[slot0[used] == 0]
     assert (np.diff(seg[firsts]) > 0).all()
