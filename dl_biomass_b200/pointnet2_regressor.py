@@ -153,6 +153,20 @@ class Sampling:
         return list(self.level1) + list(self.level2)
 
 
+class _CallInBackward(torch.autograd.Function):
+    """Identity whose backward first runs ``fn()``: a hook at a fixed point of the backward pass."""
+
+    @staticmethod
+    def forward(ctx, x, fn):
+        ctx.fn = fn
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        ctx.fn()
+        return g, None
+
+
 class Net(torch.nn.Module):
     """/root/reference/pointnet2_regressor.py:36-58.
 
@@ -205,8 +219,10 @@ class Net(torch.nn.Module):
 
     def forward(self, data, start: Optional[torch.Tensor] = None, sampling: Optional[Sampling] = None,
                 after_grouping=None):
-        """``after_grouping``: optional callable invoked once both set-abstraction levels have been enqueued
-        (train.PipelinedTrainStep joins its sampling stream there and gives the remaining kernels every SM)."""
+        """``after_grouping``: optional callable invoked when the last kernel of the two set-abstraction levels'
+        FORWARD has been enqueued and again never before their BACKWARD starts: with autograd recording it fires in
+        the backward pass right before the level-2 backward (after the global level and the head went both ways),
+        otherwise right after the level-2 forward.  train.PipelinedTrainStep joins its sampling stream there."""
         x, pos, batch = data.x, data.pos, data.batch                                     # :53
         sizes, lv = self._levels(data)
         if sampling is not None and tuple(sampling.sizes) != tuple(sizes):
@@ -217,6 +233,9 @@ class Net(torch.nn.Module):
         x1, pos1, _, _ = self.sa1_module._run(x, pos, lv[0], lv[1], start, s1)           # :54
         x2, pos2, batch2, _ = self.sa2_module._run(x1, pos1, lv[1], lv[2], None, s2)      # :55
         if after_grouping is not None:
-            after_grouping()
+            if torch.is_grad_enabled() and x2.requires_grad:
+                x2 = _CallInBackward.apply(x2, after_grouping)
+            else:
+                after_grouping()
         x3 = self.sa3_module._run(x2, pos2, batch2, len(sizes))                          # :56
         return self.mlp(x3)                                                              # :58

@@ -149,9 +149,10 @@ class PipelinedTrainStep:
         self.side.wait_stream(main)                       # nxt's tensors (an H2D copy, say) are ordered before this
         with torch.cuda.stream(self.side):
             nxt_sampling = self.model.sample(nxt)
-        # The sampling branch (~1.4 ms) is about as long as the forward pass of the two set-abstraction levels, so
-        # those kernels leave its SMs alone (grid cap); the join sits right behind them and everything after
-        # (global level, head, the whole backward pass, Adam) is launched with one CTA per SM again.
+        # The sampling branch (~1.4 ms) must not fight the persistent tcgen05 kernels for SMs: while it may be in
+        # flight they are launched with a capped grid.  The join sits in the BACKWARD pass right before the level-2
+        # backward: the forward of both SA levels runs capped, the global level and the head (small grids anyway) go
+        # forward and backward in between, and the two big backward passes get every SM again.
         self.lib.b2pn_set_sm_limit(self.sm_limit)
 
         def join():
