@@ -78,7 +78,7 @@ static EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 // box = 64 rows (128 bytes, the swizzle span) x 64 channels; channels past `channels` read as zeros
-int make_tma_feature_major(TmaMap *out, const void *base, int64_t channels, int64_t ld)
+int make_tma_feature_major(TmaMap *out, const void *base, int64_t channels, int64_t ld, int box_channels)
 {
     static_assert(sizeof(CUtensorMap) == sizeof(TmaMap), "CUtensorMap is 128 bytes");
     EncodeTiledFn fn = encode_tiled_fn();
@@ -86,7 +86,7 @@ int make_tma_feature_major(TmaMap *out, const void *base, int64_t channels, int6
     if (!base || channels <= 0 || ld <= 0 || (ld & 7) || ((uintptr_t)base & 15u)) return B2PN_EINVAL;
     const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)channels};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * 2u};
-    const cuuint32_t box[2] = {64u, 64u};
+    const cuuint32_t box[2] = {64u, (cuuint32_t)box_channels};
     const cuuint32_t estr[2] = {1u, 1u};
     const CUresult r = fn(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims,
                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -391,13 +391,38 @@ struct TmaFeatLoader {
 // =================================================================================================
 //  Epilogues of the rows GEMM (128 threads; thread tid owns TMEM lane tid = channel within the M tile)
 // =================================================================================================
+// what the kernel hands an epilogue per call: the warp's shared-memory staging area (two 32-line x 128-byte tiles,
+// only for STAGED epilogues) and the tensor maps their TMA stores go through
+struct EpCtx {
+    uint8_t *stage;
+    const TmaMap *m0;
+    const TmaMap *m1;
+    uint64_t *bar;       // the warp's own mbarrier (TMA loads into the staging area)
+    int64_t next_tile;   // the (tile, mt) this thread's epilogue handles after the current one, -1: none
+    int next_ch;         // its channel for this thread
+};
+constexpr int EPI_STAGE_PER_WARP = 2 * 32 * LINE_BYTES;  // 8 KB
+
+// a STAGED epilogue thread owns one channel = one 128-byte line of 64 rows: it writes the line (swizzled like every
+// other tile here) into the warp's staging tile and one lane sends the 32 x 64 tile out with a single TMA store --
+// 16-byte global stores 2*ld bytes apart per lane (32 lines per instruction) were what these epilogues spent their time on
+__device__ __forceinline__ void stage_chunk(uint8_t *tile32, int lane, int g, const uint4 &v)
+{
+    *reinterpret_cast<uint4 *>(tile32 + lane * LINE_BYTES + ((g ^ (lane & 7)) << 4)) = v;
+}
+__device__ __forceinline__ uint4 unstage_chunk(const uint8_t *tile32, int lane, int g)
+{
+    return *reinterpret_cast<const uint4 *>(tile32 + lane * LINE_BYTES + ((g ^ (lane & 7)) << 4));
+}
+
 struct StoreF32Ep {  // self-test: out[ch][row] = acc
+    static constexpr bool STAGED = false;
     float *out;
     int C;
     int64_t ld;
     __device__ __forceinline__ void resolve(int64_t) {}
     __device__ __forceinline__ void begin() {}
-    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half)
+    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half, const EpCtx &cx)
     {
 #pragma unroll 1
         for (int cc = half * 2; cc < half * 2 + 2; ++cc) {
@@ -415,6 +440,7 @@ struct StoreF32Ep {  // self-test: out[ch][row] = acc
 
 template <int MT>
 struct StatsEpTC {  // pass A of a BatchNorm layer: per-channel sum and sum of squares of the bias-free accumulators
+    static constexpr bool STAGED = false;
     int C;
     double *partial;  // [gridDim.x][2][cpad]
     int cpad;
@@ -425,7 +451,7 @@ struct StatsEpTC {  // pass A of a BatchNorm layer: per-channel sum and sum of s
 #pragma unroll
         for (int i = 0; i < MT; ++i) S[i] = Q[i] = 0.0;
     }
-    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half)
+    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half, const EpCtx &cx)
     {
         float s = 0.f, q = 0.f;
 #pragma unroll 1
@@ -454,10 +480,9 @@ struct StatsEpTC {  // pass A of a BatchNorm layer: per-channel sum and sum of s
 struct NormStoreEpTC {  // pass B: zT[ch][row] = bf16((acc + bias - mean) * rstd), the NORMALISED value zhat (what backward
                         // needs), and aT[ch][row] = bf16(act(gamma*zhat + beta)) with invalid rows zeroed: the operand
                         // of the next layer and of the dW GEMMs, stored so that they can take it through the TMA unit
-    __nv_bfloat16 *z;
-    __nv_bfloat16 *a;
+    static constexpr bool STAGED = true;
+    // zT and aT leave through the warp's staging tiles and two TMA stores (EpCtx::m0 = map of z, m1 = map of a)
     int C;
-    int64_t ld;
     const float *bias;
     const float *mean;
     const float *rstd;
@@ -467,8 +492,9 @@ struct NormStoreEpTC {  // pass B: zT[ch][row] = bf16((acc + bias - mean) * rstd
     RowMapTC rm;
     __device__ __forceinline__ void resolve(int64_t r) { rm.resolve(r); }
     __device__ __forceinline__ void begin() {}
-    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half)
+    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half, const EpCtx &cx)
     {
+        const int lane = threadIdx.x & 31;
         float sc = 0.f, sh = 0.f, ga = 0.f, be = 0.f;
         if (ch < C) {
             sc = rstd[ch];
@@ -476,6 +502,9 @@ struct NormStoreEpTC {  // pass B: zT[ch][row] = bf16((acc + bias - mean) * rstd
             ga = gamma[ch];
             be = beta[ch];
         }
+        uint8_t *zt = cx.stage, *at = cx.stage + 32 * LINE_BYTES;
+        if (lane == 0) bulk_wait_read_all();  // the TMA stores of my previous tile have read the staging tiles
+        __syncwarp();
 #pragma unroll 1
         for (int cc = half * 2; cc < half * 2 + 2; ++cc) {
             float v[32];
@@ -484,34 +513,43 @@ struct NormStoreEpTC {  // pass B: zT[ch][row] = bf16((acc + bias - mean) * rstd
             unsigned nvs = 0u;  // valid rows of my four 8-row groups (warp-uniform loads)
 #pragma unroll
             for (int j = 0; j < 4; ++j) nvs |= (unsigned)gi_nv(rm.info(r0 + 8 * j)) << (4 * j);
-            if (ch < C) {
-                uint4 *dz = reinterpret_cast<uint4 *>(z + (int64_t)ch * ld + r0);
-                uint4 *da = reinterpret_cast<uint4 *>(a + (int64_t)ch * ld + r0);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int nv = (int)((nvs >> (4 * j)) & 15u);
-                    float f[8], g[8];
+            for (int j = 0; j < 4; ++j) {
+                const int nv = (int)((nvs >> (4 * j)) & 15u);
+                float f[8], g[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = fmaf(v[8 * j + e], sc, sh);
-                    const uint4 zp = pack8(f);
-                    dz[j] = zp;
-                    unpack8(zp, f);  // the activation is defined on the STORED (bf16) zhat, as backward recomputes it
+                for (int e = 0; e < 8; ++e) f[e] = fmaf(v[8 * j + e], sc, sh);
+                const uint4 zp = pack8(f);
+                unpack8(zp, f);  // the activation is defined on the STORED (bf16) zhat, as backward recomputes it
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        float y = fmaf(f[e], ga, be);
-                        if (act == B2PN_ACT_RELU) y = fmaxf(y, 0.f);
-                        g[e] = e < nv ? y : 0.f;
-                    }
-                    da[j] = pack8(g);
+                for (int e = 0; e < 8; ++e) {
+                    float y = fmaf(f[e], ga, be);
+                    if (act == B2PN_ACT_RELU) y = fmaxf(y, 0.f);
+                    g[e] = e < nv ? y : 0.f;
                 }
+                const int gidx = (cc - half * 2) * 4 + j;  // 16-byte chunk of my 128-byte line (64 rows of this half)
+                stage_chunk(zt, lane, gidx, zp);
+                stage_chunk(at, lane, gidx, pack8(g));
             }
         }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {  // channels past C are clipped by the tensor map
+            const int x = (int)(tile * R + half * 64), y = ch;  // lane 0's channel = first of the warp's 32
+            tma_store_2d(cx.m0, zt, x, y);
+            tma_store_2d(cx.m1, at, x, y);
+            bulk_commit_group();
+        }
     }
-    __device__ __forceinline__ void finish_mt(int ch, int mt, int half) {}
+    __device__ __forceinline__ void finish_mt(int ch, int mt, int half)
+    {
+        if ((threadIdx.x & 31) == 0) bulk_wait_all();
+    }
 };
 
 struct SlotMaxEpTC {  // out[m][ch] = max over the valid rows of centroid m, arg = first max SLOT (compacted rows:
                       // a centroid is a run of 8-row groups that never crosses a 64-row boundary)
+    static constexpr bool STAGED = false;
     float *out;  // [n_dst][C] fp32 row-major
     int32_t *arg;
     int C;
@@ -520,7 +558,7 @@ struct SlotMaxEpTC {  // out[m][ch] = max over the valid rows of centroid m, arg
     int64_t rows;
     __device__ __forceinline__ void resolve(int64_t r) { rows = r; }
     __device__ __forceinline__ void begin() {}
-    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half)
+    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half, const EpCtx &cx)
     {
         const float b = ch < C ? bias[ch] : 0.f;
         float best = -INFINITY;
@@ -566,6 +604,7 @@ __device__ __forceinline__ unsigned f32_orderable_tc(float f)
 }
 
 struct CloudMaxEpTC {  // global_max_pool over sorted cloud ids: 64-bit atomicMax keys, unpacked by a tiny kernel
+    static constexpr bool STAGED = false;
     unsigned long long *keys;  // [n_dst][C], zero-initialised
     int C;
     const float *bias;
@@ -573,7 +612,7 @@ struct CloudMaxEpTC {  // global_max_pool over sorted cloud ids: 64-bit atomicMa
     int64_t rows;
     __device__ __forceinline__ void resolve(int64_t) {}
     __device__ __forceinline__ void begin() {}
-    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half)
+    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half, const EpCtx &cx)
     {
         const float b = ch < C ? bias[ch] : 0.f;
         int64_t curseg = -1;
@@ -608,60 +647,83 @@ struct CloudMaxEpTC {  // global_max_pool over sorted cloud ids: 64-bit atomicMa
 template <int MT>
 struct MaskSumsStoreEpTC {  // backward through activation + sums for the BatchNorm backward (thread = channel of the
                             // layer being differentiated through): dz = da * [z > 0];  S1 = sum dz, S2 = sum dz * zhat
-    __nv_bfloat16 *dz;       // [C][ld] out
-    const __nv_bfloat16 *z;  // [C][ld] saved normalised value zhat of that layer
+    static constexpr bool STAGED = true;
+    // zhat arrives and dz leaves through the warp's staging tiles: one TMA load (prefetched a tile ahead) and one TMA
+    // store per warp and tile instead of 16 global accesses per thread, 2*ld bytes apart per lane
     int C;
-    int64_t ld;
     const float *gamma;
     const float *beta;
     int act;
     double *partial;
     int cpad;
     double S[MT], Q[MT];
+    unsigned phase;
+    bool primed;
     __device__ __forceinline__ void resolve(int64_t) {}
     __device__ __forceinline__ void begin()
     {
 #pragma unroll
         for (int i = 0; i < MT; ++i) S[i] = Q[i] = 0.0;
+        phase = 0u;
+        primed = false;
     }
-    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half)
+    static __device__ __forceinline__ void fetch_z(const EpCtx &cx, uint8_t *zt, int64_t tile, int ch0, int half)
     {
+        mbar_arrive_expect_tx(cx.bar, 32 * LINE_BYTES);
+        tma_load_2d(zt, cx.m1, (int)(tile * R + half * 64), ch0, cx.bar);
+    }
+    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half, const EpCtx &cx)
+    {
+        const int lane = threadIdx.x & 31;
+        uint8_t *dt = cx.stage, *zt = cx.stage + 32 * LINE_BYTES;
+        if (!primed) {  // first tile of this warp: nothing was prefetched yet
+            if (lane == 0) fetch_z(cx, zt, tile, ch, half);
+            primed = true;
+        }
         float be = 0.f, ga = 0.f;
         if (ch < C) {
             be = beta[ch];
             ga = gamma[ch];
         }
+        if (lane == 0) bulk_wait_read_all();  // my previous dz store has read its staging tile
+        __syncwarp();
+        mbar_wait(cx.bar, phase);  // zhat tile landed
+        phase ^= 1u;
         float s = 0.f, q = 0.f;
 #pragma unroll 1
         for (int cc = half * 2; cc < half * 2 + 2; ++cc) {
             float v[32];
             tmem_ld32(taddr + cc * 32, v);
-            if (ch < C) {
-                const int64_t off = (int64_t)ch * ld + tile * R + cc * 32;
-                const uint4 *zs = reinterpret_cast<const uint4 *>(z + off);
-                uint4 *dst = reinterpret_cast<uint4 *>(dz + off);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float zf[8], o[8];
-                    unpack8(__ldg(zs + j), zf);
+            for (int j = 0; j < 4; ++j) {
+                const int gidx = (cc - half * 2) * 4 + j;
+                float zf[8], o[8];
+                unpack8(unstage_chunk(zt, lane, gidx), zf);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float da = v[8 * j + e];
-                        const bool pass = da != 0.f && (act != B2PN_ACT_RELU || fmaf(zf[e], ga, be) > 0.f);
-                        const float g = pass ? da : 0.f;
-                        s += g;
-                        q += pass ? g * zf[e] : 0.f;
-                        o[e] = g;
-                    }
-                    dst[j] = pack8(o);
+                for (int e = 0; e < 8; ++e) {
+                    const float da = v[8 * j + e];
+                    const bool pass = ch < C && da != 0.f && (act != B2PN_ACT_RELU || fmaf(zf[e], ga, be) > 0.f);
+                    const float g = pass ? da : 0.f;
+                    s += g;
+                    q += pass ? g * zf[e] : 0.f;
+                    o[e] = g;
                 }
+                stage_chunk(dt, lane, gidx, pack8(o));
             }
         }
         S[mt] += (double)s;
         Q[mt] += (double)q;
+        fence_proxy_async_smem();
+        __syncwarp();  // everybody has read zt and written dt
+        if (lane == 0) {
+            tma_store_2d(cx.m0, dt, (int)(tile * R + half * 64), ch);
+            bulk_commit_group();
+            if (cx.next_tile >= 0) fetch_z(cx, zt, cx.next_tile, cx.next_ch, half);
+        }
     }
     __device__ __forceinline__ void finish_mt(int ch, int mt, int half)
     {
+        if ((threadIdx.x & 31) == 0) bulk_wait_all();
         if (ch < C) {
             double *pt = partial + ((int64_t)blockIdx.x * 2 + half) * 2 * cpad;
             pt[ch] = S[mt];
@@ -671,12 +733,13 @@ struct MaskSumsStoreEpTC {  // backward through activation + sums for the BatchN
 };
 
 struct ScatterEpTC {  // gradient w.r.t. the gathered source features (thread = feature channel)
+    static constexpr bool STAGED = false;
     RowMapTC rm;
     float *dx;  // [n_src][C] fp32, zero-initialised by the caller in SLOTS mode
     int C;
     __device__ __forceinline__ void resolve(int64_t rows) { rm.rows = rows; }
     __device__ __forceinline__ void begin() {}
-    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half)
+    __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half, const EpCtx &cx)
     {
 #pragma unroll 1
         for (int cc = half * 2; cc < half * 2 + 2; ++cc) {
@@ -704,26 +767,32 @@ struct ScatterEpTC {  // gradient w.r.t. the gathered source features (thread = 
 // =================================================================================================
 //  The rows GEMM kernel:  D^T[channel, row] = A[channel, k] * B[k, row]
 // =================================================================================================
-template <int MT>
+template <int MT, bool STAGED>
 struct SmemPlan {
     static constexpr int A_BYTES = MT * 128 * LINE_BYTES;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = MT == 1 ? 5 : 4;
-    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    // the epilogue staging tiles (8 warps x 8 KB) come out of the operand ring: one stage less
+    static constexpr int STAGES = (MT == 1 ? 5 : 4) - (STAGED ? 1 : 0);
+    static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
+    static constexpr int EPI_BYTES = STAGED ? (NUM_EPI / 32) * EPI_STAGE_PER_WARP : 0;
+    static constexpr int BAR_OFF = EPI_OFF + EPI_BYTES;
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + alignment slack
 };
 
 template <int MT, class BL, class EP>
-__global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp, BL bl, EP ep, const __grid_constant__ TmaMap tmap)
+__global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp, BL bl, EP ep, const __grid_constant__ TmaMap tmap,
+                                                              const __grid_constant__ TmaMap tmap_e0,
+                                                              const __grid_constant__ TmaMap tmap_e1)
 {
-    using P = SmemPlan<MT>;
+    using P = SmemPlan<MT, EP::STAGED>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + P::BAR_OFF);
     uint64_t *empty = full + P::STAGES;
     uint64_t *tfull = empty + P::STAGES;
     uint64_t *tempty = tfull + 2;
-    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(tempty + 2);
+    uint64_t *ebar = tempty + 2;  // one per epilogue warp
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(ebar + NUM_EPI / 32);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int mg = blockIdx.y;
@@ -742,6 +811,7 @@ __global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp
             mbar_init(&tfull[a], 1);
             mbar_init(&tempty[a], NUM_EPI);
         }
+        for (int w = 0; w < NUM_EPI / 32; ++w) mbar_init(&ebar[w], 1);
         fence_barrier_init();
     }
     if (warp == MMA_WARP) tmem_alloc<TCOLS>(tmem_holder);
@@ -819,6 +889,11 @@ __global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp
         const int half = warp >> 2;
         const int chl = tid & 127;
         const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
+        EpCtx cx;
+        cx.stage = smem + P::EPI_OFF + warp * EPI_STAGE_PER_WARP;
+        cx.m0 = &tmap_e0;
+        cx.m1 = &tmap_e1;
+        cx.bar = &ebar[warp];
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
             const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
             mbar_wait(&tfull[acc], aph);
@@ -826,7 +901,14 @@ __global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 const int ch = (mg * MT + mt) * 128 + chl;
-                ep.tile_mt(tmem_base + lane_base + acc * (MT * R) + mt * R, tile, ch, mt, half);
+                if (mt + 1 < MT) {
+                    cx.next_tile = tile;
+                    cx.next_ch = ch + 128;
+                } else {
+                    cx.next_tile = tile + gridDim.x < num_tiles ? tile + gridDim.x : -1;
+                    cx.next_ch = mg * MT * 128 + chl;
+                }
+                ep.tile_mt(tmem_base + lane_base + acc * (MT * R) + mt * R, tile, ch, mt, half, cx);
             }
             tc_fence_before();
             mbar_arrive(&tempty[acc]);
@@ -1161,15 +1243,15 @@ static const TmaMap kNoMap = {};
 
 template <int MT, class BL, class EP>
 static int launch_gemm(const Packed &pk, const RowsArg &ra, const BL &bl, const EP &ep, cudaStream_t st,
-                       const TmaMap &map = kNoMap)
+                       const TmaMap &map = kNoMap, const TmaMap &e0 = kNoMap, const TmaMap &e1 = kNoMap)
 {
-    using P = SmemPlan<MT>;
+    using P = SmemPlan<MT, EP::STAGED>;
     auto kern = tc_rows_gemm_kernel<MT, BL, EP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
     if (e != cudaSuccess) return (int)e;
     GemmParams gp = {pk.img, pk.num_kc, ra.cap, ra.dev};
     dim3 grid((unsigned)grid_x_for(pk, ra.tiles()), (unsigned)pk.num_mg);
-    kern<<<grid, NT, P::TOTAL, st>>>(gp, bl, ep, map);
+    kern<<<grid, NT, P::TOTAL, st>>>(gp, bl, ep, map, e0, e1);
     note_launch();
     e = cudaPeekAtLastError();
     return e == cudaSuccess ? 0 : (int)e;
@@ -1177,9 +1259,9 @@ static int launch_gemm(const Packed &pk, const RowsArg &ra, const BL &bl, const 
 
 template <class BL, class EP1, class EP2>
 static int launch_by_mt(const Packed &pk, const RowsArg &ra, const BL &bl, const EP1 &e1, const EP2 &e2, cudaStream_t st,
-                        const TmaMap &map = kNoMap)
+                        const TmaMap &map = kNoMap, const TmaMap &m0 = kNoMap, const TmaMap &m1 = kNoMap)
 {
-    return pk.MT == 1 ? launch_gemm<1>(pk, ra, bl, e1, st, map) : launch_gemm<2>(pk, ra, bl, e2, st, map);
+    return pk.MT == 1 ? launch_gemm<1>(pk, ra, bl, e1, st, map, m0, m1) : launch_gemm<2>(pk, ra, bl, e2, st, map, m0, m1);
 }
 
 __global__ void count_valid_tc_kernel(const int32_t *cnt, int64_t n, double fixed, double *out)
@@ -1641,9 +1723,11 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
                                                                  a.mlp.momentum, bn1, s.cmax);
     note_launch();
     if (s.rows > 0) {
-        NormStoreEpTC e = {z1, (__nv_bfloat16 *)a.a1, s.c1, s.ld, a.mlp.b[0], bn1, bn1 + s.cmax, a.mlp.gamma[0], a.mlp.beta[0],
-                           a.mlp.act, rm};
-        if ((rc = launch_by_mt(f.pk[0], ra, gl, e, e, st))) return rc;
+        NormStoreEpTC e = {s.c1, a.mlp.b[0], bn1, bn1 + s.cmax, a.mlp.gamma[0], a.mlp.beta[0], a.mlp.act, rm};
+        TmaMap mz, ma;  // 32-channel boxes: one per epilogue warp
+        if ((rc = make_tma_feature_major(&mz, z1, s.c1, s.ld, 32))) return rc;
+        if ((rc = make_tma_feature_major(&ma, a.a1, s.c1, s.ld, 32))) return rc;
+        if ((rc = launch_by_mt(f.pk[0], ra, gl, e, e, st, kNoMap, mz, ma))) return rc;
     }
     // ---- layer 2
     // layers 2 and 3 read the stored activations a1 / a2 through the TMA unit (no loader arithmetic)
@@ -1662,9 +1746,11 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
                                                                  a.mlp.momentum, bn2, s.cmax);
     note_launch();
     if (s.rows > 0) {
-        NormStoreEpTC e = {z2, (__nv_bfloat16 *)a.a2, s.c2, s.ld, a.mlp.b[1], bn2, bn2 + s.cmax, a.mlp.gamma[1], a.mlp.beta[1],
-                           a.mlp.act, rm};
-        if ((rc = launch_by_mt(f.pk[1], ra, l2, e, e, st, map_a1))) return rc;
+        NormStoreEpTC e = {s.c2, a.mlp.b[1], bn2, bn2 + s.cmax, a.mlp.gamma[1], a.mlp.beta[1], a.mlp.act, rm};
+        TmaMap mz, ma;
+        if ((rc = make_tma_feature_major(&mz, z2, s.c2, s.ld, 32))) return rc;
+        if ((rc = make_tma_feature_major(&ma, a.a2, s.c2, s.ld, 32))) return rc;
+        if ((rc = launch_by_mt(f.pk[1], ra, l2, e, e, st, map_a1, mz, ma))) return rc;
     }
     // ---- layer 3 + max aggregation
     if (a.seg_mode == B2PN_SEG_SLOTS) {
@@ -1752,8 +1838,11 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
     note_launch();
 
     // ---- layer 3 ---------------------------------------------------------------------------------------
-    MaskSumsStoreEpTC<1> e31 = {b.dz2, z2, s.c2, s.ld, a.mlp.gamma[1], a.mlp.beta[1], a.mlp.act, b.partial, s.cpad};
-    MaskSumsStoreEpTC<2> e32 = {b.dz2, z2, s.c2, s.ld, a.mlp.gamma[1], a.mlp.beta[1], a.mlp.act, b.partial, s.cpad};
+    MaskSumsStoreEpTC<1> e31 = {s.c2, a.mlp.gamma[1], a.mlp.beta[1], a.mlp.act, b.partial, s.cpad};
+    MaskSumsStoreEpTC<2> e32 = {s.c2, a.mlp.gamma[1], a.mlp.beta[1], a.mlp.act, b.partial, s.cpad};
+    TmaMap mdz2, mz2;  // epilogue maps (32-channel boxes): dz2 out, zhat2 in
+    if ((rc = make_tma_feature_major(&mdz2, b.dz2, s.c2, s.ld, 32))) return rc;
+    if ((rc = make_tma_feature_major(&mz2, z2, s.c2, s.ld, 32))) return rc;
     LineFillK<FeatSource<1>> xa2 = {{rm, z2, s.c2, s.ld, a.mlp.act, s.c2, a.mlp.gamma[1], a.mlp.beta[1]}};
     // X sides through TMA: stored activations + the row-valid "ones" line (64-channel boxes, so c % 64 == 0)
     TmaMap map_v = kNoMap, map_a1 = kNoMap, map_a2 = kNoMap;
@@ -1771,7 +1860,7 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
         TmaMap map3;
         if ((rc = make_tma_feature_major(&map3, b.dh3, s.c3, s.ld))) return rc;
         TmaFeatLoader bl;
-        if ((rc = launch_by_mt(b.pkT[2], ra, bl, e31, e32, st, map3))) return rc;          // da2 = W3^T dh3
+        if ((rc = launch_by_mt(b.pkT[2], ra, bl, e31, e32, st, map3, mdz2, mz2))) return rc;          // da2 = W3^T dh3
         TmaSource y3 = {rm};
         if (tma_x2) {
             TmaFill xt = {s.c2};
@@ -1783,7 +1872,7 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
     } else {
         ArgGradSource y3 = {rm, g.grad_out, a.arg, s.c3};
         FeatLoaderTC<ArgGradSource> bl = {y3};
-        if ((rc = launch_by_mt(b.pkT[2], ra, bl, e31, e32, st))) return rc;
+        if ((rc = launch_by_mt(b.pkT[2], ra, bl, e31, e32, st, kNoMap, mdz2, mz2))) return rc;
         if ((rc = launch_dw(y3, xa2, s.c3, s.c2 + 1, s, ra, b.dwp, st))) return rc;
     }
     launch_dw_reduce(b.dwp, s.c3, s.c2 + 1, nullptr, s.c2, s.c2, s, g.grad_w[2], g.grad_b[2], st);
@@ -1802,9 +1891,12 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
     TmaSource y2 = {rm};
     {
         TmaFeatLoader bl;
-        MaskSumsStoreEpTC<1> e1 = {b.dz1, z1, s.c1, s.ld, a.mlp.gamma[0], a.mlp.beta[0], a.mlp.act, b.partial, s.cpad};
-        MaskSumsStoreEpTC<2> e2 = {b.dz1, z1, s.c1, s.ld, a.mlp.gamma[0], a.mlp.beta[0], a.mlp.act, b.partial, s.cpad};
-        if ((rc = launch_by_mt(b.pkT[1], ra, bl, e1, e2, st, map2))) return rc;
+        MaskSumsStoreEpTC<1> e1 = {s.c1, a.mlp.gamma[0], a.mlp.beta[0], a.mlp.act, b.partial, s.cpad};
+        MaskSumsStoreEpTC<2> e2 = {s.c1, a.mlp.gamma[0], a.mlp.beta[0], a.mlp.act, b.partial, s.cpad};
+        TmaMap mdz1, mz1;
+        if ((rc = make_tma_feature_major(&mdz1, b.dz1, s.c1, s.ld, 32))) return rc;
+        if ((rc = make_tma_feature_major(&mz1, z1, s.c1, s.ld, 32))) return rc;
+        if ((rc = launch_by_mt(b.pkT[1], ra, bl, e1, e2, st, map2, mdz1, mz1))) return rc;
         if (tma_x1) {
             TmaFill xt = {s.c1};
             rc = launch_dw(y2, xt, s.c2, s.c1 + 1, s, ra, b.dwp, st, map2, map_a1, map_v);

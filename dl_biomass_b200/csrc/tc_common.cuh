@@ -88,8 +88,18 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const TmaMap *map, i
         "l"(map), "r"(x_inner), "r"(y_outer), "r"(smem_u32(bar))
         : "memory");
 }
-// host: encode a map over a feature-major bf16 tensor (sa_tc.cu); returns 0 or a B2PN_E* / cudaError_t code
-int make_tma_feature_major(TmaMap *out, const void *base, int64_t channels, int64_t ld);
+// shared -> global tile store through the same kind of map (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const TmaMap *map, const void *smem_src, int x_inner, int y_outer)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(smem_src)),
+                 "r"(x_inner), "r"(y_outer)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// host: encode a map over a feature-major bf16 tensor (sa_tc.cu); box = 64 rows x box_channels; returns 0 or an error code
+int make_tma_feature_major(TmaMap *out, const void *base, int64_t channels, int64_t ld, int box_channels = 64);
 
 // ---- TMEM --------------------------------------------------------------------------------------------
 template <int NCOLS>
