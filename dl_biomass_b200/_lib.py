@@ -33,7 +33,7 @@ class SaArgs(ctypes.Structure):
                 ("pos_dst", _vp), ("nbr", _vp), ("cnt", _vp), ("batch", _vp), ("mlp", Mlp3), ("out", _vp),
                 ("arg", _vp), ("h1", _vp), ("h2", _vp), ("bn", _vp), ("workspace", _vp),
                 ("workspace_bytes", ctypes.c_int64), ("rgrp", _vp), ("row_src", _vp), ("num_rows", _vp),
-                ("row_capacity", ctypes.c_int64), ("row_valid", _vp), ("a1", _vp), ("a2", _vp)]
+                ("row_capacity", ctypes.c_int64), ("row_valid", _vp), ("a1", _vp), ("a2", _vp), ("g1", _vp)]
 
 
 class SaGrads(ctypes.Structure):

@@ -222,6 +222,38 @@ struct GatherLoaderTC {  // K-major B: line = row of the tile, 64 k per line
     static __device__ __forceinline__ uint64_t b_desc(uint32_t b_saddr, int ks) { return smem_desc_sw128(b_saddr + ks * 32, 16, ATOM_BYTES); }
 };
 
+// Layer-1 operand materialised once: G[k][row] (bf16, feature-major) = image column k of the gathered + concatenated
+// row ([x | x_lo | dpos_hi | dpos_lo | 1]), so that the statistics pass, the normalising pass and the dW1 GEMM all
+// read it through TMA instead of gathering three times in their loader warps.  A block transposes 64 rows through
+// shared memory: rows are gathered with 16-byte loads where the features allow it, columns leave as 128-byte lines.
+constexpr int GATHER_ROWS = 64;
+__global__ void __launch_bounds__(256) gather_l1_tc_kernel(GatherLoaderTC gl, const int64_t *rows_dev, int kg, int64_t ld,
+                                                          __nv_bfloat16 *G)
+{
+    extern __shared__ __align__(16) unsigned char gth_smem[];
+    __nv_bfloat16 *S = reinterpret_cast<__nv_bfloat16 *>(gth_smem);  // [kg8][64 rows]
+    const int64_t rows = rows_dev ? *rows_dev : gl.rm.rows;
+    gl.resolve(rows);
+    const int64_t r0 = (int64_t)blockIdx.x * GATHER_ROWS;
+    if (r0 >= (rows + 127) / 128 * 128) return;  // whole tiles, like every consumer
+    const int kg8 = (kg + 7) & ~7;
+    const int rl = threadIdx.x & 63, q = threadIdx.x >> 6;  // my row of the block, my chunk phase (0..3)
+    gl.set_row(r0 + rl);
+    for (int kk = q * 8; kk < kg8; kk += 32) {
+        const uint4 v = gl.chunk(kk);
+        const __nv_bfloat16 *e = reinterpret_cast<const __nv_bfloat16 *>(&v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) S[(kk + j) * GATHER_ROWS + rl] = e[j];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kg8 * 8; i += 256) {  // 8 chunks of 16 bytes per column line
+        const int k = i >> 3, part = i & 7;
+        if (k < kg)
+            *reinterpret_cast<uint4 *>(G + (int64_t)k * ld + r0 + part * 8) =
+                *reinterpret_cast<const uint4 *>(S + k * GATHER_ROWS + part * 8);
+    }
+}
+
 __device__ __forceinline__ void unpack8(const uint4 &raw, float (&f)[8])
 {
     f[0] = bf16_lo(raw.x); f[1] = bf16_hi(raw.x); f[2] = bf16_lo(raw.y); f[3] = bf16_hi(raw.y);
@@ -962,15 +994,17 @@ struct LineFillK {  // K-major X side from a feature-major source
 struct TmaFill {
     static constexpr bool B_MN = false;
     static constexpr bool USES_TMA = true;
-    int c;  // channels of a (multiple of 64, c + 16 <= 256)
+    int c;         // channels of the tensor; with the ones box: a multiple of 64, c + 16 <= 256
+    int ones_box;  // 1: append the row-valid box at line c; 0: the tensor carries its own ones line (layer-1 operand)
     static __host__ __device__ int bytes(int nb_lines) { return nb_lines * LINE_BYTES; }
     __device__ __forceinline__ void resolve(int64_t) {}
     __device__ __forceinline__ void fill(uint8_t *, int, int64_t, int, int, const unsigned (&)[8]) {}
     __device__ __forceinline__ void fill_tma(uint8_t *B, int64_t r0, const TmaMap *map_x, const TmaMap *map_v, uint64_t *bar) const
     {
-        mbar_expect_tx(bar, (unsigned)((c + 16) * LINE_BYTES));
-        for (int blk = 0; blk * 64 < c; ++blk) tma_load_2d(B + blk * (64 * LINE_BYTES), map_x, (int)r0, blk * 64, bar);
-        tma_load_2d(B + c * LINE_BYTES, map_v, (int)r0, 0, bar);
+        const int boxes = (c + 63) >> 6;
+        mbar_expect_tx(bar, (unsigned)((boxes * 64 + (ones_box ? 16 : 0)) * LINE_BYTES));
+        for (int blk = 0; blk < boxes; ++blk) tma_load_2d(B + blk * (64 * LINE_BYTES), map_x, (int)r0, blk * 64, bar);
+        if (ones_box) tma_load_2d(B + c * LINE_BYTES, map_v, (int)r0, 0, bar);
     }
     static __device__ __forceinline__ uint64_t b_desc(uint32_t b_saddr, int ks) { return smem_desc_sw128(b_saddr + ks * 32, 16, ATOM_BYTES); }
 };
@@ -1689,6 +1723,12 @@ int64_t sa_workspace_bytes_bf16(const b2pn_sa_args &a, int backward)
     return ws.off + 2048;
 }
 
+// layer-1 operand through the materialised tensor g1 (SLOTS levels whose image fits one dW N group)
+static bool l1_materialised(const b2pn_sa_args &a, const ShapesTC &s)
+{
+    return a.seg_mode == B2PN_SEG_SLOTS && a.g1 != nullptr && s.k1 + 1 + 15 <= 256;
+}
+
 int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
 {
     int rc = check_args_tc(a);
@@ -1712,10 +1752,22 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
 
     // ---- layer 1: gather + concat + Linear; pass A = batch statistics, pass B = normalise + store z1
     GatherLoaderTC gl = {rm, a.x, s.cols, a.pos_src, a.pos_dst, -1};
+    const bool use_g1 = l1_materialised(a, s);
+    TmaMap map_g1 = kNoMap;
+    TmaFeatLoader tl1;
+    if (use_g1 && s.rows > 0) {
+        GatherLoaderTC gg = {rm, a.x, s.cols, a.pos_src, a.pos_dst, s.k1};  // column k1 = ones (dW1 bias line)
+        const int kg = s.k1 + 1, kg8 = (kg + 7) & ~7;
+        gather_l1_tc_kernel<<<(unsigned)(s.ld / GATHER_ROWS), 256, kg8 * GATHER_ROWS * 2, st>>>(gg, ra.dev, kg, s.ld,
+                                                                                                 (__nv_bfloat16 *)a.g1);
+        note_launch();
+        if ((rc = make_tma_feature_major(&map_g1, a.g1, kg, s.ld))) return rc;
+    }
     if (train && s.rows > 0) {
         StatsEpTC<1> e1 = {s.c1, f.partial, s.cpad};
         StatsEpTC<2> e2 = {s.c1, f.partial, s.cpad};
-        if ((rc = launch_by_mt(f.pk[0], ra, gl, e1, e2, st))) return rc;
+        rc = use_g1 ? launch_by_mt(f.pk[0], ra, tl1, e1, e2, st, map_g1) : launch_by_mt(f.pk[0], ra, gl, e1, e2, st);
+        if (rc) return rc;
     }
     bn_fwd_finalize_tc_kernel<<<(s.c1 + 3) / 4, 128, 0, st>>>(f.partial, 2 * grid_x_for(f.pk[0], s.tiles), s.c1, s.cpad, f.count, train,
                                                                  a.mlp.b[0], a.mlp.gamma[0], a.mlp.beta[0], a.mlp.running_mean[0],
@@ -1727,7 +1779,8 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
         TmaMap mz, ma;  // 32-channel boxes: one per epilogue warp
         if ((rc = make_tma_feature_major(&mz, z1, s.c1, s.ld, 32))) return rc;
         if ((rc = make_tma_feature_major(&ma, a.a1, s.c1, s.ld, 32))) return rc;
-        if ((rc = launch_by_mt(f.pk[0], ra, gl, e, e, st, kNoMap, mz, ma))) return rc;
+        rc = use_g1 ? launch_by_mt(f.pk[0], ra, tl1, e, e, st, map_g1, mz, ma) : launch_by_mt(f.pk[0], ra, gl, e, e, st, kNoMap, mz, ma);
+        if (rc) return rc;
     }
     // ---- layer 2
     // layers 2 and 3 read the stored activations a1 / a2 through the TMA unit (no loader arithmetic)
@@ -1863,7 +1916,7 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
         if ((rc = launch_by_mt(b.pkT[2], ra, bl, e31, e32, st, map3, mdz2, mz2))) return rc;          // da2 = W3^T dh3
         TmaSource y3 = {rm};
         if (tma_x2) {
-            TmaFill xt = {s.c2};
+            TmaFill xt = {s.c2, 1};
             rc = launch_dw(y3, xt, s.c3, s.c2 + 1, s, ra, b.dwp, st, map3, map_a2, map_v);   // dW3 = dh3^T a2
         } else {
             rc = launch_dw(y3, xa2, s.c3, s.c2 + 1, s, ra, b.dwp, st, map3);
@@ -1898,7 +1951,7 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
         if ((rc = make_tma_feature_major(&mz1, z1, s.c1, s.ld, 32))) return rc;
         if ((rc = launch_by_mt(b.pkT[1], ra, bl, e1, e2, st, map2, mdz1, mz1))) return rc;
         if (tma_x1) {
-            TmaFill xt = {s.c1};
+            TmaFill xt = {s.c1, 1};
             rc = launch_dw(y2, xt, s.c2, s.c1 + 1, s, ra, b.dwp, st, map2, map_a1, map_v);
         } else {
             LineFillK<FeatSource<1>> xa1 = {{rm, z1, s.c1, s.ld, a.mlp.act, s.c1, a.mlp.gamma[0], a.mlp.beta[0]}};
@@ -1917,8 +1970,16 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
     // ---- layer 1 ---------------------------------------------------------------------------------------
     TmaSource y1 = {rm};
     {
-        LineFillGather xg = {{rm, a.x, s.cols, a.pos_src, a.pos_dst, s.k1}};
-        if ((rc = launch_dw(y1, xg, s.c1, s.k1 + 1, s, ra, b.dwp, st, map1))) return rc;
+        if (l1_materialised(a, s)) {
+            TmaMap map_g1;
+            if ((rc = make_tma_feature_major(&map_g1, a.g1, s.k1 + 1, s.ld))) return rc;
+            TmaFill xt = {s.k1 + 1, 0};
+            rc = launch_dw(y1, xt, s.c1, s.k1 + 1, s, ra, b.dwp, st, map1, map_g1, kNoMap);
+        } else {
+            LineFillGather xg = {{rm, a.x, s.cols, a.pos_src, a.pos_dst, s.k1}};
+            rc = launch_dw(y1, xg, s.c1, s.k1 + 1, s, ra, b.dwp, st, map1);
+        }
+        if (rc) return rc;
         launch_dw_reduce(b.dwp, s.c1, s.k1 + 1, &s.cols, s.c0, s.k1, s, g.grad_w[0], g.grad_b[0], st);
     }
     if (need_dx) {

@@ -63,6 +63,7 @@ def _fill_args(a: SaArgs, *, precision, training, seg_mode, K, n_src, n_dst, c_i
         a.row_valid = _dp(row_valid)
     if acts is not None:
         a.a1, a.a2 = _dp(acts[0]), _dp(acts[1])
+        a.g1 = _dp(acts[2]) if len(acts) > 2 else None
 
 
 def pack_rows(nbr: torch.Tensor, cnt: torch.Tensor, K: int):
@@ -131,7 +132,11 @@ class _SAFunction(torch.autograd.Function):
             ld = (rows + 127) // 128 * 128
             h1 = torch.empty(chans[1], ld, dtype=torch.bfloat16, device=dev)
             h2 = torch.empty(chans[2], ld, dtype=torch.bfloat16, device=dev)
-            acts = (torch.empty_like(h1), torch.empty_like(h2))  # post-activation copies (TMA operands)
+            acts = [torch.empty_like(h1), torch.empty_like(h2)]  # post-activation copies (TMA operands)
+            k_img = (2 * c_in if split else c_in) + 6
+            if seg_mode == SEG_SLOTS and k_img + 16 <= 256:   # gathered layer-1 operand incl. its ones line
+                acts.append(torch.empty(k_img + 1, ld, dtype=torch.bfloat16, device=dev))
+            acts = tuple(acts)
         cmax = max(chans[1], chans[2])
         bn = torch.empty(2, 4, cmax, dtype=f32, device=dev)
         a = SaArgs()
@@ -155,7 +160,7 @@ class _SAFunction(torch.autograd.Function):
         ctx.x_needs_grad = x is not None and x.requires_grad
         ctx.row_capacity = None if rowmap is None else rowmap[3]
         rmt = (None, None, None, None) if rowmap is None else (rowmap[0], rowmap[1], rowmap[2], rowmap[4])
-        at = (None, None) if acts is None else acts
+        at = (None, None, None) if acts is None else (acts + (None,))[:3]
         ctx.save_for_backward(xs, pos_src, pos_dst, nbr, cnt, batch, *ws, *bs, *gs, *bes, rm1, rv1, rm2, rv2,
                               arg, h1, h2, bn, *rmt, *at)
         ctx.mark_non_differentiable(arg)
@@ -166,9 +171,9 @@ class _SAFunction(torch.autograd.Function):
     def backward(ctx, grad_out, _grad_arg):
         lib = _lib.lib()
         (xs, pos_src, pos_dst, nbr, cnt, batch, w1, w2, w3, b1, b2, b3, g1, g2, be1, be2, rm1, rv1, rm2, rv2,
-         arg, h1, h2, bn, rgrp, row_src, num_rows, row_valid, a1, a2) = ctx.saved_tensors
+         arg, h1, h2, bn, rgrp, row_src, num_rows, row_valid, a1, a2, l1op) = ctx.saved_tensors
         rowmap = None if rgrp is None else (rgrp, row_src, num_rows, ctx.row_capacity, row_valid)
-        acts = None if a1 is None else (a1, a2)
+        acts = None if a1 is None else ((a1, a2) if l1op is None else (a1, a2, l1op))
         prec, training, seg_mode, K, n_dst, act, eps, momentum = ctx.cfg
         dev = pos_src.device
         chans = ctx.chans

@@ -169,6 +169,10 @@ typedef struct b2pn_sa_args {
      * [c, ld] like h1/h2, invalid rows zero.  Written by forward, read by backward: stored next to the
      * normalised values so that every later consumer is a plain tensor-map (TMA) copy.                  */
     void *a1, *a2;
+    /* PREC_BF16 + SEG_SLOTS, optional (NULL = gather in the loader warps): the gathered + concatenated layer-1
+     * operand, bf16 feature-major [c_img + 1, ld] with c_img = (x fp32 ? 2 : 1) * c_in + 6 image columns
+     * [x | x_lo | dpos_hi | dpos_lo] and a last line of ones on valid rows.  Written by forward, read by backward. */
+    void *g1;
 } b2pn_sa_args;
 
 typedef struct b2pn_sa_grads {
