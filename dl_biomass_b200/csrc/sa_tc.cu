@@ -317,46 +317,6 @@ struct FeatSource {
     }
 };
 
-// routed gradient of the max aggregation, dh3^T[ch][row] = dout[seg][ch] if arg[seg][ch] names this row
-struct ArgGradSource {
-    static constexpr bool USES_TMA = false;
-    RowMapTC rm;
-    const float *dout;
-    const int32_t *arg;  // SLOTS: arg-max SLOT of the centroid; CLOUDS: arg-max source row
-    int C;
-    __device__ __forceinline__ void resolve(int64_t r) { rm.resolve(r); }
-    __device__ __forceinline__ uint4 chunk_i(int ch, int64_t r8, unsigned inf) const
-    {
-        if (ch >= C || gi_nv(inf) == 0) return make_uint4(0u, 0u, 0u, 0u);
-        float f[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = 0.f;
-        if (!rm.seg_mode) {
-            const int64_t m = gi_seg(inf);
-            const int a = __ldg(arg + m * C + ch) - gi_slot0(inf);
-            if (a < 0 || a >= 8) return make_uint4(0u, 0u, 0u, 0u);
-            const float g = __ldg(dout + m * C + ch);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = e == a ? g : 0.f;
-        } else {
-            bool any = false;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int64_t row = r8 + e;
-                if (row < rm.rows) {
-                    const int64_t sg = rm.batch[row];
-                    if ((int64_t)arg[sg * C + ch] == row) {
-                        f[e] = dout[sg * C + ch];
-                        any = true;
-                    }
-                }
-            }
-            if (!any) return make_uint4(0u, 0u, 0u, 0u);
-        }
-        return pack8(f);
-    }
-};
-
 // Y side of the dW GEMM fetched by TMA (a stored feature-major tensor whose invalid rows are already zero, e.g. dh after
 // the BatchNorm-backward pass): the kernel issues the tensor-map copies itself, this only carries the row structure.
 struct TmaSource {
@@ -994,17 +954,22 @@ struct LineFillK {  // K-major X side from a feature-major source
 struct TmaFill {
     static constexpr bool B_MN = false;
     static constexpr bool USES_TMA = true;
-    int c;         // channels of the tensor; with the ones box: a multiple of 64, c + 16 <= 256
+    int c;         // channels of the tensor; with the ones box: a multiple of 64 with (c % 256) + 16 <= 256
     int ones_box;  // 1: append the row-valid box at line c; 0: the tensor carries its own ones line (layer-1 operand)
     static __host__ __device__ int bytes(int nb_lines) { return nb_lines * LINE_BYTES; }
     __device__ __forceinline__ void resolve(int64_t) {}
     __device__ __forceinline__ void fill(uint8_t *, int, int64_t, int, int, const unsigned (&)[8]) {}
-    __device__ __forceinline__ void fill_tma(uint8_t *B, int64_t r0, const TmaMap *map_x, const TmaMap *map_v, uint64_t *bar) const
+    // N group ng covers lines [256 ng, 256 ng + 256) of [tensor channels | ones line | zero padding]
+    __device__ __forceinline__ void fill_tma(uint8_t *B, int64_t r0, int ng, const TmaMap *map_x, const TmaMap *map_v,
+                                             uint64_t *bar) const
     {
-        const int boxes = (c + 63) >> 6;
-        mbar_expect_tx(bar, (unsigned)((boxes * 64 + (ones_box ? 16 : 0)) * LINE_BYTES));
-        for (int blk = 0; blk < boxes; ++blk) tma_load_2d(B + blk * (64 * LINE_BYTES), map_x, (int)r0, blk * 64, bar);
-        if (ones_box) tma_load_2d(B + c * LINE_BYTES, map_v, (int)r0, 0, bar);
+        const int ch0 = ng * 256;
+        const int left = c - ch0;
+        const int boxes = left <= 0 ? 0 : ((left < 256 ? left : 256) + 63) >> 6;
+        const bool ones_here = ones_box && c >= ch0 && c < ch0 + 256;
+        mbar_expect_tx(bar, (unsigned)((boxes * 64 + (ones_here ? 16 : 0)) * LINE_BYTES));
+        for (int blk = 0; blk < boxes; ++blk) tma_load_2d(B + blk * (64 * LINE_BYTES), map_x, (int)r0, ch0 + blk * 64, bar);
+        if (ones_here) tma_load_2d(B + (c - ch0) * LINE_BYTES, map_v, (int)r0, 0, bar);
     }
     static __device__ __forceinline__ uint64_t b_desc(uint32_t b_saddr, int ks) { return smem_desc_sw128(b_saddr + ks * 32, 16, ATOM_BYTES); }
 };
@@ -1118,7 +1083,7 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
                 }
             }
             if constexpr (XF::USES_TMA) {
-                if (lt == 0) xf.fill_tma(B, r0, &tmap_x, &tmap_v, &full[s]);
+                if (lt == 0) xf.fill_tma(B, r0, ng, &tmap_x, &tmap_v, &full[s]);
             } else {
                 xf.fill(B, lt, r0, ng, nb_lines, inf);
             }
@@ -1394,6 +1359,7 @@ __global__ void bn_bwd_finalize_tc_kernel(const double *partial, int gx, int C, 
 // Written once so that both consumers (dX of the last layer and dW3) take it through the TMA unit instead of
 // re-deriving it per (channel, row group) in their loader warps.  Thread = (channel, 8-row group), groups fastest:
 // 16-byte stores coalesce along the rows, the (arg, dout) reads stay L2-resident.
+template <bool CLOUDS>
 __global__ void route_grad_tc_kernel(RowMapTC rm, const int64_t *rows_dev, const float *dout, const int32_t *arg, int C, int64_t ld,
                                      __nv_bfloat16 *dh)
 {
@@ -1405,7 +1371,23 @@ __global__ void route_grad_tc_kernel(RowMapTC rm, const int64_t *rows_dev, const
         const int64_t g = i - (int64_t)ch * groups;
         const unsigned inf = rm.info(g * 8);
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (gi_nv(inf) > 0) {
+        if (CLOUDS) {  // arg names a source row of the cloud batch[row]
+            float f[8];
+            bool any = false;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int64_t row = g * 8 + e;
+                f[e] = 0.f;
+                if (e < gi_nv(inf)) {
+                    const int64_t sg = __ldg(rm.batch + row);
+                    if ((int64_t)__ldg(arg + sg * C + ch) == row) {
+                        f[e] = __ldg(dout + sg * C + ch);
+                        any = true;
+                    }
+                }
+            }
+            if (any) v = pack8(f);
+        } else if (gi_nv(inf) > 0) {
             const int64_t m = gi_seg(inf);
             const int a = __ldg(arg + m * C + ch) - gi_slot0(inf);
             if (a >= 0 && a < 8) {
@@ -1689,7 +1671,7 @@ struct BwdWsTC {
     double *count;
     double *partial;
     __nv_bfloat16 *dz1, *dz2;
-    __nv_bfloat16 *dh3;  // SLOTS: materialised routed gradient [c3][ld]
+    __nv_bfloat16 *dh3;  // materialised routed gradient [c3][ld]
     float *sbar;
     float *dwp;
 };
@@ -1704,7 +1686,7 @@ static BwdWsTC carve_bwd_tc(const b2pn_sa_args &a, const ShapesTC &s, WsTC &ws)
     b.partial = ws.take<double>((int64_t)MAX_GX * 2 * 2 * s.cpad);
     b.dz1 = ws.take<__nv_bfloat16>((int64_t)s.c1 * s.ld);
     b.dz2 = ws.take<__nv_bfloat16>((int64_t)s.c2 * s.ld);
-    b.dh3 = a.seg_mode == B2PN_SEG_SLOTS ? ws.take<__nv_bfloat16>((int64_t)s.c3 * s.ld) : nullptr;
+    b.dh3 = ws.take<__nv_bfloat16>((int64_t)s.c3 * s.ld);
     b.sbar = ws.take<float>(2 * s.cmax);
     int64_t mx = plan_dw(s.c3, s.c2 + 1, s.ld).floats;
     const int64_t m2 = plan_dw(s.c2, s.c1 + 1, s.ld).floats, m1 = plan_dw(s.c1, s.k1 + 1, s.ld).floats;
@@ -1899,16 +1881,19 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
     LineFillK<FeatSource<1>> xa2 = {{rm, z2, s.c2, s.ld, a.mlp.act, s.c2, a.mlp.gamma[1], a.mlp.beta[1]}};
     // X sides through TMA: stored activations + the row-valid "ones" line (64-channel boxes, so c % 64 == 0)
     TmaMap map_v = kNoMap, map_a1 = kNoMap, map_a2 = kNoMap;
-    const bool tma_x = a.seg_mode == B2PN_SEG_SLOTS && a.row_valid != nullptr;
-    const bool tma_x2 = tma_x && s.c2 % 64 == 0 && s.c2 + 16 <= 256, tma_x1 = tma_x && s.c1 % 64 == 0 && s.c1 + 16 <= 256;
+    const bool tma_x = a.row_valid != nullptr;
+    const bool tma_x2 = tma_x && s.c2 % 64 == 0 && (s.c2 % 256) + 16 <= 256, tma_x1 = tma_x && s.c1 % 64 == 0 && (s.c1 % 256) + 16 <= 256;
     if (tma_x2 || tma_x1) {
         if ((rc = make_tma_row_valid(&map_v, a.row_valid, s.ld))) return rc;
     }
     if (tma_x2 && (rc = make_tma_feature_major(&map_a2, a.a2, s.c2, s.ld))) return rc;
     if (tma_x1 && (rc = make_tma_feature_major(&map_a1, a.a1, s.c1, s.ld))) return rc;
-    if (a.seg_mode == B2PN_SEG_SLOTS) {
+    {
         // materialise dh3 once, then both consumers read it through TMA
-        route_grad_tc_kernel<<<apply_grid(s.ld, s.c3), 256, 0, st>>>(rm, ra.dev, g.grad_out, a.arg, s.c3, s.ld, b.dh3);
+        if (a.seg_mode == B2PN_SEG_CLOUDS)
+            route_grad_tc_kernel<true><<<apply_grid(s.ld, s.c3), 256, 0, st>>>(rm, ra.dev, g.grad_out, a.arg, s.c3, s.ld, b.dh3);
+        else
+            route_grad_tc_kernel<false><<<apply_grid(s.ld, s.c3), 256, 0, st>>>(rm, ra.dev, g.grad_out, a.arg, s.c3, s.ld, b.dh3);
         note_launch();
         TmaMap map3;
         if ((rc = make_tma_feature_major(&map3, b.dh3, s.c3, s.ld))) return rc;
@@ -1922,11 +1907,6 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
             rc = launch_dw(y3, xa2, s.c3, s.c2 + 1, s, ra, b.dwp, st, map3);
         }
         if (rc) return rc;
-    } else {
-        ArgGradSource y3 = {rm, g.grad_out, a.arg, s.c3};
-        FeatLoaderTC<ArgGradSource> bl = {y3};
-        if ((rc = launch_by_mt(b.pkT[2], ra, bl, e31, e32, st, kNoMap, mdz2, mz2))) return rc;
-        if ((rc = launch_dw(y3, xa2, s.c3, s.c2 + 1, s, ra, b.dwp, st))) return rc;
     }
     launch_dw_reduce(b.dwp, s.c3, s.c2 + 1, nullptr, s.c2, s.c2, s, g.grad_w[2], g.grad_b[2], st);
     bn_bwd_finalize_tc_kernel<<<(s.c2 + 3) / 4, 128, 0, st>>>(b.partial, 2 * grid_x_for(b.pkT[2], s.tiles), s.c2, s.cpad, b.count,

@@ -57,7 +57,9 @@ def _fill_args(a: SaArgs, *, precision, training, seg_mode, K, n_src, n_dst, c_i
         m.running_mean[i], m.running_var[i] = _dp(rmeans[i]), _dp(rvars[i])
         m.num_batches_tracked[i] = _dp(nbts[i])
     a.out, a.arg, a.h1, a.h2, a.bn = _dp(out), _dp(arg), _dp(h1), _dp(h2), _dp(bn)
-    if rowmap is not None:
+    if rowmap is not None and rowmap[0] is None:      # CLOUDS levels: only the row-valid vector
+        a.row_valid = _dp(rowmap[4])
+    elif rowmap is not None:
         rgrp, row_src, num_rows, cap, row_valid = rowmap
         a.rgrp, a.row_src, a.num_rows, a.row_capacity = _dp(rgrp), _dp(row_src), _dp(num_rows), cap
         a.row_valid = _dp(row_valid)
@@ -133,6 +135,10 @@ class _SAFunction(torch.autograd.Function):
             h1 = torch.empty(chans[1], ld, dtype=torch.bfloat16, device=dev)
             h2 = torch.empty(chans[2], ld, dtype=torch.bfloat16, device=dev)
             acts = [torch.empty_like(h1), torch.empty_like(h2)]  # post-activation copies (TMA operands)
+            if seg_mode == SEG_CLOUDS:   # the "ones" operand line of the dW GEMMs: 1 on every real row
+                rv = torch.zeros(ld, dtype=torch.bfloat16, device=dev)
+                rv[:n_src] = 1
+                rowmap = (None, None, None, 0, rv)
             k_img = (2 * c_in if split else c_in) + 6
             if seg_mode == SEG_SLOTS and k_img + 16 <= 256:   # gathered layer-1 operand incl. its ones line
                 acts.append(torch.empty(k_img + 1, ld, dtype=torch.bfloat16, device=dev))
@@ -172,7 +178,7 @@ class _SAFunction(torch.autograd.Function):
         lib = _lib.lib()
         (xs, pos_src, pos_dst, nbr, cnt, batch, w1, w2, w3, b1, b2, b3, g1, g2, be1, be2, rm1, rv1, rm2, rv2,
          arg, h1, h2, bn, rgrp, row_src, num_rows, row_valid, a1, a2, l1op) = ctx.saved_tensors
-        rowmap = None if rgrp is None else (rgrp, row_src, num_rows, ctx.row_capacity, row_valid)
+        rowmap = None if (rgrp is None and row_valid is None) else (rgrp, row_src, num_rows, ctx.row_capacity, row_valid)
         acts = None if a1 is None else ((a1, a2) if l1op is None else (a1, a2, l1op))
         prec, training, seg_mode, K, n_dst, act, eps, momentum = ctx.cfg
         dev = pos_src.device
