@@ -203,10 +203,10 @@ def run_b200(args):
     torch.manual_seed(7)
     net = Net(1, "ReLU", 0, 0.5, precision=precision).to(dev)
     net.train()
-    # one graph per step on a single GPU; with the NCCL all-reduce on its side stream (world > 1) the step is
-    # launched eagerly (capturing the bucketed all-reduce hung on the 2-GPU box in round 1)
-    use_graph = not args.no_graph and world == 1
-    opt = make_optimizer(net.parameters(), capturable=use_graph)
+    # one graph per step; with world > 1 the graph holds forward + backward and the NCCL all-reduce + Adam follow it
+    # eagerly (capturing the collective itself hung on the 2-GPU box in round 1)
+    use_graph = not args.no_graph
+    opt = make_optimizer(net.parameters(), capturable=use_graph and world == 1)
     reducer = GradReducer(net) if world > 1 else None
 
     pool_host = make_pool(args, rank, pin=True)

@@ -36,6 +36,9 @@ class GradReducer:
         # stream already shares the GPU with backward (train.PipelinedTrainStep): NCCL's CTAs would otherwise queue
         # behind the persistent kernels and the sampling kernels and stall both ranks.
         self.overlap = overlap
+        # inline=True (only with overlap=False): the all-reduce is issued on the CURRENT stream, no side stream and no
+        # events -- the form that can be captured into the step's CUDA graph.
+        self.inline = False
         self.world_size = dist.get_world_size(process_group)
         self.module = module
         named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
@@ -94,6 +97,11 @@ class GradReducer:
 
     def _launch(self, i: int) -> None:
         flat = self.flat[i]
+        if self.inline and self.comm_stream is not None:
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+            self.works[i] = True
+            self.done_events[i] = None
+            return
         if self.comm_stream is not None:
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream(self.device))
@@ -113,7 +121,8 @@ class GradReducer:
             if self.works[i] is None:  # a bucket none of whose parameters received a gradient
                 self._launch(i)
             if self.comm_stream is not None:
-                torch.cuda.current_stream(self.device).wait_event(self.done_events[i])
+                if self.done_events[i] is not None:
+                    torch.cuda.current_stream(self.device).wait_event(self.done_events[i])
             else:
                 self.works[i].wait()
                 self.flat[i].div_(self.world_size)

@@ -36,9 +36,8 @@ def make_optimizer(params, lr: float = ADAM_LR, weight_decay: float = ADAM_WEIGH
     return torch.optim.Adam(params, lr=lr, weight_decay=weight_decay, fused=fused, capturable=capturable and fused)
 
 
-def train_step(model, optimizer, batch, reducer=None, sampling=None, after_grouping=None) -> torch.Tensor:
-    """One iteration of main.py:150-172.  ``reducer`` is the data-parallel gradient reducer (parallel.py);
-    ``sampling`` an optional ``Net.sample(batch)`` computed ahead of time."""
+def forward_backward(model, optimizer, batch, reducer=None, sampling=None, after_grouping=None) -> torch.Tensor:
+    """zero_grad + forward + loss + backward of main.py:150-171 (everything of a step that involves no collective)."""
     optimizer.zero_grad(set_to_none=reducer is None)
     if reducer is not None:
         reducer.prepare()
@@ -48,10 +47,22 @@ def train_step(model, optimizer, batch, reducer=None, sampling=None, after_group
         outs = model(batch, sampling=sampling, after_grouping=after_grouping)
     loss = weighted_mse_loss(outs, batch.y)
     loss.backward()
+    return loss.detach()
+
+
+def reduce_and_update(optimizer, reducer=None) -> None:
+    """gradient all-reduce (data parallel) + optimizer.step() of main.py:172."""
     if reducer is not None:
         reducer.finish()
     optimizer.step()
-    return loss.detach()
+
+
+def train_step(model, optimizer, batch, reducer=None, sampling=None, after_grouping=None) -> torch.Tensor:
+    """One iteration of main.py:150-172.  ``reducer`` is the data-parallel gradient reducer (parallel.py);
+    ``sampling`` an optional ``Net.sample(batch)`` computed ahead of time."""
+    loss = forward_backward(model, optimizer, batch, reducer, sampling, after_grouping)
+    reduce_and_update(optimizer, reducer)
+    return loss
 
 
 class GraphedTrainStep:
@@ -130,8 +141,12 @@ class PipelinedTrainStep:
         sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
         ncl = len(self.sizes)
         self.sm_limit = sms - ncl if ncl * 4 <= sms else 0
+        # data parallel + graph: forward/backward are captured, the NCCL all-reduce and Adam follow the replay eagerly
+        # (capturing the collective hung on the 2-GPU box in round 1) -- ~5 launches per step instead of ~170
+        self.split = reducer is not None and bool(graph)
         if reducer is not None:
             reducer.overlap = False  # see GradReducer: reduce after backward, the side stream already shares the GPU
+            reducer.inline = self.split  # on the current stream, no side stream needed
         self.graph = None
         self.launches_per_step = 0
         if graph:
@@ -159,7 +174,8 @@ class PipelinedTrainStep:
             main.wait_stream(self.side)
             self.lib.b2pn_set_sm_limit(0)
 
-        loss = train_step(self.model, self.optimizer, cur, self.reducer, sampling=cur_sampling, after_grouping=join)
+        step = forward_backward if self.split else train_step
+        loss = step(self.model, self.optimizer, cur, self.reducer, sampling=cur_sampling, after_grouping=join)
         return loss, nxt_sampling
 
     # ---- graph ---------------------------------------------------------------------------------------------------
@@ -196,6 +212,8 @@ class PipelinedTrainStep:
         with torch.cuda.stream(warm):
             for _ in range(max(warmup, 1)):
                 body()
+                if self.split:
+                    reduce_and_update(self.optimizer, self.reducer)
         torch.cuda.current_stream(self.dev).wait_stream(warm)
         torch.cuda.synchronize(self.dev)
         self.graph = torch.cuda.CUDAGraph()
@@ -212,6 +230,8 @@ class PipelinedTrainStep:
         if self.graph is not None:
             self._copy_batch(self.s_nxt, next_batch)
             self.graph.replay()
+            if self.split:
+                reduce_and_update(self.optimizer, self.reducer)
             return self.loss
         l0 = self.lib.b2pn_launch_count()
         nb = next_batch if next_batch.pos.is_cuda else next_batch.to(self.dev, non_blocking=True)
