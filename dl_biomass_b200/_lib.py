@@ -52,6 +52,8 @@ SIGNATURES = {
     "b2pn_fps_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
     "b2pn_fps_set_variant": (ctypes.c_int, [_i32, _i32]),
     "b2pn_ball_query_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _f64, _i32, _vp, _vp, _vp]),
+    "b2pn_ball_query_workspace_bytes": (_i64, [_i32, _i64]),
+    "b2pn_ball_query_grid_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _f64, _i32, _vp, _vp, _vp, _i64, _vp]),
     "b2pn_pack_rows_capacity": (_i64, [_i64, _i32]),
     "b2pn_pack_rows_workspace_bytes": (_i64, [_i64]),
     "b2pn_pack_rows": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),

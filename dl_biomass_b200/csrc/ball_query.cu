@@ -176,3 +176,318 @@ extern "C" int b2pn_ball_query_f32(const float *src_pos, const float *qry_pos, c
     B2PN_LAUNCH_CHECK();
     return B2PN_OK;
 }
+
+// =================================================================================================
+//  Kernel 2b -- the same query through a uniform grid (large clouds).
+//
+//  The brute-force kernel above tests every source of the cloud against every query (m*n tests, early exit once K
+//  hits are found in ascending index order).  At the reference's level-1 radius a query has ~24 neighbours among
+//  10 000 points, so almost all of that scan is wasted.  Here the sources of a cloud are binned into cells of edge
+//  >= 1.0001 r (counting sort in shared memory, one CTA per cloud); a query only visits the 27 cells around its own,
+//  collects the hits of the SAME fp32 distance test into a per-warp list and sorts the list by source index, which
+//  restores the canonical "first K by ascending index" result bit for bit whatever order the cells were visited in.
+// =================================================================================================
+namespace b2pn {
+
+constexpr int GRID_MAX_CELLS = 8192;    // per cloud: 32 KB of counters in shared memory
+constexpr int GRID_LIST_CAP = 1024;     // hits a warp can hold before it falls back to the plain scan
+
+struct GridInfo {   // one per cloud, written by the build kernel
+    float lo[3];
+    float inv[3];   // 1 / cell edge
+    int n[3];       // cells per axis
+    int pad;
+};
+
+struct BqGridParams {
+    const float *src;
+    const float *qry;
+    const int64_t *src_ptr;
+    const int64_t *qry_ptr;
+    int32_t *nbr;
+    int32_t *cnt;
+    float r, r2;
+    int K;
+    GridInfo *info;         // [B]
+    int32_t *cell_start;    // [B][GRID_MAX_CELLS + 1]
+    int32_t *cell_pts;      // [N] cloud-local source indices grouped by cell
+};
+
+__device__ __forceinline__ int grid_cell_of(const GridInfo &g, float x, float y, float z)
+{
+    int cx = (int)((x - g.lo[0]) * g.inv[0]), cy = (int)((y - g.lo[1]) * g.inv[1]), cz = (int)((z - g.lo[2]) * g.inv[2]);
+    cx = min(max(cx, 0), g.n[0] - 1);
+    cy = min(max(cy, 0), g.n[1] - 1);
+    cz = min(max(cz, 0), g.n[2] - 1);
+    return (cz * g.n[1] + cy) * g.n[0] + cx;
+}
+
+__global__ void __launch_bounds__(1024) bq_grid_build_kernel(const BqGridParams p)
+{
+    __shared__ int s_cnt[GRID_MAX_CELLS];
+    __shared__ float s_red[6][32];
+    __shared__ GridInfo s_g;
+    __shared__ int s_warp[32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t s0 = p.src_ptr[b];
+    const int n = (int)(p.src_ptr[b + 1] - s0);
+    const float *g = p.src + 3 * s0;
+    // bounding box
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = tid; i < n; i += 1024) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float v = __ldg(g + 3 * i + a);
+            mn[a] = fminf(mn[a], v);
+            mx[a] = fmaxf(mx[a], v);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+        if (lane == 0) {
+            s_red[a][warp] = mn[a];
+            s_red[3 + a][warp] = mx[a];
+        }
+    }
+    for (int i = tid; i < GRID_MAX_CELLS; i += 1024) s_cnt[i] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        GridInfo gi;
+        int nc[3];
+        const float edge = p.r * 1.0001f;  // strictly larger than r: two points closer than r are at most one cell apart
+        for (int a = 0; a < 3; ++a) {
+            float lo = INFINITY, hi = -INFINITY;
+            for (int w = 0; w < 32; ++w) {
+                lo = fminf(lo, s_red[a][w]);
+                hi = fmaxf(hi, s_red[3 + a][w]);
+            }
+            if (!(lo <= hi)) lo = hi = 0.f;
+            const float ext = hi - lo;
+            int c = edge > 0.f ? (int)fminf(ext / edge, 64.f) : 1;
+            nc[a] = c < 1 ? 1 : c;
+            gi.lo[a] = lo;
+        }
+        while ((int64_t)nc[0] * nc[1] * nc[2] > GRID_MAX_CELLS) {  // halve the finest axis: cells only grow
+            int a = nc[0] >= nc[1] ? (nc[0] >= nc[2] ? 0 : 2) : (nc[1] >= nc[2] ? 1 : 2);
+            nc[a] = (nc[a] + 1) / 2;
+        }
+        for (int a = 0; a < 3; ++a) {
+            float lo = gi.lo[a], hi = -INFINITY;
+            for (int w = 0; w < 32; ++w) hi = fmaxf(hi, s_red[3 + a][w]);
+            if (!(lo <= hi)) hi = lo;
+            const float ext = hi - lo;
+            gi.n[a] = nc[a];
+            gi.inv[a] = ext > 0.f ? (float)nc[a] / ext : 0.f;  // cell edge = ext / n >= 1.0001 r
+        }
+        gi.pad = 0;
+        s_g = gi;
+        p.info[b] = gi;
+    }
+    __syncthreads();
+    const GridInfo gi = s_g;
+    const int ncell = gi.n[0] * gi.n[1] * gi.n[2];
+    for (int i = tid; i < n; i += 1024) atomicAdd(&s_cnt[grid_cell_of(gi, __ldg(g + 3 * i), __ldg(g + 3 * i + 1), __ldg(g + 3 * i + 2))], 1);
+    __syncthreads();
+    // exclusive scan of the counters (ncell <= 8192 = 8 per thread)
+    const int per = (ncell + 1023) / 1024;
+    const int c0 = tid * per;
+    int sum = 0;
+    for (int j = 0; j < per; ++j)
+        if (c0 + j < ncell) sum += s_cnt[c0 + j];
+    int v = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    if (lane == 31) s_warp[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
+        }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    int run = (warp > 0 ? s_warp[warp - 1] : 0) + v - sum;
+    int32_t *cs = p.cell_start + (int64_t)b * (GRID_MAX_CELLS + 1);
+    for (int j = 0; j < per; ++j) {
+        if (c0 + j < ncell) {
+            const int c = s_cnt[c0 + j];
+            cs[c0 + j] = run;
+            s_cnt[c0 + j] = run;  // becomes the running insert position
+            run += c;
+        }
+    }
+    if (tid == 0) cs[ncell] = n;
+    __syncthreads();
+    int32_t *pts = p.cell_pts + s0;
+    for (int i = tid; i < n; i += 1024) {
+        const int c = grid_cell_of(gi, __ldg(g + 3 * i), __ldg(g + 3 * i + 1), __ldg(g + 3 * i + 2));
+        pts[atomicAdd(&s_cnt[c], 1)] = i;  // order inside a cell is arbitrary: the query sorts its hits
+    }
+}
+
+// one warp per query
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) bq_grid_query_kernel(const BqGridParams p)
+{
+    __shared__ int s_list[WARPS][GRID_LIST_CAP];
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t s0 = p.src_ptr[b];
+    const int n = (int)(p.src_ptr[b + 1] - s0);
+    const int64_t q0 = p.qry_ptr[b];
+    const int mq = (int)(p.qry_ptr[b + 1] - q0);
+    const int ql = blockIdx.x * WARPS + warp;
+    if (ql >= mq) return;
+    const GridInfo gi = p.info[b];
+    const float *gsrc = p.src + 3 * s0;
+    const int32_t *cs = p.cell_start + (int64_t)b * (GRID_MAX_CELLS + 1);
+    const int32_t *pts = p.cell_pts + s0;
+    const float qx = __ldg(p.qry + 3 * (q0 + ql)), qy = __ldg(p.qry + 3 * (q0 + ql) + 1), qz = __ldg(p.qry + 3 * (q0 + ql) + 2);
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int *list = s_list[warp];
+    const int K = p.K;
+    int h = 0;            // hits collected (warp-uniform)
+    bool overflow = false;
+    {
+        int cx = (int)((qx - gi.lo[0]) * gi.inv[0]), cy = (int)((qy - gi.lo[1]) * gi.inv[1]), cz = (int)((qz - gi.lo[2]) * gi.inv[2]);
+        cx = min(max(cx, 0), gi.n[0] - 1);
+        cy = min(max(cy, 0), gi.n[1] - 1);
+        cz = min(max(cz, 0), gi.n[2] - 1);
+        // Dense neighbourhood?  The ball holds ~15 % of the 27 cells' points; once that is several times K the
+        // ascending scan finds its K hits after a short prefix of the cloud and beats collecting + sorting them all.
+        {
+            int cand = 0;
+            if (lane < 9) {
+                const int z = cz + lane / 3 - 1, y = cy + lane % 3 - 1;
+                if (z >= 0 && z < gi.n[2] && y >= 0 && y < gi.n[1]) {
+                    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, gi.n[0] - 1);
+                    const int c_lo = (z * gi.n[1] + y) * gi.n[0] + x0;
+                    cand = cs[c_lo + (x1 - x0) + 1] - cs[c_lo];
+                }
+            }
+            cand = __reduce_add_sync(0xffffffffu, cand);
+            overflow = cand > 13 * K;
+        }
+        for (int dz = -1; dz <= 1 && !overflow; ++dz) {
+            const int z = cz + dz;
+            if (z < 0 || z >= gi.n[2]) continue;
+            for (int dy = -1; dy <= 1 && !overflow; ++dy) {
+                const int y = cy + dy;
+                if (y < 0 || y >= gi.n[1]) continue;
+                // the three x-neighbours are consecutive cells: one contiguous range of cell_pts
+                const int x0 = max(cx - 1, 0), x1 = min(cx + 1, gi.n[0] - 1);
+                const int c_lo = (z * gi.n[1] + y) * gi.n[0] + x0;
+                const int beg = cs[c_lo], end = cs[c_lo + (x1 - x0) + 1];
+                for (int j0 = beg; j0 < end; j0 += 32) {
+                    const int j = j0 + lane;
+                    int idx = -1;
+                    bool hit = false;
+                    if (j < end) {
+                        idx = __ldg(pts + j);
+                        const float d = dist2_scalar(__ldg(gsrc + 3 * idx), __ldg(gsrc + 3 * idx + 1), __ldg(gsrc + 3 * idx + 2), qx, qy, qz);
+                        hit = d < p.r2;
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, hit);
+                    if (m != 0u) {
+                        const int pos = h + __popc(m & lt_mask);
+                        if (hit && pos < GRID_LIST_CAP) list[pos] = idx;
+                        h += __popc(m);
+                        if (h > GRID_LIST_CAP) {
+                            overflow = true;
+                            break;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    int32_t *row = p.nbr + (q0 + ql) * (int64_t)K;
+    if (overflow) {
+        // (rare) more hits than the list holds: plain ascending scan with early exit, like Kernel 2
+        int c = 0;
+        for (int j0 = 0; j0 < n && c < K; j0 += 32) {
+            const int j = j0 + lane;
+            bool hit = false;
+            if (j < n) hit = dist2_scalar(__ldg(gsrc + 3 * j), __ldg(gsrc + 3 * j + 1), __ldg(gsrc + 3 * j + 2), qx, qy, qz) < p.r2;
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            const int slot = c + __popc(m & lt_mask);
+            if (hit && slot < K) row[slot] = (int)(s0 + j);
+            c += __popc(m);
+        }
+        c = min(c, K);
+        for (int s = c + lane; s < K; s += 32) row[s] = -1;
+        if (lane == 0) p.cnt[q0 + ql] = c;
+        return;
+    }
+    __syncwarp();
+    // sort the h hits by source index (bitonic over the next power of two, padded with INT_MAX)
+    int np = 32;
+    while (np < h) np <<= 1;
+    for (int i = h + lane; i < np; i += 32) list[i] = 0x7fffffff;
+    __syncwarp();
+    for (int k = 2; k <= np; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < (np >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const int a = list[i], c = list[l];
+                const bool up = (i & k) == 0;
+                if ((a > c) == up) {
+                    list[i] = c;
+                    list[l] = a;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    const int c = min(h, K);
+    for (int s = lane; s < K; s += 32) row[s] = s < c ? (int)(s0 + list[s]) : -1;
+    if (lane == 0) p.cnt[q0 + ql] = c;
+}
+
+}  // namespace b2pn
+
+extern "C" int64_t b2pn_ball_query_workspace_bytes(int32_t B, int64_t n_src_total)
+{
+    if (B < 0 || n_src_total < 0) return B2PN_EINVAL;
+    return (int64_t)B * (sizeof(b2pn::GridInfo) + (b2pn::GRID_MAX_CELLS + 1) * sizeof(int32_t)) + n_src_total * sizeof(int32_t) + 1024;
+}
+
+extern "C" int b2pn_ball_query_grid_f32(const float *src_pos, const float *qry_pos, const int64_t *src_ptr,
+                                        const int64_t *qry_ptr, int32_t B, int64_t n_src_total, int64_t max_qry, double r,
+                                        int32_t K, int32_t *nbr, int32_t *cnt, void *workspace, int64_t workspace_bytes,
+                                        b2pn_stream_t stream)
+{
+    using namespace b2pn;
+    if (B < 0 || n_src_total < 0 || max_qry < 0 || K <= 0 || !(r >= 0.0)) return B2PN_EINVAL;
+    if (B == 0 || max_qry == 0) return B2PN_OK;
+    if (!src_pos || !qry_pos || !src_ptr || !qry_ptr || !nbr || !cnt || !workspace) return B2PN_EINVAL;
+    if (workspace_bytes < b2pn_ball_query_workspace_bytes(B, n_src_total)) return B2PN_EINVAL;
+    char *w = (char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    GridInfo *info = (GridInfo *)w;
+    w += ((int64_t)B * sizeof(GridInfo) + 255) / 256 * 256;
+    int32_t *cell_start = (int32_t *)w;
+    w += (int64_t)B * (GRID_MAX_CELLS + 1) * sizeof(int32_t);
+    int32_t *cell_pts = (int32_t *)w;
+    BqGridParams p = {src_pos, qry_pos, src_ptr, qry_ptr, nbr, cnt, (float)r, (float)(r * r), K, info, cell_start, cell_pts};
+    cudaStream_t st = (cudaStream_t)stream;
+    bq_grid_build_kernel<<<(unsigned)B, 1024, 0, st>>>(p);
+    note_launch();
+    constexpr int WARPS = 8;
+    dim3 grid((unsigned)((max_qry + WARPS - 1) / WARPS), (unsigned)B);
+    bq_grid_query_kernel<WARPS><<<grid, WARPS * 32, 0, st>>>(p);
+    note_launch();
+    B2PN_LAUNCH_CHECK();
+    return B2PN_OK;
+}

@@ -52,6 +52,18 @@ def _fps_cuda(pos, ptr, out_ptr, start, max_n, num_out):
     return idx, pos_out, batch_out
 
 
+GRID_MIN_SOURCES = 4096   # below this the plain scan with early exit wins (level 2: most sources are neighbours)
+GRID_MAX_SOURCES = 32768  # above this the clouds are so dense that K hits come early in the scan (100k-point trees)
+_BQ_MODE = "auto"         # "scan" forces the brute-force kernel (tests compare both)
+
+
+def set_ball_query_mode(mode: str) -> None:
+    global _BQ_MODE
+    if mode not in ("auto", "scan"):
+        raise ValueError("mode must be 'auto' or 'scan'")
+    _BQ_MODE = mode
+
+
 def _ball_query_cuda(src, qry, src_ptr, qry_ptr, max_src, max_qry, r, K):
     _require_cuda(src, qry, src_ptr, qry_ptr)
     if src.dtype != torch.float32 or qry.dtype != torch.float32:
@@ -61,6 +73,16 @@ def _ball_query_cuda(src, qry, src_ptr, qry_ptr, max_src, max_qry, r, K):
     M = qry.size(0)
     nbr = torch.empty(M, K, dtype=torch.int32, device=src.device)
     cnt = torch.empty(M, dtype=torch.int32, device=src.device)
+    lib = _lib.lib()
+    if GRID_MIN_SOURCES <= max_src <= GRID_MAX_SOURCES and _BQ_MODE != "scan":
+        # large clouds: uniform-grid kernel (same result, two orders of magnitude fewer distance tests)
+        ws = torch.empty(int(lib.b2pn_ball_query_workspace_bytes(B, src.size(0))), dtype=torch.uint8, device=src.device)
+        with torch.cuda.device(src.device):
+            rc = lib.b2pn_ball_query_grid_f32(src.data_ptr(), qry.data_ptr(), src_ptr.data_ptr(), qry_ptr.data_ptr(), B,
+                                              src.size(0), max_qry, float(r), K, nbr.data_ptr(), cnt.data_ptr(),
+                                              ws.data_ptr(), ws.numel(), _stream(src))
+        _lib.check(rc, "b2pn_ball_query_grid_f32")
+        return nbr, cnt
     with torch.cuda.device(src.device):
         rc = _lib.lib().b2pn_ball_query_f32(src.data_ptr(), qry.data_ptr(), src_ptr.data_ptr(), qry_ptr.data_ptr(),
                                             B, max_src, max_qry, float(r), K, nbr.data_ptr(), cnt.data_ptr(),

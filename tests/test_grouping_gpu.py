@@ -77,6 +77,39 @@ def test_ties_and_duplicates_all_variants(cuda_device, cluster, threads):
         _lib.lib().b2pn_fps_set_variant(0, 0)
 
 
+@pytest.mark.parametrize("n,r,K", [(3000, 2.0, 64), (3000, 0.3, 64), (3000, 9.0, 64), (3000, 40.0, 64), (5000, 2.0, 8),
+                                   (700, 1.0, 16), (40, 2.0, 64)])
+def test_grid_ball_query_equals_scan(cuda_device, n, r, K):
+    """The uniform-grid kernel (large clouds) returns exactly what the ascending scan returns: sparse and dense
+    radii, a radius that swallows the whole cloud (list overflow -> in-kernel fall-back), duplicates, flat clouds."""
+    clouds = synthetic_clouds(321, 3, n, 1, True)
+    clouds[1].pos[:, 2] = 0.25                       # a flat cloud: one layer of cells
+    clouds[2].pos[: n // 3] = clouds[2].pos[n // 3: 2 * (n // 3)][: n // 3]   # duplicates
+    b = Batch.from_data_list(clouds)
+    sizes = b.cloud_sizes
+    lv = ops.build_levels(sizes, [0.2], cuda_device)
+    pos = b.pos.to(cuda_device)
+    _, qpos, _ = ops.fps(pos, lv[0], lv[1])
+    old = ops.GRID_MIN_SOURCES
+    try:
+        ops.set_ball_query_mode("scan")
+        nbr0, cnt0 = ops.ball_query(pos, qpos, lv[0], lv[1], r, K)
+        ops.set_ball_query_mode("auto")
+        ops.GRID_MIN_SOURCES = 0
+        nbr1, cnt1 = ops.ball_query(pos, qpos, lv[0], lv[1], r, K)
+        torch.cuda.synchronize()
+    finally:
+        ops.GRID_MIN_SOURCES = old
+        ops.set_ball_query_mode("auto")
+    assert torch.equal(cnt0, cnt1)
+    assert torch.equal(nbr0, nbr1)
+    # and the scan itself against the oracle
+    qptr = ref.sample_ptr(b.ptr, 0.2)
+    idx = ref.fps_ref(b.pos, b.ptr, 0.2)
+    want_nbr, want_cnt = ref.ball_query_ref(b.pos, b.pos[idx], b.ptr, qptr, r, K)
+    assert torch.equal(cnt1.cpu(), want_cnt) and torch.equal(nbr1.cpu(), want_nbr)
+
+
 def test_reference_numpy_fps_golden(cuda_device):
     """The reference's own FPS (downsampling_point_clouds.py:55-92) on fp32-exact clouds."""
     g = np.load(os.path.join(GOLD, "fps_reference_numpy.npz"))
