@@ -33,10 +33,15 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_rows_scan_kernel(const int3
 {
     __shared__ int s_warp[PACK_THREADS / 32];
     __shared__ int s_carry;
+    __shared__ unsigned long long s_edges;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t chunks = (n_dst + PACK_G - 1) / PACK_G;
-    if (tid == 0) s_carry = 0;
+    if (tid == 0) {
+        s_carry = 0;
+        s_edges = 0ull;
+    }
     __syncthreads();
+    long long my_edges = 0;
     for (int64_t c0 = 0; c0 < chunks; c0 += PACK_THREADS) {
         const int64_t ch = c0 + tid;
         int blocks = 0;  // 64-row blocks used by my chunk
@@ -50,6 +55,7 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_rows_scan_kernel(const int3
 #pragma unroll
                 for (int i = 0; i < PACK_G / 4; ++i) {
                     const int4 v = __ldg(src + i);
+                    my_edges += min(max(v.x, 0), K) + min(max(v.y, 0), K) + min(max(v.z, 0), K) + min(max(v.w, 0), K);
                     c8[4 * i + 0] = c8_of(v.x, K);
                     c8[4 * i + 1] = c8_of(v.y, K);
                     c8[4 * i + 2] = c8_of(v.z, K);
@@ -57,7 +63,11 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_rows_scan_kernel(const int3
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < PACK_G; ++i) c8[i] = m0 + i < m1 ? c8_of(__ldg(cnt + m0 + i), K) : 0;
+                for (int i = 0; i < PACK_G; ++i) {
+                    const int cv = m0 + i < m1 ? __ldg(cnt + m0 + i) : 0;
+                    my_edges += min(max(cv, 0), K);
+                    c8[i] = m0 + i < m1 ? c8_of(cv, K) : 0;
+                }
             }
             int off = 0;
             int lo[PACK_G];
@@ -104,7 +114,12 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_rows_scan_kernel(const int3
         if (tid == PACK_THREADS - 1) s_carry = carry + s_warp[PACK_THREADS / 32 - 1];
         __syncthreads();
     }
-    if (tid == 0) *num_rows = (int64_t)s_carry * 64;
+    if (my_edges) atomicAdd(&s_edges, (unsigned long long)my_edges);  // integer sum: order does not matter
+    __syncthreads();
+    if (tid == 0) {
+        num_rows[0] = (int64_t)s_carry * 64;
+        num_rows[1] = (int64_t)s_edges;  // valid rows = edges: the sample count of the BatchNorm statistics
+    }
 }
 
 // one thread per (centroid, 8-row group): group descriptors and per-row source index
@@ -169,7 +184,7 @@ extern "C" int b2pn_pack_rows(const int32_t *cnt, const int32_t *nbr, int64_t n_
     if (!num_rows) return B2PN_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     if (n_dst == 0) {
-        B2PN_CUDA(cudaMemsetAsync(num_rows, 0, sizeof(int64_t), st));
+        B2PN_CUDA(cudaMemsetAsync(num_rows, 0, 2 * sizeof(int64_t), st));
         return B2PN_OK;
     }
     if (!cnt || !nbr || !rgrp || !row_src || !workspace) return B2PN_EINVAL;

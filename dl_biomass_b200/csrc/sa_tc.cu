@@ -1152,30 +1152,43 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
 // bf16 operand image of a weight matrix: element (m, k) = w[m*sm + col(k)*sk] for m < M, k < Kimg (col(k) is the
 // identity, or InCols::src_col for the layer-1 operand), else 0.
 // Layout: [m_group][k_chunk][MT*128 lines][128 B] with the 128B swizzle applied per line.
-__global__ void pack_weights_kernel(const float *w, int M, int Kimg, int64_t sm, int64_t sk, int use_map, InCols cols, int MT,
-                                    int num_mg, int num_kc, uint8_t *img)
+struct PackJob {
+    const float *w;
+    int M, Kimg;
+    int64_t sm, sk;
+    int use_map;
+    InCols cols;
+    int MT, num_mg, num_kc;
+    uint8_t *img;
+};
+struct PackJobs {
+    PackJob j[3];
+};
+// blockIdx.y selects the matrix: all weight images of a forward / backward call in ONE launch
+__global__ void pack_weights_kernel(const PackJobs jobs)
 {
-    const int lines = MT * 128;
-    const int64_t total = (int64_t)num_mg * num_kc * lines * 8;  // one thread per 16-byte chunk
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int c = (int)(i & 7);
-    const int64_t t = i >> 3;
-    const int line = (int)(t % lines);
-    const int64_t t2 = t / lines;
-    const int kc = (int)(t2 % num_kc);
-    const int mgi = (int)(t2 / num_kc);
-    const int m = mgi * lines + line;
-    float f[8];
+    const PackJob &jb = jobs.j[blockIdx.y];
+    const int lines = jb.MT * 128;
+    const int64_t total = (int64_t)jb.num_mg * jb.num_kc * lines * 8;  // one thread per 16-byte chunk
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i & 7);
+        const int64_t t = i >> 3;
+        const int line = (int)(t % lines);
+        const int64_t t2 = t / lines;
+        const int kc = (int)(t2 % jb.num_kc);
+        const int mgi = (int)(t2 / jb.num_kc);
+        const int m = mgi * lines + line;
+        float f[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int k = kc * KC + c * 8 + e;
-        int col = k < Kimg ? k : -1;
-        if (use_map && col >= 0) col = cols.src_col(k);
-        f[e] = (m < M && col >= 0) ? w[(int64_t)m * sm + (int64_t)col * sk] : 0.f;
+        for (int e = 0; e < 8; ++e) {
+            const int k = kc * KC + c * 8 + e;
+            int col = k < jb.Kimg ? k : -1;
+            if (jb.use_map && col >= 0) col = jb.cols.src_col(k);
+            f[e] = (m < jb.M && col >= 0) ? jb.w[(int64_t)m * jb.sm + (int64_t)col * jb.sk] : 0.f;
+        }
+        uint8_t *dst = jb.img + (((int64_t)mgi * jb.num_kc + kc) * lines) * LINE_BYTES + line_chunk_off(line, c);
+        *reinterpret_cast<uint4 *>(dst) = pack8(f);
     }
-    uint8_t *dst = img + (((int64_t)mgi * num_kc + kc) * lines) * LINE_BYTES + line_chunk_off(line, c);
-    *reinterpret_cast<uint4 *>(dst) = pack8(f);
 }
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
@@ -1196,14 +1209,31 @@ static Packed plan_pack(int M, int Kimg)
     p.img = nullptr;
     return p;
 }
+static PackJob pack_job(const float *w, int M, int Kimg, int64_t sm, int64_t sk, const InCols *map, const Packed &p)
+{
+    PackJob j = {w, M, Kimg, sm, sk, map ? 1 : 0, map ? *map : InCols{0, 0}, p.MT, p.num_mg, p.num_kc, p.img};
+    return j;
+}
+static void launch_packs(const PackJob *jobs, int n, cudaStream_t st)
+{
+    if (n <= 0) return;
+    PackJobs pj;
+    int64_t mx = 0;
+    for (int i = 0; i < 3; ++i) {
+        pj.j[i] = jobs[i < n ? i : 0];
+        const int64_t tot = (int64_t)pj.j[i].num_mg * pj.j[i].num_kc * pj.j[i].MT * 128 * 8;
+        mx = tot > mx ? tot : mx;
+    }
+    int64_t bx = (mx + 255) / 256;
+    if (bx > 592) bx = 592;  // grid-stride beyond 4 blocks per SM
+    pack_weights_kernel<<<dim3((unsigned)bx, (unsigned)n), 256, 0, st>>>(pj);
+    note_launch();
+}
 static void launch_pack(const float *w, int M, int Kimg, int64_t sm, int64_t sk, const InCols *map, const Packed &p,
                         cudaStream_t st)
 {
-    const int64_t total = p.bytes / 16;
-    InCols cols = map ? *map : InCols{0, 0};
-    pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, M, Kimg, sm, sk, map ? 1 : 0, cols, p.MT, p.num_mg,
-                                                                         p.num_kc, p.img);
-    note_launch();
+    const PackJob j = pack_job(w, M, Kimg, sm, sk, map, p);
+    launch_packs(&j, 1, st);
 }
 
 static int sm_count()
@@ -1263,24 +1293,13 @@ static int launch_by_mt(const Packed &pk, const RowsArg &ra, const BL &bl, const
     return pk.MT == 1 ? launch_gemm<1>(pk, ra, bl, e1, st, map, m0, m1) : launch_gemm<2>(pk, ra, bl, e2, st, map, m0, m1);
 }
 
-__global__ void count_valid_tc_kernel(const int32_t *cnt, int64_t n, double fixed, double *out)
-{
-    __shared__ double red[32];
-    if (cnt == nullptr) {
-        if (threadIdx.x == 0) *out = fixed;
-        return;
-    }
-    double s = 0.0;
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += (double)cnt[i];
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-        *out = t;
-    }
-}
+// number of rows the BatchNorm statistics run over: a host constant (CLOUDS) or the edge count b2pn_pack_rows left next
+// to the row count (SLOTS: num_rows[1])
+struct CountArg {
+    const int64_t *dev;
+    double host;
+    __device__ __forceinline__ double get() const { return dev ? (double)*dev : host; }
+};
 
 // partial[g][2][cpad]: per-CTA sums of the bias-free accumulators over ALL rows (invalid rows are exact zeros):
 //   mean(h) = S/E + bias,  var(h) = Q/E - (S/E)^2.   bn = [mean, rstd, scale, shift] x cmax
@@ -1302,7 +1321,7 @@ __device__ __forceinline__ void warp_sum_partials(const double *partial, int gx,
 }
 
 // one warp per channel
-__global__ void bn_fwd_finalize_tc_kernel(const double *partial, int gx, int C, int cpad, const double *count, int training,
+__global__ void bn_fwd_finalize_tc_kernel(const double *partial, int gx, int C, int cpad, const CountArg count, int training,
                                           const float *bias, const float *gamma, const float *beta, float *running_mean,
                                           float *running_var, int64_t *nbt, float eps, float momentum, float *bn, int cmax)
 {
@@ -1312,7 +1331,7 @@ __global__ void bn_fwd_finalize_tc_kernel(const double *partial, int gx, int C, 
     if (training) {
         double S, Q;
         warp_sum_partials(partial, gx, cpad, c, S, Q);
-        const double E = *count;
+        const double E = count.get();
         const double ma = E > 0 ? S / E : 0.0;
         mean = ma + (double)bias[c];
         var = E > 0 ? Q / E - ma * ma : 0.0;
@@ -1338,7 +1357,7 @@ __global__ void bn_fwd_finalize_tc_kernel(const double *partial, int gx, int C, 
 }
 
 // S1 = sum dz, S2 = sum dz*zhat -> dbeta, dgamma, and the per-channel means the BN backward needs
-__global__ void bn_bwd_finalize_tc_kernel(const double *partial, int gx, int C, int cpad, const double *count, int training,
+__global__ void bn_bwd_finalize_tc_kernel(const double *partial, int gx, int C, int cpad, const CountArg count, int training,
                                           float *grad_gamma, float *grad_beta, float *sbar)
 {
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1346,7 +1365,7 @@ __global__ void bn_bwd_finalize_tc_kernel(const double *partial, int gx, int C, 
     double S, Q;
     warp_sum_partials(partial, gx, cpad, c, S, Q);
     if ((threadIdx.x & 31) == 0) {
-        const double E = *count;
+        const double E = count.get();
         if (grad_beta) grad_beta[c] = (float)S;
         if (grad_gamma) grad_gamma[c] = (float)Q;
         sbar[c] = (training && E > 0) ? (float)(S / E) : 0.f;
@@ -1626,7 +1645,6 @@ static RowsArg rowsarg_tc(const b2pn_sa_args &a, const ShapesTC &s)
 
 struct FwdWsTC {
     Packed pk[3];
-    double *count;
     double *partial;
     unsigned long long *keys;
 };
@@ -1637,7 +1655,6 @@ static FwdWsTC carve_fwd_tc(const b2pn_sa_args &a, const ShapesTC &s, WsTC &ws)
     f.pk[1] = plan_pack(s.c2, s.c1);
     f.pk[2] = plan_pack(s.c3, s.c2);
     for (int l = 0; l < 3; ++l) f.pk[l].img = ws.take<uint8_t>(f.pk[l].bytes);
-    f.count = ws.take<double>(1);
     f.partial = ws.take<double>((int64_t)MAX_GX * 2 * 2 * s.cpad);
     f.keys = a.seg_mode == B2PN_SEG_CLOUDS ? ws.take<unsigned long long>(a.n_dst * (int64_t)s.c3) : nullptr;
     return f;
@@ -1668,7 +1685,6 @@ static DwPlanHost plan_dw(int n_out, int k_total, int64_t ld)
 
 struct BwdWsTC {
     Packed pkT[3];
-    double *count;
     double *partial;
     __nv_bfloat16 *dz1, *dz2;
     __nv_bfloat16 *dh3;  // materialised routed gradient [c3][ld]
@@ -1682,7 +1698,6 @@ static BwdWsTC carve_bwd_tc(const b2pn_sa_args &a, const ShapesTC &s, WsTC &ws)
     b.pkT[1] = plan_pack(s.c1, s.c2);               // W2^T
     b.pkT[0] = plan_pack(a.c_in > 0 ? a.c_in : 1, s.c1);  // feature rows of W1^T
     for (int l = 0; l < 3; ++l) b.pkT[l].img = ws.take<uint8_t>(b.pkT[l].bytes);
-    b.count = ws.take<double>(1);
     b.partial = ws.take<double>((int64_t)MAX_GX * 2 * 2 * s.cpad);
     b.dz1 = ws.take<__nv_bfloat16>((int64_t)s.c1 * s.ld);
     b.dz2 = ws.take<__nv_bfloat16>((int64_t)s.c2 * s.ld);
@@ -1726,11 +1741,13 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
     float *bn1 = a.bn, *bn2 = a.bn + 4 * s.cmax;
     const int train = a.training;
 
-    launch_pack(a.mlp.w[0], s.c1, s.k1, s.c0, 1, &s.cols, f.pk[0], st);
-    launch_pack(a.mlp.w[1], s.c2, s.c1, s.c1, 1, nullptr, f.pk[1], st);
-    launch_pack(a.mlp.w[2], s.c3, s.c2, s.c2, 1, nullptr, f.pk[2], st);
-    count_valid_tc_kernel<<<1, 1024, 0, st>>>(a.seg_mode == B2PN_SEG_SLOTS ? a.cnt : nullptr, a.n_dst, (double)s.rows, f.count);
-    note_launch();
+    {
+        const PackJob jobs[3] = {pack_job(a.mlp.w[0], s.c1, s.k1, s.c0, 1, &s.cols, f.pk[0]),
+                                 pack_job(a.mlp.w[1], s.c2, s.c1, s.c1, 1, nullptr, f.pk[1]),
+                                 pack_job(a.mlp.w[2], s.c3, s.c2, s.c2, 1, nullptr, f.pk[2])};
+        launch_packs(jobs, 3, st);
+    }
+    const CountArg count = {a.seg_mode == B2PN_SEG_SLOTS ? a.num_rows + 1 : nullptr, (double)s.rows};
 
     // ---- layer 1: gather + concat + Linear; pass A = batch statistics, pass B = normalise + store z1
     GatherLoaderTC gl = {rm, a.x, s.cols, a.pos_src, a.pos_dst, -1};
@@ -1751,7 +1768,7 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
         rc = use_g1 ? launch_by_mt(f.pk[0], ra, tl1, e1, e2, st, map_g1) : launch_by_mt(f.pk[0], ra, gl, e1, e2, st);
         if (rc) return rc;
     }
-    bn_fwd_finalize_tc_kernel<<<(s.c1 + 3) / 4, 128, 0, st>>>(f.partial, 2 * grid_x_for(f.pk[0], s.tiles), s.c1, s.cpad, f.count, train,
+    bn_fwd_finalize_tc_kernel<<<(s.c1 + 3) / 4, 128, 0, st>>>(f.partial, 2 * grid_x_for(f.pk[0], s.tiles), s.c1, s.cpad, count, train,
                                                                  a.mlp.b[0], a.mlp.gamma[0], a.mlp.beta[0], a.mlp.running_mean[0],
                                                                  a.mlp.running_var[0], a.mlp.num_batches_tracked[0], a.mlp.eps,
                                                                  a.mlp.momentum, bn1, s.cmax);
@@ -1775,7 +1792,7 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
         StatsEpTC<2> e2 = {s.c2, f.partial, s.cpad};
         if ((rc = launch_by_mt(f.pk[1], ra, l2, e1, e2, st, map_a1))) return rc;
     }
-    bn_fwd_finalize_tc_kernel<<<(s.c2 + 3) / 4, 128, 0, st>>>(f.partial, 2 * grid_x_for(f.pk[1], s.tiles), s.c2, s.cpad, f.count, train,
+    bn_fwd_finalize_tc_kernel<<<(s.c2 + 3) / 4, 128, 0, st>>>(f.partial, 2 * grid_x_for(f.pk[1], s.tiles), s.c2, s.cpad, count, train,
                                                                  a.mlp.b[1], a.mlp.gamma[1], a.mlp.beta[1], a.mlp.running_mean[1],
                                                                  a.mlp.running_var[1], a.mlp.num_batches_tracked[1], a.mlp.eps,
                                                                  a.mlp.momentum, bn2, s.cmax);
@@ -1866,11 +1883,13 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
     float *bn1 = a.bn, *bn2 = a.bn + 4 * s.cmax;
     const bool need_dx = g.grad_x != nullptr && a.c_in > 0;
 
-    launch_pack(a.mlp.w[2], s.c2, s.c3, 1, s.c2, nullptr, b.pkT[2], st);  // (m, k) = W3[k][m]
-    launch_pack(a.mlp.w[1], s.c1, s.c2, 1, s.c1, nullptr, b.pkT[1], st);
-    if (need_dx) launch_pack(a.mlp.w[0], a.c_in, s.c1, 1, s.c0, nullptr, b.pkT[0], st);
-    count_valid_tc_kernel<<<1, 1024, 0, st>>>(a.seg_mode == B2PN_SEG_SLOTS ? a.cnt : nullptr, a.n_dst, (double)s.rows, b.count);
-    note_launch();
+    {
+        const PackJob jobs[3] = {pack_job(a.mlp.w[2], s.c2, s.c3, 1, s.c2, nullptr, b.pkT[2]),  // (m, k) = W3[k][m]
+                                 pack_job(a.mlp.w[1], s.c1, s.c2, 1, s.c1, nullptr, b.pkT[1]),
+                                 pack_job(a.mlp.w[0], a.c_in, s.c1, 1, s.c0, nullptr, b.pkT[0])};
+        launch_packs(jobs, need_dx ? 3 : 2, st);
+    }
+    const CountArg count = {a.seg_mode == B2PN_SEG_SLOTS ? a.num_rows + 1 : nullptr, (double)s.rows};
 
     // ---- layer 3 ---------------------------------------------------------------------------------------
     MaskSumsStoreEpTC<1> e31 = {s.c2, a.mlp.gamma[1], a.mlp.beta[1], a.mlp.act, b.partial, s.cpad};
@@ -1909,7 +1928,7 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
         if (rc) return rc;
     }
     launch_dw_reduce(b.dwp, s.c3, s.c2 + 1, nullptr, s.c2, s.c2, s, g.grad_w[2], g.grad_b[2], st);
-    bn_bwd_finalize_tc_kernel<<<(s.c2 + 3) / 4, 128, 0, st>>>(b.partial, 2 * grid_x_for(b.pkT[2], s.tiles), s.c2, s.cpad, b.count,
+    bn_bwd_finalize_tc_kernel<<<(s.c2 + 3) / 4, 128, 0, st>>>(b.partial, 2 * grid_x_for(b.pkT[2], s.tiles), s.c2, s.cpad, count,
                                                                  a.training, g.grad_gamma[1], g.grad_beta[1], b.sbar);
     note_launch();
     {
@@ -1940,7 +1959,7 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
         if (rc) return rc;
         launch_dw_reduce(b.dwp, s.c2, s.c1 + 1, nullptr, s.c1, s.c1, s, g.grad_w[1], g.grad_b[1], st);
     }
-    bn_bwd_finalize_tc_kernel<<<(s.c1 + 3) / 4, 128, 0, st>>>(b.partial, 2 * grid_x_for(b.pkT[1], s.tiles), s.c1, s.cpad, b.count,
+    bn_bwd_finalize_tc_kernel<<<(s.c1 + 3) / 4, 128, 0, st>>>(b.partial, 2 * grid_x_for(b.pkT[1], s.tiles), s.c1, s.cpad, count,
                                                                  a.training, g.grad_gamma[0], g.grad_beta[0], b.sbar);
     note_launch();
     {

@@ -81,7 +81,7 @@ def pack_rows(nbr: torch.Tensor, cnt: torch.Tensor, K: int):
         _lib.check(cap, "b2pn_pack_rows_capacity")
     rgrp = torch.empty(cap // 8, dtype=torch.int32, device=dev)
     row_src = torch.empty(cap, dtype=torch.int32, device=dev)
-    num_rows = torch.empty(1, dtype=torch.int64, device=dev)
+    num_rows = torch.empty(2, dtype=torch.int64, device=dev)
     row_valid = torch.empty(cap, dtype=torch.bfloat16, device=dev)
     wsb = torch.empty(int(lib.b2pn_pack_rows_workspace_bytes(n_dst)), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):

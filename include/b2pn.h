@@ -105,7 +105,7 @@ int b2pn_ball_query_grid_f32(const float *src_pos, const float *qry_pos, const i
  *   row_src [capacity]   i32      gathered source point of the row, -1 = padding
  *   row_valid [capacity] bf16     1.0 for valid rows, 0 elsewhere (optional, may be NULL): the "ones" operand
  *                                 line that yields the bias gradients in the dW GEMMs
- *   num_rows [1]         i64      rows in use (multiple of 64)
+ *   num_rows [2]         i64      [0] rows in use (multiple of 64), [1] valid rows = edges (sum of cnt)
  * Centroid m owns max(8, round_up(cnt[m], 8)) consecutive rows that never cross a 64-row boundary.
  * capacity = b2pn_pack_rows_capacity(n_dst, K) rows (host-side upper bound used to size every buffer).
  */

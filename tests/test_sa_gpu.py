@@ -198,7 +198,8 @@ def test_pack_rows_structure(cuda_device, K, n, r):
     nbr, cnt = ref.ball_query_ref(b.pos, b.pos[idx], b.ptr, qptr, r, K)
     rgrp, row_src, num_rows, cap, row_valid = sa.pack_rows(nbr.to(cuda_device), cnt.to(cuda_device), K)
     torch.cuda.synchronize()
-    rows = int(num_rows.item())
+    rows, edges = (int(v) for v in num_rows.tolist())
+    assert edges == int(cnt.clamp(0, K).sum())
     assert rows % 64 == 0 and 0 < rows <= cap
     g = rgrp.cpu().numpy().astype("uint32")
     src = row_src.cpu().numpy()
