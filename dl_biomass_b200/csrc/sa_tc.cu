@@ -27,6 +27,10 @@ constexpr int NUM_LOAD = 128;   // threads per loader group
 constexpr int LOAD_GROUPS = 2;  // warps 8-11 and 12-15 fill alternate pipeline stages (hides global-load latency)
 constexpr int MMA_WARP = (NUM_EPI + LOAD_GROUPS * NUM_LOAD) / 32;  // warp 16: MMA issuer / TMEM owner
 constexpr int NT = NUM_EPI + LOAD_GROUPS * NUM_LOAD + 32;
+// TMA-fed rows kernels need no loader warps: warps 8-15 become a SECOND epilogue group (group g drains the tiles of
+// parity g, i.e. TMEM accumulator buffer g), warp 16 issues the MMAs and warp 17 the TMA copies
+constexpr int NT_TMA = 2 * NUM_EPI + 64;
+constexpr int PROD_WARP_TMA = MMA_WARP + 1;
 constexpr int B_BYTES = R * LINE_BYTES;  // 16 KB: [128 row lines x 64 k] or [2 row blocks][64 k lines x 64 rows]
 
 // Row structure of a level.
@@ -434,8 +438,9 @@ template <int MT>
 struct StatsEpTC {  // pass A of a BatchNorm layer: per-channel sum and sum of squares of the bias-free accumulators
     static constexpr bool STAGED = false;
     int C;
-    double *partial;  // [gridDim.x][2][cpad]
+    double *partial;  // [gridDim.x * nslot][2][cpad]
     int cpad;
+    int nslot;        // epilogue thread groups per CTA writing partials (2 column halves x epilogue groups)
     double S[MT], Q[MT];
     __device__ __forceinline__ void resolve(int64_t) {}
     __device__ __forceinline__ void begin()
@@ -459,10 +464,10 @@ struct StatsEpTC {  // pass A of a BatchNorm layer: per-channel sum and sum of s
         S[mt] += (double)s;
         Q[mt] += (double)q;
     }
-    __device__ __forceinline__ void finish_mt(int ch, int mt, int half)
+    __device__ __forceinline__ void finish_mt(int ch, int mt, int slot)
     {
         if (ch < C) {
-            double *pt = partial + ((int64_t)blockIdx.x * 2 + half) * 2 * cpad;
+            double *pt = partial + ((int64_t)blockIdx.x * nslot + slot) * 2 * cpad;
             pt[ch] = S[mt];
             pt[cpad + ch] = Q[mt];
         }
@@ -648,6 +653,7 @@ struct MaskSumsStoreEpTC {  // backward through activation + sums for the BatchN
     int act;
     double *partial;
     int cpad;
+    int nslot;
     double S[MT], Q[MT];
     unsigned phase;
     bool primed;
@@ -713,11 +719,11 @@ struct MaskSumsStoreEpTC {  // backward through activation + sums for the BatchN
             if (cx.next_tile >= 0) fetch_z(cx, zt, cx.next_tile, cx.next_ch, half);
         }
     }
-    __device__ __forceinline__ void finish_mt(int ch, int mt, int half)
+    __device__ __forceinline__ void finish_mt(int ch, int mt, int slot)
     {
         if ((threadIdx.x & 31) == 0) bulk_wait_all();
         if (ch < C) {
-            double *pt = partial + ((int64_t)blockIdx.x * 2 + half) * 2 * cpad;
+            double *pt = partial + ((int64_t)blockIdx.x * nslot + slot) * 2 * cpad;
             pt[ch] = S[mt];
             pt[cpad + ch] = Q[mt];
         }
@@ -759,24 +765,28 @@ struct ScatterEpTC {  // gradient w.r.t. the gathered source features (thread = 
 // =================================================================================================
 //  The rows GEMM kernel:  D^T[channel, row] = A[channel, k] * B[k, row]
 // =================================================================================================
-template <int MT, bool STAGED>
+template <int MT, bool STAGED, bool TMA>
 struct SmemPlan {
     static constexpr int A_BYTES = MT * 128 * LINE_BYTES;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    // the epilogue staging tiles (8 warps x 8 KB) come out of the operand ring: one stage less
-    static constexpr int STAGES = (MT == 1 ? 5 : 4) - (STAGED ? 1 : 0);
+    static constexpr int EPI_WARPS = (TMA ? 2 : 1) * (NUM_EPI / 32);
+    // the epilogue staging tiles (8 KB per epilogue warp) come out of the operand ring
+    static constexpr int STAGES = !STAGED ? (MT == 1 ? 5 : 4) : (TMA ? (MT == 1 ? 3 : 2) : (MT == 1 ? 4 : 3));
     static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
-    static constexpr int EPI_BYTES = STAGED ? (NUM_EPI / 32) * EPI_STAGE_PER_WARP : 0;
+    static constexpr int EPI_BYTES = STAGED ? EPI_WARPS * EPI_STAGE_PER_WARP : 0;
     static constexpr int BAR_OFF = EPI_OFF + EPI_BYTES;
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + alignment slack
 };
 
 template <int MT, class BL, class EP>
-__global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp, BL bl, EP ep, const __grid_constant__ TmaMap tmap,
-                                                              const __grid_constant__ TmaMap tmap_e0,
-                                                              const __grid_constant__ TmaMap tmap_e1)
+__global__ void __launch_bounds__(BL::USES_TMA ? NT_TMA : NT, 1)
+    tc_rows_gemm_kernel(const GemmParams gp, BL bl, EP ep, const __grid_constant__ TmaMap tmap, const __grid_constant__ TmaMap tmap_e0,
+                        const __grid_constant__ TmaMap tmap_e1)
 {
-    using P = SmemPlan<MT, EP::STAGED>;
+    constexpr bool TMA = BL::USES_TMA;
+    constexpr int EPI_GROUPS = TMA ? 2 : 1;
+    constexpr int EPI_WARPS = EPI_GROUPS * (NUM_EPI / 32);
+    using P = SmemPlan<MT, EP::STAGED, TMA>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + P::BAR_OFF);
@@ -784,7 +794,7 @@ __global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp
     uint64_t *tfull = empty + P::STAGES;
     uint64_t *tempty = tfull + 2;
     uint64_t *ebar = tempty + 2;  // one per epilogue warp
-    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(ebar + NUM_EPI / 32);
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(ebar + EPI_WARPS);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int mg = blockIdx.y;
@@ -796,14 +806,14 @@ __global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp
 
     if (tid == 0) {
         for (int s = 0; s < P::STAGES; ++s) {
-            mbar_init(&full[s], NUM_LOAD);
+            mbar_init(&full[s], TMA ? 1 : NUM_LOAD);
             mbar_init(&empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
             mbar_init(&tempty[a], NUM_EPI);
         }
-        for (int w = 0; w < NUM_EPI / 32; ++w) mbar_init(&ebar[w], 1);
+        for (int w = 0; w < EPI_WARPS; ++w) mbar_init(&ebar[w], 1);
         fence_barrier_init();
     }
     if (warp == MMA_WARP) tmem_alloc<TCOLS>(tmem_holder);
@@ -812,36 +822,54 @@ __global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
-    if (warp >= NUM_EPI / 32 && warp < MMA_WARP) {
-        // ------------------------------------------------------------------ loaders: group g takes every
+    if (TMA && warp == PROD_WARP_TMA) {
+        // ------------------------------------------------------------------ producer: one thread, TMA only
+        if constexpr (TMA) {
+            if (lane == 0) {
+                uint32_t it = 0;
+                for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                    for (int kc = 0; kc < gp.num_kc; ++kc, ++it) {
+                        const int s = it % P::STAGES;
+                        const uint32_t ph = (it / P::STAGES) & 1u;
+                        mbar_wait(&empty[s], ph ^ 1u);
+                        uint8_t *A = smem + s * P::STAGE_BYTES;
+                        uint8_t *B = A + P::A_BYTES;
+                        mbar_expect_tx(&full[s], P::A_BYTES);
+                        bulk_g2s(A, gp.a_packed + ((int64_t)mg * gp.num_kc + kc) * P::A_BYTES, P::A_BYTES, &full[s]);
+                        bl.produce_tma(B, tile, kc, &tmap, &full[s]);
+                        mbar_arrive(&full[s]);
+                    }
+                }
+            }
+        }
+    } else if (!TMA && warp >= NUM_EPI / 32 && warp < MMA_WARP) {
+        // ------------------------------------------------------------------ SIMT loaders: group g takes every
         // LOAD_GROUPS-th (tile, k-chunk) item, so the groups' global-load latencies overlap
-        const int g = (tid - NUM_EPI) / NUM_LOAD;
-        const int lt = (tid - NUM_EPI) % NUM_LOAD;
-        uint32_t it = 0;
-        int64_t cur_tile = -1;
-        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            for (int kc = 0; kc < gp.num_kc; ++kc, ++it) {
-                if ((int)(it % LOAD_GROUPS) != g) continue;
-                if (tile != cur_tile) {
-                    bl.begin_tile(tile, lt);
-                    cur_tile = tile;
-                }
-                const int s = it % P::STAGES;
-                const uint32_t ph = (it / P::STAGES) & 1u;
-                mbar_wait(&empty[s], ph ^ 1u);
-                uint8_t *A = smem + s * P::STAGE_BYTES;
-                uint8_t *B = A + P::A_BYTES;
-                if (lt == 0) {
-                    mbar_expect_tx(&full[s], P::A_BYTES);
-                    bulk_g2s(A, gp.a_packed + ((int64_t)mg * gp.num_kc + kc) * P::A_BYTES, P::A_BYTES, &full[s]);
-                }
-                if constexpr (BL::USES_TMA) {
-                    if (lt == 0) bl.produce_tma(B, tile, kc, &tmap, &full[s]);
-                } else {
+        if constexpr (!TMA) {
+            const int g = (tid - NUM_EPI) / NUM_LOAD;
+            const int lt = (tid - NUM_EPI) % NUM_LOAD;
+            uint32_t it = 0;
+            int64_t cur_tile = -1;
+            for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int kc = 0; kc < gp.num_kc; ++kc, ++it) {
+                    if ((int)(it % LOAD_GROUPS) != g) continue;
+                    if (tile != cur_tile) {
+                        bl.begin_tile(tile, lt);
+                        cur_tile = tile;
+                    }
+                    const int s = it % P::STAGES;
+                    const uint32_t ph = (it / P::STAGES) & 1u;
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    uint8_t *A = smem + s * P::STAGE_BYTES;
+                    uint8_t *B = A + P::A_BYTES;
+                    if (lt == 0) {
+                        mbar_expect_tx(&full[s], P::A_BYTES);
+                        bulk_g2s(A, gp.a_packed + ((int64_t)mg * gp.num_kc + kc) * P::A_BYTES, P::A_BYTES, &full[s]);
+                    }
                     bl.produce(B, kc, lt);
                     fence_proxy_async_smem();
+                    mbar_arrive(&full[s]);
                 }
-                mbar_arrive(&full[s]);
             }
         }
     } else if (warp == MMA_WARP) {
@@ -874,11 +902,12 @@ __global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp
                 umma_commit(&tfull[acc]);
             }
         }
-    } else {
-        // ------------------------------------------------------------------ epilogue (warps 0-7)
+    } else if (warp < EPI_WARPS) {
+        // ------------------------------------------------------------------ epilogue: group g = warp / 8 drains the
+        // tiles with tl % EPI_GROUPS == g (with two groups: tile parity = accumulator buffer)
         ep.begin();
-        uint32_t tl = 0;
-        const int half = warp >> 2;
+        const int grp = warp >> 3, w8 = warp & 7;
+        const int half = w8 >> 2;
         const int chl = tid & 127;
         const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
         EpCtx cx;
@@ -886,7 +915,9 @@ __global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp
         cx.m0 = &tmap_e0;
         cx.m1 = &tmap_e1;
         cx.bar = &ebar[warp];
-        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+        const int64_t tstep = (int64_t)EPI_GROUPS * gridDim.x;
+        uint32_t tl = (uint32_t)grp;
+        for (int64_t tile = blockIdx.x + (int64_t)grp * gridDim.x; tile < num_tiles; tile += tstep, tl += EPI_GROUPS) {
             const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
             mbar_wait(&tfull[acc], aph);
             tc_fence_after();
@@ -897,7 +928,7 @@ __global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp
                     cx.next_tile = tile;
                     cx.next_ch = ch + 128;
                 } else {
-                    cx.next_tile = tile + gridDim.x < num_tiles ? tile + gridDim.x : -1;
+                    cx.next_tile = tile + tstep < num_tiles ? tile + tstep : -1;
                     cx.next_ch = mg * MT * 128 + chl;
                 }
                 ep.tile_mt(tmem_base + lane_base + acc * (MT * R) + mt * R, tile, ch, mt, half, cx);
@@ -906,7 +937,7 @@ __global__ void __launch_bounds__(NT, 1) tc_rows_gemm_kernel(const GemmParams gp
             mbar_arrive(&tempty[acc]);
         }
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) ep.finish_mt((mg * MT + mt) * 128 + chl, mt, half);
+        for (int mt = 0; mt < MT; ++mt) ep.finish_mt((mg * MT + mt) * 128 + chl, mt, grp * 2 + half);
     }
     tc_fence_before();
     __syncthreads();
@@ -1274,13 +1305,13 @@ template <int MT, class BL, class EP>
 static int launch_gemm(const Packed &pk, const RowsArg &ra, const BL &bl, const EP &ep, cudaStream_t st,
                        const TmaMap &map = kNoMap, const TmaMap &e0 = kNoMap, const TmaMap &e1 = kNoMap)
 {
-    using P = SmemPlan<MT, EP::STAGED>;
+    using P = SmemPlan<MT, EP::STAGED, BL::USES_TMA>;
     auto kern = tc_rows_gemm_kernel<MT, BL, EP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
     if (e != cudaSuccess) return (int)e;
     GemmParams gp = {pk.img, pk.num_kc, ra.cap, ra.dev};
     dim3 grid((unsigned)grid_x_for(pk, ra.tiles()), (unsigned)pk.num_mg);
-    kern<<<grid, NT, P::TOTAL, st>>>(gp, bl, ep, map, e0, e1);
+    kern<<<grid, BL::USES_TMA ? NT_TMA : NT, P::TOTAL, st>>>(gp, bl, ep, map, e0, e1);
     note_launch();
     e = cudaPeekAtLastError();
     return e == cudaSuccess ? 0 : (int)e;
@@ -1597,7 +1628,7 @@ static ShapesTC shapes_tc(const b2pn_sa_args &a)
     return s;
 }
 
-constexpr int MAX_GX = 160;  // >= SM count: rows of the per-CTA partial buffers
+constexpr int MAX_GX = 160;  // >= SM count: CTAs writing per-CTA partial buffers (4 slots each)
 
 static int check_args_tc(const b2pn_sa_args &a)
 {
@@ -1655,7 +1686,7 @@ static FwdWsTC carve_fwd_tc(const b2pn_sa_args &a, const ShapesTC &s, WsTC &ws)
     f.pk[1] = plan_pack(s.c2, s.c1);
     f.pk[2] = plan_pack(s.c3, s.c2);
     for (int l = 0; l < 3; ++l) f.pk[l].img = ws.take<uint8_t>(f.pk[l].bytes);
-    f.partial = ws.take<double>((int64_t)MAX_GX * 2 * 2 * s.cpad);
+    f.partial = ws.take<double>((int64_t)MAX_GX * 4 * 2 * s.cpad);
     f.keys = a.seg_mode == B2PN_SEG_CLOUDS ? ws.take<unsigned long long>(a.n_dst * (int64_t)s.c3) : nullptr;
     return f;
 }
@@ -1698,7 +1729,7 @@ static BwdWsTC carve_bwd_tc(const b2pn_sa_args &a, const ShapesTC &s, WsTC &ws)
     b.pkT[1] = plan_pack(s.c1, s.c2);               // W2^T
     b.pkT[0] = plan_pack(a.c_in > 0 ? a.c_in : 1, s.c1);  // feature rows of W1^T
     for (int l = 0; l < 3; ++l) b.pkT[l].img = ws.take<uint8_t>(b.pkT[l].bytes);
-    b.partial = ws.take<double>((int64_t)MAX_GX * 2 * 2 * s.cpad);
+    b.partial = ws.take<double>((int64_t)MAX_GX * 4 * 2 * s.cpad);
     b.dz1 = ws.take<__nv_bfloat16>((int64_t)s.c1 * s.ld);
     b.dz2 = ws.take<__nv_bfloat16>((int64_t)s.c2 * s.ld);
     b.dh3 = ws.take<__nv_bfloat16>((int64_t)s.c3 * s.ld);
@@ -1762,13 +1793,14 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
         note_launch();
         if ((rc = make_tma_feature_major(&map_g1, a.g1, kg, s.ld))) return rc;
     }
+    const int ns1 = use_g1 ? 4 : 2;  // partial slots per CTA: 2 column halves x epilogue groups (2 when TMA-fed)
     if (train && s.rows > 0) {
-        StatsEpTC<1> e1 = {s.c1, f.partial, s.cpad};
-        StatsEpTC<2> e2 = {s.c1, f.partial, s.cpad};
+        StatsEpTC<1> e1 = {s.c1, f.partial, s.cpad, ns1};
+        StatsEpTC<2> e2 = {s.c1, f.partial, s.cpad, ns1};
         rc = use_g1 ? launch_by_mt(f.pk[0], ra, tl1, e1, e2, st, map_g1) : launch_by_mt(f.pk[0], ra, gl, e1, e2, st);
         if (rc) return rc;
     }
-    bn_fwd_finalize_tc_kernel<<<(s.c1 + 3) / 4, 128, 0, st>>>(f.partial, 2 * grid_x_for(f.pk[0], s.tiles), s.c1, s.cpad, count, train,
+    bn_fwd_finalize_tc_kernel<<<(s.c1 + 3) / 4, 128, 0, st>>>(f.partial, ns1 * grid_x_for(f.pk[0], s.tiles), s.c1, s.cpad, count, train,
                                                                  a.mlp.b[0], a.mlp.gamma[0], a.mlp.beta[0], a.mlp.running_mean[0],
                                                                  a.mlp.running_var[0], a.mlp.num_batches_tracked[0], a.mlp.eps,
                                                                  a.mlp.momentum, bn1, s.cmax);
@@ -1788,11 +1820,11 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
     if ((rc = make_tma_feature_major(&map_a1, a.a1, s.c1, s.ld))) return rc;
     if ((rc = make_tma_feature_major(&map_a2, a.a2, s.c2, s.ld))) return rc;
     if (train && s.rows > 0) {
-        StatsEpTC<1> e1 = {s.c2, f.partial, s.cpad};
-        StatsEpTC<2> e2 = {s.c2, f.partial, s.cpad};
+        StatsEpTC<1> e1 = {s.c2, f.partial, s.cpad, 4};
+        StatsEpTC<2> e2 = {s.c2, f.partial, s.cpad, 4};
         if ((rc = launch_by_mt(f.pk[1], ra, l2, e1, e2, st, map_a1))) return rc;
     }
-    bn_fwd_finalize_tc_kernel<<<(s.c2 + 3) / 4, 128, 0, st>>>(f.partial, 2 * grid_x_for(f.pk[1], s.tiles), s.c2, s.cpad, count, train,
+    bn_fwd_finalize_tc_kernel<<<(s.c2 + 3) / 4, 128, 0, st>>>(f.partial, 4 * grid_x_for(f.pk[1], s.tiles), s.c2, s.cpad, count, train,
                                                                  a.mlp.b[1], a.mlp.gamma[1], a.mlp.beta[1], a.mlp.running_mean[1],
                                                                  a.mlp.running_var[1], a.mlp.num_batches_tracked[1], a.mlp.eps,
                                                                  a.mlp.momentum, bn2, s.cmax);
@@ -1892,8 +1924,8 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
     const CountArg count = {a.seg_mode == B2PN_SEG_SLOTS ? a.num_rows + 1 : nullptr, (double)s.rows};
 
     // ---- layer 3 ---------------------------------------------------------------------------------------
-    MaskSumsStoreEpTC<1> e31 = {s.c2, a.mlp.gamma[1], a.mlp.beta[1], a.mlp.act, b.partial, s.cpad};
-    MaskSumsStoreEpTC<2> e32 = {s.c2, a.mlp.gamma[1], a.mlp.beta[1], a.mlp.act, b.partial, s.cpad};
+    MaskSumsStoreEpTC<1> e31 = {s.c2, a.mlp.gamma[1], a.mlp.beta[1], a.mlp.act, b.partial, s.cpad, 4};
+    MaskSumsStoreEpTC<2> e32 = {s.c2, a.mlp.gamma[1], a.mlp.beta[1], a.mlp.act, b.partial, s.cpad, 4};
     TmaMap mdz2, mz2;  // epilogue maps (32-channel boxes): dz2 out, zhat2 in
     if ((rc = make_tma_feature_major(&mdz2, b.dz2, s.c2, s.ld, 32))) return rc;
     if ((rc = make_tma_feature_major(&mz2, z2, s.c2, s.ld, 32))) return rc;
@@ -1928,7 +1960,7 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
         if (rc) return rc;
     }
     launch_dw_reduce(b.dwp, s.c3, s.c2 + 1, nullptr, s.c2, s.c2, s, g.grad_w[2], g.grad_b[2], st);
-    bn_bwd_finalize_tc_kernel<<<(s.c2 + 3) / 4, 128, 0, st>>>(b.partial, 2 * grid_x_for(b.pkT[2], s.tiles), s.c2, s.cpad, count,
+    bn_bwd_finalize_tc_kernel<<<(s.c2 + 3) / 4, 128, 0, st>>>(b.partial, 4 * grid_x_for(b.pkT[2], s.tiles), s.c2, s.cpad, count,
                                                                  a.training, g.grad_gamma[1], g.grad_beta[1], b.sbar);
     note_launch();
     {
@@ -1943,8 +1975,8 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
     TmaSource y2 = {rm};
     {
         TmaFeatLoader bl;
-        MaskSumsStoreEpTC<1> e1 = {s.c1, a.mlp.gamma[0], a.mlp.beta[0], a.mlp.act, b.partial, s.cpad};
-        MaskSumsStoreEpTC<2> e2 = {s.c1, a.mlp.gamma[0], a.mlp.beta[0], a.mlp.act, b.partial, s.cpad};
+        MaskSumsStoreEpTC<1> e1 = {s.c1, a.mlp.gamma[0], a.mlp.beta[0], a.mlp.act, b.partial, s.cpad, 4};
+        MaskSumsStoreEpTC<2> e2 = {s.c1, a.mlp.gamma[0], a.mlp.beta[0], a.mlp.act, b.partial, s.cpad, 4};
         TmaMap mdz1, mz1;
         if ((rc = make_tma_feature_major(&mdz1, b.dz1, s.c1, s.ld, 32))) return rc;
         if ((rc = make_tma_feature_major(&mz1, z1, s.c1, s.ld, 32))) return rc;
@@ -1959,7 +1991,7 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
         if (rc) return rc;
         launch_dw_reduce(b.dwp, s.c2, s.c1 + 1, nullptr, s.c1, s.c1, s, g.grad_w[1], g.grad_b[1], st);
     }
-    bn_bwd_finalize_tc_kernel<<<(s.c1 + 3) / 4, 128, 0, st>>>(b.partial, 2 * grid_x_for(b.pkT[1], s.tiles), s.c1, s.cpad, count,
+    bn_bwd_finalize_tc_kernel<<<(s.c1 + 3) / 4, 128, 0, st>>>(b.partial, 4 * grid_x_for(b.pkT[1], s.tiles), s.c1, s.cpad, count,
                                                                  a.training, g.grad_gamma[0], g.grad_beta[0], b.sbar);
     note_launch();
     {
