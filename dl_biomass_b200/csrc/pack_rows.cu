@@ -33,15 +33,15 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_rows_scan_kernel(const int3
 {
     __shared__ int s_warp[PACK_THREADS / 32];
     __shared__ int s_carry;
-    __shared__ unsigned long long s_edges;
+    __shared__ int s_edges;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t chunks = (n_dst + PACK_G - 1) / PACK_G;
     if (tid == 0) {
         s_carry = 0;
-        s_edges = 0ull;
+        s_edges = 0;
     }
     __syncthreads();
-    long long my_edges = 0;
+    int my_edges = 0;  // < 2^31: n_dst < 2^24 centroids x 64 slots
     for (int64_t c0 = 0; c0 < chunks; c0 += PACK_THREADS) {
         const int64_t ch = c0 + tid;
         int blocks = 0;  // 64-row blocks used by my chunk
@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_rows_scan_kernel(const int3
         if (tid == PACK_THREADS - 1) s_carry = carry + s_warp[PACK_THREADS / 32 - 1];
         __syncthreads();
     }
-    if (my_edges) atomicAdd(&s_edges, (unsigned long long)my_edges);  // integer sum: order does not matter
+    my_edges = __reduce_add_sync(0xffffffffu, my_edges);
+    if (lane == 0 && my_edges) atomicAdd(&s_edges, my_edges);  // integer sum: order does not matter
     __syncthreads();
     if (tid == 0) {
         num_rows[0] = (int64_t)s_carry * 64;

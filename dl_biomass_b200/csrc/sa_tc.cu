@@ -1338,9 +1338,22 @@ __device__ __forceinline__ void warp_sum_partials(const double *partial, int gx,
 {
     const int lane = threadIdx.x & 31;
     double s = 0.0, q = 0.0;
-    for (int g = lane; g < gx; g += 32) {
-        s += partial[(int64_t)g * 2 * cpad + c];
-        q += partial[(int64_t)g * 2 * cpad + cpad + c];
+    {
+        double s4[4] = {0.0, 0.0, 0.0, 0.0}, q4[4] = {0.0, 0.0, 0.0, 0.0};  // independent chains, fixed order
+        int g = lane;
+        for (; g + 96 < gx; g += 128) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                s4[u] += partial[(int64_t)(g + 32 * u) * 2 * cpad + c];
+                q4[u] += partial[(int64_t)(g + 32 * u) * 2 * cpad + cpad + c];
+            }
+        }
+        for (; g < gx; g += 32) {
+            s4[0] += partial[(int64_t)g * 2 * cpad + c];
+            q4[0] += partial[(int64_t)g * 2 * cpad + cpad + c];
+        }
+        s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        q = (q4[0] + q4[1]) + (q4[2] + q4[3]);
     }
     // fixed-order butterfly: deterministic
     for (int o = 16; o > 0; o >>= 1) {
@@ -1482,32 +1495,44 @@ __global__ void bn_bwd_apply_tc_kernel(RowMapTC rm, const int64_t *rows_dev, __n
 }
 
 // dW = sum over the split partials; image columns that share a weight column (hi/lo parts) are added up;
-// the "ones" image column is the bias gradient.
-__global__ void dw_reduce_tc_kernel(const float *partial, int splits, int n_out, int k_total, int use_map, InCols cols,
-                                    int k_true, int ones_idx, float *grad_w, float *grad_b)
+// the "ones" image column is the bias gradient.  blockIdx.y selects the layer: the three weight gradients of a level are
+// reduced by ONE launch at the end of its backward pass (each is a string of dependent L2 round trips, not bandwidth).
+struct DwReduceJob {
+    const float *partial;
+    int splits, n_out, k_total, use_map;
+    InCols cols;
+    int k_true, ones_idx;
+    float *grad_w, *grad_b;
+};
+struct DwReduceJobs {
+    DwReduceJob j[3];
+};
+__global__ void dw_reduce_tc_kernel(const DwReduceJobs jobs)
 {
+    const DwReduceJob &jb = jobs.j[blockIdx.y];
+    const int k_true = jb.k_true, k_total = jb.k_total, n_out = jb.n_out, splits = jb.splits;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per output element (coalesced)
     if (i >= (int64_t)n_out * (k_true + 1)) return;
     const int n = (int)(i / (k_true + 1));
     const int k = (int)(i - (int64_t)n * (k_true + 1));
     int c0 = -1, c1 = -1;
     if (k == k_true) {
-        c0 = ones_idx;
-    } else if (!use_map) {
+        c0 = jb.ones_idx;
+    } else if (!jb.use_map) {
         c0 = k;
     } else {
-        const int nx = cols.nx();
-        if (k < cols.c_in) {
+        const int nx = jb.cols.nx();
+        if (k < jb.cols.c_in) {
             c0 = k;
-            c1 = cols.x_f32 ? k + cols.c_in : -1;
+            c1 = jb.cols.x_f32 ? k + jb.cols.c_in : -1;
         } else {
-            c0 = nx + (k - cols.c_in);
+            c0 = nx + (k - jb.cols.c_in);
             c1 = c0 + 3;
         }
     }
     const int64_t stride = (int64_t)n_out * k_total;
-    const float *base = partial + (int64_t)n * k_total;
-    constexpr int U = 16;  // independent chains: the loop is a string of L2 round trips, keep 16 in flight; fixed order
+    const float *base = jb.partial + (int64_t)n * k_total;
+    constexpr int U = 16;  // independent chains: keep 16 loads in flight; fixed order
     double acc[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) acc[u] = 0.0;
@@ -1530,11 +1555,11 @@ __global__ void dw_reduce_tc_kernel(const float *partial, int splits, int n_out,
     for (int w = U / 2; w > 0; w >>= 1)
 #pragma unroll
         for (int u = 0; u < w; ++u) acc[u] += acc[u + w];
-    const double s = acc[0];
+    const double sum = acc[0];
     if (k == k_true) {
-        if (grad_b) grad_b[n] = (float)s;
-    } else if (grad_w) {
-        grad_w[(int64_t)n * k_true + k] = (float)s;
+        if (jb.grad_b) jb.grad_b[n] = (float)sum;
+    } else if (jb.grad_w) {
+        jb.grad_w[(int64_t)n * k_true + k] = (float)sum;
     }
 }
 
@@ -1720,7 +1745,7 @@ struct BwdWsTC {
     __nv_bfloat16 *dz1, *dz2;
     __nv_bfloat16 *dh3;  // materialised routed gradient [c3][ld]
     float *sbar;
-    float *dwp;
+    float *dwp[3];  // split partials of dW1, dW2, dW3 (reduced together at the end)
 };
 static BwdWsTC carve_bwd_tc(const b2pn_sa_args &a, const ShapesTC &s, WsTC &ws)
 {
@@ -1734,11 +1759,9 @@ static BwdWsTC carve_bwd_tc(const b2pn_sa_args &a, const ShapesTC &s, WsTC &ws)
     b.dz2 = ws.take<__nv_bfloat16>((int64_t)s.c2 * s.ld);
     b.dh3 = ws.take<__nv_bfloat16>((int64_t)s.c3 * s.ld);
     b.sbar = ws.take<float>(2 * s.cmax);
-    int64_t mx = plan_dw(s.c3, s.c2 + 1, s.ld).floats;
-    const int64_t m2 = plan_dw(s.c2, s.c1 + 1, s.ld).floats, m1 = plan_dw(s.c1, s.k1 + 1, s.ld).floats;
-    mx = mx > m2 ? mx : m2;
-    mx = mx > m1 ? mx : m1;
-    b.dwp = ws.take<float>(mx);
+    b.dwp[2] = ws.take<float>(plan_dw(s.c3, s.c2 + 1, s.ld).floats);
+    b.dwp[1] = ws.take<float>(plan_dw(s.c2, s.c1 + 1, s.ld).floats);
+    b.dwp[0] = ws.take<float>(plan_dw(s.c1, s.k1 + 1, s.ld).floats);
     return b;
 }
 
@@ -1888,14 +1911,23 @@ static unsigned apply_grid(int64_t ld, int C)
     return (unsigned)(blocks > 0 ? blocks : 1);
 }
 
-static void launch_dw_reduce(const float *dwp, int n_out, int k_total, const InCols *map, int k_true, int ones_idx,
-                             const ShapesTC &s, float *gw, float *gb, cudaStream_t st)
+static DwReduceJob dw_reduce_job(const float *dwp, int n_out, int k_total, const InCols *map, int k_true, int ones_idx,
+                                 const ShapesTC &s, float *gw, float *gb)
 {
     const DwPlanHost d = plan_dw(n_out, k_total, s.ld);
-    const int64_t tot = (int64_t)n_out * (k_true + 1);
-    InCols cols = map ? *map : InCols{0, 0};
-    dw_reduce_tc_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(dwp, d.splits, n_out, k_total, map ? 1 : 0, cols, k_true,
-                                                                       ones_idx, gw, gb);
+    DwReduceJob j = {dwp, d.splits, n_out, k_total, map ? 1 : 0, map ? *map : InCols{0, 0}, k_true, ones_idx, gw, gb};
+    return j;
+}
+static void launch_dw_reduces(const DwReduceJob *jobs, int n, cudaStream_t st)
+{
+    DwReduceJobs dj;
+    int64_t mx = 0;
+    for (int i = 0; i < 3; ++i) {
+        dj.j[i] = jobs[i < n ? i : 0];
+        const int64_t tot = (int64_t)dj.j[i].n_out * (dj.j[i].k_true + 1);
+        mx = tot > mx ? tot : mx;
+    }
+    dw_reduce_tc_kernel<<<dim3((unsigned)((mx + 127) / 128), (unsigned)n), 128, 0, st>>>(dj);
     note_launch();
 }
 
@@ -1953,13 +1985,12 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
         TmaSource y3 = {rm};
         if (tma_x2) {
             TmaFill xt = {s.c2, 1};
-            rc = launch_dw(y3, xt, s.c3, s.c2 + 1, s, ra, b.dwp, st, map3, map_a2, map_v);   // dW3 = dh3^T a2
+            rc = launch_dw(y3, xt, s.c3, s.c2 + 1, s, ra, b.dwp[2], st, map3, map_a2, map_v);   // dW3 = dh3^T a2
         } else {
-            rc = launch_dw(y3, xa2, s.c3, s.c2 + 1, s, ra, b.dwp, st, map3);
+            rc = launch_dw(y3, xa2, s.c3, s.c2 + 1, s, ra, b.dwp[2], st, map3);
         }
         if (rc) return rc;
     }
-    launch_dw_reduce(b.dwp, s.c3, s.c2 + 1, nullptr, s.c2, s.c2, s, g.grad_w[2], g.grad_b[2], st);
     bn_bwd_finalize_tc_kernel<<<(s.c2 + 3) / 4, 128, 0, st>>>(b.partial, 4 * grid_x_for(b.pkT[2], s.tiles), s.c2, s.cpad, count,
                                                                  a.training, g.grad_gamma[1], g.grad_beta[1], b.sbar);
     note_launch();
@@ -1983,13 +2014,12 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
         if ((rc = launch_by_mt(b.pkT[1], ra, bl, e1, e2, st, map2, mdz1, mz1))) return rc;
         if (tma_x1) {
             TmaFill xt = {s.c1, 1};
-            rc = launch_dw(y2, xt, s.c2, s.c1 + 1, s, ra, b.dwp, st, map2, map_a1, map_v);
+            rc = launch_dw(y2, xt, s.c2, s.c1 + 1, s, ra, b.dwp[1], st, map2, map_a1, map_v);
         } else {
             LineFillK<FeatSource<1>> xa1 = {{rm, z1, s.c1, s.ld, a.mlp.act, s.c1, a.mlp.gamma[0], a.mlp.beta[0]}};
-            rc = launch_dw(y2, xa1, s.c2, s.c1 + 1, s, ra, b.dwp, st, map2);
+            rc = launch_dw(y2, xa1, s.c2, s.c1 + 1, s, ra, b.dwp[1], st, map2);
         }
         if (rc) return rc;
-        launch_dw_reduce(b.dwp, s.c2, s.c1 + 1, nullptr, s.c1, s.c1, s, g.grad_w[1], g.grad_b[1], st);
     }
     bn_bwd_finalize_tc_kernel<<<(s.c1 + 3) / 4, 128, 0, st>>>(b.partial, 4 * grid_x_for(b.pkT[1], s.tiles), s.c1, s.cpad, count,
                                                                  a.training, g.grad_gamma[0], g.grad_beta[0], b.sbar);
@@ -2005,13 +2035,16 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
             TmaMap map_g1;
             if ((rc = make_tma_feature_major(&map_g1, a.g1, s.k1 + 1, s.ld))) return rc;
             TmaFill xt = {s.k1 + 1, 0};
-            rc = launch_dw(y1, xt, s.c1, s.k1 + 1, s, ra, b.dwp, st, map1, map_g1, kNoMap);
+            rc = launch_dw(y1, xt, s.c1, s.k1 + 1, s, ra, b.dwp[0], st, map1, map_g1, kNoMap);
         } else {
             LineFillGather xg = {{rm, a.x, s.cols, a.pos_src, a.pos_dst, s.k1}};
-            rc = launch_dw(y1, xg, s.c1, s.k1 + 1, s, ra, b.dwp, st, map1);
+            rc = launch_dw(y1, xg, s.c1, s.k1 + 1, s, ra, b.dwp[0], st, map1);
         }
         if (rc) return rc;
-        launch_dw_reduce(b.dwp, s.c1, s.k1 + 1, &s.cols, s.c0, s.k1, s, g.grad_w[0], g.grad_b[0], st);
+        const DwReduceJob jobs[3] = {dw_reduce_job(b.dwp[2], s.c3, s.c2 + 1, nullptr, s.c2, s.c2, s, g.grad_w[2], g.grad_b[2]),
+                                     dw_reduce_job(b.dwp[1], s.c2, s.c1 + 1, nullptr, s.c1, s.c1, s, g.grad_w[1], g.grad_b[1]),
+                                     dw_reduce_job(b.dwp[0], s.c1, s.k1 + 1, &s.cols, s.c0, s.k1, s, g.grad_w[0], g.grad_b[0])};
+        launch_dw_reduces(jobs, 3, st);
     }
     if (need_dx) {
         TmaFeatLoader bl;
