@@ -40,6 +40,17 @@ class SaGrads(ctypes.Structure):
     _fields_ = [("grad_out", _vp), ("grad_w", _vp * 3), ("grad_b", _vp * 3), ("grad_gamma", _vp * 2),
                 ("grad_beta", _vp * 2), ("grad_x", _vp)]
 
+class HeadArgs(ctypes.Structure):
+    _fields_ = [("B", ctypes.c_int32), ("c", ctypes.c_int32 * 4), ("training", ctypes.c_int32), ("p", ctypes.c_float),
+                ("eps", ctypes.c_float), ("momentum", ctypes.c_float), ("x", _vp), ("w", _vp * 3), ("b", _vp * 3),
+                ("gamma", _vp * 2), ("beta", _vp * 2), ("running_mean", _vp * 2), ("running_var", _vp * 2),
+                ("num_batches_tracked", _vp * 2), ("seed", ctypes.c_uint64), ("rng_counter", _vp), ("out", _vp),
+                ("xhat", _vp * 2), ("mask", _vp * 2), ("rstd", _vp * 2)]
+
+
+class HeadGrads(ctypes.Structure):
+    _fields_ = [("grad_out", _vp), ("grad_x", _vp), ("grad_w", _vp * 3), ("grad_b", _vp * 3), ("grad_gamma", _vp * 2),
+                ("grad_beta", _vp * 2)]
 
 
 # name -> (restype, argtypes); must list every symbol include/b2pn.h declares (tests check this)
@@ -60,6 +71,8 @@ SIGNATURES = {
     "b2pn_sa_workspace_bytes": (_i64, [ctypes.POINTER(SaArgs), _i32]),
     "b2pn_sa_forward": (ctypes.c_int, [ctypes.POINTER(SaArgs), _vp]),
     "b2pn_sa_backward": (ctypes.c_int, [ctypes.POINTER(SaArgs), ctypes.POINTER(SaGrads), _vp]),
+    "b2pn_head_forward": (ctypes.c_int, [ctypes.POINTER(HeadArgs), _vp]),
+    "b2pn_head_backward": (ctypes.c_int, [ctypes.POINTER(HeadArgs), ctypes.POINTER(HeadGrads), _vp]),
     "b2pn_tc_gemm_selftest": (ctypes.c_int, [_vp, _i32, _i32, _vp, _i32, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _vp]),
 }
 

@@ -21,7 +21,7 @@ from typing import List, Optional, Sequence
 import torch
 import torch.nn.functional as F
 
-from . import ops, sa
+from . import head, ops, sa
 
 _PRECISIONS = {"fp32": sa.PREC_F32, "f32": sa.PREC_F32, "float32": sa.PREC_F32,
                "bf16": sa.PREC_BF16, "bfloat16": sa.PREC_BF16}
@@ -184,6 +184,11 @@ class Net(torch.nn.Module):
         self.sa2_module = SAModule(0.25, 8, MLP([128 * nm + 3, 128 * nm, 128 * nm, 256 * nm], act=activation_function))
         self.sa3_module = GlobalSAModule(MLP([256 * nm + 3, 256 * nm, 512 * nm, 1024 * nm], act=activation_function))
         self.mlp = MLP([1024 * nm, 128 * nm, 128 * nm, 4], act=None, dropout=dropout_probability)
+        # dropout noise of the fused head: (seed, counter, layer, element); the counter is a device scalar bumped by the
+        # forward kernel, so a CUDA-graph replay draws fresh noise every step.  (A plain attribute, not a buffer: the
+        # module's buffers stay exactly the reference's.)
+        self._head_rng_counter = None
+        self._head_seed = int(torch.initial_seed() & 0x7fffffffffffffff)
         self.set_precision(precision)
 
     def set_precision(self, precision: str) -> "Net":
@@ -238,4 +243,8 @@ class Net(torch.nn.Module):
             else:
                 after_grouping()
         x3 = self.sa3_module._run(x2, pos2, batch2, len(sizes))                          # :56
-        return self.mlp(x3)                                                              # :58
+        if head.supported(self.mlp, x3):                                                 # :58
+            if self._head_rng_counter is None or self._head_rng_counter.device != x3.device:
+                self._head_rng_counter = torch.zeros((), dtype=torch.int64, device=x3.device)
+            return head.head_apply(self.mlp, x3, self._head_rng_counter, self._head_seed)
+        return self.mlp(x3)   # shapes outside the fused head's range (batch > 32 clouds, wide heads): ATen on the GPU

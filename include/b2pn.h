@@ -199,6 +199,44 @@ int64_t b2pn_sa_workspace_bytes(const b2pn_sa_args *args, int32_t backward);
 int b2pn_sa_forward(const b2pn_sa_args *args, b2pn_stream_t stream);
 int b2pn_sa_backward(const b2pn_sa_args *args, const b2pn_sa_grads *grads, b2pn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Regression head: the MLP([c0, c1, c2, c3], act=None, dropout=p) of /root/reference/pointnet2_regressor.py:50,58
+ * (torch_geometric.nn.MLP: Lin -> BatchNorm1d -> dropout -> Lin -> BatchNorm1d -> dropout -> Lin) on B <= 32 rows,
+ * one forward and one backward kernel instead of ~60 ATen launches.  fp32.  c1, c2 <= 256, c3 <= 8.
+ * Dropout noise is counter based: (seed, *rng_counter, layer, element); forward bumps *rng_counter when training,
+ * which keeps the op replayable from a CUDA graph.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct b2pn_head_args {
+    int32_t B;                   /* rows (tree clouds)                                                */
+    int32_t c[4];                /* channel list                                                      */
+    int32_t training;            /* 1: batch statistics, running-stat update, dropout; 0: eval        */
+    float p, eps, momentum;      /* dropout probability; BatchNorm eps, momentum                      */
+    const float *x;              /* [B, c0]                                                           */
+    const float *w[3];           /* Linear weights [c_{l+1}, c_l]                                     */
+    const float *b[3];
+    const float *gamma[2];
+    const float *beta[2];
+    float *running_mean[2];
+    float *running_var[2];
+    int64_t *num_batches_tracked[2];
+    uint64_t seed;
+    int64_t *rng_counter;        /* device scalar, may be NULL when p == 0 or not training            */
+    float *out;                  /* [B, c3]                                                           */
+    float *xhat[2];              /* saved for backward: normalised hidden values [B, c_{l+1}]         */
+    uint8_t *mask[2];            /* saved dropout keep-masks [B, c_{l+1}] (may be NULL when p == 0)   */
+    float *rstd[2];              /* saved 1/sqrt(var + eps) [c_{l+1}]                                 */
+} b2pn_head_args;
+
+typedef struct b2pn_head_grads {
+    const float *grad_out;       /* [B, c3]                                                           */
+    float *grad_x;               /* [B, c0] or NULL                                                   */
+    float *grad_w[3], *grad_b[3];
+    float *grad_gamma[2], *grad_beta[2];
+} b2pn_head_grads;
+
+int b2pn_head_forward(const b2pn_head_args *args, b2pn_stream_t stream);
+int b2pn_head_backward(const b2pn_head_args *args, const b2pn_head_grads *grads, b2pn_stream_t stream);
+
 /*
  * Hardware self-test of the tcgen05 GEMM pipeline (debug aid used by tests/test_tc_gpu.py; not part of
  * the reference's surface).  out[m][row] (fp32, leading dimension ld_out) = sum_k w[m][k] * b(row, k) with
