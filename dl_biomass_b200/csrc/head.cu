@@ -111,18 +111,57 @@ __device__ __forceinline__ void head_bn_dropout(float *h, int ld, int B, int C, 
     if (threadIdx.x == 0 && a.training && a.num_batches_tracked[layer]) *a.num_batches_tracked[layer] += 1;
 }
 
+// First Linear (c0 = 1024 inputs: 512 KB of weights) spread over the GPU: one warp per output channel, the B input
+// rows come straight from global memory (48 KB, cache resident).  h1 lands in the xhat[0] buffer, which the second
+// kernel overwrites with the normalised values.
+template <int MAXB>
+__global__ void __launch_bounds__(256) head_lin0_kernel(const b2pn_head_args a)
+{
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int B = a.B, K = a.c[0], J = a.c[1];
+    if (j >= J) return;
+    float acc[MAXB];
+#pragma unroll
+    for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
+    const float *w = a.w[0] + (int64_t)j * K;
+    for (int k0 = 0; k0 < K; k0 += 128) {  // four independent 128-byte weight loads in flight per lane
+        float wv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u * 32 + lane;
+            wv[u] = k < K ? __ldg(w + k) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u * 32 + lane;
+            if (k < K) {
+#pragma unroll
+                for (int b = 0; b < MAXB; ++b)
+                    if (b < B) acc[b] = fmaf(__ldg(a.x + b * K + k), wv[u], acc[b]);
+            }
+        }
+    }
+    const float bj = a.b[0][j];
+#pragma unroll
+    for (int b = 0; b < MAXB; ++b) {
+        if (b < B) {
+            const float s = warp_sum(acc[b]);
+            if (lane == 0) a.xhat[0][b * J + j] = s + bj;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(HEAD_THREADS, 1) head_forward_kernel(const b2pn_head_args a)
 {
     extern __shared__ float hs[];
     const int B = a.B, c0 = a.c[0], c1 = a.c[1], c2 = a.c[2], c3 = a.c[3];
-    float *sx = hs;              // [B][c0]
-    float *s1 = sx + B * c0;     // [B][c1]
+    float *s1 = hs;              // [B][c1]  h1 from head_lin0_kernel (parked in xhat[0])
     float *s2 = s1 + B * c1;     // [B][c2]
     unsigned long long call = 0ull;
     if (a.rng_counter) call = (unsigned long long)*a.rng_counter;
-    for (int i = threadIdx.x; i < B * c0; i += blockDim.x) sx[i] = a.x[i];
-    __syncthreads();
-    head_linear<HEAD_MAX_B>(sx, c0, B, c0, a.w[0], a.b[0], c1, s1, c1);
+    (void)c0;
+    for (int i = threadIdx.x; i < B * c1; i += blockDim.x) s1[i] = a.xhat[0][i];
     __syncthreads();
     head_bn_dropout(s1, c1, B, c1, a, 0, call);
     __syncthreads();
@@ -290,9 +329,13 @@ extern "C" int b2pn_head_forward(const b2pn_head_args *args, b2pn_stream_t strea
     int rc = head_check(*args, true);
     if (rc) return rc;
     const b2pn_head_args &a = *args;
-    const int smem = (a.B * (a.c[0] + a.c[1] + a.c[2])) * (int)sizeof(float);
-    if (smem > 200 * 1024) return B2PN_ENOTSUP;
+    if (!a.xhat[0]) return B2PN_EINVAL;  // doubles as the scratch for the first layer's output
+    const int smem = (a.B * (a.c[1] + a.c[2])) * (int)sizeof(float);
     B2PN_CUDA(cudaFuncSetAttribute(head_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const unsigned g0 = (unsigned)((a.c[1] + 7) / 8);
+    if (a.B <= 16) head_lin0_kernel<16><<<g0, 256, 0, (cudaStream_t)stream>>>(a);
+    else head_lin0_kernel<32><<<g0, 256, 0, (cudaStream_t)stream>>>(a);
+    note_launch();
     head_forward_kernel<<<1, HEAD_THREADS, smem, (cudaStream_t)stream>>>(a);
     note_launch();
     B2PN_LAUNCH_CHECK();

@@ -20,8 +20,7 @@ def supported(mlp, x: torch.Tensor) -> bool:
     if len(mlp.lins) != 3 or len(mlp.norms) != 2 or mlp.act_name is not None:
         return False
     c = mlp.channel_list
-    return 0 < x.size(0) <= MAX_ROWS and c[1] <= MAX_HIDDEN and c[2] <= MAX_HIDDEN and c[3] <= MAX_OUT and \
-        x.size(0) * (c[0] + c[1] + c[2]) * 4 <= 200 * 1024
+    return 0 < x.size(0) <= MAX_ROWS and c[1] <= MAX_HIDDEN and c[2] <= MAX_HIDDEN and c[3] <= MAX_OUT
 
 
 def _fill(a, x, mlp, training, p, out, saved, seed, counter):

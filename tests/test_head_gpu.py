@@ -40,7 +40,7 @@ def _torch_forward(m, x, masks, p):
 
 
 @pytest.mark.parametrize("B,chans,train", [(12, [1024, 128, 128, 4], True), (12, [1024, 128, 128, 4], False),
-                                           (5, [300, 64, 96, 3], True), (32, [1024, 128, 128, 4], True),
+                                           (5, [300, 64, 96, 3], True), (32, [2048, 256, 256, 4], True),
                                            (1, [64, 32, 32, 4], False)])
 def test_head_matches_torch(cuda_device, B, chans, train):
     m, mr = _pair(chans, 0.0, cuda_device)
