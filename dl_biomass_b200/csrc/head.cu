@@ -111,44 +111,37 @@ __device__ __forceinline__ void head_bn_dropout(float *h, int ld, int B, int C, 
     if (threadIdx.x == 0 && a.training && a.num_batches_tracked[layer]) *a.num_batches_tracked[layer] += 1;
 }
 
-// First Linear (c0 = 1024 inputs: 512 KB of weights) spread over the GPU: one warp per output channel, the B input
-// rows come straight from global memory (48 KB, cache resident).  h1 lands in the xhat[0] buffer, which the second
-// kernel overwrites with the normalised values.
+// First Linear (c0 = 1024 inputs: 512 KB of weights) spread over the GPU: one CTA per output channel, 128 threads
+// split the input columns (coalesced loads of the weight row and of the B input rows, which stay cache resident).
+// h1 lands in the xhat[0] buffer, which the second kernel overwrites with the normalised values.
 template <int MAXB>
-__global__ void __launch_bounds__(256) head_lin0_kernel(const b2pn_head_args a)
+__global__ void __launch_bounds__(128) head_lin0_kernel(const b2pn_head_args a)
 {
-    const int lane = threadIdx.x & 31;
-    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    __shared__ float s_part[4][MAXB];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = blockIdx.x;
     const int B = a.B, K = a.c[0], J = a.c[1];
-    if (j >= J) return;
     float acc[MAXB];
 #pragma unroll
     for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
     const float *w = a.w[0] + (int64_t)j * K;
-    for (int k0 = 0; k0 < K; k0 += 128) {  // four independent 128-byte weight loads in flight per lane
-        float wv[4];
+    for (int k = threadIdx.x; k < K; k += 128) {
+        const float wv = __ldg(w + k);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int k = k0 + u * 32 + lane;
-            wv[u] = k < K ? __ldg(w + k) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int k = k0 + u * 32 + lane;
-            if (k < K) {
-#pragma unroll
-                for (int b = 0; b < MAXB; ++b)
-                    if (b < B) acc[b] = fmaf(__ldg(a.x + b * K + k), wv[u], acc[b]);
-            }
-        }
+        for (int b = 0; b < MAXB; ++b)
+            if (b < B) acc[b] = fmaf(__ldg(a.x + b * K + k), wv, acc[b]);
     }
-    const float bj = a.b[0][j];
 #pragma unroll
     for (int b = 0; b < MAXB; ++b) {
         if (b < B) {
             const float s = warp_sum(acc[b]);
-            if (lane == 0) a.xhat[0][b * J + j] = s + bj;
+            if (lane == 0) s_part[warp][b] = s;
         }
+    }
+    __syncthreads();
+    if (threadIdx.x < B) {
+        const int b = threadIdx.x;
+        a.xhat[0][b * J + j] = ((s_part[0][b] + s_part[1][b]) + (s_part[2][b] + s_part[3][b])) + a.b[0][j];
     }
 }
 
@@ -332,9 +325,9 @@ extern "C" int b2pn_head_forward(const b2pn_head_args *args, b2pn_stream_t strea
     if (!a.xhat[0]) return B2PN_EINVAL;  // doubles as the scratch for the first layer's output
     const int smem = (a.B * (a.c[1] + a.c[2])) * (int)sizeof(float);
     B2PN_CUDA(cudaFuncSetAttribute(head_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const unsigned g0 = (unsigned)((a.c[1] + 7) / 8);
-    if (a.B <= 16) head_lin0_kernel<16><<<g0, 256, 0, (cudaStream_t)stream>>>(a);
-    else head_lin0_kernel<32><<<g0, 256, 0, (cudaStream_t)stream>>>(a);
+    const unsigned g0 = (unsigned)a.c[1];
+    if (a.B <= 16) head_lin0_kernel<16><<<g0, 128, 0, (cudaStream_t)stream>>>(a);
+    else head_lin0_kernel<32><<<g0, 128, 0, (cudaStream_t)stream>>>(a);
     note_launch();
     head_forward_kernel<<<1, HEAD_THREADS, smem, (cudaStream_t)stream>>>(a);
     note_launch();
