@@ -316,7 +316,9 @@ def run_b200(args):
                 "traffic": traffic, "peak_kind": f"{peak_kind} (burst copy bandwidth)",
                 "bytes_model": "scan-equivalent m*n*16 B per cloud (SURVEY 8(d)); register-resident, so DRAM traffic is "
                                "the compulsory n*12+m*8 B",
-                "ms_per_launch": round(fps_ms, 4), "share_of_step": round(fps_ms / (total_ms / args.steps), 3)}
+                "ms_per_launch": round(fps_ms, 4), "share_of_step": round(fps_ms / (total_ms / args.steps), 3),
+                "note": "timed alone here; inside the step it runs on the sampling branch of the graph, concurrently with "
+                        "the training kernels" if stepper is not None else "timed alone"}
 
     if rank != 0:
         if world > 1:

@@ -74,3 +74,26 @@ def test_grouping_sass_has_no_fma(built_lib):
             bad.append((cur, line.strip()))
     assert not bad, bad[:3]
     assert "FMUL2" in sass and "FADD2" in sass and "REDUX" in sass
+
+
+def test_host_side_sizing_helpers(built_lib):
+    """Host-only entry points: capacity / workspace bounds and argument checks (no GPU involved)."""
+    h = built_lib.lib()
+    # compacted-row capacity: never below the slots in use, grows with n_dst, rejects K > 64
+    for n_dst, K in ((1, 64), (24000, 64), (6000, 64), (1000, 16), (1000, 40), (7, 8)):
+        cap = h.b2pn_pack_rows_capacity(n_dst, K)
+        assert cap % 128 == 0 and cap >= n_dst * min(64, (K + 7) // 8 * 8) // max(1, 64 // ((K + 7) // 8 * 8)) // 64 * 64
+        assert h.b2pn_pack_rows_capacity(n_dst + 64, K) >= cap
+    assert h.b2pn_pack_rows_capacity(10, 128) == -2          # B2PN_ENOTSUP
+    assert h.b2pn_pack_rows_capacity(-1, 64) == -1           # B2PN_EINVAL
+    assert h.b2pn_pack_rows_workspace_bytes(24000) >= 24000 * 4
+    assert h.b2pn_ball_query_workspace_bytes(12, 120000) >= 120000 * 4 + 12 * 8192 * 4
+    assert h.b2pn_ball_query_workspace_bytes(-1, 10) == -1
+    assert h.b2pn_set_sm_limit(-3) == -1 and h.b2pn_set_sm_limit(0) == 0
+    assert h.b2pn_head_forward(None, None) == -1 and h.b2pn_head_backward(None, None, None) == -1
+    a = built_lib.HeadArgs()
+    a.B = 40                                                  # more rows than the fused head takes
+    for i, c in enumerate((1024, 128, 128, 4)):
+        a.c[i] = c
+    import ctypes
+    assert h.b2pn_head_forward(ctypes.byref(a), None) == -2
