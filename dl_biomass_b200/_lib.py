@@ -61,6 +61,7 @@ SIGNATURES = {
     "b2pn_fps_num_samples": (_i64, [_i64, _f32]),
     "b2pn_set_sm_limit": (ctypes.c_int, [_i32]),
     "b2pn_fps_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
+    "b2pn_fps_f64": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "b2pn_fps_set_variant": (ctypes.c_int, [_i32, _i32]),
     "b2pn_ball_query_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _f64, _i32, _vp, _vp, _vp]),
     "b2pn_ball_query_workspace_bytes": (_i64, [_i32, _i64]),

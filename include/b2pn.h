@@ -65,6 +65,17 @@ int b2pn_fps_f32(const float *pos, const int64_t *ptr, const int64_t *out_ptr, c
                  int32_t B, int64_t max_n, int64_t *out_idx, float *out_pos, int64_t *out_batch,
                  b2pn_stream_t stream);
 
+/*
+ * Farthest-point sampling in float64: the offline resampler that prepares the training clouds.  Replaces the numpy
+ * farthest_point_sampling(coords, k) of /root/reference/downsampling_point_clouds.py:55-92 (called at :153), bit for
+ * bit: float64 distances ((cx-x)^2+(cy-y)^2)+(cz-z)^2, first arg-max, start 0 unless `start` says otherwise, selected
+ * points never compete again.  m <= n samples per cloud (out_ptr), no duplicates in the output.
+ *   pos [N,3] f64, ptr / out_ptr [B+1] i64, start [B] i64 or NULL, out_idx [M] i64 GLOBAL indices,
+ *   dist_workspace [N] f64 scratch.  One CTA per cloud: batch the plots.
+ */
+int b2pn_fps_f64(const double *pos, const int64_t *ptr, const int64_t *out_ptr, const int64_t *start, int32_t B,
+                 int64_t *out_idx, double *dist_workspace, b2pn_stream_t stream);
+
 /* Force a kernel variant (benchmark sweeps): cluster size (1,2,4,8,16), threads per CTA; 0 = auto. */
 int b2pn_fps_set_variant(int32_t cluster, int32_t threads);
 

@@ -146,7 +146,10 @@ int oracle_fps_f32(const float *pos, const int64_t *ptr, const int64_t *out_ptr,
     return 0;
 }
 
-/* float64 twin, used only to pin against the reference's float64 numpy FPS. */
+/* float64 twin of the reference's numpy farthest_point_sampling (/root/reference/downsampling_point_clouds.py:55-92):
+ * distances ((cx-x)^2 + (cy-y)^2) + (cz-z)^2 in separately rounded float64, running minimum, first arg-max, and -- like
+ * the reference's np.delete(idx, selected) -- a selected point never competes again (only visible when duplicates
+ * exhaust the cloud: the next pick is then the first UNSELECTED index, not the first index with distance 0). */
 int oracle_fps_f64(const double *pos, int64_t n, int64_t m, int64_t start, int64_t *out)
 {
     if (!pos || !out || n <= 0 || m <= 0 || m > n) return -1;
@@ -154,11 +157,13 @@ int oracle_fps_f64(const double *pos, int64_t n, int64_t m, int64_t start, int64
     int64_t cur = start;
     out[0] = cur;
     for (int64_t j = 0; j < n; ++j) dist[j] = INFINITY;
+    dist[cur] = -1.0; /* selected */
     for (int64_t i = 1; i < m; ++i) {
         const double *c = pos + 3 * cur;
         int64_t best = -1;
         double bestd = -1.0;
         for (int64_t j = 0; j < n; ++j) {
+            if (dist[j] < 0.0) continue;
             const double dx = c[0] - pos[3 * j], dy = c[1] - pos[3 * j + 1], dz = c[2] - pos[3 * j + 2];
             const double qx = dx * dx, qy = dy * dy, qz = dz * dz;
             const double s = qx + qy;
@@ -168,6 +173,7 @@ int oracle_fps_f64(const double *pos, int64_t n, int64_t m, int64_t start, int64
         }
         cur = best;
         out[i] = cur;
+        dist[cur] = -1.0;
     }
     free(dist);
     return 0;

@@ -44,13 +44,20 @@ def gen_fps_reference():
     out = {}
     cases = []
     for i, (n, k, kind) in enumerate([(300, 60, "dyadic"), (1000, 200, "dyadic"), (2048, 410, "dyadic"),
-                                      (777, 156, "float64"), (1500, 300, "float64"), (64, 64, "dyadic")]):
+                                      (777, 156, "float64"), (1500, 300, "float64"), (64, 64, "dyadic"),
+                                      (1200, 300, "utm"), (600, 400, "dups"), (5000, 1024, "float64")]):
         if kind == "dyadic":
             pts = dyadic_cloud(rng, n)
             if k == n:  # avoid exhausting duplicates: make the points distinct
                 pts = np.unique(pts, axis=0)
                 rng.shuffle(pts)
                 n = k = pts.shape[0]
+        elif kind == "utm":     # raw lidar coordinates: UTM easting / northing, ellipsoidal height
+            pts = rng.normal(size=(n, 3)) * np.array([4.0, 4.0, 8.0]) + np.array([512345.67, 5412345.89, 312.5])
+        elif kind == "dups":    # 200 distinct points three times over, more samples than distinct points
+            base = rng.normal(size=(n // 3, 3)) * np.array([4.0, 4.0, 8.0])
+            pts = np.concatenate([base, base, base], 0)
+            rng.shuffle(pts)
         else:
             pts = rng.normal(size=(n, 3)) * np.array([4.0, 4.0, 8.0])
         idx = fps_np(pts, k)

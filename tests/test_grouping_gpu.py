@@ -184,3 +184,35 @@ def test_dense_cloud_properties(cuda_device):
         want_n, want_c = ref.ball_query_ref(b.pos, b.pos[idx_c[m]][None], torch.tensor([0, 100000, 200000]),
                                             torch.tensor([0, 1, 1]) if m < 20000 else torch.tensor([0, 0, 1]), 4.0, 64)
         assert int(want_c[0]) == k and torch.equal(want_n[0, :k].long(), row)
+
+
+# ---------------------------------------------------------------------------------------------------
+#  offline resampler: float64 FPS == the reference's numpy farthest_point_sampling
+# ---------------------------------------------------------------------------------------------------
+def test_resampler_matches_reference_numpy_golden(cuda_device):
+    """Every golden case of /root/reference/downsampling_point_clouds.py:55-92 (run in place by oracle/gen_golden.py):
+    dyadic, float64, raw UTM coordinates, duplicates that exhaust the cloud -- bit-exact, singly and as one batch."""
+    from dl_biomass_b200 import resample
+    g = np.load(os.path.join(GOLD, "fps_reference_numpy.npz"))
+    n_cases = len(g["kinds"])
+    for i in range(n_cases):
+        got = resample.farthest_point_sampling(g[f"pos_{i}"], len(g[f"idx_{i}"]))
+        assert np.array_equal(got, g[f"idx_{i}"]), (i, str(g["kinds"][i]))
+    # batched: clouds that share k
+    same_k = [i for i in range(n_cases) if len(g[f"idx_{i}"]) == 300]
+    assert len(same_k) >= 2
+    outs = resample.farthest_point_sampling_batch([g[f"pos_{i}"] for i in same_k], 300)
+    for i, got in zip(same_k, outs):
+        assert np.array_equal(got, g[f"idx_{i}"])
+
+
+def test_resampler_matches_oracle_on_large_plot(cuda_device):
+    from dl_biomass_b200 import resample
+    rng = np.random.default_rng(11)
+    pts = rng.normal(size=(20000, 3)) * np.array([5.0, 5.0, 9.0]) + np.array([431234.5, 5312345.25, 250.0])
+    got = resample.farthest_point_sampling(pts, 2048)
+    want = ref.fps_ref_f64(pts, 2048, 0)
+    assert np.array_equal(got, want)
+    assert len(set(got.tolist())) == 2048
+    with pytest.raises(ValueError):
+        resample.farthest_point_sampling(pts[:100], 200)
