@@ -957,6 +957,7 @@ struct DwParams {
     int nbl_total;             // X lines over all N groups (blockIdx.z), multiple of 16; a group handles <= 256
     int k_total;               // columns of the partial (all N groups)
     float *partial;            // [splits = gridDim.x][n_out][k_total]
+    int stages, stage_bytes;   // operand ring (set by launch_dw)
 };
 
 template <class SRC>
@@ -987,7 +988,8 @@ struct TmaFill {
     static constexpr bool USES_TMA = true;
     int c;         // channels of the tensor; with the ones box: a multiple of 64 with (c % 256) + 16 <= 256
     int ones_box;  // 1: append the row-valid box at line c; 0: the tensor carries its own ones line (layer-1 operand)
-    static __host__ __device__ int bytes(int nb_lines) { return nb_lines * LINE_BYTES; }
+    // the copies come in whole 64-line boxes: the tile must hold them even when fewer lines are used
+    static __host__ __device__ int bytes(int nb_lines) { return ((nb_lines + 63) / 64) * 64 * LINE_BYTES; }
     __device__ __forceinline__ void resolve(int64_t) {}
     __device__ __forceinline__ void fill(uint8_t *, int, int64_t, int, int, const unsigned (&)[8]) {}
     // N group ng covers lines [256 ng, 256 ng + 256) of [tensor channels | ones line | zero padding]
@@ -1035,11 +1037,8 @@ struct LineFillGather {  // MN-major X side: [column blocks of 64][64 row lines]
 template <int MTA>
 struct DwPlan {
     static constexpr int A_BYTES = MTA * 128 * LINE_BYTES;
-    static constexpr int B_MAX = 256 * LINE_BYTES;
-    static constexpr int STAGE_BYTES = A_BYTES + B_MAX;
-    static constexpr int STAGES = 3;
-    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+    static constexpr int MAX_STAGES = 8;
+    static constexpr int SMEM_BUDGET = 222 * 1024;  // of the 227 KB a CTA may have
 };
 
 template <int MTA, class YS, class XF>
@@ -1047,11 +1046,14 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
                                                        const __grid_constant__ TmaMap tmap_x, const __grid_constant__ TmaMap tmap_v)
 {
     using P = DwPlan<MTA>;
+    // the operand ring is sized at launch: stage = A tile + the X lines actually used, as many stages as fit (<= 8) --
+    // with TMA-fed operands the kernel is a pure stream and lives off the bytes it keeps in flight
+    const int nst = p.stages, sbytes = p.stage_bytes;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + P::BAR_OFF);
-    uint64_t *empty = full + P::STAGES;
-    uint64_t *done = empty + P::STAGES;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + nst * sbytes);
+    uint64_t *empty = full + nst;
+    uint64_t *done = empty + nst;
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(done + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1068,7 +1070,7 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
     const int nb_lines = min(256, p.nbl_total - ng * 256);
 
     if (tid == 0) {
-        for (int s = 0; s < P::STAGES; ++s) {
+        for (int s = 0; s < nst; ++s) {
             mbar_init(&full[s], NUM_LOAD);
             mbar_init(&empty[s], 1);
         }
@@ -1085,10 +1087,10 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
         const int grp = (tid - NUM_EPI) / NUM_LOAD;
         const int lt = (tid - NUM_EPI) % NUM_LOAD;
         for (int64_t i = grp; i < nchunks; i += LOAD_GROUPS) {
-            const int s = (int)(i % P::STAGES);
-            const uint32_t ph = (uint32_t)(i / P::STAGES) & 1u;
+            const int s = (int)(i % nst);
+            const uint32_t ph = (uint32_t)(i / nst) & 1u;
             mbar_wait(&empty[s], ph ^ 1u);
-            uint8_t *A = smem + s * P::STAGE_BYTES;
+            uint8_t *A = smem + s * sbytes;
             uint8_t *B = A + P::A_BYTES;
             const int64_t r0 = (c_beg + i) * 64;
             unsigned inf[8];
@@ -1125,11 +1127,11 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
         if (lane == 0 && nchunks > 0) {
             const uint32_t idesc = idesc_bf16(128, nb_lines, false, XF::B_MN);
             for (int64_t i = 0; i < nchunks; ++i) {
-                const int s = (int)(i % P::STAGES);
-                const uint32_t ph = (uint32_t)(i / P::STAGES) & 1u;
+                const int s = (int)(i % nst);
+                const uint32_t ph = (uint32_t)(i / nst) & 1u;
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                const uint32_t a_s = smem_u32(smem + s * P::STAGE_BYTES);
+                const uint32_t a_s = smem_u32(smem + s * sbytes);
                 const uint32_t b_s = a_s + P::A_BYTES;
 #pragma unroll
                 for (int mt = 0; mt < MTA; ++mt) {
@@ -1882,19 +1884,30 @@ static int launch_dw(const YS &ys, const XF &xf, int n_out, int k_total, const S
                      cudaStream_t st, const TmaMap &map_y = kNoMap, const TmaMap &map_x = kNoMap, const TmaMap &map_v = kNoMap)
 {
     const DwPlanHost d = plan_dw(n_out, k_total, s.ld);
-    DwParams p = {ra.cap, ra.dev, n_out, d.nbl_total, k_total, dwp};
+    DwParams p = {ra.cap, ra.dev, n_out, d.nbl_total, k_total, dwp, 0, 0};
+    const int nb_max = d.nbl_total < 256 ? d.nbl_total : 256;
+    const int b_bytes = (int)align_up(XF::bytes(nb_max), 1024);
     dim3 grid((unsigned)d.splits, (unsigned)d.num_mg, (unsigned)d.num_ng);
     cudaError_t e;
+    auto plan = [&](int a_bytes) {
+        p.stage_bytes = a_bytes + b_bytes;
+        p.stages = (DwPlan<1>::SMEM_BUDGET - 1280) / p.stage_bytes;
+        if (p.stages > DwPlan<1>::MAX_STAGES) p.stages = DwPlan<1>::MAX_STAGES;
+        if (p.stages < 2) p.stages = 2;
+        return p.stages * p.stage_bytes + 256 + 1024;
+    };
     if (d.MTA == 1) {
         auto kern = tc_dw_kernel<1, YS, XF>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DwPlan<1>::TOTAL);
+        const int smem = plan(DwPlan<1>::A_BYTES);
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        kern<<<grid, NT, DwPlan<1>::TOTAL, st>>>(p, ys, xf, map_y, map_x, map_v);
+        kern<<<grid, NT, smem, st>>>(p, ys, xf, map_y, map_x, map_v);
     } else {
         auto kern = tc_dw_kernel<2, YS, XF>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DwPlan<2>::TOTAL);
+        const int smem = plan(DwPlan<2>::A_BYTES);
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        kern<<<grid, NT, DwPlan<2>::TOTAL, st>>>(p, ys, xf, map_y, map_x, map_v);
+        kern<<<grid, NT, smem, st>>>(p, ys, xf, map_y, map_x, map_v);
     }
     note_launch();
     e = cudaPeekAtLastError();
