@@ -8,10 +8,13 @@
 // 16-byte vector stores.  Feature-major activations are exactly the MN-major B operand of the next
 // layer and the K-major operands of the dW GEMMs, so no transposes are ever needed.
 //
-// Pipeline (persistent CTAs, 9 warps): warps 4-7 build the B tile in shared memory (gather + concat,
-// or BatchNorm + ReLU on load) and fetch the pre-packed weight chunk with a bulk copy (TMA unit);
-// warp 8 issues tcgen05.mma; warps 0-3 drain TMEM and run the epilogue.  K is streamed in chunks of
-// 64 through a ring of shared-memory stages; two TMEM accumulator buffers overlap epilogue and MMA.
+// Pipeline of the rows kernel (persistent CTAs): a producer thread fetches the B tile with two TMA tensor-map copies of a
+// stored feature-major tensor (or, for the few operands that still need arithmetic on the way in, two groups of SIMT
+// loader warps build it) and the pre-packed weight chunk with a bulk copy; one thread issues tcgen05.mma; the epilogue
+// warps -- two groups of eight when the operands come by TMA, one group per TMEM accumulator buffer -- drain TMEM and
+// send result tiles out through shared-memory staging tiles and TMA stores.  K is streamed in chunks of 64 through a
+// ring of shared-memory stages.  tc_dw_kernel is the same machinery with K = rows and the accumulator kept in TMEM
+// over the CTA's whole row range.
 #include <cuda.h>  // CUtensorMap types only; the encoder is fetched through the runtime (no libcuda link)
 #include <math.h>
 

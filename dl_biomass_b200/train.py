@@ -122,7 +122,8 @@ class PipelinedTrainStep:
     current batch goes through forward / loss / backward / Adam, and returns the loss of the current batch; the
     persistent tensor-core kernels are told to leave one SM per cloud free (``b2pn_set_sm_limit``).  With
     ``graph=True`` both branches are captured in ONE CUDA graph (fork / join inside the graph) and every call is a
-    single replay; the batches must then keep the cloud sizes of the example batch.
+    single replay; the batches must then keep the cloud sizes of the example batch (``graph=False`` takes ragged
+    batches, e.g. after the reference's point-removal / duplication augmentation).
 
         stepper = PipelinedTrainStep(model, opt, first_batch)       # also samples first_batch
         for nxt in loader:                                          # loader yields the batches after the first
@@ -157,6 +158,13 @@ class PipelinedTrainStep:
 
     def close(self) -> None:
         self.lib.b2pn_set_sm_limit(0)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
 
     # ---- eager -------------------------------------------------------------------------------------------------
     def _eager_step(self, cur, cur_sampling, nxt):
@@ -225,8 +233,9 @@ class PipelinedTrainStep:
 
     def step(self, next_batch) -> torch.Tensor:
         """Train on the batch submitted by the previous call (or the constructor) while sampling ``next_batch``."""
-        if tuple(getattr(next_batch, "cloud_sizes", ())) != self.sizes:
-            raise ValueError("PipelinedTrainStep: the batch layout (cloud sizes) must stay fixed")
+        if self.graph is not None and tuple(getattr(next_batch, "cloud_sizes", ())) != self.sizes:
+            raise ValueError("PipelinedTrainStep(graph=True): the batch layout (cloud sizes) must stay fixed; "
+                             "use graph=False for ragged batches")
         if self.graph is not None:
             self._copy_batch(self.s_nxt, next_batch)
             self.graph.replay()

@@ -445,3 +445,26 @@ def test_pipelined_train_step_matches_eager(cuda_device, graph):
     for a, b in zip(want, got):
         assert abs(a - b) <= 2e-3 * max(abs(a), 1e-6)
     assert _lib.lib().b2pn_set_sm_limit(0) == 0
+
+
+def test_pipelined_eager_step_takes_ragged_batches(cuda_device):
+    """graph=False: batches may change their cloud sizes from step to step (augmented data)."""
+    from dl_biomass_b200.train import PipelinedTrainStep, make_optimizer, train_step
+    batches = [Batch.from_data_list(synthetic_clouds(700 + 13 * i, 3, 512, 1, True)).to(cuda_device) for i in range(3)]
+    assert len({tuple(b.cloud_sizes) for b in batches}) == 3
+
+    def fresh():
+        torch.manual_seed(9)
+        net = Net(1, "ReLU", 0, 0.0, precision="bf16").to(cuda_device).set_random_start(False)
+        net.train()
+        return net
+
+    net = fresh()
+    opt = make_optimizer(net.parameters())
+    want = [float(train_step(net, opt, b)) for b in batches[:2]]
+    net = fresh()
+    opt = make_optimizer(net.parameters())
+    with PipelinedTrainStep(net, opt, batches[0], graph=False) as stepper:
+        got = [float(stepper.step(b)) for b in batches[1:3]]
+    for a, b in zip(want, got):
+        assert abs(a - b) <= 2e-3 * max(abs(a), 1e-6)
