@@ -41,6 +41,10 @@ def parse_args():
     ap.add_argument("--pool", type=int, default=4, help="distinct batches rotated through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
+    ap.add_argument("--join", default="end", choices=["backward", "end"], help="where the sampling branch joins")
+    ap.add_argument("--no-cap", action="store_true", help="do not cap persistent kernels while the branch runs")
+    ap.add_argument("--no-pregroup", action="store_true", help="ball query / row packing inside forward")
+    ap.add_argument("--aux", action="store_true", help="third stream for the level-1 grouping")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="sample (FPS) every batch inside its own step instead of one step ahead on a second stream")
     return ap.parse_args()
@@ -242,7 +246,8 @@ def run_b200(args):
     pipeline = not args.no_pipeline
     graphed = stepper = None
     if pipeline:
-        stepper = PipelinedTrainStep(net, opt, pool_dev[0], reducer, graph=use_graph)
+        stepper = PipelinedTrainStep(net, opt, pool_dev[0], reducer, graph=use_graph, join=args.join,
+                                     cap=not args.no_cap, grouping=not args.no_pregroup, aux=args.aux)
     elif use_graph:
         graphed = GraphedTrainStep(net, opt, pool_dev[0], reducer)
 
@@ -343,8 +348,10 @@ def run_b200(args):
                        "parallelism": f"dp{world}", "l2": "256 MB buffer rewritten before every timed step",
                        "timing": "per-step CUDA events on the launching stream, summed; max over ranks",
                        "launch": "one CUDA graph replay per step" if use_graph else "eager kernel launches",
-                       "pipeline": ("FPS of batch i+1 on a second stream during step i; persistent kernels capped at "
-                                    f"{sm_limit_note} CTAs") if stepper is not None else "none"},
+                       "pipeline": ("FPS" + (" + ball query + row compaction + level-1 gather" if stepper.grouping else "")
+                                    + " of batch i+1 on a second stream during step i (every timed step contains one "
+                                    f"full sampling and one full training pass); join at {stepper.join_at}; persistent "
+                                    f"kernels capped at {sm_limit_note} CTAs") if stepper is not None else "none"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(e2e_ms / args.steps, 4),
                     "h2d_bytes_per_step": batch_h2d_bytes(pool_host[0], with_batch_vector=not use_graph),

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libb2pn.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 _lib = None
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _vp, _i32, _i64, _f32, _f64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double
 
@@ -33,7 +33,7 @@ class SaArgs(ctypes.Structure):
                 ("pos_dst", _vp), ("nbr", _vp), ("cnt", _vp), ("batch", _vp), ("mlp", Mlp3), ("out", _vp),
                 ("arg", _vp), ("h1", _vp), ("h2", _vp), ("bn", _vp), ("workspace", _vp),
                 ("workspace_bytes", ctypes.c_int64), ("rgrp", _vp), ("row_src", _vp), ("num_rows", _vp),
-                ("row_capacity", ctypes.c_int64), ("row_valid", _vp), ("a1", _vp), ("a2", _vp), ("g1", _vp)]
+                ("row_capacity", ctypes.c_int64), ("row_valid", _vp), ("a1", _vp), ("a2", _vp), ("g1", _vp), ("g1_ready", ctypes.c_int32)]
 
 
 class SaGrads(ctypes.Structure):
@@ -71,6 +71,7 @@ SIGNATURES = {
     "b2pn_pack_rows": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "b2pn_sa_workspace_bytes": (_i64, [ctypes.POINTER(SaArgs), _i32]),
     "b2pn_sa_forward": (ctypes.c_int, [ctypes.POINTER(SaArgs), _vp]),
+    "b2pn_sa_gather_rows": (ctypes.c_int, [ctypes.POINTER(SaArgs), _vp]),
     "b2pn_sa_backward": (ctypes.c_int, [ctypes.POINTER(SaArgs), ctypes.POINTER(SaGrads), _vp]),
     "b2pn_head_forward": (ctypes.c_int, [ctypes.POINTER(HeadArgs), _vp]),
     "b2pn_head_backward": (ctypes.c_int, [ctypes.POINTER(HeadArgs), ctypes.POINTER(HeadGrads), _vp]),

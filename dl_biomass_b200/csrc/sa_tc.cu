@@ -1785,6 +1785,35 @@ static bool l1_materialised(const b2pn_sa_args &a, const ShapesTC &s)
     return a.seg_mode == B2PN_SEG_SLOTS && a.g1 != nullptr && s.k1 + 1 + 15 <= 256;
 }
 
+static void launch_gather_l1(const b2pn_sa_args &a, const ShapesTC &s, cudaStream_t st)
+{
+    const RowMapTC rm = rowmap_tc(a, s);
+    const RowsArg ra = rowsarg_tc(a, s);
+    GatherLoaderTC gg = {rm, a.x, s.cols, a.pos_src, a.pos_dst, s.k1};  // column k1 = ones (dW1 bias line)
+    const int kg = s.k1 + 1, kg8 = (kg + 7) & ~7;
+    gather_l1_tc_kernel<<<(unsigned)(s.ld / GATHER_ROWS), 256, kg8 * GATHER_ROWS * 2, st>>>(gg, ra.dev, kg, s.ld,
+                                                                                             (__nv_bfloat16 *)a.g1);
+    note_launch();
+}
+
+// b2pn_sa_gather_rows: the gather alone (geometry + raw inputs only; include/b2pn.h)
+int sa_gather_rows_bf16(const b2pn_sa_args &a, cudaStream_t st)
+{
+    if (a.n_src < 0 || a.n_dst < 0 || a.c_in < 0 || a.mlp.c[0] != a.c_in + 3) return B2PN_EINVAL;
+    if (a.x_dtype != B2PN_X_F32 && a.x_dtype != B2PN_X_BF16) return B2PN_EINVAL;
+    if (a.seg_mode != B2PN_SEG_SLOTS) return B2PN_ENOTSUP;
+    if (a.K <= 0) return B2PN_EINVAL;
+    if (a.K > 64) return B2PN_ENOTSUP;
+    if (a.n_dst == 0) return B2PN_OK;
+    if (!a.pos_dst || !a.pos_src || (a.c_in > 0 && !a.x) || !a.rgrp || !a.row_src || !a.num_rows) return B2PN_EINVAL;
+    if (a.row_capacity < b2pn_pack_rows_capacity(a.n_dst, a.K)) return B2PN_EINVAL;
+    const ShapesTC s = shapes_tc(a);
+    if (!l1_materialised(a, s)) return a.g1 ? B2PN_ENOTSUP : B2PN_EINVAL;
+    launch_gather_l1(a, s, st);
+    B2PN_LAUNCH_CHECK();
+    return B2PN_OK;
+}
+
 int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
 {
     int rc = check_args_tc(a);
@@ -1814,12 +1843,8 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
     TmaMap map_g1 = kNoMap;
     TmaFeatLoader tl1;
     if (use_g1 && s.rows > 0) {
-        GatherLoaderTC gg = {rm, a.x, s.cols, a.pos_src, a.pos_dst, s.k1};  // column k1 = ones (dW1 bias line)
-        const int kg = s.k1 + 1, kg8 = (kg + 7) & ~7;
-        gather_l1_tc_kernel<<<(unsigned)(s.ld / GATHER_ROWS), 256, kg8 * GATHER_ROWS * 2, st>>>(gg, ra.dev, kg, s.ld,
-                                                                                                 (__nv_bfloat16 *)a.g1);
-        note_launch();
-        if ((rc = make_tma_feature_major(&map_g1, a.g1, kg, s.ld))) return rc;
+        if (!a.g1_ready) launch_gather_l1(a, s, st);
+        if ((rc = make_tma_feature_major(&map_g1, a.g1, s.k1 + 1, s.ld))) return rc;
     }
     const int ns1 = use_g1 ? 4 : 2;  // partial slots per CTA: 2 column halves x epilogue groups (2 when TMA-fed)
     if (train && s.rows > 0) {

@@ -107,11 +107,24 @@ class SAModule(torch.nn.Module):
             start = (torch.rand(len(src.sizes), device=pos.device) * n).to(torch.int64)
         return ops.fps(pos, src, dst, start)
 
-    def _run(self, x, pos, src: ops.Level, dst: ops.Level, start=None, sampled=None):
+    def _group(self, pos, pos_dst, src: ops.Level, dst: ops.Level, x=None, gather: bool = False):
+        """radius (:14-16) and, for the tensor-core path, the compaction of the filled slots into rows and
+        (``gather``: when ``x`` is raw input data, not an activation) the gathered message inputs of :17-18:
+        no weights involved, like ``_sample``.  Returns (nbr, cnt, rowmap or None, l1op or None)."""
+        nbr, cnt = ops.ball_query(pos, pos_dst, src, dst, self.r, self.max_num_neighbors)
+        rowmap = l1op = None
+        if _PRECISIONS[self.precision] == sa.PREC_BF16:
+            rowmap = sa.pack_rows(nbr, cnt, self.max_num_neighbors)
+            if gather and dst.total > 0 and (x is None or not x.requires_grad):
+                l1op = sa.gather_rows(x, pos, pos_dst, self.max_num_neighbors, rowmap)
+        return nbr, cnt, rowmap, l1op
+
+    def _run(self, x, pos, src: ops.Level, dst: ops.Level, start=None, sampled=None, grouped=None):
         idx, pos_dst, batch_dst = sampled if sampled is not None else self._sample(pos, src, dst, start)
-        nbr, cnt = ops.ball_query(pos, pos_dst, src, dst, self.r, self.max_num_neighbors)   # :14-16
+        nbr, cnt, rowmap, l1op = grouped if grouped is not None else self._group(pos, pos_dst, src, dst)
         out, _ = sa.sa_apply(self.conv.local_nn, x, pos, pos_dst, nbr, cnt, None, seg_mode=sa.SEG_SLOTS,
-                             K=self.max_num_neighbors, n_dst=dst.total, precision=_PRECISIONS[self.precision])  # :18
+                             K=self.max_num_neighbors, n_dst=dst.total, precision=_PRECISIONS[self.precision],
+                             rowmap=rowmap, l1op=l1op)                                       # :18
         return out, pos_dst, batch_dst, idx
 
     def forward(self, x, pos, batch):
@@ -142,15 +155,35 @@ class GlobalSAModule(torch.nn.Module):
 
 
 class Sampling:
-    """Farthest-point samples of both set-abstraction levels of one batch (``Net.sample``): (idx, pos, batch) per
-    level.  They depend on the point positions only, so a training loop can compute them for the NEXT batch on a
-    second stream while the current batch trains (``train.PipelinedTrainStep``)."""
+    """Everything about one batch that depends on the point positions only (``Net.sample``): per set-abstraction
+    level the farthest-point samples (idx, pos, batch) and, optionally, the neighbourhoods (nbr, cnt, compacted
+    rows, gathered level-1 message inputs).  A training loop can compute them for the NEXT batch on a second stream
+    while the current batch trains (``train.PipelinedTrainStep``)."""
 
-    def __init__(self, sizes, level1, level2):
+    def __init__(self, sizes, level1, level2, group1=None, group2=None):
         self.sizes, self.level1, self.level2 = tuple(sizes), tuple(level1), tuple(level2)
+        self.group1, self.group2 = group1, group2
+
+    @staticmethod
+    def _flat(group):
+        if group is None:
+            return []
+        nbr, cnt, rowmap, l1op = group
+        return ([nbr, cnt] + ([] if rowmap is None else [t for t in rowmap if isinstance(t, torch.Tensor)])
+                + ([] if l1op is None else [l1op]))
 
     def tensors(self):
-        return list(self.level1) + list(self.level2)
+        return list(self.level1) + list(self.level2) + self._flat(self.group1) + self._flat(self.group2)
+
+    def clone(self) -> "Sampling":
+        def cg(group):
+            if group is None:
+                return None
+            nbr, cnt, rowmap, l1op = group
+            rm = None if rowmap is None else tuple(t.clone() if isinstance(t, torch.Tensor) else t for t in rowmap)
+            return nbr.clone(), cnt.clone(), rm, None if l1op is None else l1op.clone()
+        return Sampling(self.sizes, [t.clone() for t in self.level1], [t.clone() for t in self.level2],
+                        cg(self.group1), cg(self.group2))
 
 
 class _CallInBackward(torch.autograd.Function):
@@ -213,14 +246,35 @@ class Net(torch.nn.Module):
             sizes = _cloud_sizes(data.batch, getattr(data, "ptr", None))
         return sizes, ops.build_levels(sizes, [self.sa1_module.ratio, self.sa2_module.ratio], pos.device)
 
-    def sample(self, data, start: Optional[torch.Tensor] = None) -> Sampling:
-        """Farthest-point sampling of both levels for ``data`` (no weights involved); pass the result to
-        ``forward(data, sampling=...)``."""
+    def _usable(self, group):
+        """A precomputed neighbourhood is reused only if it carries what the current precision needs."""
+        if group is None or ((group[2] is None) != (_PRECISIONS[self.precision] != sa.PREC_BF16)):
+            return None
+        return group
+
+    def sample(self, data, start: Optional[torch.Tensor] = None, grouping: bool = True, aux_stream=None) -> Sampling:
+        """Farthest-point sampling and (``grouping``) ball query + row compaction of both levels for ``data`` (no
+        weights involved); pass the result to ``forward(data, sampling=...)``.  ``aux_stream``: a second CUDA stream
+        on which the level-1 grouping runs while the level-2 sampling (one CTA per cloud) occupies the current one."""
         sizes, lv = self._levels(data)
         pos = data.pos.to(torch.float32)
         l1 = self.sa1_module._sample(pos, lv[0], lv[1], start)
+        g1 = g2 = None
+        if grouping and aux_stream is not None:
+            cur = torch.cuda.current_stream(pos.device)
+            aux_stream.wait_stream(cur)
+            with torch.cuda.stream(aux_stream):
+                g1 = self.sa1_module._group(pos, l1[1], lv[0], lv[1], data.x, gather=True)
+                for t in Sampling._flat(g1):
+                    t.record_stream(cur)
         l2 = self.sa2_module._sample(l1[1], lv[1], lv[2])
-        return Sampling(sizes, l1, l2)
+        if grouping:
+            if g1 is None:
+                g1 = self.sa1_module._group(pos, l1[1], lv[0], lv[1], data.x, gather=True)
+            g2 = self.sa2_module._group(l1[1], l2[1], lv[1], lv[2])
+            if aux_stream is not None:
+                cur.wait_stream(aux_stream)
+        return Sampling(sizes, l1, l2, g1, g2)
 
     def forward(self, data, start: Optional[torch.Tensor] = None, sampling: Optional[Sampling] = None,
                 after_grouping=None):
@@ -235,8 +289,10 @@ class Net(torch.nn.Module):
         pos = pos.to(torch.float32)
         s1 = None if sampling is None else sampling.level1
         s2 = None if sampling is None else sampling.level2
-        x1, pos1, _, _ = self.sa1_module._run(x, pos, lv[0], lv[1], start, s1)           # :54
-        x2, pos2, batch2, _ = self.sa2_module._run(x1, pos1, lv[1], lv[2], None, s2)      # :55
+        g1 = None if sampling is None else self._usable(sampling.group1)
+        g2 = None if sampling is None else self._usable(sampling.group2)
+        x1, pos1, _, _ = self.sa1_module._run(x, pos, lv[0], lv[1], start, s1, g1)       # :54
+        x2, pos2, batch2, _ = self.sa2_module._run(x1, pos1, lv[1], lv[2], None, s2, g2)  # :55
         if after_grouping is not None:
             if torch.is_grad_enabled() and x2.requires_grad:
                 x2 = _CallInBackward.apply(x2, after_grouping)

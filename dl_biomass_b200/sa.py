@@ -92,11 +92,47 @@ def pack_rows(nbr: torch.Tensor, cnt: torch.Tensor, K: int):
     return rgrp, row_src, num_rows, cap, row_valid
 
 
+def _l1_input(x: Optional[torch.Tensor]):
+    """How the kernels take the level's input features: (tensor or None, c_in, image columns).  Raw low-dimensional
+    inputs (e.g. lidar intensity) stay fp32 -- the kernels feed them to the tensor cores as bf16 hi+lo column pairs --
+    wide feature maps from the previous level go in as bf16."""
+    c_in = 0 if x is None else x.shape[1]
+    split = x is not None and x.dtype == torch.float32 and c_in <= 16
+    xs = None if x is None else x.detach().to(torch.float32 if split else torch.bfloat16).contiguous()
+    return xs, c_in, (2 * c_in if split else c_in) + 6
+
+
+def gather_rows(x: Optional[torch.Tensor], pos_src: torch.Tensor, pos_dst: torch.Tensor, K: int, rowmap):
+    """The gathered + concatenated layer-1 operand of a SLOTS level (include/b2pn.h, b2pn_sa_gather_rows) for the
+    compacted rows ``rowmap``; None when the level is too wide to take one.  Needs no weights, so it can be built
+    ahead of the forward pass; hand it to ``sa_apply(..., l1op=...)``."""
+    lib = _lib.lib()
+    xs, c_in, k_img = _l1_input(x)
+    if k_img + 16 > 256:
+        return None
+    rgrp, row_src, num_rows, cap, row_valid = rowmap
+    ld = (cap + 127) // 128 * 128
+    dev = pos_src.device
+    g = torch.empty(k_img + 1, ld, dtype=torch.bfloat16, device=dev)
+    a = SaArgs()
+    a.precision, a.seg_mode, a.K = PREC_BF16, SEG_SLOTS, K
+    a.n_src, a.n_dst, a.c_in = pos_src.shape[0], pos_dst.shape[0], c_in
+    a.x_dtype = 1 if (xs is not None and xs.dtype == torch.bfloat16) else 0
+    a.x, a.pos_src, a.pos_dst = _dp(xs), _dp(pos_src.contiguous()), _dp(pos_dst)
+    a.mlp.c[0] = c_in + 3
+    a.rgrp, a.row_src, a.num_rows, a.row_capacity = _dp(rgrp), _dp(row_src), _dp(num_rows), cap
+    a.g1 = g.data_ptr()
+    with torch.cuda.device(dev):
+        rc = lib.b2pn_sa_gather_rows(ctypes.byref(a), torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "b2pn_sa_gather_rows")
+    return g
+
+
 class _SAFunction(torch.autograd.Function):
     """forward/backward of one set-abstraction level through libb2pn."""
 
     @staticmethod
-    def forward(ctx, cfg, x, pos_src, pos_dst, nbr, cnt, batch, w1, b1, g1, be1, w2, b2, g2, be2, w3, b3,
+    def forward(ctx, cfg, rowmap_in, l1op_in, x, pos_src, pos_dst, nbr, cnt, batch, w1, b1, g1, be1, w2, b2, g2, be2, w3, b3,
                 rm1, rv1, nbt1, rm2, rv2, nbt2):
         lib = _lib.lib()
         dev = pos_src.device
@@ -117,7 +153,7 @@ class _SAFunction(torch.autograd.Function):
         rows = n_src if seg_mode == SEG_CLOUDS else n_dst * K
         rowmap = None
         if prec == PREC_BF16 and seg_mode == SEG_SLOTS:
-            rowmap = pack_rows(nbr, cnt, K)
+            rowmap = rowmap_in if rowmap_in is not None else pack_rows(nbr, cnt, K)
             rows = rowmap[3]
         out = torch.empty(n_dst, chans[3], dtype=f32, device=dev)
         arg = torch.empty(n_dst, chans[3], dtype=torch.int32, device=dev)
@@ -127,10 +163,7 @@ class _SAFunction(torch.autograd.Function):
             h1 = torch.empty(rows, chans[1], dtype=f32, device=dev)
             h2 = torch.empty(rows, chans[2], dtype=f32, device=dev)
         else:                  # feature-major bf16 activations [c, ld], ld = rows rounded up to whole 128-row tiles
-            # raw low-dimensional inputs (e.g. lidar intensity) stay fp32: the kernel feeds them to the tensor
-            # cores as bf16 hi+lo column pairs; wide feature maps from the previous level go in as bf16
-            split = x is not None and x.dtype == f32 and c_in <= 16
-            xs = None if x is None else x.detach().to(f32 if split else torch.bfloat16).contiguous()
+            xs, _, k_img = _l1_input(x)
             ld = (rows + 127) // 128 * 128
             h1 = torch.empty(chans[1], ld, dtype=torch.bfloat16, device=dev)
             h2 = torch.empty(chans[2], ld, dtype=torch.bfloat16, device=dev)
@@ -139,9 +172,13 @@ class _SAFunction(torch.autograd.Function):
                 rv = torch.zeros(ld, dtype=torch.bfloat16, device=dev)
                 rv[:n_src] = 1
                 rowmap = (None, None, None, 0, rv)
-            k_img = (2 * c_in if split else c_in) + 6
             if seg_mode == SEG_SLOTS and k_img + 16 <= 256:   # gathered layer-1 operand incl. its ones line
-                acts.append(torch.empty(k_img + 1, ld, dtype=torch.bfloat16, device=dev))
+                if l1op_in is not None and tuple(l1op_in.shape) != (k_img + 1, ld):
+                    raise ValueError("l1op does not belong to these rows / features")
+                acts.append(l1op_in if l1op_in is not None else
+                            torch.empty(k_img + 1, ld, dtype=torch.bfloat16, device=dev))
+            else:
+                l1op_in = None
             acts = tuple(acts)
         cmax = max(chans[1], chans[2])
         bn = torch.empty(2, 4, cmax, dtype=f32, device=dev)
@@ -151,6 +188,7 @@ class _SAFunction(torch.autograd.Function):
                    eps=eps, momentum=momentum, ws=ws, bs=bs, gammas=gs, betas=bes, rmeans=(rm1, rm2),
                    rvars=(rv1, rv2), nbts=(nbt1, nbt2), out=out, arg=arg, h1=h1, h2=h2, bn=bn, rowmap=rowmap,
                    acts=acts)
+        a.g1_ready = 1 if (prec == PREC_BF16 and l1op_in is not None) else 0
         nbytes = lib.b2pn_sa_workspace_bytes(ctypes.byref(a), 0)
         if nbytes < 0:
             _lib.check(int(nbytes), "b2pn_sa_workspace_bytes")
@@ -211,12 +249,15 @@ class _SAFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             rc = lib.b2pn_sa_backward(ctypes.byref(a), ctypes.byref(g), torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, "b2pn_sa_backward")
-        return (None, gx, None, None, None, None, None, gw[0], gb[0], gg[0], gbe[0], gw[1], gb[1], gg[1], gbe[1],
+        return (None, None, None, gx, None, None, None, None, None, gw[0], gb[0], gg[0], gbe[0], gw[1], gb[1], gg[1], gbe[1],
                 gw[2], gb[2], None, None, None, None, None, None)
 
 
-def sa_apply(mlp, x, pos_src, pos_dst, nbr, cnt, batch, *, seg_mode: int, K: int, n_dst: int, precision: int):
-    """Run one set-abstraction level with the parameters of ``mlp`` (a b2pn ``MLP`` of three Linear layers)."""
+def sa_apply(mlp, x, pos_src, pos_dst, nbr, cnt, batch, *, seg_mode: int, K: int, n_dst: int, precision: int,
+             rowmap=None, l1op=None):
+    """Run one set-abstraction level with the parameters of ``mlp`` (a b2pn ``MLP`` of three Linear layers).
+    ``rowmap`` / ``l1op``: the results of ``pack_rows(nbr, cnt, K)`` and ``gather_rows(x, ...)`` if the caller already
+    has them (bf16 path; ``l1op`` must have been built from this very ``x``)."""
     if len(mlp.lins) != 3 or len(mlp.norms) != 2:
         raise NotImplementedError("set-abstraction kernels are built for the reference's 3-layer MLPs with BatchNorm")
     if mlp.dropout != 0.0 and mlp.training:
@@ -225,7 +266,7 @@ def sa_apply(mlp, x, pos_src, pos_dst, nbr, cnt, batch, *, seg_mode: int, K: int
     cfg = (precision, bool(mlp.training), seg_mode, K, n_dst, act_code(mlp.act_name), float(n0.eps),
            float(n0.momentum if n0.momentum is not None else 0.1))
     l0, l1, l2 = mlp.lins
-    out, arg = _SAFunction.apply(cfg, x, pos_src, pos_dst, nbr, cnt, batch,
+    out, arg = _SAFunction.apply(cfg, rowmap, l1op if rowmap is not None else None, x, pos_src, pos_dst, nbr, cnt, batch,
                                  l0.weight, l0.bias, n0.weight, n0.bias, l1.weight, l1.bias, n1.weight, n1.bias,
                                  l2.weight, l2.bias, n0.running_mean, n0.running_var, n0.num_batches_tracked,
                                  n1.running_mean, n1.running_var, n1.num_batches_tracked)

@@ -114,34 +114,45 @@ class GraphedTrainStep:
 
 
 class PipelinedTrainStep:
-    """Training step that overlaps the farthest-point sampling of the NEXT batch with the training of the current one.
+    """Training step that overlaps everything that depends on the point positions only -- farthest-point sampling,
+    ball query, row compaction, the gathered level-1 message inputs (``Net.sample``) -- of the NEXT batch with the
+    training of the current one.
 
     FPS is a chain of ~2 500 dependent arg-max iterations per batch: it keeps one SM per cloud busy for ~1.4 ms
-    (12 of 148 SMs at the reference's batch size) while the rest of the GPU idles, and it needs nothing but the
-    point positions.  ``step(next_batch)`` therefore runs ``Net.sample(next_batch)`` on a second stream while the
-    current batch goes through forward / loss / backward / Adam, and returns the loss of the current batch; the
-    persistent tensor-core kernels are told to leave one SM per cloud free (``b2pn_set_sm_limit``).  With
-    ``graph=True`` both branches are captured in ONE CUDA graph (fork / join inside the graph) and every call is a
-    single replay; the batches must then keep the cloud sizes of the example batch (``graph=False`` takes ragged
-    batches, e.g. after the reference's point-removal / duplication augmentation).
+    (12 of 148 SMs at the reference's batch size) while the rest of the GPU idles.  ``step(next_batch)`` therefore
+    runs ``Net.sample(next_batch)`` on a second stream while the current batch goes through forward / loss /
+    backward / Adam, and returns the loss of the current batch; the persistent tensor-core kernels are told to leave
+    one SM per cloud free (``b2pn_set_sm_limit``; ``cap=False`` disables it).  ``join``: where the training stream
+    waits for the branch -- "end" (after the step; measured best, round 1) or "backward" (inside the backward pass,
+    before the level-2 backward, lifting the SM cap from there on).  With ``graph=True`` both branches are captured
+    in CUDA graphs (fork / join inside the graph; two graphs over a double buffer, replayed alternately, so that no
+    hand-over copy sits on the training stream) and every call is a single replay; the batches must then keep the
+    cloud sizes of the example batch (``graph=False`` takes ragged batches, e.g. after the reference's point-removal
+    / duplication augmentation).  ``grouping=False`` leaves ball query and row compaction inside forward;
+    ``aux=True`` runs the level-1 grouping on a third stream beside the level-2 sampling.
 
         stepper = PipelinedTrainStep(model, opt, first_batch)       # also samples first_batch
         for nxt in loader:                                          # loader yields the batches after the first
             loss = stepper.step(nxt)                                # trains on the batch submitted before
     """
 
-    def __init__(self, model, optimizer, first_batch, reducer=None, graph: bool = True, warmup: int = 2):
+    def __init__(self, model, optimizer, first_batch, reducer=None, graph: bool = True, warmup: int = 2,
+                 join: str = "end", cap: bool = True, grouping: bool = True, aux: bool = False):
         from . import _lib
+        if join not in ("backward", "end"):
+            raise ValueError("join must be 'backward' or 'end'")
+        self.join_at, self.grouping = join, bool(grouping)
         self.model, self.optimizer, self.reducer = model, optimizer, reducer
         self.dev = first_batch.pos.device
         if self.dev.type != "cuda":
             raise RuntimeError("PipelinedTrainStep needs the batch on a B200")
         self.lib = _lib.lib()
         self.side = torch.cuda.Stream(self.dev)
+        self.aux = torch.cuda.Stream(self.dev) if (aux and grouping) else None
         self.sizes = tuple(first_batch.cloud_sizes)
         sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
         ncl = len(self.sizes)
-        self.sm_limit = sms - ncl if ncl * 4 <= sms else 0
+        self.sm_limit = sms - ncl if (cap and ncl * 4 <= sms) else 0
         # data parallel + graph: forward/backward are captured, the NCCL all-reduce and Adam follow the replay eagerly
         # (capturing the collective hung on the 2-GPU box in round 1) -- ~5 launches per step instead of ~170
         self.split = reducer is not None and bool(graph)
@@ -154,7 +165,7 @@ class PipelinedTrainStep:
             self._capture(first_batch, warmup)
         else:
             self.cur = first_batch
-            self.cur_sampling = model.sample(first_batch)
+            self.cur_sampling = model.sample(first_batch, grouping=self.grouping, aux_stream=self.aux)
 
     def close(self) -> None:
         self.lib.b2pn_set_sm_limit(0)
@@ -167,15 +178,18 @@ class PipelinedTrainStep:
         return False
 
     # ---- eager -------------------------------------------------------------------------------------------------
-    def _eager_step(self, cur, cur_sampling, nxt):
+    def _eager_step(self, cur, cur_sampling, nxt, publish=None):
         main = torch.cuda.current_stream(self.dev)
         self.side.wait_stream(main)                       # nxt's tensors (an H2D copy, say) are ordered before this
         with torch.cuda.stream(self.side):
-            nxt_sampling = self.model.sample(nxt)
-        # The sampling branch (~1.4 ms) must not fight the persistent tcgen05 kernels for SMs: while it may be in
-        # flight they are launched with a capped grid.  The join sits in the BACKWARD pass right before the level-2
-        # backward: the forward of both SA levels runs capped, the global level and the head (small grids anyway) go
-        # forward and backward in between, and the two big backward passes get every SM again.
+            nxt_sampling = self.model.sample(nxt, grouping=self.grouping, aux_stream=self.aux)
+            if publish is not None:                       # graph mode: into the other half of the double buffer
+                for d, s in zip(publish.tensors(), nxt_sampling.tensors()):
+                    d.copy_(s)
+        # The sampling branch (~1.8 ms) must not fight the persistent tcgen05 kernels for SMs: while it may be in
+        # flight they are launched with a capped grid.  join="end": the whole step runs capped and waits for the
+        # branch after the optimiser (the HBM-bound kernels lose little on 136 of 148 SMs; 2.59 vs 2.93 ms/step).
+        # join="backward": the wait sits in the backward pass right before the level-2 backward and lifts the cap.
         self.lib.b2pn_set_sm_limit(self.sm_limit)
 
         def join():
@@ -183,7 +197,11 @@ class PipelinedTrainStep:
             self.lib.b2pn_set_sm_limit(0)
 
         step = forward_backward if self.split else train_step
-        loss = step(self.model, self.optimizer, cur, self.reducer, sampling=cur_sampling, after_grouping=join)
+        early = self.join_at == "backward"
+        loss = step(self.model, self.optimizer, cur, self.reducer, sampling=cur_sampling,
+                    after_grouping=join if early else None)
+        if not early:
+            join()
         return loss, nxt_sampling
 
     # ---- graph ---------------------------------------------------------------------------------------------------
@@ -204,32 +222,39 @@ class PipelinedTrainStep:
             dst.y.copy_(src.y, non_blocking=True)
 
     def _capture(self, first_batch, warmup):
-        self.s_cur, self.s_nxt = self._clone_batch(first_batch), self._clone_batch(first_batch)
-        samp = self.model.sample(self.s_cur)
-        self.s_sampling = type(samp)(samp.sizes, [t.clone() for t in samp.level1], [t.clone() for t in samp.level2])
+        # Double buffer: graph i trains on bufs[i] with samp[i] while its sampling branch works on bufs[1 - i] and
+        # leaves the result in samp[1 - i]; step() alternates between the two graphs, so nothing is copied on the
+        # training stream (the publishing copies ride on the sampling stream, which has slack).
+        self.bufs = [self._clone_batch(first_batch), self._clone_batch(first_batch)]
+        samp = self.model.sample(self.bufs[0], grouping=self.grouping)
+        self.samp = [samp.clone(), samp.clone()]
 
-        def body():
-            loss, nxt_sampling = self._eager_step(self.s_cur, self.s_sampling, self.s_nxt)
-            for d, s in zip(self.s_sampling.tensors(), nxt_sampling.tensors()):
-                d.copy_(s)
-            self._copy_batch(self.s_cur, self.s_nxt)
+        def body(i):
+            loss, _ = self._eager_step(self.bufs[i], self.samp[i], self.bufs[1 - i], publish=self.samp[1 - i])
             return loss
 
         warm = torch.cuda.Stream(self.dev)
         warm.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(warm):
             for _ in range(max(warmup, 1)):
-                body()
-                if self.split:
-                    reduce_and_update(self.optimizer, self.reducer)
+                for i in (0, 1):
+                    body(i)
+                    if self.split:
+                        reduce_and_update(self.optimizer, self.reducer)
         torch.cuda.current_stream(self.dev).wait_stream(warm)
         torch.cuda.synchronize(self.dev)
-        self.graph = torch.cuda.CUDAGraph()
-        l0 = self.lib.b2pn_launch_count()
-        with torch.cuda.graph(self.graph):
-            self.loss = body()
-        self.launches_per_step = int(self.lib.b2pn_launch_count() - l0)
-        # the warm-up iterations trained on copies of the first batch; the pipeline now holds it as "current"
+        self.graphs, self.losses = [], []
+        for i in (0, 1):
+            g = torch.cuda.CUDAGraph()
+            l0 = self.lib.b2pn_launch_count()
+            with torch.cuda.graph(g, pool=None if i == 0 else self.graphs[0].pool()):
+                self.losses.append(body(i))
+            self.launches_per_step = int(self.lib.b2pn_launch_count() - l0)
+            self.graphs.append(g)
+        self.graph = self.graphs[0]
+        self.parity = 0
+        # the warm-up iterations trained on copies of the first batch (both buffers held it, so samp[0] belongs to
+        # bufs[0]); the pipeline now holds it as "current"
 
     def step(self, next_batch) -> torch.Tensor:
         """Train on the batch submitted by the previous call (or the constructor) while sampling ``next_batch``."""
@@ -237,11 +262,13 @@ class PipelinedTrainStep:
             raise ValueError("PipelinedTrainStep(graph=True): the batch layout (cloud sizes) must stay fixed; "
                              "use graph=False for ragged batches")
         if self.graph is not None:
-            self._copy_batch(self.s_nxt, next_batch)
-            self.graph.replay()
+            i = self.parity
+            self._copy_batch(self.bufs[1 - i], next_batch)
+            self.graphs[i].replay()
             if self.split:
                 reduce_and_update(self.optimizer, self.reducer)
-            return self.loss
+            self.parity = 1 - i
+            return self.losses[i]
         l0 = self.lib.b2pn_launch_count()
         nb = next_batch if next_batch.pos.is_cuda else next_batch.to(self.dev, non_blocking=True)
         loss, nxt_sampling = self._eager_step(self.cur, self.cur_sampling, nb)

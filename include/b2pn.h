@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B2PN_ABI_VERSION 3
+#define B2PN_ABI_VERSION 4
 #define B2PN_OK 0
 #define B2PN_EINVAL (-1)   /* null pointer / negative size / bad flag            */
 #define B2PN_ENOTSUP (-2)  /* shape outside what the sm_100a kernels are built for */
@@ -194,8 +194,10 @@ typedef struct b2pn_sa_args {
     void *a1, *a2;
     /* PREC_BF16 + SEG_SLOTS, optional (NULL = gather in the loader warps): the gathered + concatenated layer-1
      * operand, bf16 feature-major [c_img + 1, ld] with c_img = (x fp32 ? 2 : 1) * c_in + 6 image columns
-     * [x | x_lo | dpos_hi | dpos_lo] and a last line of ones on valid rows.  Written by forward, read by backward. */
+     * [x | x_lo | dpos_hi | dpos_lo] and a last line of ones on valid rows.  Written by forward (or ahead of it by
+     * b2pn_sa_gather_rows: set g1_ready = 1 and forward skips the gather), read by backward.                    */
     void *g1;
+    int32_t g1_ready;
 } b2pn_sa_args;
 
 typedef struct b2pn_sa_grads {
@@ -208,6 +210,11 @@ typedef struct b2pn_sa_grads {
 /* scratch bytes needed by forward (backward=0) or backward (backward=1) for these shapes */
 int64_t b2pn_sa_workspace_bytes(const b2pn_sa_args *args, int32_t backward);
 int b2pn_sa_forward(const b2pn_sa_args *args, b2pn_stream_t stream);
+/* PREC_BF16 + SEG_SLOTS: only the gather + concat of /root/reference/pointnet2_regressor.py:17-18's message inputs
+ * ([x_j | pos_j - pos_i]) into args->g1.  Needs x, pos_src, pos_dst, the compacted rows and c_in / mlp.c[0..1]; no
+ * weights, no workspace: a caller may run it ahead of the forward pass (e.g. for the next batch on another stream).
+ * B2PN_ENOTSUP when the level does not take a materialised operand (b2pn_sa_forward then gathers in its loaders). */
+int b2pn_sa_gather_rows(const b2pn_sa_args *args, b2pn_stream_t stream);
 int b2pn_sa_backward(const b2pn_sa_args *args, const b2pn_sa_grads *grads, b2pn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -82,6 +82,7 @@ def test_grouping_sass_has_no_fma(built_lib):
 
 def test_host_side_sizing_helpers(built_lib):
     """Host-only entry points: capacity / workspace bounds and argument checks (no GPU involved)."""
+    import ctypes
     h = built_lib.lib()
     # compacted-row capacity: never below the slots in use, grows with n_dst, rejects K > 64
     for n_dst, K in ((1, 64), (24000, 64), (6000, 64), (1000, 16), (1000, 40), (7, 8)):
@@ -95,9 +96,11 @@ def test_host_side_sizing_helpers(built_lib):
     assert h.b2pn_ball_query_workspace_bytes(-1, 10) == -1
     assert h.b2pn_set_sm_limit(-3) == -1 and h.b2pn_set_sm_limit(0) == 0
     assert h.b2pn_head_forward(None, None) == -1 and h.b2pn_head_backward(None, None, None) == -1
+    assert h.b2pn_sa_gather_rows(None, None) == -1
+    sa_args = built_lib.SaArgs()                              # fp32 levels gather inside their loaders
+    assert h.b2pn_sa_gather_rows(ctypes.byref(sa_args), None) == -2
     a = built_lib.HeadArgs()
     a.B = 40                                                  # more rows than the fused head takes
     for i, c in enumerate((1024, 128, 128, 4)):
         a.c[i] = c
-    import ctypes
     assert h.b2pn_head_forward(ctypes.byref(a), None) == -2

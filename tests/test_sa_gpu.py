@@ -468,3 +468,32 @@ def test_pipelined_eager_step_takes_ragged_batches(cuda_device):
         got = [float(stepper.step(b)) for b in batches[1:3]]
     for a, b in zip(want, got):
         assert abs(a - b) <= 2e-3 * max(abs(a), 1e-6)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_precomputed_grouping_gives_identical_results(cuda_device, precision):
+    """Net.sample(grouping=True) (FPS + ball query + row compaction + gathered level-1 operand ahead of time) feeds
+    forward/backward the very same numbers as computing them inside forward."""
+    b = Batch.from_data_list(synthetic_clouds(321, 3, 640, 1, True)).to(cuda_device)
+    torch.manual_seed(11)
+    net = Net(1, "ReLU", 0, 0.0, precision=precision).to(cuda_device).set_random_start(False)
+    net.train()
+    state = {k: v.clone() for k, v in net.state_dict().items()}
+    outs, grads = [], []
+    for pre in (False, True):
+        net.load_state_dict(state)
+        net.zero_grad(set_to_none=True)
+        samp = net.sample(b) if pre else None
+        if pre:
+            assert samp.group1 is not None and (samp.group1[2] is not None) == (precision == "bf16")
+            assert (samp.group1[3] is not None) == (precision == "bf16") and samp.group2[3] is None
+            assert len(samp.clone().tensors()) == len(samp.tensors())
+        out = net(b, sampling=samp)
+        out.square().sum().backward()
+        outs.append(out.detach().clone())
+        grads.append([p.grad.detach().clone() for p in net.parameters()])
+    assert torch.equal(outs[0], outs[1])
+    scale = max(float(g.abs().max()) for g in grads[0])
+    for ga, gb in zip(*grads):
+        # same products; the order of the partial sums (atomics, dynamic tile schedule) may differ in the last bits
+        assert float((ga - gb).abs().max()) <= 1e-4 * float(ga.abs().max()) + 1e-6 * scale
