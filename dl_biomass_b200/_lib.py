@@ -40,6 +40,12 @@ class SaGrads(ctypes.Structure):
     _fields_ = [("grad_out", _vp), ("grad_w", _vp * 3), ("grad_b", _vp * 3), ("grad_gamma", _vp * 2),
                 ("grad_beta", _vp * 2), ("grad_x", _vp)]
 
+class AugmentCloud(ctypes.Structure):
+    _fields_ = [("src_off", ctypes.c_int64), ("out_off", ctypes.c_int64), ("uid", ctypes.c_uint64),
+                ("n_src", ctypes.c_int32), ("n_keep", ctypes.c_int32), ("n_dup", ctypes.c_int32),
+                ("noise_sd", ctypes.c_float), ("cos_a", ctypes.c_float), ("sin_a", ctypes.c_float)]
+
+
 class HeadArgs(ctypes.Structure):
     _fields_ = [("B", ctypes.c_int32), ("c", ctypes.c_int32 * 4), ("training", ctypes.c_int32), ("p", ctypes.c_float),
                 ("eps", ctypes.c_float), ("momentum", ctypes.c_float), ("x", _vp), ("w", _vp * 3), ("b", _vp * 3),
@@ -71,6 +77,11 @@ SIGNATURES = {
     "b2pn_pack_rows": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "b2pn_sa_workspace_bytes": (_i64, [ctypes.POINTER(SaArgs), _i32]),
     "b2pn_sa_forward": (ctypes.c_int, [ctypes.POINTER(SaArgs), _vp]),
+    "b2pn_augment_batch": (ctypes.c_int, [_vp, _vp, ctypes.c_int32, ctypes.POINTER(AugmentCloud), ctypes.c_int32,
+                                          ctypes.c_uint64, _vp, _vp, _vp, _vp, _vp]),
+    "b2pn_augment_draw": (ctypes.c_uint64, [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64]),
+    "b2pn_augment_max_points": (ctypes.c_int32, []),
+    "b2pn_weighted_mse": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, _vp, _vp, _vp]),
     "b2pn_sa_gather_rows": (ctypes.c_int, [ctypes.POINTER(SaArgs), _vp]),
     "b2pn_sa_backward": (ctypes.c_int, [ctypes.POINTER(SaArgs), ctypes.POINTER(SaGrads), _vp]),
     "b2pn_head_forward": (ctypes.c_int, [ctypes.POINTER(HeadArgs), _vp]),

@@ -315,6 +315,44 @@ static int head_check(const b2pn_head_args &a, bool forward)
 
 }  // namespace b2pn
 
+// ---- weighted per-component MSE (/root/reference/main.py:157-169): value and gradient in one launch -----------
+namespace b2pn {
+constexpr int LOSS_MAX_C = 32;
+__global__ void __launch_bounds__(32) weighted_mse_kernel(const float *pred, const float *y, const float *w, int B, int C,
+                                                          float *loss, float *grad)
+{
+    // lane c owns component c: mse_c = mean_b (y - pred)^2 summed in row order, then loss = sum_c mse_c * w_c in
+    // component order (the order main.py:169 adds them up)
+    const int c = threadIdx.x;
+    float term = 0.f;
+    if (c < C) {
+        float acc = 0.f;
+        const float wc = w[c], inv = 1.f / (float)B;
+        for (int b = 0; b < B; ++b) {
+            const float d = pred[b * C + c] - y[b * C + c];
+            acc += d * d;
+            if (grad) grad[b * C + c] = 2.f * wc * inv * d;
+        }
+        term = acc * inv * wc;
+    }
+    float tot = 0.f;
+    for (int i = 0; i < C; ++i) tot += __shfl_sync(0xffffffffu, term, i);
+    if (c == 0) *loss = tot;
+}
+}  // namespace b2pn
+
+extern "C" int b2pn_weighted_mse(const float *pred, const float *y, const float *w, int32_t B, int32_t C, float *loss,
+                                 float *grad, b2pn_stream_t stream)
+{
+    if (B <= 0 || C <= 0) return B2PN_EINVAL;
+    if (C > b2pn::LOSS_MAX_C) return B2PN_ENOTSUP;
+    if (!pred || !y || !w || !loss) return B2PN_EINVAL;
+    b2pn::weighted_mse_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pred, y, w, B, C, loss, grad);
+    b2pn::note_launch();
+    B2PN_LAUNCH_CHECK();
+    return B2PN_OK;
+}
+
 extern "C" int b2pn_head_forward(const b2pn_head_args *args, b2pn_stream_t stream)
 {
     using namespace b2pn;

@@ -21,10 +21,38 @@ def _loss_weights(dtype, device) -> torch.Tensor:
     return w
 
 
+class _WeightedMSE(torch.autograd.Function):
+    """Loss value and its gradient from one kernel (include/b2pn.h, b2pn_weighted_mse)."""
+
+    @staticmethod
+    def forward(ctx, outs, y, w):
+        from . import _lib
+        outs = outs.contiguous()
+        loss = torch.empty((), dtype=torch.float32, device=outs.device)
+        grad = torch.empty_like(outs) if ctx.needs_input_grad[0] else None
+        with torch.cuda.device(outs.device):
+            rc = _lib.lib().b2pn_weighted_mse(outs.data_ptr(), y.data_ptr(), w.data_ptr(), outs.size(0), outs.size(1),
+                                              loss.data_ptr(), None if grad is None else grad.data_ptr(),
+                                              torch.cuda.current_stream(outs.device).cuda_stream)
+        _lib.check(rc, "b2pn_weighted_mse")
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None
+
+
 def weighted_mse_loss(outs: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-    """sum_c w_c * mse(y[:, c], outs[:, c])  (main.py:154-169); ``y`` may come flat ([4B]) as PyG collates it."""
-    y = y.reshape(outs.size(0), 4).to(outs.dtype)
-    return (((outs - y) ** 2).mean(0) * _loss_weights(outs.dtype, outs.device)).sum()
+    """sum_c w_c * mse(y[:, c], outs[:, c])  (main.py:154-169); ``y`` may come flat ([4B]) as PyG collates it.
+    Value and gradient come from one libb2pn launch, in fp32; there is no CPU path."""
+    if not outs.is_cuda:
+        raise RuntimeError("weighted_mse_loss runs on a B200 only: there is no CPU fallback")
+    outs = outs.to(torch.float32)
+    y = y.reshape(outs.size(0), 4).to(device=outs.device, dtype=torch.float32).contiguous()
+    return _WeightedMSE.apply(outs, y, _loss_weights(torch.float32, outs.device))
 
 
 def make_optimizer(params, lr: float = ADAM_LR, weight_decay: float = ADAM_WEIGHT_DECAY,

@@ -255,6 +255,42 @@ typedef struct b2pn_head_grads {
 int b2pn_head_forward(const b2pn_head_args *args, b2pn_stream_t stream);
 int b2pn_head_backward(const b2pn_head_args *args, const b2pn_head_grads *grads, b2pn_stream_t stream);
 
+/* The training loss of /root/reference/main.py:157-169: loss = sum_c w[c] * mean_b (y[b,c] - pred[b,c])^2 over
+ * pred, y [B, C] row-major (C <= 32; the reference has C = 4 with w = 1/11, 1/12, 1/5, 1/72), and in the same launch
+ * its gradient grad[b,c] = 2 w[c] (pred - y) / B (grad may be NULL).  fp32, fixed summation order. */
+int b2pn_weighted_mse(const float *pred, const float *y, const float *w, int32_t B, int32_t C, float *loss,
+                      float *grad, b2pn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training-time augmentation on the device: point_removal -> random_noise -> rotate_points of
+ * /root/reference/augmentation.py:54-122 as applied by AugmentPointCloudsInFiles.__getitem__ (:287-289), for B clouds
+ * of a resident cloud cache, written straight into the concatenated batch layout (pos, x, batch) the model takes.
+ * The caller draws the per-cloud scalars (they fix the layout); per-point randomness is counter based:
+ * b2pn_augment_draw(seed, uid, stream, counter) is the 64-bit draw the kernel uses (stream 0: order key of source
+ * point `counter`, top 32 bits; stream 1: duplication key of kept position `counter`; stream 2: deviate number
+ * `counter` = kept position * (3 + F) + component, Box-Muller on bits 63..40 and 39..16).
+ * ---------------------------------------------------------------------------------------------- */
+#define B2PN_AUG_MAX_POINTS 16384   /* per source cloud (one CTA sorts a cloud in shared memory)                */
+typedef struct b2pn_augment_cloud {
+    int64_t src_off;             /* first point of the cloud in the cache                                      */
+    int64_t out_off;             /* first output point of the cloud in the batch                               */
+    uint64_t uid;                /* generator stream of this sample (e.g. epoch * dataset size + cloud id)     */
+    int32_t n_src;               /* points of the cached cloud                                                 */
+    int32_t n_keep;              /* points kept by point_removal: round(0.9 n_src) .. n_src                    */
+    int32_t n_dup;               /* jittered copies appended by random_noise: 0 .. round(0.1 n_keep)           */
+    float noise_sd;              /* jitter sd 0.01 .. 0.025, NEGATIVE when the deviates are subtracted         */
+    float cos_a, sin_a;          /* rotation about z by a in (-180, 180] degrees                               */
+} b2pn_augment_cloud;
+
+/* clouds: HOST array of B records (copied into the launch parameters; nothing is read after return).
+ * out_pos [sum(n_keep + n_dup), 3], out_x [.., F] (F > 0), optional out_batch (int64 cloud number 0..B-1 per point) and
+ * out_src (int32 index of the source point inside its cached cloud, for carrying further attributes). */
+int b2pn_augment_batch(const float *pos, const float *x, int32_t F, const b2pn_augment_cloud *clouds, int32_t B,
+                       uint64_t seed, float *out_pos, float *out_x, int64_t *out_batch, int32_t *out_src,
+                       b2pn_stream_t stream);
+uint64_t b2pn_augment_draw(uint64_t seed, uint64_t uid, uint32_t stream, uint64_t counter);
+int32_t b2pn_augment_max_points(void);
+
 /*
  * Hardware self-test of the tcgen05 GEMM pipeline (debug aid used by tests/test_tc_gpu.py; not part of
  * the reference's surface).  out[m][row] (fp32, leading dimension ld_out) = sum_k w[m][k] * b(row, k) with

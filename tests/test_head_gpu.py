@@ -109,3 +109,23 @@ def test_head_falls_back_when_unsupported(cuda_device):
     m = MLP([64, 32, 32, 4], act=None).to(cuda_device)
     assert not head.supported(m, torch.zeros(33, 64, device=cuda_device))          # more than 32 clouds
     assert not head.supported(MLP([64, 32, 32, 4], act="relu").to(cuda_device), torch.zeros(4, 64, device=cuda_device))
+
+
+def test_weighted_mse_loss_matches_reference_formula(cuda_device):
+    """train.weighted_mse_loss == the four F.mse_loss terms of /root/reference/main.py:157-169, value and gradient."""
+    import torch.nn.functional as F
+    from dl_biomass_b200.train import LOSS_WEIGHTS, weighted_mse_loss
+    g = torch.Generator().manual_seed(4)
+    for B in (1, 12, 37):
+        outs = (torch.randn(B, 4, generator=g) * 3).to(cuda_device).requires_grad_(True)
+        y = (torch.rand(4 * B, generator=g) * 40).to(cuda_device)          # flat, as PyG collates it
+        loss = weighted_mse_loss(outs, y)
+        (loss * 1.5).backward()
+        o = outs.detach().cpu().double().requires_grad_(True)
+        yy = y.cpu().double().reshape(B, 4)
+        want = sum(F.mse_loss(yy[:, c], o[:, c]) * LOSS_WEIGHTS[c] for c in range(4))
+        (want * 1.5).backward()
+        assert abs(float(loss.detach()) - float(want.detach())) <= 1e-5 * abs(float(want.detach()))
+        assert torch.allclose(outs.grad.cpu().double(), o.grad, rtol=1e-5, atol=1e-7)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        weighted_mse_loss(torch.zeros(2, 4), torch.zeros(8))
