@@ -34,6 +34,8 @@ constexpr int NT = NUM_EPI + LOAD_GROUPS * NUM_LOAD + 32;
 // parity g, i.e. TMEM accumulator buffer g), warp 16 issues the MMAs and warp 17 the TMA copies
 constexpr int NT_TMA = 2 * NUM_EPI + 64;
 constexpr int PROD_WARP_TMA = MMA_WARP + 1;
+// wide layout with SIMT loaders: warps 0-15 two epilogue groups, warp 16 MMA, warps 17-20 one loader group
+constexpr int NT_WIDE = 2 * NUM_EPI + 32 + NUM_LOAD;
 constexpr int B_BYTES = R * LINE_BYTES;  // 16 KB: [128 row lines x 64 k] or [2 row blocks][64 k lines x 64 rows]
 
 // Row structure of a level.
@@ -66,6 +68,13 @@ struct RowMapTC {
         return gi_none(b) ? GI_NONE : b;
     }
     __device__ __forceinline__ int valid8(int64_t r8) const { return gi_nv(info(r8)); }
+    // SLOTS only, r8 below the row capacity: the same word without a branch around the load, so that a loader
+    // thread's eight descriptor loads (and what depends on them) go out back to back
+    __device__ __forceinline__ unsigned info_slots(int64_t r8) const
+    {
+        const unsigned b = __ldg(rgrp + (r8 >> 3));
+        return (r8 >= rows || gi_none(b)) ? GI_NONE : b;
+    }
 };
 
 // ---- TMA tensor maps ------------------------------------------------------------------------------------------
@@ -152,6 +161,7 @@ __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(_
 struct GatherLoaderTC {  // K-major B: line = row of the tile, 64 k per line
     static constexpr bool B_MN = false;
     static constexpr bool USES_TMA = false;
+    static constexpr bool WIDE = false;
     RowMapTC rm;
     const void *x;  // [n_src, c_in] row-major, fp32 (cols.x_f32) or bf16
     InCols cols;
@@ -282,6 +292,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8])
 template <int MODE>
 struct FeatSource {
     static constexpr bool USES_TMA = false;
+    static constexpr bool SCATTER = false;
     RowMapTC rm;
     const __nv_bfloat16 *t;  // [C][ld]; MODE 1: the normalised value zhat, activation input is gamma*zhat+beta
     int C;
@@ -328,17 +339,83 @@ struct FeatSource {
 // the BatchNorm-backward pass): the kernel issues the tensor-map copies itself, this only carries the row structure.
 struct TmaSource {
     static constexpr bool USES_TMA = true;
+    static constexpr bool SCATTER = false;
     RowMapTC rm;
     __device__ __forceinline__ void resolve(int64_t r) { rm.resolve(r); }
     __device__ __forceinline__ uint4 chunk_i(int, int64_t, unsigned) const { return make_uint4(0u, 0u, 0u, 0u); }
 };
 
+// The routed gradient of the max aggregation (SLOTS levels), generated on the fly instead of being stored:
+//   dh3[ch][row] = dout[m][ch] if row is the arg-max slot of (centroid m, ch), else 0
+// -- one value per (centroid, channel), i.e. 1 element in ~20..60 of the dense [c3][rows] tensor.  A chunk (8 rows of
+// one channel) costs two L2-resident loads (arg, dout) in a loader thread; the dense tensor cost c3 * rows * 2 bytes of
+// HBM written once and read twice per level.
+struct RouteSource {
+    static constexpr bool USES_TMA = false;
+    RowMapTC rm;
+    const float *dout;   // [n_dst][C]
+    const int32_t *arg;  // [n_dst][C] arg-max slot
+    int C;
+    __device__ __forceinline__ void resolve(int64_t r) { rm.resolve(r); }
+    static constexpr bool SCATTER = true;
+    // One 128-byte line = 64 rows of channel ch, built as: zero the line, then drop the gradient of every centroid
+    // that STARTS in these 64 rows (a centroid never crosses a 64-row boundary) at its arg-max row.  `line` is the
+    // shared-memory address of the line (128-byte aligned inside a 1024-byte swizzle atom), `sw` = (line index & 7) << 4
+    // its swizzle.  Branch-free: the eight (arg, dout) pairs are in flight together, the 2-byte stores are predicated.
+    __device__ __forceinline__ void fill_line(int ch, const unsigned (&inf)[8], uint32_t line, uint32_t sw) const
+    {
+        int a[8];
+        float d[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const bool first = ch < C && gi_nv(inf[g]) > 0 && gi_slot0(inf[g]) == 0;
+            const int64_t idx = first ? (int64_t)gi_seg(inf[g]) * C + ch : 0;
+            a[g] = __ldg(arg + idx);
+            d[g] = __ldg(dout + idx);
+            if (!first) a[g] = -1;
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(line + (((uint32_t)g << 4) ^ sw)), "r"(0u) : "memory");
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const unsigned row = (unsigned)(g * 8 + a[g]);  // a = -1 (no centroid starts here) -> row >= 64 or wraps
+            const unsigned ok = (a[g] >= 0 && row < 64u) ? 1u : 0u;
+            const uint32_t addr = line + ((((row >> 3) & 7u) << 4) ^ sw) + ((row & 7u) << 1);
+            const unsigned short gb = __bfloat16_as_ushort(__float2bfloat16(d[g]));
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.b16 [%0], %1;\n\t}" ::"r"(addr), "h"(gb), "r"(ok)
+                         : "memory");
+        }
+    }
+    // 8 rows of channel ch as one 16-byte chunk; no branch around the loads: a thread's eight (arg, dout) pairs are in
+    // flight together
+    __device__ __forceinline__ uint4 chunk_i(int ch, int64_t, unsigned inf) const
+    {
+        const bool live = ch < C && gi_nv(inf) > 0;
+        const int64_t idx = live ? (int64_t)gi_seg(inf) * C + ch : 0;
+        const int a = __ldg(arg + idx) - gi_slot0(inf);
+        const float d = __ldg(dout + idx);
+        const bool hit = live && a >= 0 && a < 8;
+        const unsigned short gb = __bfloat16_as_ushort(__float2bfloat16(d));
+        const unsigned w = (a & 1) ? ((unsigned)gb << 16) : (unsigned)gb;
+        const int q = hit ? (a >> 1) : -1;
+        uint4 v;
+        v.x = q == 0 ? w : 0u;
+        v.y = q == 1 ? w : 0u;
+        v.z = q == 2 ? w : 0u;
+        v.w = q == 3 ? w : 0u;
+        return v;
+    }
+};
+
 // MN-major B tile of the rows GEMM from a feature-major source: [2 row blocks of 64][64 channel lines];
 // thread lt fills channel line (lt >> 1) of the chunk for row block (lt & 1)
-template <class SRC>
+// WIDE_: run under the wide kernel layout (two epilogue groups + one loader group, see tc_rows_gemm_kernel)
+template <class SRC, bool WIDE_ = false>
 struct FeatLoaderTC {
     static constexpr bool B_MN = true;
     static constexpr bool USES_TMA = false;
+    static constexpr bool WIDE = WIDE_;
     SRC src;
     int64_t row0;
     unsigned inf[8];  // descriptors of the 8 row groups of my row block
@@ -346,19 +423,28 @@ struct FeatLoaderTC {
     __device__ __forceinline__ void begin_tile(int64_t tile, int lt)
     {
         row0 = tile * R + (lt & 1) * 64;
+        if (src.rm.seg_mode) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) inf[g] = src.rm.info(row0 + g * 8);
+            for (int g = 0; g < 8; ++g) inf[g] = src.rm.info(row0 + g * 8);
+        } else {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) inf[g] = src.rm.info_slots(row0 + g * 8);
+        }
     }
     __device__ __forceinline__ void produce(uint8_t *B, int kc, int lt) const
     {
         const int cl = lt >> 1, nb = lt & 1;
         uint8_t *dst = B + nb * (64 * LINE_BYTES);
         const int ch = kc * KC + cl;
-        uint4 v[8];
+        if constexpr (SRC::SCATTER) {
+            src.fill_line(ch, inf, smem_u32(dst) + cl * LINE_BYTES, (uint32_t)(cl & 7) << 4);
+        } else {
+            uint4 v[8];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) v[g] = src.chunk_i(ch, row0 + g * 8, inf[g]);
+            for (int g = 0; g < 8; ++g) v[g] = src.chunk_i(ch, row0 + g * 8, inf[g]);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4 *>(dst + line_chunk_off(cl, g)) = v[g];
+            for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4 *>(dst + line_chunk_off(cl, g)) = v[g];
+        }
     }
     // MN-major: 16 k lines per step; LBO = stride between the two 64-row blocks, SBO = 8 lines
     static __device__ __forceinline__ uint64_t b_desc(uint32_t b_saddr, int ks)
@@ -373,6 +459,7 @@ struct FeatLoaderTC {
 struct TmaFeatLoader {
     static constexpr bool B_MN = true;
     static constexpr bool USES_TMA = true;
+    static constexpr bool WIDE = true;
     __device__ __forceinline__ void resolve(int64_t) {}
     __device__ __forceinline__ void begin_tile(int64_t, int) {}
     __device__ __forceinline__ void produce_tma(uint8_t *B, int64_t tile, int kc, const TmaMap *map, uint64_t *bar) const
@@ -781,15 +868,23 @@ struct SmemPlan {
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + alignment slack
 };
 
+template <class BL>
+constexpr int gemm_threads() { return BL::USES_TMA ? NT_TMA : (BL::WIDE ? NT_WIDE : NT); }
+
 template <int MT, class BL, class EP>
-__global__ void __launch_bounds__(BL::USES_TMA ? NT_TMA : NT, 1)
+__global__ void __launch_bounds__(gemm_threads<BL>(), 1)
     tc_rows_gemm_kernel(const GemmParams gp, BL bl, EP ep, const __grid_constant__ TmaMap tmap, const __grid_constant__ TmaMap tmap_e0,
                         const __grid_constant__ TmaMap tmap_e1)
 {
     constexpr bool TMA = BL::USES_TMA;
-    constexpr int EPI_GROUPS = TMA ? 2 : 1;
+    constexpr bool WIDE = BL::WIDE;
+    static_assert(!TMA || WIDE, "TMA-fed kernels use the wide layout");
+    constexpr int EPI_GROUPS = WIDE ? 2 : 1;
     constexpr int EPI_WARPS = EPI_GROUPS * (NUM_EPI / 32);
-    using P = SmemPlan<MT, EP::STAGED, TMA>;
+    // SIMT loaders: two groups in warps 8-15 (narrow layout) or one group in warps 17-20 (wide layout)
+    constexpr int LGROUPS = WIDE ? 1 : LOAD_GROUPS;
+    constexpr int LOAD_T0 = WIDE ? (MMA_WARP + 1) * 32 : NUM_EPI;
+    using P = SmemPlan<MT, EP::STAGED, WIDE>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + P::BAR_OFF);
@@ -845,33 +940,35 @@ __global__ void __launch_bounds__(BL::USES_TMA ? NT_TMA : NT, 1)
                 }
             }
         }
-    } else if (!TMA && warp >= NUM_EPI / 32 && warp < MMA_WARP) {
+    } else if (!TMA && tid >= LOAD_T0 && tid < LOAD_T0 + LGROUPS * NUM_LOAD) {
         // ------------------------------------------------------------------ SIMT loaders: group g takes every
-        // LOAD_GROUPS-th (tile, k-chunk) item, so the groups' global-load latencies overlap
+        // LGROUPS-th (tile, k-chunk) item, so the groups' global-load latencies overlap
         if constexpr (!TMA) {
-            const int g = (tid - NUM_EPI) / NUM_LOAD;
-            const int lt = (tid - NUM_EPI) % NUM_LOAD;
-            uint32_t it = 0;
-            int64_t cur_tile = -1;
-            for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                for (int kc = 0; kc < gp.num_kc; ++kc, ++it) {
-                    if ((int)(it % LOAD_GROUPS) != g) continue;
-                    if (tile != cur_tile) {
-                        bl.begin_tile(tile, lt);
-                        cur_tile = tile;
+            const int g = (tid - LOAD_T0) / NUM_LOAD;
+            const int lt = (tid - LOAD_T0) % NUM_LOAD;
+            {
+                uint32_t it = 0;
+                int64_t cur_tile = -1;
+                for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                    for (int kc = 0; kc < gp.num_kc; ++kc, ++it) {
+                        if ((int)(it % LGROUPS) != g) continue;
+                        if (tile != cur_tile) {
+                            bl.begin_tile(tile, lt);
+                            cur_tile = tile;
+                        }
+                        const int s = it % P::STAGES;
+                        const uint32_t ph = (it / P::STAGES) & 1u;
+                        mbar_wait(&empty[s], ph ^ 1u);
+                        uint8_t *A = smem + s * P::STAGE_BYTES;
+                        uint8_t *B = A + P::A_BYTES;
+                        if (lt == 0) {
+                            mbar_expect_tx(&full[s], P::A_BYTES);
+                            bulk_g2s(A, gp.a_packed + ((int64_t)mg * gp.num_kc + kc) * P::A_BYTES, P::A_BYTES, &full[s]);
+                        }
+                        bl.produce(B, kc, lt);
+                        fence_proxy_async_smem();
+                        mbar_arrive(&full[s]);
                     }
-                    const int s = it % P::STAGES;
-                    const uint32_t ph = (it / P::STAGES) & 1u;
-                    mbar_wait(&empty[s], ph ^ 1u);
-                    uint8_t *A = smem + s * P::STAGE_BYTES;
-                    uint8_t *B = A + P::A_BYTES;
-                    if (lt == 0) {
-                        mbar_expect_tx(&full[s], P::A_BYTES);
-                        bulk_g2s(A, gp.a_packed + ((int64_t)mg * gp.num_kc + kc) * P::A_BYTES, P::A_BYTES, &full[s]);
-                    }
-                    bl.produce(B, kc, lt);
-                    fence_proxy_async_smem();
-                    mbar_arrive(&full[s]);
                 }
             }
         }
@@ -934,7 +1031,10 @@ __global__ void __launch_bounds__(BL::USES_TMA ? NT_TMA : NT, 1)
                     cx.next_tile = tile + tstep < num_tiles ? tile + tstep : -1;
                     cx.next_ch = mg * MT * 128 + chl;
                 }
-                ep.tile_mt(tmem_base + lane_base + acc * (MT * R) + mt * R, tile, ch, mt, half, cx);
+                // a warp whose 32 channels all lie past the layer's width has nothing to drain (TMEM lane quarters are
+                // tied to warp % 4, so it cannot help the others either): it only keeps the barrier protocol
+                // (MT == 1 only: with two M tiles a staged epilogue prefetches across them)
+                if (MT > 1 || ch - lane < ep.C) ep.tile_mt(tmem_base + lane_base + acc * (MT * R) + mt * R, tile, ch, mt, half, cx);
             }
             tc_fence_before();
             mbar_arrive(&tempty[acc]);
@@ -1089,17 +1189,28 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
     if (warp >= NUM_EPI / 32 && warp < MMA_WARP) {
         const int grp = (tid - NUM_EPI) / NUM_LOAD;
         const int lt = (tid - NUM_EPI) % NUM_LOAD;
+        // group descriptors of the 64 rows of a chunk (unused, and dropped by the compiler, for TMA-fed operands); the ones
+        // of the group's NEXT chunk are requested before the current chunk is built
+        auto load_inf = [&](unsigned (&inf)[8], int64_t r0) {
+            if (ys.rm.seg_mode) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g) inf[g] = ys.rm.info(r0 + g * 8);
+            } else {
+#pragma unroll
+                for (int g = 0; g < 8; ++g) inf[g] = ys.rm.info_slots(r0 + g * 8);
+            }
+        };
+        unsigned inf[8], infn[8];
+        if (grp < nchunks) load_inf(inf, (c_beg + grp) * 64);
         for (int64_t i = grp; i < nchunks; i += LOAD_GROUPS) {
             const int s = (int)(i % nst);
             const uint32_t ph = (uint32_t)(i / nst) & 1u;
-            mbar_wait(&empty[s], ph ^ 1u);
             uint8_t *A = smem + s * sbytes;
             uint8_t *B = A + P::A_BYTES;
             const int64_t r0 = (c_beg + i) * 64;
-            unsigned inf[8];
-#pragma unroll
-            for (int g = 0; g < 8; ++g) inf[g] = ys.rm.info(r0 + g * 8);
+            if (i + LOAD_GROUPS < nchunks) load_inf(infn, (c_beg + i + LOAD_GROUPS) * 64);
             if constexpr (YS::USES_TMA) {
+                mbar_wait(&empty[s], ph ^ 1u);
                 if (lt == 0) {  // MTA*128 lines x 64 rows straight from the feature-major tensor, 64 lines per copy
                     mbar_expect_tx(&full[s], P::A_BYTES);
 #pragma unroll
@@ -1107,15 +1218,29 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
                         tma_load_2d(A + m * (64 * LINE_BYTES), &tmap_y, (int)r0, mg * (MTA * 128) + m * 64, &full[s]);
                 }
             } else {
+                if constexpr (YS::SCATTER) {
+                    mbar_wait(&empty[s], ph ^ 1u);
 #pragma unroll
-                for (int m = 0; m < MTA; ++m) {
-                    const int line = m * 128 + lt;
-                    const int ch = mg * (MTA * 128) + line;
-                    uint4 v[8];
+                    for (int m = 0; m < MTA; ++m) {
+                        const int line = m * 128 + lt;
+                        ys.fill_line(mg * (MTA * 128) + line, inf, smem_u32(A) + line * LINE_BYTES, (uint32_t)(line & 7) << 4);
+                    }
+                } else {
+                    // the operand loads go out before the wait for the slot: their latency overlaps it
+                    uint4 v[MTA][8];
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) v[g] = ys.chunk_i(ch, r0 + g * 8, inf[g]);
+                    for (int m = 0; m < MTA; ++m) {
+                        const int ch = mg * (MTA * 128) + m * 128 + lt;
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4 *>(A + line_chunk_off(line, g)) = v[g];
+                        for (int g = 0; g < 8; ++g) v[m][g] = ys.chunk_i(ch, r0 + g * 8, inf[g]);
+                    }
+                    mbar_wait(&empty[s], ph ^ 1u);
+#pragma unroll
+                    for (int m = 0; m < MTA; ++m) {
+                        const int line = m * 128 + lt;
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4 *>(A + line_chunk_off(line, g)) = v[m][g];
+                    }
                 }
             }
             if constexpr (XF::USES_TMA) {
@@ -1125,6 +1250,8 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
             }
             if constexpr (!(YS::USES_TMA && XF::USES_TMA)) fence_proxy_async_smem();
             mbar_arrive(&full[s]);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) inf[g] = infn[g];
         }
     } else if (warp == MMA_WARP) {
         if (lane == 0 && nchunks > 0) {
@@ -1310,13 +1437,13 @@ template <int MT, class BL, class EP>
 static int launch_gemm(const Packed &pk, const RowsArg &ra, const BL &bl, const EP &ep, cudaStream_t st,
                        const TmaMap &map = kNoMap, const TmaMap &e0 = kNoMap, const TmaMap &e1 = kNoMap)
 {
-    using P = SmemPlan<MT, EP::STAGED, BL::USES_TMA>;
+    using P = SmemPlan<MT, EP::STAGED, BL::WIDE>;
     auto kern = tc_rows_gemm_kernel<MT, BL, EP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
     if (e != cudaSuccess) return (int)e;
     GemmParams gp = {pk.img, pk.num_kc, ra.cap, ra.dev};
     dim3 grid((unsigned)grid_x_for(pk, ra.tiles()), (unsigned)pk.num_mg);
-    kern<<<grid, BL::USES_TMA ? NT_TMA : NT, P::TOTAL, st>>>(gp, bl, ep, map, e0, e1);
+    kern<<<grid, gemm_threads<BL>(), P::TOTAL, st>>>(gp, bl, ep, map, e0, e1);
     note_launch();
     e = cudaPeekAtLastError();
     return e == cudaSuccess ? 0 : (int)e;
@@ -1762,7 +1889,8 @@ static BwdWsTC carve_bwd_tc(const b2pn_sa_args &a, const ShapesTC &s, WsTC &ws)
     b.partial = ws.take<double>((int64_t)MAX_GX * 4 * 2 * s.cpad);
     b.dz1 = ws.take<__nv_bfloat16>((int64_t)s.c1 * s.ld);
     b.dz2 = ws.take<__nv_bfloat16>((int64_t)s.c2 * s.ld);
-    b.dh3 = ws.take<__nv_bfloat16>((int64_t)s.c3 * s.ld);
+    // the dense routed gradient exists only at the global level (SLOTS levels generate it on the fly)
+    b.dh3 = a.seg_mode == B2PN_SEG_CLOUDS ? ws.take<__nv_bfloat16>((int64_t)s.c3 * s.ld) : nullptr;
     b.sbar = ws.take<float>(2 * s.cmax);
     b.dwp[2] = ws.take<float>(plan_dw(s.c3, s.c2 + 1, s.ld).floats);
     b.dwp[1] = ws.take<float>(plan_dw(s.c2, s.c1 + 1, s.ld).floats);
@@ -2012,12 +2140,9 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
     }
     if (tma_x2 && (rc = make_tma_feature_major(&map_a2, a.a2, s.c2, s.ld))) return rc;
     if (tma_x1 && (rc = make_tma_feature_major(&map_a1, a.a1, s.c1, s.ld))) return rc;
-    {
-        // materialise dh3 once, then both consumers read it through TMA
-        if (a.seg_mode == B2PN_SEG_CLOUDS)
-            route_grad_tc_kernel<true><<<apply_grid(s.ld, s.c3), 256, 0, st>>>(rm, ra.dev, g.grad_out, a.arg, s.c3, s.ld, b.dh3);
-        else
-            route_grad_tc_kernel<false><<<apply_grid(s.ld, s.c3), 256, 0, st>>>(rm, ra.dev, g.grad_out, a.arg, s.c3, s.ld, b.dh3);
+    if (a.seg_mode == B2PN_SEG_CLOUDS) {
+        // global level (few rows): materialise dh3 once, then both consumers read it through TMA
+        route_grad_tc_kernel<true><<<apply_grid(s.ld, s.c3), 256, 0, st>>>(rm, ra.dev, g.grad_out, a.arg, s.c3, s.ld, b.dh3);
         note_launch();
         TmaMap map3;
         if ((rc = make_tma_feature_major(&map3, b.dh3, s.c3, s.ld))) return rc;
@@ -2029,6 +2154,19 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
             rc = launch_dw(y3, xt, s.c3, s.c2 + 1, s, ra, b.dwp[2], st, map3, map_a2, map_v);   // dW3 = dh3^T a2
         } else {
             rc = launch_dw(y3, xa2, s.c3, s.c2 + 1, s, ra, b.dwp[2], st, map3);
+        }
+        if (rc) return rc;
+    } else {
+        // SLOTS levels: dh3 is one value per (centroid, channel) -- both consumers generate their operand tiles from
+        // (arg, grad_out) in their loader warps instead of streaming a dense [c3][rows] tensor
+        RouteSource rs = {rm, g.grad_out, a.arg, s.c3};
+        FeatLoaderTC<RouteSource, true> bl = {rs};
+        if ((rc = launch_by_mt(b.pkT[2], ra, bl, e31, e32, st, kNoMap, mdz2, mz2))) return rc;        // da2 = W3^T dh3
+        if (tma_x2) {
+            TmaFill xt = {s.c2, 1};
+            rc = launch_dw(rs, xt, s.c3, s.c2 + 1, s, ra, b.dwp[2], st, kNoMap, map_a2, map_v);  // dW3 = dh3^T a2
+        } else {
+            rc = launch_dw(rs, xa2, s.c3, s.c2 + 1, s, ra, b.dwp[2], st);
         }
         if (rc) return rc;
     }
