@@ -820,8 +820,12 @@ struct MaskSumsStoreEpTC {  // backward through activation + sums for the BatchN
     }
 };
 
-struct ScatterEpTC {  // gradient w.r.t. the gathered source features (thread = feature channel)
-    static constexpr bool STAGED = false;
+struct ScatterEpTC {  // gradient w.r.t. the gathered source features
+    // A thread drains one channel (TMEM lane) over 64 rows, but dx is row-major [n_src][C]: the warp transposes its
+    // 32 channels x 64 rows through its staging tile (fp32, swizzled per float4), after which a lane owns a ROW and
+    // adds four consecutive channels per instruction (red.global.add.v4.f32: a quarter of the atomic operations the
+    // channel-per-thread form needed; CLOUDS levels: plain 16-byte stores).
+    static constexpr bool STAGED = true;
     RowMapTC rm;
     float *dx;  // [n_src][C] fp32, zero-initialised by the caller in SLOTS mode
     int C;
@@ -829,21 +833,53 @@ struct ScatterEpTC {  // gradient w.r.t. the gathered source features (thread = 
     __device__ __forceinline__ void begin() {}
     __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half, const EpCtx &cx)
     {
+        const int lane = threadIdx.x & 31;
+        const int ch0 = ch - lane;  // first channel of this warp
+        float *st = reinterpret_cast<float *>(cx.stage);  // [64 rows][32 channels]
+        __syncwarp();  // the previous tile's reads are done
 #pragma unroll 1
-        for (int cc = half * 2; cc < half * 2 + 2; ++cc) {
+        for (int cc = 0; cc < 2; ++cc) {
             float v[32];
-            tmem_ld32(taddr + cc * 32, v);
-            if (ch < C) {
+            tmem_ld32(taddr + (half * 2 + cc) * 32, v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int64_t row = tile * R + cc * 32 + j;
-                    if (row < rm.rows) {
-                        if (rm.seg_mode) {
-                            dx[row * C + ch] = v[j];
-                        } else {
-                            const int s = __ldg(rm.row_src + row);
-                            if (s >= 0 && v[j] != 0.f) atomicAdd(dx + (int64_t)s * C + ch, v[j]);
-                        }
+            for (int j = 0; j < 32; ++j) {
+                const int r = cc * 32 + j;
+                st[r * 32 + ((((lane >> 2) ^ (r & 7))) << 2) + (lane & 3)] = v[j];
+            }
+        }
+        __syncwarp();
+        const bool vec = (C & 3) == 0;
+#pragma unroll 1
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = rr * 32 + lane;
+            const int64_t row = tile * R + half * 64 + r;
+            if (row >= rm.rows) continue;
+            int64_t dst = row;
+            if (!rm.seg_mode) {
+                const int sidx = __ldg(rm.row_src + row);
+                if (sidx < 0) continue;
+                dst = sidx;
+            }
+            float *base = dx + dst * C + ch0;
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+                if (ch0 + c4 * 4 >= C) break;
+                const float4 q = *reinterpret_cast<const float4 *>(st + r * 32 + ((c4 ^ (r & 7)) << 2));
+                if (vec) {
+                    if (rm.seg_mode) {
+                        *reinterpret_cast<float4 *>(base + c4 * 4) = q;
+                    } else if (q.x != 0.f || q.y != 0.f || q.z != 0.f || q.w != 0.f) {
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(base + c4 * 4), "f"(q.x), "f"(q.y), "f"(q.z),
+                                     "f"(q.w)
+                                     : "memory");
+                    }
+                } else {
+                    const float e[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (ch0 + c4 * 4 + k >= C) break;
+                        if (rm.seg_mode) base[c4 * 4 + k] = e[k];
+                        else if (e[k] != 0.f) atomicAdd(base + c4 * 4 + k, e[k]);
                     }
                 }
             }
