@@ -53,7 +53,7 @@ __device__ __forceinline__ void head_linear(const float *in, int ldin, int B, in
         for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
         const float *w = W + (int64_t)j * K;
         for (int k = lane; k < K; k += 32) {
-            const float wv = __ldg(w + k);
+            const float wv = w[k];
 #pragma unroll
             for (int b = 0; b < MAXB; ++b)
                 if (b < B) acc[b] = fmaf(in[b * ldin + k], wv, acc[b]);
@@ -145,24 +145,41 @@ __global__ void __launch_bounds__(128) head_lin0_kernel(const b2pn_head_args a)
     }
 }
 
-__global__ void __launch_bounds__(HEAD_THREADS, 1) head_forward_kernel(const b2pn_head_args a)
+// cooperative copy of n floats (16-byte aligned source, n % 4 == 0 handled by the tail loop) into shared memory
+__device__ __forceinline__ void head_stage(float *dst, const float *src, int n)
 {
-    extern __shared__ float hs[];
+    const int n4 = (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0) ? (n >> 2) : 0;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x)
+        reinterpret_cast<float4 *>(dst)[i] = __ldg(reinterpret_cast<const float4 *>(src) + i);
+    for (int i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+// stage_w: the two small weight matrices are copied into shared memory up front (one memory latency for all of them)
+// instead of being fetched row by row from L2 inside the dependent phases below
+__global__ void __launch_bounds__(HEAD_THREADS, 1) head_forward_kernel(const b2pn_head_args a, int stage_w)
+{
+    extern __shared__ __align__(16) float hs[];
     const int B = a.B, c0 = a.c[0], c1 = a.c[1], c2 = a.c[2], c3 = a.c[3];
     float *s1 = hs;              // [B][c1]  h1 from head_lin0_kernel (parked in xhat[0])
     float *s2 = s1 + B * c1;     // [B][c2]
+    float *sw1 = s2 + B * c2;    // [c2][c1] (stage_w)
+    float *sw2 = sw1 + c2 * c1;  // [c3][c2] (stage_w)
     unsigned long long call = 0ull;
     if (a.rng_counter) call = (unsigned long long)*a.rng_counter;
     (void)c0;
     for (int i = threadIdx.x; i < B * c1; i += blockDim.x) s1[i] = a.xhat[0][i];
+    if (stage_w) {
+        head_stage(sw1, a.w[1], c2 * c1);
+        head_stage(sw2, a.w[2], c3 * c2);
+    }
     __syncthreads();
     head_bn_dropout(s1, c1, B, c1, a, 0, call);
     __syncthreads();
-    head_linear<HEAD_MAX_B>(s1, c1, B, c1, a.w[1], a.b[1], c2, s2, c2);
+    head_linear<HEAD_MAX_B>(s1, c1, B, c1, stage_w ? sw1 : a.w[1], a.b[1], c2, s2, c2);
     __syncthreads();
     head_bn_dropout(s2, c2, B, c2, a, 1, call);
     __syncthreads();
-    head_linear<HEAD_MAX_B>(s2, c2, B, c2, a.w[2], a.b[2], c3, a.out, c3);
+    head_linear<HEAD_MAX_B>(s2, c2, B, c2, stage_w ? sw2 : a.w[2], a.b[2], c3, a.out, c3);
     // every thread has read the counter before anybody bumps it
     __syncthreads();
     if (threadIdx.x == 0 && a.rng_counter && a.training) *a.rng_counter += 1;
@@ -210,16 +227,34 @@ __device__ __forceinline__ float head_act(const b2pn_head_args &a, int layer, in
     return y;
 }
 
-__global__ void __launch_bounds__(HEAD_THREADS, 1) head_backward_kernel(const b2pn_head_args a, const b2pn_head_grads g)
+__global__ void __launch_bounds__(HEAD_THREADS, 1) head_backward_kernel(const b2pn_head_args a, const b2pn_head_grads g, int stage_w)
 {
-    extern __shared__ float hs[];
+    extern __shared__ __align__(16) float hs[];
     const int B = a.B, c0 = a.c[0], c1 = a.c[1], c2 = a.c[2], c3 = a.c[3];
+    const int cm = c1 > c2 ? c1 : c2;
+    const int per = (c0 + gridDim.x - 1) / gridDim.x;  // my slice of the input columns (layer 1)
+    const int k0 = blockIdx.x * per, k1 = min(c0, k0 + per);
+    const int kw = k1 - k0 > 0 ? k1 - k0 : 0;
     float *sdo = hs;              // [B][c3]   dout
     float *sd2 = sdo + B * c3;    // [B][c2]   da2 -> dh2
     float *sd1 = sd2 + B * c2;    // [B][c1]   da1 -> dh1
     float *sa = sd1 + B * c1;     // [B][max(c1,c2)] recomputed activation of the layer below
+    float *sw1 = sa + B * cm;     // [c2][c1]  W1                        (stage_w)
+    float *sw0 = sw1 + c2 * c1;   // [c1][per] my column slice of W0     (stage_w)
+    float *sx = sw0 + c1 * per;   // [B][per]  my column slice of x      (stage_w)
     const bool lead = blockIdx.x == 0;
     const int tid = threadIdx.x;
+    if (stage_w) {  // everything the dependent phases below would fetch from L2 row by row: one latency, up front
+        head_stage(sw1, a.w[1], c2 * c1);
+        for (int i = tid; i < c1 * kw; i += blockDim.x) {
+            const int j = i / kw, k = i - j * kw;
+            sw0[j * per + k] = __ldg(a.w[0] + (int64_t)j * c0 + k0 + k);
+        }
+        for (int i = tid; i < B * kw; i += blockDim.x) {
+            const int b = i / kw, k = i - b * kw;
+            sx[b * per + k] = __ldg(a.x + (int64_t)b * c0 + k0 + k);
+        }
+    }
     for (int i = tid; i < B * c3; i += blockDim.x) sdo[i] = g.grad_out[i];
     for (int i = tid; i < B * c2; i += blockDim.x) sa[i] = head_act(a, 1, i / c2, i % c2, c2);
     __syncthreads();
@@ -265,7 +300,11 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) head_backward_kernel(const b2
     for (int i = tid; i < B * c1; i += blockDim.x) {
         const int b = i / c1, j = i - b * c1;
         float s = 0.f;
-        for (int o = 0; o < c2; ++o) s = fmaf(sd2[b * c2 + o], __ldg(a.w[1] + o * c1 + j), s);
+        if (stage_w) {
+            for (int o = 0; o < c2; ++o) s = fmaf(sd2[b * c2 + o], sw1[o * c1 + j], s);
+        } else {
+            for (int o = 0; o < c2; ++o) s = fmaf(sd2[b * c2 + o], __ldg(a.w[1] + o * c1 + j), s);
+        }
         sd1[i] = s;
     }
     __syncthreads();
@@ -279,22 +318,27 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) head_backward_kernel(const b2
         }
     }
     // ---- layer 1 over my slice of the input columns: dW0[j][k] = sum_b dh1[b][j] x[b][k];  dx[b][k] = sum_j dh1[b][j] W0[j][k]
-    const int per = (c0 + gridDim.x - 1) / gridDim.x;
-    const int k0 = blockIdx.x * per, k1 = min(c0, k0 + per);
-    const int kw = k1 - k0;
     if (kw <= 0) return;
     for (int i = tid; i < c1 * kw; i += blockDim.x) {
-        const int j = i / kw, k = k0 + (i - j * kw);
+        const int j = i / kw, k = i - j * kw;
         float s = 0.f;
-        for (int b = 0; b < B; ++b) s = fmaf(sd1[b * c1 + j], __ldg(a.x + b * c0 + k), s);
-        g.grad_w[0][(int64_t)j * c0 + k] = s;
+        if (stage_w) {
+            for (int b = 0; b < B; ++b) s = fmaf(sd1[b * c1 + j], sx[b * per + k], s);
+        } else {
+            for (int b = 0; b < B; ++b) s = fmaf(sd1[b * c1 + j], __ldg(a.x + b * c0 + k0 + k), s);
+        }
+        g.grad_w[0][(int64_t)j * c0 + k0 + k] = s;
     }
     if (g.grad_x) {
         for (int i = tid; i < B * kw; i += blockDim.x) {
-            const int b = i / kw, k = k0 + (i - b * kw);
+            const int b = i / kw, k = i - b * kw;
             float s = 0.f;
-            for (int j = 0; j < c1; ++j) s = fmaf(sd1[b * c1 + j], __ldg(a.w[0] + (int64_t)j * c0 + k), s);
-            g.grad_x[b * c0 + k] = s;
+            if (stage_w) {
+                for (int j = 0; j < c1; ++j) s = fmaf(sd1[b * c1 + j], sw0[j * per + k], s);
+            } else {
+                for (int j = 0; j < c1; ++j) s = fmaf(sd1[b * c1 + j], __ldg(a.w[0] + (int64_t)j * c0 + k0 + k), s);
+            }
+            g.grad_x[b * c0 + k0 + k] = s;
         }
     }
 }
@@ -361,13 +405,16 @@ extern "C" int b2pn_head_forward(const b2pn_head_args *args, b2pn_stream_t strea
     if (rc) return rc;
     const b2pn_head_args &a = *args;
     if (!a.xhat[0]) return B2PN_EINVAL;  // doubles as the scratch for the first layer's output
-    const int smem = (a.B * (a.c[1] + a.c[2])) * (int)sizeof(float);
+    const int base = a.B * (a.c[1] + a.c[2]);
+    const int wts = a.c[2] * a.c[1] + a.c[3] * a.c[2];
+    const int stage_w = (base + wts) * (int)sizeof(float) <= 200 * 1024 ? 1 : 0;
+    const int smem = (base + (stage_w ? wts : 0)) * (int)sizeof(float);
     B2PN_CUDA(cudaFuncSetAttribute(head_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const unsigned g0 = (unsigned)a.c[1];
     if (a.B <= 16) head_lin0_kernel<16><<<g0, 128, 0, (cudaStream_t)stream>>>(a);
     else head_lin0_kernel<32><<<g0, 128, 0, (cudaStream_t)stream>>>(a);
     note_launch();
-    head_forward_kernel<<<1, HEAD_THREADS, smem, (cudaStream_t)stream>>>(a);
+    head_forward_kernel<<<1, HEAD_THREADS, smem, (cudaStream_t)stream>>>(a, stage_w);
     note_launch();
     B2PN_LAUNCH_CHECK();
     return B2PN_OK;
@@ -388,11 +435,15 @@ extern "C" int b2pn_head_backward(const b2pn_head_args *args, const b2pn_head_gr
         if (!g.grad_gamma[l] || !g.grad_beta[l] || !a.xhat[l] || !a.rstd[l]) return B2PN_EINVAL;
     if (a.training && a.p > 0.f && (!a.mask[0] || !a.mask[1])) return B2PN_EINVAL;
     const int cm = a.c[1] > a.c[2] ? a.c[1] : a.c[2];
-    const int smem = (a.B * (a.c[3] + a.c[2] + a.c[1] + cm)) * (int)sizeof(float);
-    B2PN_CUDA(cudaFuncSetAttribute(head_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int grid = (a.c[0] + 63) / 64;  // 64 input columns per CTA
     if (grid > 32) grid = 32;
-    head_backward_kernel<<<grid, HEAD_THREADS, smem, (cudaStream_t)stream>>>(a, g);
+    const int per = (a.c[0] + grid - 1) / grid;
+    const int base = a.B * (a.c[3] + a.c[2] + a.c[1] + cm);
+    const int wts = a.c[2] * a.c[1] + a.c[1] * per + a.B * per;
+    const int stage_w = (base + wts) * (int)sizeof(float) <= 200 * 1024 ? 1 : 0;
+    const int smem = (base + (stage_w ? wts : 0)) * (int)sizeof(float);
+    B2PN_CUDA(cudaFuncSetAttribute(head_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    head_backward_kernel<<<grid, HEAD_THREADS, smem, (cudaStream_t)stream>>>(a, g, stage_w);
     note_launch();
     B2PN_LAUNCH_CHECK();
     return B2PN_OK;
