@@ -68,6 +68,28 @@ struct RowMapTC {
         return gi_none(b) ? GI_NONE : b;
     }
     __device__ __forceinline__ int valid8(int64_t r8) const { return gi_nv(info(r8)); }
+    // valid rows (0..8) of the eight 8-row groups of the 64 rows starting at row0 (row0 % 64 == 0, below the row
+    // capacity), packed 4 bits per group: two 16-byte descriptor loads and no branch (SLOTS), or arithmetic (CLOUDS)
+    __device__ __forceinline__ unsigned valid64(int64_t row0) const
+    {
+        const int64_t left64 = rows - row0;
+        const int left = left64 > 64 ? 64 : (left64 < 0 ? 0 : (int)left64);  // logical rows among my 64
+        unsigned out = 0u;
+        if (seg_mode) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) out |= (unsigned)min(max(left - 8 * g, 0), 8) << (4 * g);
+            return out;
+        }
+        const uint4 *p = reinterpret_cast<const uint4 *>(rgrp + (row0 >> 3));
+        const uint4 a = __ldg(p), b = __ldg(p + 1);
+        const unsigned d[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const bool dead = 8 * g >= left || gi_none(d[g]);
+            out |= (dead ? 0u : (unsigned)gi_nv(d[g])) << (4 * g);
+        }
+        return out;
+    }
     // SLOTS only, r8 below the row capacity: the same word without a branch around the load, so that a loader
     // thread's eight descriptor loads (and what depends on them) go out back to back
     __device__ __forceinline__ unsigned info_slots(int64_t r8) const
@@ -590,16 +612,14 @@ struct NormStoreEpTC {  // pass B: zT[ch][row] = bf16((acc + bias - mean) * rstd
             be = beta[ch];
         }
         uint8_t *zt = cx.stage, *at = cx.stage + 32 * LINE_BYTES;
+        const unsigned nv64 = rm.valid64(tile * R + half * 64);  // valid rows of my eight 8-row groups (warp-uniform)
         if (lane == 0) bulk_wait_read_all();  // the TMA stores of my previous tile have read the staging tiles
         __syncwarp();
 #pragma unroll 1
         for (int cc = half * 2; cc < half * 2 + 2; ++cc) {
             float v[32];
             tmem_ld32(taddr + cc * 32, v);
-            const int64_t r0 = tile * R + cc * 32;
-            unsigned nvs = 0u;  // valid rows of my four 8-row groups (warp-uniform loads)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) nvs |= (unsigned)gi_nv(rm.info(r0 + 8 * j)) << (4 * j);
+            const unsigned nvs = nv64 >> (16 * (cc - half * 2));
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int nv = (int)((nvs >> (4 * j)) & 15u);
