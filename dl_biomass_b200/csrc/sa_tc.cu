@@ -798,6 +798,7 @@ struct MaskSumsStoreEpTC {  // backward through activation + sums for the BatchN
         mbar_wait(cx.bar, phase);  // zhat tile landed
         phase ^= 1u;
         float s = 0.f, q = 0.f;
+        const bool relu = act == B2PN_ACT_RELU;
 #pragma unroll 1
         for (int cc = half * 2; cc < half * 2 + 2; ++cc) {
             float v[32];
@@ -809,11 +810,12 @@ struct MaskSumsStoreEpTC {  // backward through activation + sums for the BatchN
                 unpack8(unstage_chunk(zt, lane, gidx), zf);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
+                    // channels past C: zero-padded weight rows give da = 0 exactly (and ga = be = 0 mask them under ReLU);
+                    // invalid rows: da = 0 because their operand columns are zero
                     const float da = v[8 * j + e];
-                    const bool pass = ch < C && da != 0.f && (act != B2PN_ACT_RELU || fmaf(zf[e], ga, be) > 0.f);
-                    const float g = pass ? da : 0.f;
+                    const float g = (!relu || fmaf(zf[e], ga, be) > 0.f) ? da : 0.f;
                     s += g;
-                    q += pass ? g * zf[e] : 0.f;
+                    q = fmaf(g, zf[e], q);
                     o[e] = g;
                 }
                 stage_chunk(dt, lane, gidx, pack8(o));
