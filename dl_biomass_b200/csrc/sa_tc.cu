@@ -1697,7 +1697,8 @@ struct DwReduceJob {
 struct DwReduceJobs {
     DwReduceJob j[3];
 };
-__global__ void dw_reduce_tc_kernel(const DwReduceJobs jobs)
+// (a) one thread per output element, 16 loads in flight: for large outputs / few splits (bandwidth bound)
+__global__ void dw_reduce_flat_tc_kernel(const DwReduceJobs jobs)
 {
     const DwReduceJob &jb = jobs.j[blockIdx.y];
     const int k_true = jb.k_true, k_total = jb.k_total, n_out = jb.n_out, splits = jb.splits;
@@ -1746,6 +1747,66 @@ __global__ void dw_reduce_tc_kernel(const DwReduceJobs jobs)
 #pragma unroll
         for (int u = 0; u < w; ++u) acc[u] += acc[u + w];
     const double sum = acc[0];
+    if (k == k_true) {
+        if (jb.grad_b) jb.grad_b[n] = (float)sum;
+    } else if (jb.grad_w) {
+        jb.grad_w[(int64_t)n * k_true + k] = (float)sum;
+    }
+}
+
+// (b) eight warps per 32 output elements: for small outputs reduced over many splits (latency bound)
+constexpr int DWR_WARPS = 8;
+constexpr int DWR_MAX_SPLITS = 160;  // >= the SM count (plan_dw never splits further)
+__global__ void __launch_bounds__(32 * DWR_WARPS) dw_reduce_tc_kernel(const DwReduceJobs jobs)
+{
+    const DwReduceJob &jb = jobs.j[blockIdx.y];
+    const int k_true = jb.k_true, k_total = jb.k_total, n_out = jb.n_out, splits = jb.splits;
+    const int w = threadIdx.y;                                         // blockDim = (32, DWR_WARPS)
+    const int64_t i = (int64_t)blockIdx.x * 32 + threadIdx.x;           // 32 output elements per block (coalesced)
+    const bool live = i < (int64_t)n_out * (k_true + 1);
+    const int n = live ? (int)(i / (k_true + 1)) : 0;
+    const int k = live ? (int)(i - (int64_t)n * (k_true + 1)) : 0;
+    int c0 = 0, c1 = -1;
+    if (k == k_true) {
+        c0 = jb.ones_idx;
+    } else if (!jb.use_map) {
+        c0 = k;
+    } else {
+        const int nx = jb.cols.nx();
+        if (k < jb.cols.c_in) {
+            c0 = k;
+            c1 = jb.cols.x_f32 ? k + jb.cols.c_in : -1;
+        } else {
+            c0 = nx + (k - jb.cols.c_in);
+            c1 = c0 + 3;
+        }
+    }
+    const int64_t stride = (int64_t)n_out * k_total;
+    const float *base = jb.partial + (int64_t)n * k_total;
+    // warp w of the block takes the splits p = w, w + 8, ...: all of a thread's loads are in flight together (one L2
+    // round trip instead of splits / 16 dependent ones), 128-byte coalesced per split; fixed summation order
+    constexpr int PER = (DWR_MAX_SPLITS + DWR_WARPS - 1) / DWR_WARPS;
+    float v[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int p = w + u * DWR_WARPS;
+        v[u] = 0.f;
+        if (live && p < splits) {
+            const float *row = base + (int64_t)p * stride;
+            v[u] = row[c0];
+            if (c1 >= 0) v[u] += row[c1];
+        }
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) acc += (double)v[u];
+    __shared__ double part[DWR_WARPS][32];
+    part[w][threadIdx.x] = acc;
+    __syncthreads();
+    if (w != 0 || !live) return;
+    double sum = 0.0;
+#pragma unroll
+    for (int q = 0; q < DWR_WARPS; ++q) sum += part[q][threadIdx.x];
     if (k == k_true) {
         if (jb.grad_b) jb.grad_b[n] = (float)sum;
     } else if (jb.grad_w) {
@@ -1923,6 +1984,7 @@ static DwPlanHost plan_dw(int n_out, int k_total, int64_t ld)
     const int64_t chunks = ld / 64;
     int sp = sm_count() / (d.num_mg * d.num_ng);
     if (sp < 1) sp = 1;
+    if (sp > DWR_MAX_SPLITS) sp = DWR_MAX_SPLITS;
     if ((int64_t)sp > chunks) sp = (int)(chunks > 0 ? chunks : 1);
     d.splits = sp;
     d.floats = (int64_t)sp * n_out * k_total;
@@ -2154,7 +2216,10 @@ static void launch_dw_reduces(const DwReduceJob *jobs, int n, cudaStream_t st)
         const int64_t tot = (int64_t)dj.j[i].n_out * (dj.j[i].k_true + 1);
         mx = tot > mx ? tot : mx;
     }
-    dw_reduce_tc_kernel<<<dim3((unsigned)((mx + 127) / 128), (unsigned)n), 128, 0, st>>>(dj);
+    if (mx <= 16384)
+        dw_reduce_tc_kernel<<<dim3((unsigned)((mx + 31) / 32), (unsigned)n), dim3(32, DWR_WARPS), 0, st>>>(dj);
+    else
+        dw_reduce_flat_tc_kernel<<<dim3((unsigned)((mx + 127) / 128), (unsigned)n), 128, 0, st>>>(dj);
     note_launch();
 }
 
