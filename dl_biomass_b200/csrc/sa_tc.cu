@@ -1116,7 +1116,7 @@ struct DwParams {
     const int64_t *rows_dev;   // ... the device scalar of the compacted SLOTS layout (wins when non-NULL)
     int n_out;                 // Y channels (rows of dW)
     int nbl_total;             // X lines over all N groups (blockIdx.z), multiple of 16; a group handles <= 256
-    int k_total;               // columns of the partial (all N groups)
+    int k_total;               // columns of the partial (all N groups), rounded up to a multiple of 4 (row stride)
     float *partial;            // [splits = gridDim.x][n_out][k_total]
     int stages, stage_bytes;   // operand ring (set by launch_dw)
 };
@@ -1352,11 +1352,12 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = 0.f;
                 }
-                if (ch < p.n_out) {
+                if (ch < p.n_out) {  // k_total (the partial's row stride) is a multiple of 4: 16-byte stores
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = cc * 32 + j;
-                        if (col < nb_lines && ng * 256 + col < p.k_total) dst[col] = v[j];
+                    for (int q = 0; q < 8; ++q) {
+                        const int col = cc * 32 + q * 4;
+                        if (col < nb_lines && ng * 256 + col < p.k_total)
+                            *reinterpret_cast<float4 *>(dst + col) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                     }
                 }
             }
@@ -1968,7 +1969,7 @@ static FwdWsTC carve_fwd_tc(const b2pn_sa_args &a, const ShapesTC &s, WsTC &ws)
 }
 
 struct DwPlanHost {
-    int MTA, num_mg, num_ng, splits, nbl_total;
+    int MTA, num_mg, num_ng, splits, nbl_total, k_stride;
     int64_t floats;
 };
 // one launch covers all (row split, M group, N group) blocks; the row range is split so that the launch fills
@@ -1987,7 +1988,8 @@ static DwPlanHost plan_dw(int n_out, int k_total, int64_t ld)
     if (sp > DWR_MAX_SPLITS) sp = DWR_MAX_SPLITS;
     if ((int64_t)sp > chunks) sp = (int)(chunks > 0 ? chunks : 1);
     d.splits = sp;
-    d.floats = (int64_t)sp * n_out * k_total;
+    d.k_stride = (int)align_up(k_total, 4);  // row stride of the partials: 16-byte aligned rows (<= nbl_total)
+    d.floats = (int64_t)sp * n_out * d.k_stride;
     return d;
 }
 
@@ -2160,7 +2162,7 @@ static int launch_dw(const YS &ys, const XF &xf, int n_out, int k_total, const S
                      cudaStream_t st, const TmaMap &map_y = kNoMap, const TmaMap &map_x = kNoMap, const TmaMap &map_v = kNoMap)
 {
     const DwPlanHost d = plan_dw(n_out, k_total, s.ld);
-    DwParams p = {ra.cap, ra.dev, n_out, d.nbl_total, k_total, dwp, 0, 0};
+    DwParams p = {ra.cap, ra.dev, n_out, d.nbl_total, d.k_stride, dwp, 0, 0};
     const int nb_max = d.nbl_total < 256 ? d.nbl_total : 256;
     const int b_bytes = (int)align_up(XF::bytes(nb_max), 1024);
     dim3 grid((unsigned)d.splits, (unsigned)d.num_mg, (unsigned)d.num_ng);
@@ -2204,7 +2206,7 @@ static DwReduceJob dw_reduce_job(const float *dwp, int n_out, int k_total, const
                                  const ShapesTC &s, float *gw, float *gb)
 {
     const DwPlanHost d = plan_dw(n_out, k_total, s.ld);
-    DwReduceJob j = {dwp, d.splits, n_out, k_total, map ? 1 : 0, map ? *map : InCols{0, 0}, k_true, ones_idx, gw, gb};
+    DwReduceJob j = {dwp, d.splits, n_out, d.k_stride, map ? 1 : 0, map ? *map : InCols{0, 0}, k_true, ones_idx, gw, gb};
     return j;
 }
 static void launch_dw_reduces(const DwReduceJob *jobs, int n, cudaStream_t st)
