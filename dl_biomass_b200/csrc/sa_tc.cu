@@ -1530,21 +1530,24 @@ __device__ __forceinline__ void warp_sum_partials(const double *partial, int gx,
     const int lane = threadIdx.x & 31;
     double s = 0.0, q = 0.0;
     {
-        double s4[4] = {0.0, 0.0, 0.0, 0.0}, q4[4] = {0.0, 0.0, 0.0, 0.0};  // independent chains, fixed order
-        int g = lane;
-        for (; g + 96 < gx; g += 128) {
+        // all of a lane's partials (<= 4 slots x MAX_GX CTAs / 32 lanes) are requested before the first one is used:
+        // one L2 round trip; fixed summation order
+        constexpr int PER = (4 * 160 + 31) / 32;
+        double sv[PER], qv[PER];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                s4[u] += partial[(int64_t)(g + 32 * u) * 2 * cpad + c];
-                q4[u] += partial[(int64_t)(g + 32 * u) * 2 * cpad + cpad + c];
-            }
+        for (int u = 0; u < PER; ++u) {
+            const int g = lane + 32 * u;
+            const bool in = g < gx;
+            const int64_t o = in ? (int64_t)g * 2 * cpad + c : c;
+            sv[u] = partial[o];
+            qv[u] = partial[o + cpad];
+            if (!in) sv[u] = qv[u] = 0.0;
         }
-        for (; g < gx; g += 32) {
-            s4[0] += partial[(int64_t)g * 2 * cpad + c];
-            q4[0] += partial[(int64_t)g * 2 * cpad + cpad + c];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            s += sv[u];
+            q += qv[u];
         }
-        s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-        q = (q4[0] + q4[1]) + (q4[2] + q4[3]);
     }
     // fixed-order butterfly: deterministic
     for (int o = 16; o > 0; o >>= 1) {
