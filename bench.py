@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     ap.add_argument("--join", default="end", choices=["backward", "end"], help="where the sampling branch joins")
+    ap.add_argument("--no-uncap-l1", action="store_true", help="keep the SM cap through the level-1 backward")
     ap.add_argument("--no-cap", action="store_true", help="do not cap persistent kernels while the branch runs")
     ap.add_argument("--no-pregroup", action="store_true", help="ball query / row packing inside forward")
     ap.add_argument("--aux", action="store_true", help="third stream for the level-1 grouping")
@@ -247,7 +248,8 @@ def run_b200(args):
     graphed = stepper = None
     if pipeline:
         stepper = PipelinedTrainStep(net, opt, pool_dev[0], reducer, graph=use_graph, join=args.join,
-                                     cap=not args.no_cap, grouping=not args.no_pregroup, aux=args.aux)
+                                     cap=not args.no_cap, grouping=not args.no_pregroup, aux=args.aux,
+                                     uncap_level1_backward=not args.no_uncap_l1)
     elif use_graph:
         graphed = GraphedTrainStep(net, opt, pool_dev[0], reducer)
 
@@ -351,7 +353,8 @@ def run_b200(args):
                        "pipeline": ("FPS" + (" + ball query + row compaction + level-1 gather" if stepper.grouping else "")
                                     + " of batch i+1 on a second stream during step i (every timed step contains one "
                                     f"full sampling and one full training pass); join at {stepper.join_at}; persistent "
-                                    f"kernels capped at {sm_limit_note} CTAs") if stepper is not None else "none"},
+                                    f"kernels capped at {sm_limit_note} CTAs" + (" until the level-1 backward" if stepper.uncap_l1 else ""))
+                                   if stepper is not None else "none"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(e2e_ms / args.steps, 4),
                     "h2d_bytes_per_step": batch_h2d_bytes(pool_host[0], with_batch_vector=not use_graph),

@@ -277,11 +277,13 @@ class Net(torch.nn.Module):
         return Sampling(sizes, l1, l2, g1, g2)
 
     def forward(self, data, start: Optional[torch.Tensor] = None, sampling: Optional[Sampling] = None,
-                after_grouping=None):
+                after_grouping=None, before_level1_backward=None):
         """``after_grouping``: optional callable invoked when the last kernel of the two set-abstraction levels'
         FORWARD has been enqueued and again never before their BACKWARD starts: with autograd recording it fires in
         the backward pass right before the level-2 backward (after the global level and the head went both ways),
-        otherwise right after the level-2 forward.  train.PipelinedTrainStep joins its sampling stream there."""
+        otherwise right after the level-2 forward.  train.PipelinedTrainStep joins its sampling stream there.
+        ``before_level1_backward``: optional callable fired in the backward pass between the level-2 and the level-1
+        backward (only with autograd recording)."""
         x, pos, batch = data.x, data.pos, data.batch                                     # :53
         sizes, lv = self._levels(data)
         if sampling is not None and tuple(sampling.sizes) != tuple(sizes):
@@ -292,6 +294,8 @@ class Net(torch.nn.Module):
         g1 = None if sampling is None else self._usable(sampling.group1)
         g2 = None if sampling is None else self._usable(sampling.group2)
         x1, pos1, _, _ = self.sa1_module._run(x, pos, lv[0], lv[1], start, s1, g1)       # :54
+        if before_level1_backward is not None and torch.is_grad_enabled() and x1.requires_grad:
+            x1 = _CallInBackward.apply(x1, before_level1_backward)
         x2, pos2, batch2, _ = self.sa2_module._run(x1, pos1, lv[1], lv[2], None, s2, g2)  # :55
         if after_grouping is not None:
             if torch.is_grad_enabled() and x2.requires_grad:
