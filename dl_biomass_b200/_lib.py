@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libb2pn.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 _lib = None
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _vp, _i32, _i64, _f32, _f64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double
 
@@ -66,6 +66,7 @@ SIGNATURES = {
     "b2pn_launch_count": (_i64, []),
     "b2pn_fps_num_samples": (_i64, [_i64, _f32]),
     "b2pn_set_sm_limit": (ctypes.c_int, [_i32]),
+    "b2pn_set_deterministic": (ctypes.c_int, [_i32]),
     "b2pn_fps_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
     "b2pn_fps_f64": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "b2pn_fps_set_variant": (ctypes.c_int, [_i32, _i32]),

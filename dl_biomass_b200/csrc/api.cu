@@ -6,6 +6,14 @@
 namespace b2pn {
 long long g_launches = 0;
 int g_sm_limit = 0;
+int g_deterministic = 0;
+}
+
+extern "C" int b2pn_set_deterministic(int32_t on)
+{
+    const int prev = b2pn::g_deterministic;
+    b2pn::g_deterministic = on ? 1 : 0;
+    return prev;
 }
 
 extern "C" int b2pn_set_sm_limit(int32_t n)

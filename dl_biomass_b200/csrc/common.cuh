@@ -29,6 +29,8 @@ typedef unsigned long long u64;
 extern long long g_launches;
 // upper bound on the CTAs of the persistent tcgen05 kernels (0 = every SM), see b2pn_set_sm_limit
 extern int g_sm_limit;
+// 1: bit-reproducible weight gradients (fixed-order reduction of the dW split partials), see b2pn_set_deterministic
+extern int g_deterministic;
 static inline void note_launch(int n = 1) { __atomic_fetch_add(&g_launches, (long long)n, __ATOMIC_RELAXED); }
 
 // ---- packed fp32x2 arithmetic (Blackwell FADD2/FMUL2), each half rounded separately ----------

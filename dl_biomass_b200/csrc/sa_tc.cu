@@ -1117,7 +1117,8 @@ struct DwParams {
     int n_out;                 // Y channels (rows of dW)
     int nbl_total;             // X lines over all N groups (blockIdx.z), multiple of 16; a group handles <= 256
     int k_total;               // columns of the partial (all N groups), rounded up to a multiple of 4 (row stride)
-    float *partial;            // [splits = gridDim.x][n_out][k_total]
+    float *partial;            // [splits = gridDim.x][n_out][k_total]; atomic mode: ONE zeroed [n_out][k_total] all splits add to
+    int atomic;
     int stages, stage_bytes;   // operand ring (set by launch_dw)
 };
 
@@ -1343,7 +1344,8 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
 #pragma unroll
         for (int mt = 0; mt < MTA; ++mt) {
             const int ch = (mg * MTA + mt) * 128 + tid;
-            float *dst = p.partial + ((int64_t)split * p.n_out + ch) * p.k_total + ng * 256;
+            float *dst = p.partial + ((int64_t)(p.atomic ? 0 : split) * p.n_out + ch) * p.k_total + ng * 256;
+            if (p.atomic && nchunks == 0) continue;  // nothing to add
             for (int cc = 0; cc * 32 < nb_lines; ++cc) {
                 float v[32];
                 if (nchunks > 0) {
@@ -1356,8 +1358,14 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const int col = cc * 32 + q * 4;
-                        if (col < nb_lines && ng * 256 + col < p.k_total)
-                            *reinterpret_cast<float4 *>(dst + col) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        if (col < nb_lines && ng * 256 + col < p.k_total) {
+                            if (p.atomic)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + col), "f"(v[4 * q]),
+                                             "f"(v[4 * q + 1]), "f"(v[4 * q + 2]), "f"(v[4 * q + 3])
+                                             : "memory");
+                            else
+                                *reinterpret_cast<float4 *>(dst + col) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        }
                     }
                 }
             }
@@ -1971,6 +1979,11 @@ static FwdWsTC carve_fwd_tc(const b2pn_sa_args &a, const ShapesTC &s, WsTC &ws)
     return f;
 }
 
+// atomic mode (default): the row splits of a dW GEMM add their partials into one zeroed buffer with
+// red.global.add.v4.f32 (no partial tensor, the reduction kernel only maps columns); b2pn_set_deterministic(1): per-split
+// partials summed in a fixed order (bit-reproducible)
+static inline bool dw_atomic() { return g_deterministic == 0; }
+
 struct DwPlanHost {
     int MTA, num_mg, num_ng, splits, nbl_total, k_stride;
     int64_t floats;
@@ -2165,7 +2178,11 @@ static int launch_dw(const YS &ys, const XF &xf, int n_out, int k_total, const S
                      cudaStream_t st, const TmaMap &map_y = kNoMap, const TmaMap &map_x = kNoMap, const TmaMap &map_v = kNoMap)
 {
     const DwPlanHost d = plan_dw(n_out, k_total, s.ld);
-    DwParams p = {ra.cap, ra.dev, n_out, d.nbl_total, d.k_stride, dwp, 0, 0};
+    DwParams p = {ra.cap, ra.dev, n_out, d.nbl_total, d.k_stride, dwp, dw_atomic() ? 1 : 0, 0, 0};
+    if (dw_atomic()) {
+        cudaError_t em = cudaMemsetAsync(dwp, 0, (size_t)n_out * d.k_stride * sizeof(float), st);
+        if (em != cudaSuccess) return (int)em;
+    }
     const int nb_max = d.nbl_total < 256 ? d.nbl_total : 256;
     const int b_bytes = (int)align_up(XF::bytes(nb_max), 1024);
     dim3 grid((unsigned)d.splits, (unsigned)d.num_mg, (unsigned)d.num_ng);
@@ -2209,7 +2226,7 @@ static DwReduceJob dw_reduce_job(const float *dwp, int n_out, int k_total, const
                                  const ShapesTC &s, float *gw, float *gb)
 {
     const DwPlanHost d = plan_dw(n_out, k_total, s.ld);
-    DwReduceJob j = {dwp, d.splits, n_out, d.k_stride, map ? 1 : 0, map ? *map : InCols{0, 0}, k_true, ones_idx, gw, gb};
+    DwReduceJob j = {dwp, dw_atomic() ? 1 : d.splits, n_out, d.k_stride, map ? 1 : 0, map ? *map : InCols{0, 0}, k_true, ones_idx, gw, gb};
     return j;
 }
 static void launch_dw_reduces(const DwReduceJob *jobs, int n, cudaStream_t st)

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B2PN_ABI_VERSION 4
+#define B2PN_ABI_VERSION 5
 #define B2PN_OK 0
 #define B2PN_EINVAL (-1)   /* null pointer / negative size / bad flag            */
 #define B2PN_ENOTSUP (-2)  /* shape outside what the sm_100a kernels are built for */
@@ -43,6 +43,15 @@ int64_t b2pn_launch_count(void);
  * Process-wide setting; change it only between steps.
  */
 int b2pn_set_sm_limit(int32_t n);
+
+/*
+ * Weight-gradient summation of the bf16 set-abstraction backward.  0 (default): the row splits of a dW GEMM add their
+ * partial sums into one buffer with fp32 atomics (red.global.add.v4.f32) -- fastest, but the order of the additions,
+ * hence the last bits of the gradients, varies from run to run (as it does in the reference's scatter / cuBLAS
+ * kernels).  1: every split keeps its own partial and a reduction kernel adds them in a fixed order: bit-reproducible
+ * gradients for ~1 % of the step time.  Process-wide; returns the previous setting.
+ */
+int b2pn_set_deterministic(int32_t on);
 
 /* samples per cloud: ceil(float32(n) * float32(ratio)) -- torch_cluster.fps sizing
  * (reached from /root/reference/pointnet2_regressor.py:13).  Host-side helper. */

@@ -95,6 +95,7 @@ def test_host_side_sizing_helpers(built_lib):
     assert h.b2pn_ball_query_workspace_bytes(12, 120000) >= 120000 * 4 + 12 * 8192 * 4
     assert h.b2pn_ball_query_workspace_bytes(-1, 10) == -1
     assert h.b2pn_set_sm_limit(-3) == -1 and h.b2pn_set_sm_limit(0) == 0
+    assert h.b2pn_set_deterministic(1) == 0 and h.b2pn_set_deterministic(0) == 1 and h.b2pn_set_deterministic(0) == 0
     assert h.b2pn_head_forward(None, None) == -1 and h.b2pn_head_backward(None, None, None) == -1
     assert h.b2pn_sa_gather_rows(None, None) == -1
     sa_args = built_lib.SaArgs()                              # fp32 levels gather inside their loaders

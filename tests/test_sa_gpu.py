@@ -497,3 +497,32 @@ def test_precomputed_grouping_gives_identical_results(cuda_device, precision):
     for ga, gb in zip(*grads):
         # same products; the order of the partial sums (atomics, dynamic tile schedule) may differ in the last bits
         assert float((ga - gb).abs().max()) <= 1e-4 * float(ga.abs().max()) + 1e-6 * scale
+
+
+def test_deterministic_mode_gives_bit_identical_weight_gradients(cuda_device):
+    """b2pn_set_deterministic(1): the dW split partials are summed in a fixed order -> bit-identical gradients from run
+    to run; the default (fp32 atomics) agrees with it to rounding."""
+    from dl_biomass_b200 import _lib
+    lib = _lib.lib()
+    b = Batch.from_data_list(synthetic_clouds(77, 3, 1024, 1, False)).to(cuda_device)
+    torch.manual_seed(2)
+    net = Net(1, "ReLU", 0, 0.0, precision="bf16").to(cuda_device).set_random_start(False)
+    net.train()
+    state = {k: v.clone() for k, v in net.state_dict().items()}
+
+    def grads():
+        net.load_state_dict(state)
+        net.zero_grad(set_to_none=True)
+        net(b).square().sum().backward()
+        return [p.grad.detach().clone() for p in net.parameters()]
+
+    try:
+        assert lib.b2pn_set_deterministic(1) == 0
+        g1, g2 = grads(), grads()
+        assert all(torch.equal(a, c) for a, c in zip(g1, g2))
+    finally:
+        lib.b2pn_set_deterministic(0)
+    g3 = grads()
+    scale = max(float(g.abs().max()) for g in g1)
+    for a, c in zip(g1, g3):
+        assert float((a - c).abs().max()) <= 1e-4 * float(a.abs().max()) + 1e-6 * scale
