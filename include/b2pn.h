@@ -49,7 +49,9 @@ int b2pn_set_sm_limit(int32_t n);
  * partial sums into one buffer with fp32 atomics (red.global.add.v4.f32) -- fastest, but the order of the additions,
  * hence the last bits of the gradients, varies from run to run (as it does in the reference's scatter / cuBLAS
  * kernels).  1: every split keeps its own partial and a reduction kernel adds them in a fixed order: bit-reproducible
- * gradients for ~1 % of the step time.  Process-wide; returns the previous setting.
+ * dW sums for ~1 % of the step time.  (The scatter-add of a level's feature gradient into its source points stays
+ * atomic in both modes, as in torch_scatter: weight gradients of levels BELOW such a scatter inherit its rounding
+ * order.)  Process-wide; returns the previous setting.
  */
 int b2pn_set_deterministic(int32_t on);
 

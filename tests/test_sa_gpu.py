@@ -500,8 +500,10 @@ def test_precomputed_grouping_gives_identical_results(cuda_device, precision):
 
 
 def test_deterministic_mode_gives_bit_identical_weight_gradients(cuda_device):
-    """b2pn_set_deterministic(1): the dW split partials are summed in a fixed order -> bit-identical gradients from run
-    to run; the default (fp32 atomics) agrees with it to rounding."""
+    """b2pn_set_deterministic(1): the dW split partials are summed in a fixed order -> bit-identical weight gradients
+    from run to run wherever no scatter-add sits upstream (levels 2, 3 and the head; level 1 receives the feature
+    gradient that level 2 scatter-adds into the source points with atomics, like torch_scatter does); the default
+    (fp32 atomics for the dW sums too) agrees to rounding."""
     from dl_biomass_b200 import _lib
     lib = _lib.lib()
     b = Batch.from_data_list(synthetic_clouds(77, 3, 1024, 1, False)).to(cuda_device)
@@ -509,6 +511,7 @@ def test_deterministic_mode_gives_bit_identical_weight_gradients(cuda_device):
     net = Net(1, "ReLU", 0, 0.0, precision="bf16").to(cuda_device).set_random_start(False)
     net.train()
     state = {k: v.clone() for k, v in net.state_dict().items()}
+    names = [n for n, _ in net.named_parameters()]
 
     def grads():
         net.load_state_dict(state)
@@ -519,10 +522,17 @@ def test_deterministic_mode_gives_bit_identical_weight_gradients(cuda_device):
     try:
         assert lib.b2pn_set_deterministic(1) == 0
         g1, g2 = grads(), grads()
-        assert all(torch.equal(a, c) for a, c in zip(g1, g2))
     finally:
         lib.b2pn_set_deterministic(0)
     g3 = grads()
     scale = max(float(g.abs().max()) for g in g1)
-    for a, c in zip(g1, g3):
-        assert float((a - c).abs().max()) <= 1e-4 * float(a.abs().max()) + 1e-6 * scale
+    scale1 = max(float(g.abs().max()) for n, g in zip(names, g1) if n.startswith("sa1_module"))
+    for n, a, c, e in zip(names, g1, g2, g3):
+        if n.startswith("sa1_module"):
+            # downstream of level 2's atomic scatter-add: equal up to the rounding order of those atomics, which the
+            # BatchNorm backward of level 1 (differences of nearly equal sums) amplifies
+            for other in (c, e):
+                assert float((a - other).abs().max()) <= 2e-2 * scale1, n
+        else:
+            assert torch.equal(a, c), n
+            assert float((a - e).abs().max()) <= 1e-4 * float(a.abs().max()) + 1e-6 * scale, n
