@@ -115,3 +115,56 @@ def test_state_dict_keys_are_pyg_shaped():
               "sa3_module.nn.lins.2.bias", "mlp.lins.2.weight", "mlp.norms.0.num_batches_tracked"):
         assert k in keys
     assert sum(p.numel() for p in net.parameters()) == 953732
+
+
+def test_ball_query_against_scipy_kdtree():
+    """Independent cross-check of the oracle's neighbourhoods (membership, per-cloud restriction, first-K-by-index cap)
+    against scipy's cKDTree -- the same family of structure torch_cluster's CPU path (nanoflann) uses.  Coordinates
+    sit on a 1/16 grid so fp32 (oracle) and float64 (scipy) distances are both exact; the radius is chosen off the
+    grid's distance set, and a separate case pins the strict '<' of SURVEY.md A.2."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(3)
+    sizes = [300, 1, 157, 420]
+    pts = [rng.integers(-32, 32, size=(n, 3)).astype(np.float64) / 16.0 for n in sizes]
+    ptr = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]))
+    pos = torch.from_numpy(np.concatenate(pts).astype(np.float32))
+    q_idx, qptr = [], [0]
+    for c, n in enumerate(sizes):
+        take = np.sort(rng.choice(n, size=max(1, n // 5), replace=False))
+        q_idx.append(take + int(ptr[c]))
+        qptr.append(qptr[-1] + len(take))
+    q_idx = torch.from_numpy(np.concatenate(q_idx))
+    qptr = torch.tensor(qptr)
+    r, K = 1.3, 12                                # 1.69 is not a sum of three squares of multiples of 1/16
+    nbr, cnt = ref.ball_query_ref(pos, pos[q_idx], ptr, qptr, r, K)
+    full = 0
+    for c, n in enumerate(sizes):
+        tree = cKDTree(pts[c])
+        for i in range(int(qptr[c]), int(qptr[c + 1])):
+            local = np.sort(np.asarray(tree.query_ball_point(pts[c][int(q_idx[i]) - int(ptr[c])], r)))
+            want = local[:K] + int(ptr[c])
+            full += len(local) > K
+            assert int(cnt[i]) == len(want)
+            assert np.array_equal(nbr[i, :len(want)].numpy(), want)
+            assert bool((nbr[i, len(want):] == -1).all())
+    assert full > 10                              # the cap was exercised
+    # strictness: a source at distance exactly r is NOT a neighbour
+    src = torch.tensor([[0.0, 0.0, 0.0], [2.0, 0.0, 0.0], [1.9375, 0.0, 0.0]])
+    nbr, cnt = ref.ball_query_ref(src, src[:1], torch.tensor([0, 3]), torch.tensor([0, 1]), 2.0, 4)
+    assert int(cnt[0]) == 2 and nbr[0, :2].tolist() == [0, 2]
+
+
+def test_segment_max_against_torch_scatter_reduce():
+    """Values of the max aggregation against torch's own scatter_reduce(amax) (the ATen op behind current
+    torch_geometric's `aggr='max'`); the arg rule (first row attaining the max) against numpy."""
+    g = torch.Generator().manual_seed(1)
+    seg = torch.sort(torch.randint(0, 40, (500,), generator=g)).values
+    msg = torch.randint(-3, 4, (500, 7), generator=g).float()          # many ties
+    out, arg = ref.segment_max_first(msg, seg, 41)                    # segment 40 may be empty
+    want = torch.full((41, 7), float("-inf")).scatter_reduce(0, seg[:, None].expand(-1, 7), msg, "amax", include_self=True)
+    present = torch.bincount(seg, minlength=41) > 0
+    assert torch.equal(out[present], want[present]) and bool((out[~present] == 0).all())
+    m, s = msg.numpy(), seg.numpy()
+    for k in np.nonzero(present.numpy())[0]:
+        rows = np.nonzero(s == k)[0]
+        assert np.array_equal(arg[k].numpy(), rows[np.argmax(m[rows], axis=0)])
