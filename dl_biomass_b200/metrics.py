@@ -36,3 +36,28 @@ def regression_metrics(obs: torch.Tensor, pred: torch.Tensor) -> Dict[str, Dict[
     stacked = torch.stack([torch.stack([_r2(o, p), _rmse(o, p), _mape(o, p)]) for o, p in cols.values()]).cpu()
     return {name: {"r2": float(stacked[i, 0]), "rmse": float(stacked[i, 1]), "mape": float(stacked[i, 2])}
             for i, name in enumerate(cols)}
+
+
+@torch.no_grad()
+def evaluate(model: torch.nn.Module, batches, return_predictions: bool = False):
+    """The evaluation loop of /root/reference/testing_model.py:60-98: ``model.eval()``, predictions for every batch,
+    observed values from ``batch.y``, the metric table at the end.  The reference pushes the whole test set through
+    the model as ONE batch and moves predictions to the CPU per batch; here ``batches`` may be any iterable of batches
+    (e.g. chunks of 256 clouds) and everything stays on the device until the final table: one device->host read in
+    total.  The model's training flag is restored afterwards.  Returns the ``regression_metrics`` table (and, with
+    ``return_predictions``, the stacked ``(obs, pred)`` tensors as a second value)."""
+    was_training = model.training
+    model.eval()
+    obs, pred = [], []
+    try:
+        for b in batches:
+            out = model(b)
+            pred.append(out.reshape(-1, 4))
+            obs.append(b.y.reshape(-1, 4).to(out.device))
+    finally:
+        model.train(was_training)
+    if not pred:
+        raise ValueError("evaluate needs at least one batch")
+    o, p = torch.cat(obs, 0), torch.cat(pred, 0)
+    table = regression_metrics(o, p)
+    return (table, (o, p)) if return_predictions else table

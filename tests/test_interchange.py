@@ -49,3 +49,36 @@ def test_metrics_match_scikit_learn():
         assert math.isclose(got[name]["r2"], sk.r2_score(o, p), rel_tol=1e-9, abs_tol=1e-12)
         assert math.isclose(got[name]["rmse"], math.sqrt(sk.mean_squared_error(o, p)), rel_tol=1e-9)
         assert math.isclose(got[name]["mape"], sk.mean_absolute_percentage_error(o, p), rel_tol=1e-9)
+
+
+def test_evaluate_loop_with_a_stub_model():
+    """metrics.evaluate: eval mode inside, training flag restored, chunked batches == one batch, table == scikit-learn."""
+    import numpy as np
+    import torch
+    from sklearn import metrics as skm
+    from dl_biomass_b200.data import Batch, synthetic_clouds
+    from dl_biomass_b200.metrics import evaluate
+
+    class Stub(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.seen_training = []
+
+        def forward(self, batch):
+            self.seen_training.append(self.training)
+            y = batch.y.reshape(-1, 4)
+            return y * torch.tensor([1.1, 0.9, 1.0, 1.05]) + 0.01
+
+    clouds = synthetic_clouds(900, 10, 64)
+    chunks = [Batch.from_data_list(clouds[:4]), Batch.from_data_list(clouds[4:7]), Batch.from_data_list(clouds[7:])]
+    m = Stub().train()
+    table, (obs, pred) = evaluate(m, chunks, return_predictions=True)
+    assert m.training and m.seen_training == [False, False, False]
+    assert table == evaluate(m, [Batch.from_data_list(clouds)])
+    o, p = obs.numpy().astype(np.float64), pred.numpy().astype(np.float64)
+    assert abs(table["wood_btphr"]["r2"] - skm.r2_score(o[:, 3], p[:, 3])) < 1e-9
+    assert abs(table["tree_btphr"]["rmse"] - np.sqrt(skm.mean_squared_error(o.sum(1), p.sum(1)))) < 1e-9
+    assert abs(table["bark_btphr"]["mape"] - skm.mean_absolute_percentage_error(o[:, 0], p[:, 0])) < 1e-9
+    import pytest
+    with pytest.raises(ValueError):
+        evaluate(m, [])
