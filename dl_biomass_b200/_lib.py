@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libb2pn.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 _lib = None
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _vp, _i32, _i64, _f32, _f64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double
 
@@ -33,7 +33,13 @@ class SaArgs(ctypes.Structure):
                 ("pos_dst", _vp), ("nbr", _vp), ("cnt", _vp), ("batch", _vp), ("mlp", Mlp3), ("out", _vp),
                 ("arg", _vp), ("h1", _vp), ("h2", _vp), ("bn", _vp), ("workspace", _vp),
                 ("workspace_bytes", ctypes.c_int64), ("rgrp", _vp), ("row_src", _vp), ("num_rows", _vp),
-                ("row_capacity", ctypes.c_int64), ("row_valid", _vp), ("a1", _vp), ("a2", _vp), ("g1", _vp), ("g1_ready", ctypes.c_int32)]
+                ("row_capacity", ctypes.c_int64), ("row_valid", _vp), ("a1", _vp), ("a2", _vp), ("g1", _vp),
+                ("g1_ready", ctypes.c_int32), ("sm_limit", ctypes.c_int32), ("deterministic", ctypes.c_int32),
+                ("out_bf16", _vp)]
+
+
+class FpsOptions(ctypes.Structure):
+    _fields_ = [("cluster", ctypes.c_int32), ("threads", ctypes.c_int32), ("seed", ctypes.c_uint64), ("rng_state", _vp)]
 
 
 class SaGrads(ctypes.Structure):
@@ -65,11 +71,10 @@ SIGNATURES = {
     "b2pn_error_string": (ctypes.c_char_p, [ctypes.c_int]),
     "b2pn_launch_count": (_i64, []),
     "b2pn_fps_num_samples": (_i64, [_i64, _f32]),
-    "b2pn_set_sm_limit": (ctypes.c_int, [_i32]),
-    "b2pn_set_deterministic": (ctypes.c_int, [_i32]),
-    "b2pn_fps_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
+    "b2pn_fps_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, ctypes.POINTER(FpsOptions), _vp]),
+    "b2pn_fps_random_start": (_i64, [ctypes.c_uint64, _i64, _i32, _i64]),
+    "b2pn_adam_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp]),
     "b2pn_fps_f64": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
-    "b2pn_fps_set_variant": (ctypes.c_int, [_i32, _i32]),
     "b2pn_ball_query_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _f64, _i32, _vp, _vp, _vp]),
     "b2pn_ball_query_workspace_bytes": (_i64, [_i32, _i64]),
     "b2pn_ball_query_grid_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _f64, _i32, _vp, _vp, _vp, _i64, _vp]),

@@ -77,7 +77,11 @@ class CloudCache:
                 n_keep, n_dup, sd, angle = n, 0, 0.0, 0.0
             if n_keep + n_dup < MIN_POINTS:
                 continue
-            recs.append((int(cid), n, n_keep, n_dup, sd, angle, int(epoch) * len(self.sizes) + int(cid)))
+            # uid = the per-point random stream of THIS sample: fresh 64 bits per record.  The reference puts every cloud
+            # into an epoch 1 + num_augs times, each copy augmented independently (/root/reference/main.py:100-112); a uid
+            # derived from (epoch, cloud id) alone would give all those copies the same permutation and the same noise.
+            uid = rng.getrandbits(64) if augment else (int(epoch) * len(self.sizes) + int(cid))
+            recs.append((int(cid), n, n_keep, n_dup, sd, angle, uid))
         return recs
 
     def batch(self, cloud_ids: Sequence[int], rng: Optional[random.Random] = None, seed: int = 0, epoch: int = 0,

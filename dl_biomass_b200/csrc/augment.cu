@@ -168,10 +168,14 @@ extern "C" int b2pn_augment_batch(const float *pos, const float *x, int32_t F, c
             return B2PN_EINVAL;
         if (c.n_src > B2PN_AUG_MAX_POINTS) return B2PN_ENOTSUP;
     }
-    static bool attr_set = false;  // idempotent: a race just sets it twice
-    if (!attr_set) {
-        B2PN_CUDA(cudaFuncSetAttribute(augment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B2PN_AUG_MAX_POINTS * 12));
-        attr_set = true;
+    {   // the attribute is per DEVICE: remember it per device (idempotent: a race just sets it twice)
+        static bool attr_set[64] = {};
+        int dev = 0;
+        B2PN_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+            B2PN_CUDA(cudaFuncSetAttribute(augment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B2PN_AUG_MAX_POINTS * 12));
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
     }
     for (int b0 = 0; b0 < B; b0 += AUG_CHUNK) {
         AugChunk ch;

@@ -27,10 +27,11 @@ typedef unsigned long long u64;
 
 // number of kernels this library has enqueued (bench.py reports it as gpu_launches)
 extern long long g_launches;
-// upper bound on the CTAs of the persistent tcgen05 kernels (0 = every SM), see b2pn_set_sm_limit
-extern int g_sm_limit;
-// 1: bit-reproducible weight gradients (fixed-order reduction of the dW split partials), see b2pn_set_deterministic
-extern int g_deterministic;
+// per-CALL launch options of the set-abstraction entry points (b2pn_sa_args::sm_limit / ::deterministic): the entry
+// point copies them into these thread-local slots for the helpers below it, so two host threads driving two GPUs (the
+// reference's thread-per-GPU DataParallel, /root/reference/main.py:140) never see each other's settings
+extern thread_local int t_sm_limit;       // upper bound on the CTAs of the persistent tcgen05 kernels (0 = every SM)
+extern thread_local int t_deterministic;  // 1: fixed-order reduction of the dW split partials (bit-reproducible)
 static inline void note_launch(int n = 1) { __atomic_fetch_add(&g_launches, (long long)n, __ATOMIC_RELAXED); }
 
 // ---- packed fp32x2 arithmetic (Blackwell FADD2/FMUL2), each half rounded separately ----------

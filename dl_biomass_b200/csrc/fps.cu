@@ -26,7 +26,37 @@ struct FpsParams {
     int64_t *out_idx;
     float *out_pos;
     int64_t *out_batch;
+    // random_start drawn inside the kernel (torch_cluster.fps default): start_b = floor(u * n_b) with u a
+    // counter-based uniform of (seed, rng_state[0], b).  rng_state[0] is a DEVICE call counter so that a CUDA-graph
+    // replay draws fresh starts; every block reads it on entry and the last block to leave bumps it (ticket rng_state[1]).
+    unsigned long long seed;
+    int64_t *rng_state;
 };
+
+// start index of cloud b for call number `call`: floor(u * n), u uniform in [0, 1) with 24 random bits
+__host__ __device__ __forceinline__ int fps_random_start(unsigned long long seed, long long call, int b, int n)
+{
+    unsigned long long z = seed * 0x9e3779b97f4a7c15ull + (unsigned long long)call * 0x100000001b3ull + (unsigned long long)b;
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    z ^= z >> 31;
+    const float u = (float)(unsigned)(z >> 40) * (1.0f / 16777216.0f);
+    int s = (int)(u * (float)n);
+    return s < n ? s : n - 1;
+}
+// called once per block on every exit path (one thread): the last block publishes the next call number
+__device__ __forceinline__ void fps_rng_leave(const FpsParams &p, long long call)
+{
+    if (p.rng_state == nullptr) return;
+    __threadfence();
+    const unsigned long long t = atomicAdd(reinterpret_cast<unsigned long long *>(p.rng_state + 1), 1ull);
+    if (t == (unsigned long long)gridDim.x - 1ull) {
+        p.rng_state[1] = 0;
+        p.rng_state[0] = call + 1;
+        __threadfence();
+    }
+}
 
 template <int CLUSTER, int THREADS, int PPT>
 __global__ void __launch_bounds__(THREADS, 1) fps_kernel(const FpsParams p)
@@ -41,7 +71,11 @@ __global__ void __launch_bounds__(THREADS, 1) fps_kernel(const FpsParams p)
     const int n = (int)(p.ptr[b + 1] - p0);
     const int64_t o0 = p.out_ptr[b];
     const int m = (int)(p.out_ptr[b + 1] - o0);
-    if (n <= 0 || m <= 0) return;  // uniform over the cluster
+    const long long call = p.rng_state ? (long long)p.rng_state[0] : 0ll;
+    if (n <= 0 || m <= 0) {  // uniform over the cluster
+        if (tid == 0) fps_rng_leave(p, call);
+        return;
+    }
 
     __shared__ int s_wmax[NW];
     __shared__ __align__(16) unsigned s_rec[2][CLUSTER][8];  // {key, idx, x, y, z, -, -, -}
@@ -78,6 +112,8 @@ __global__ void __launch_bounds__(THREADS, 1) fps_kernel(const FpsParams p)
     if (p.start != nullptr) {
         const int64_t s = p.start[b];
         cur = (s >= 0 && s < n) ? (int)s : 0;
+    } else if (p.rng_state != nullptr) {
+        cur = fps_random_start(p.seed, call, b, n);
     }
     float cx = __ldg(p.pos + 3 * (p0 + cur) + 0);
     float cy = __ldg(p.pos + 3 * (p0 + cur) + 1);
@@ -189,6 +225,7 @@ __global__ void __launch_bounds__(THREADS, 1) fps_kernel(const FpsParams p)
         cluster_arrive_release();
         cluster_wait_acquire();
     }
+    if (tid == 0) fps_rng_leave(p, call);
 }
 
 // =================================================================================================
@@ -810,9 +847,6 @@ static int dispatch_sorted(const FpsParams &p, int B, int64_t max_n, int threads
     return B2PN_EINVAL;
 }
 
-static int g_force_cluster = 0;
-static int g_force_threads = 0;
-
 template <int CLUSTER, int THREADS, int PPT>
 static int launch_fps(const FpsParams &p, int B, cudaStream_t stream)
 {
@@ -885,32 +919,33 @@ static int dispatch_cluster(const FpsParams &p, int B, int64_t max_n, int cluste
 
 }  // namespace b2pn
 
-extern "C" int b2pn_fps_set_variant(int32_t cluster, int32_t threads)
+extern "C" int64_t b2pn_fps_random_start(uint64_t seed, int64_t call, int32_t cloud, int64_t n)
 {
-    if (!(cluster == -2 || cluster == -1 || cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8 || cluster == 16))
-        return B2PN_EINVAL;
-    if (!(threads == 0 || threads == 256 || threads == 512 || threads == 640 || threads == 768 || threads == 1024))
-        return B2PN_EINVAL;
-    b2pn::g_force_cluster = cluster;
-    b2pn::g_force_threads = threads;
-    return B2PN_OK;
+    if (n <= 0 || n > 0x7fffffff) return B2PN_EINVAL;
+    return (int64_t)b2pn::fps_random_start((unsigned long long)seed, (long long)call, (int)cloud, (int)n);
 }
 
 extern "C" int b2pn_fps_f32(const float *pos, const int64_t *ptr, const int64_t *out_ptr, const int64_t *start,
                             int32_t B, int64_t max_n, int64_t *out_idx, float *out_pos, int64_t *out_batch,
-                            b2pn_stream_t stream)
+                            const b2pn_fps_options *opts, b2pn_stream_t stream)
 {
     using namespace b2pn;
     if (B < 0 || max_n < 0) return B2PN_EINVAL;
+    int threads = opts ? opts->threads : 0, cluster = opts ? opts->cluster : 0;
+    if (!(cluster == -2 || cluster == -1 || cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8 || cluster == 16))
+        return B2PN_EINVAL;
+    if (!(threads == 0 || threads == 256 || threads == 512 || threads == 640 || threads == 768 || threads == 1024))
+        return B2PN_EINVAL;
     if (B == 0 || max_n == 0) return B2PN_OK;
     if (!pos || !ptr || !out_ptr || !out_idx) return B2PN_EINVAL;
-    FpsParams p = {pos, ptr, out_ptr, start, out_idx, out_pos, out_batch};
+    int64_t *rng_state = (opts && !start) ? opts->rng_state : nullptr;
+    FpsParams p = {pos, ptr, out_ptr, start, out_idx, out_pos, out_batch, opts ? (unsigned long long)opts->seed : 0ull, rng_state};
 
-    int threads = g_force_threads, cluster = g_force_cluster;
     // cluster == -1: the spatially pruned kernel (bit-identical results).  Measured on B200
     // (profiles/r01_fps_experiments.md) it prunes ~75 % of the scan but its serial chain of uniform-datapath
     // reductions (CREDUX / VOTE / FLO at 50-70 cycles each) makes an iteration SLOWER than the plain register scan
     // at 10k points, so it is opt-in and the register scan below stays the default.
+    if (cluster < 0 && rng_state) return B2PN_ENOTSUP;  // the opt-in variants take explicit starts only
     if (cluster == -1) return dispatch_pruned(p, B, max_n, threads, (cudaStream_t)stream);
     if (cluster == -2) return dispatch_sorted(p, B, max_n, threads, (cudaStream_t)stream);
     if (threads == 0) threads = 512;

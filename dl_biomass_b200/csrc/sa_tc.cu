@@ -663,6 +663,7 @@ struct SlotMaxEpTC {  // out[m][ch] = max over the valid rows of centroid m, arg
     const float *bias;
     const uint32_t *rgrp;
     int64_t rows;
+    __nv_bfloat16 *out16;  // optional bf16 copy of out (the next level's gather operand)
     __device__ __forceinline__ void resolve(int64_t r) { rows = r; }
     __device__ __forceinline__ void begin() {}
     __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half, const EpCtx &cx)
@@ -695,8 +696,10 @@ struct SlotMaxEpTC {  // out[m][ch] = max over the valid rows of centroid m, arg
                 }
                 if (gi_last(inf) && ch < C) {
                     const int64_t m = gi_seg(inf);
-                    out[m * C + ch] = bk >= 0 ? best : 0.f;
+                    const float o = bk >= 0 ? best : 0.f;
+                    out[m * C + ch] = o;
                     arg[m * C + ch] = bk;
+                    if (out16) out16[m * C + ch] = __float2bfloat16(o);
                 }
             }
         }
@@ -842,15 +845,26 @@ struct MaskSumsStoreEpTC {  // backward through activation + sums for the BatchN
     }
 };
 
+constexpr float FIXED_ONE = 1099511627776.f;  // 2^40: fixed-point unit of the deterministic scatter accumulator
+__global__ void fixed_to_f32_kernel(const long long *acc, float *out, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)((double)acc[i] * (1.0 / 1099511627776.0));
+}
+
 struct ScatterEpTC {  // gradient w.r.t. the gathered source features
     // A thread drains one channel (TMEM lane) over 64 rows, but dx is row-major [n_src][C]: the warp transposes its
     // 32 channels x 64 rows through its staging tile (fp32, swizzled per float4), after which a lane owns a ROW and
     // adds four consecutive channels per instruction (red.global.add.v4.f32: a quarter of the atomic operations the
     // channel-per-thread form needed; CLOUDS levels: plain 16-byte stores).
+    // Deterministic mode (b2pn_sa_args::deterministic, SLOTS levels): the addends go into a 64-bit FIXED-POINT
+    // accumulator (2^-40 units) with integer atomics -- integer addition is associative, so the sums do not depend on the
+    // order in which the rows arrive -- and fixed_to_f32_kernel converts the result; bit-reproducible feature gradients.
     static constexpr bool STAGED = true;
     RowMapTC rm;
     float *dx;  // [n_src][C] fp32, zero-initialised by the caller in SLOTS mode
     int C;
+    long long *dxi;  // [n_src][C] fixed-point accumulator (zeroed), or NULL: fp32 atomics straight into dx
     __device__ __forceinline__ void resolve(int64_t rows) { rm.rows = rows; }
     __device__ __forceinline__ void begin() {}
     __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half, const EpCtx &cx)
@@ -887,7 +901,15 @@ struct ScatterEpTC {  // gradient w.r.t. the gathered source features
             for (int c4 = 0; c4 < 8; ++c4) {
                 if (ch0 + c4 * 4 >= C) break;
                 const float4 q = *reinterpret_cast<const float4 *>(st + r * 32 + ((c4 ^ (r & 7)) << 2));
-                if (vec) {
+                if (dxi != nullptr && !rm.seg_mode) {
+                    const float e[4] = {q.x, q.y, q.z, q.w};
+                    unsigned long long *acc = reinterpret_cast<unsigned long long *>(dxi + dst * C + ch0 + c4 * 4);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (ch0 + c4 * 4 + k >= C) break;
+                        if (e[k] != 0.f) atomicAdd(acc + k, (unsigned long long)__float2ll_rn(e[k] * FIXED_ONE));
+                    }
+                } else if (vec) {
                     if (rm.seg_mode) {
                         *reinterpret_cast<float4 *>(base + c4 * 4) = q;
                     } else if (q.x != 0.f || q.y != 0.f || q.z != 0.f || q.w != 0.f) {
@@ -1468,16 +1490,18 @@ static void launch_pack(const float *w, int M, int Kimg, int64_t sm, int64_t sk,
 
 static int sm_count()
 {
-    static int sms = 0;
+    static int sms_of[64] = {};  // per device; a racing first call writes the same value twice
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int sms = (dev >= 0 && dev < 64) ? sms_of[dev] : 0;
     if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
+        if (dev >= 0 && dev < 64) sms_of[dev] = sms;
     }
-    // b2pn_set_sm_limit: leave SMs free for kernels of a concurrent stream (the persistent kernels below take one
+    // b2pn_sa_args::sm_limit: leave SMs free for kernels of a concurrent stream (the persistent kernels below take one
     // CTA per SM and stride over tiles by gridDim.x, so a CTA that cannot become resident would double their time)
-    const int lim = g_sm_limit;
+    const int lim = t_sm_limit;
     return (lim > 0 && lim < sms) ? lim : sms;
 }
 
@@ -1980,9 +2004,9 @@ static FwdWsTC carve_fwd_tc(const b2pn_sa_args &a, const ShapesTC &s, WsTC &ws)
 }
 
 // atomic mode (default): the row splits of a dW GEMM add their partials into one zeroed buffer with
-// red.global.add.v4.f32 (no partial tensor, the reduction kernel only maps columns); b2pn_set_deterministic(1): per-split
+// red.global.add.v4.f32 (no partial tensor, the reduction kernel only maps columns); b2pn_sa_args::deterministic: per-split
 // partials summed in a fixed order (bit-reproducible)
-static inline bool dw_atomic() { return g_deterministic == 0; }
+static inline bool dw_atomic() { return t_deterministic == 0; }
 
 struct DwPlanHost {
     int MTA, num_mg, num_ng, splits, nbl_total, k_stride;
@@ -2016,6 +2040,7 @@ struct BwdWsTC {
     __nv_bfloat16 *dh3;  // materialised routed gradient [c3][ld]
     float *sbar;
     float *dwp[3];  // split partials of dW1, dW2, dW3 (reduced together at the end)
+    long long *dxi; // deterministic mode, SLOTS levels with features: fixed-point accumulator of grad_x
 };
 static BwdWsTC carve_bwd_tc(const b2pn_sa_args &a, const ShapesTC &s, WsTC &ws)
 {
@@ -2033,6 +2058,7 @@ static BwdWsTC carve_bwd_tc(const b2pn_sa_args &a, const ShapesTC &s, WsTC &ws)
     b.dwp[2] = ws.take<float>(plan_dw(s.c3, s.c2 + 1, s.ld).floats);
     b.dwp[1] = ws.take<float>(plan_dw(s.c2, s.c1 + 1, s.ld).floats);
     b.dwp[0] = ws.take<float>(plan_dw(s.c1, s.k1 + 1, s.ld).floats);
+    b.dxi = (t_deterministic && a.seg_mode == B2PN_SEG_SLOTS && a.c_in > 0) ? ws.take<long long>(a.n_src * (int64_t)a.c_in) : nullptr;
     return b;
 }
 
@@ -2157,7 +2183,7 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
     }
     // ---- layer 3 + max aggregation
     if (a.seg_mode == B2PN_SEG_SLOTS) {
-        SlotMaxEpTC e = {a.out, a.arg, s.c3, a.mlp.b[2], a.rgrp, s.rows};
+        SlotMaxEpTC e = {a.out, a.arg, s.c3, a.mlp.b[2], a.rgrp, s.rows, (__nv_bfloat16 *)a.out_bf16};
         if ((rc = launch_by_mt(f.pk[2], ra, l3, e, e, st, map_a2))) return rc;
     } else {
         const int64_t n = a.n_dst * (int64_t)s.c3;
@@ -2372,8 +2398,14 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
     }
     if (need_dx) {
         TmaFeatLoader bl;
-        ScatterEpTC e = {rm, g.grad_x, a.c_in};
+        const int64_t nx = a.n_src * (int64_t)a.c_in;
+        if (b.dxi) B2PN_CUDA(cudaMemsetAsync(b.dxi, 0, (size_t)nx * sizeof(long long), st));
+        ScatterEpTC e = {rm, g.grad_x, a.c_in, b.dxi};
         if ((rc = launch_by_mt(b.pkT[0], ra, bl, e, e, st, map1))) return rc;
+        if (b.dxi) {
+            fixed_to_f32_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(b.dxi, g.grad_x, nx);
+            note_launch();
+        }
     }
     B2PN_LAUNCH_CHECK();
     return B2PN_OK;

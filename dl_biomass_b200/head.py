@@ -9,6 +9,7 @@ import ctypes
 import torch
 
 from . import _lib
+from .optim import grad_dst
 
 MAX_ROWS, MAX_HIDDEN, MAX_OUT = 32, 256, 8
 
@@ -51,6 +52,7 @@ class _HeadFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mlp, training, p, seed, counter, x, *params):
         lib = _lib.lib()
+        ctx.grad_dsts = tuple(grad_dst(t) for t in params)
         for t in params:
             if not (t.is_contiguous() and t.dtype == torch.float32):
                 raise ValueError("head parameters must be contiguous float32 tensors")
@@ -83,10 +85,14 @@ class _HeadFunction(torch.autograd.Function):
         g.grad_out = grad_out.data_ptr()
         gx = torch.empty_like(x) if ctx.needs_input_grad[5] else None
         g.grad_x = None if gx is None else gx.data_ptr()
-        gw = [torch.empty_like(l.weight) for l in mlp.lins]
-        gb = [torch.empty_like(l.bias) for l in mlp.lins]
-        gg = [torch.empty_like(n.weight) for n in mlp.norms]
-        gbe = [torch.empty_like(n.bias) for n in mlp.norms]
+        # parameter order of forward: w0 b0 g0 be0 w1 b1 g1 be1 w2 b2; gradients land in the parameter arena when
+        # there is one (optim.ParamArena), else in fresh tensors
+        d = ctx.grad_dsts
+        fresh = lambda dst, like: dst if dst is not None else torch.empty_like(like)  # noqa: E731
+        gw = [fresh(d[0], mlp.lins[0].weight), fresh(d[4], mlp.lins[1].weight), fresh(d[8], mlp.lins[2].weight)]
+        gb = [fresh(d[1], mlp.lins[0].bias), fresh(d[5], mlp.lins[1].bias), fresh(d[9], mlp.lins[2].bias)]
+        gg = [fresh(d[2], mlp.norms[0].weight), fresh(d[6], mlp.norms[1].weight)]
+        gbe = [fresh(d[3], mlp.norms[0].bias), fresh(d[7], mlp.norms[1].bias)]
         for i in range(3):
             g.grad_w[i], g.grad_b[i] = gw[i].data_ptr(), gb[i].data_ptr()
         for i in range(2):

@@ -3,7 +3,7 @@ sum, as /root/reference/testing_model.py:72-98 computes them with scikit-learn -
 the predictions live on, so an evaluation loop needs no ``.to('cpu')`` per batch (testing_model.py:64-65)."""
 from __future__ import annotations
 
-from typing import Dict
+from typing import Dict, Sequence
 
 import torch
 
@@ -59,5 +59,47 @@ def evaluate(model: torch.nn.Module, batches, return_predictions: bool = False):
     if not pred:
         raise ValueError("evaluate needs at least one batch")
     o, p = torch.cat(obs, 0), torch.cat(pred, 0)
+    table = regression_metrics(o, p)
+    return (table, (o, p)) if return_predictions else table
+
+
+@torch.no_grad()
+def evaluate_distributed(model: torch.nn.Module, clouds: Sequence, device, batch_size: int = 256, process_group=None,
+                         return_predictions: bool = False):
+    """The same evaluation over several GPUs, one process per GPU (the reference evaluates through its DataParallel
+    wrapper, /root/reference/testing_model.py:30-37,56-64, which scatters the ONE giant batch over the devices by point
+    count and gathers the ``[B, 4]`` outputs on device 0 -- SURVEY.md A.8, rows C3 / 8(e)).  ``clouds``: the whole test set
+    as a list of per-cloud ``Data`` (what ``DataListLoader`` yields), identical on every rank.  Rank r takes the r-th
+    contiguous chunk balanced by point count (``parallel.shard_by_points``), runs it in batches of ``batch_size`` clouds,
+    and ONE all-gather of the ``[n, 8]`` (observed | predicted) rows gives every rank the full table, in input order."""
+    import torch.distributed as dist
+    from .data import Batch
+    from .parallel import shard_by_points
+    if not dist.is_initialized():
+        raise RuntimeError("evaluate_distributed needs torch.distributed to be initialised")
+    world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+    parts = shard_by_points([int(d.pos.size(0)) for d in clouds], world)
+    mine = [clouds[i] for i in parts[rank]]
+    was_training = model.training
+    model.eval()
+    rows = []
+    try:
+        for i in range(0, len(mine), batch_size):
+            b = Batch.from_data_list(mine[i:i + batch_size]).to(device)
+            out = model(b).reshape(-1, 4).to(torch.float32)
+            rows.append(torch.cat([b.y.reshape(-1, 4).to(out.device, torch.float32), out], 1))
+    finally:
+        model.train(was_training)
+    counts = [len(r) for r in parts]
+    dev = torch.device(device)
+    local = torch.zeros(max(counts + [1]), 8, dtype=torch.float32, device=dev)
+    if rows:
+        local[:counts[rank]] = torch.cat(rows, 0)
+    gathered = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local, group=process_group)
+    full = torch.cat([g[:c] for g, c in zip(gathered, counts)], 0)
+    if full.size(0) == 0:
+        raise ValueError("evaluate_distributed needs at least one cloud")
+    o, p = full[:, :4].contiguous(), full[:, 4:].contiguous()
     table = regression_metrics(o, p)
     return (table, (o, p)) if return_predictions else table

@@ -8,6 +8,7 @@ device->host synchronisation anywhere in the forward pass.
 """
 from __future__ import annotations
 
+import ctypes
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -16,10 +17,10 @@ import torch
 from . import _lib
 
 _DEF = torch.library.Library("b2pn", "DEF")
-_DEF.define("fps(Tensor pos, Tensor ptr, Tensor out_ptr, Tensor? start, int max_n, int num_out) "
-            "-> (Tensor, Tensor, Tensor)")
+_DEF.define("fps(Tensor pos, Tensor ptr, Tensor out_ptr, Tensor? start, int max_n, int num_out, int seed=0, "
+            "Tensor? rng_state=None, int cluster=0, int threads=0) -> (Tensor, Tensor, Tensor)")
 _DEF.define("ball_query(Tensor src, Tensor qry, Tensor src_ptr, Tensor qry_ptr, int max_src, int max_qry, "
-            "float r, int K) -> (Tensor, Tensor)")
+            "float r, int K, str mode='auto') -> (Tensor, Tensor)")
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -36,8 +37,8 @@ def _require_cuda(*ts: torch.Tensor) -> None:
             raise RuntimeError("b2pn ops run on a B200 only: got a CPU tensor and there is no CPU fallback")
 
 
-def _fps_cuda(pos, ptr, out_ptr, start, max_n, num_out):
-    _require_cuda(pos, ptr, out_ptr, start)
+def _fps_cuda(pos, ptr, out_ptr, start, max_n, num_out, seed=0, rng_state=None, cluster=0, threads=0):
+    _require_cuda(pos, ptr, out_ptr, start, rng_state)
     if pos.dtype != torch.float32 or pos.dim() != 2 or pos.size(1) != 3:
         raise ValueError("fps: pos must be [N,3] float32")
     pos = pos.contiguous()
@@ -45,27 +46,27 @@ def _fps_cuda(pos, ptr, out_ptr, start, max_n, num_out):
     idx = torch.empty(num_out, dtype=torch.int64, device=pos.device)
     pos_out = torch.empty(num_out, 3, dtype=torch.float32, device=pos.device)
     batch_out = torch.empty(num_out, dtype=torch.int64, device=pos.device)
+    if rng_state is not None and (rng_state.dtype != torch.int64 or rng_state.numel() < 2):
+        raise ValueError("fps: rng_state must be an int64 tensor of 2 elements")
+    opts = _lib.FpsOptions(int(cluster), int(threads), int(seed) & 0xffffffffffffffff, _ptr(rng_state))
     with torch.cuda.device(pos.device):
         rc = _lib.lib().b2pn_fps_f32(pos.data_ptr(), ptr.data_ptr(), out_ptr.data_ptr(), _ptr(start), B, max_n,
-                                     idx.data_ptr(), pos_out.data_ptr(), batch_out.data_ptr(), _stream(pos))
+                                     idx.data_ptr(), pos_out.data_ptr(), batch_out.data_ptr(), ctypes.byref(opts),
+                                     _stream(pos))
     _lib.check(rc, "b2pn_fps_f32")
     return idx, pos_out, batch_out
 
 
 GRID_MIN_SOURCES = 4096   # below this the plain scan with early exit wins (level 2: most sources are neighbours)
 GRID_MAX_SOURCES = 32768  # above this the clouds are so dense that K hits come early in the scan (100k-point trees)
-_BQ_MODE = "auto"         # "scan" forces the brute-force kernel (tests compare both)
 
 
-def set_ball_query_mode(mode: str) -> None:
-    global _BQ_MODE
+def _ball_query_cuda(src, qry, src_ptr, qry_ptr, max_src, max_qry, r, K, mode="auto"):
+    """``mode``: "auto" picks the kernel by cloud size, "scan" forces the brute-force kernel (tests compare both);
+    a per-call argument -- there is no process-wide switch."""
+    _require_cuda(src, qry, src_ptr, qry_ptr)
     if mode not in ("auto", "scan"):
         raise ValueError("mode must be 'auto' or 'scan'")
-    _BQ_MODE = mode
-
-
-def _ball_query_cuda(src, qry, src_ptr, qry_ptr, max_src, max_qry, r, K):
-    _require_cuda(src, qry, src_ptr, qry_ptr)
     if src.dtype != torch.float32 or qry.dtype != torch.float32:
         raise ValueError("ball_query: positions must be float32")
     src, qry = src.contiguous(), qry.contiguous()
@@ -74,7 +75,7 @@ def _ball_query_cuda(src, qry, src_ptr, qry_ptr, max_src, max_qry, r, K):
     nbr = torch.empty(M, K, dtype=torch.int32, device=src.device)
     cnt = torch.empty(M, dtype=torch.int32, device=src.device)
     lib = _lib.lib()
-    if GRID_MIN_SOURCES <= max_src <= GRID_MAX_SOURCES and _BQ_MODE != "scan":
+    if GRID_MIN_SOURCES <= max_src <= GRID_MAX_SOURCES and mode != "scan":
         # large clouds: uniform-grid kernel (same result, two orders of magnitude fewer distance tests)
         ws = torch.empty(int(lib.b2pn_ball_query_workspace_bytes(B, src.size(0))), dtype=torch.uint8, device=src.device)
         with torch.cuda.device(src.device):
@@ -105,13 +106,13 @@ _IMPL.impl("ball_query", _no_cpu, "CPU")
 
 
 @torch.library.register_fake("b2pn::fps")
-def _fps_fake(pos, ptr, out_ptr, start, max_n, num_out):
+def _fps_fake(pos, ptr, out_ptr, start, max_n, num_out, seed=0, rng_state=None, cluster=0, threads=0):
     return (pos.new_empty(num_out, dtype=torch.int64), pos.new_empty(num_out, 3),
             pos.new_empty(num_out, dtype=torch.int64))
 
 
 @torch.library.register_fake("b2pn::ball_query")
-def _bq_fake(src, qry, src_ptr, qry_ptr, max_src, max_qry, r, K):
+def _bq_fake(src, qry, src_ptr, qry_ptr, max_src, max_qry, r, K, mode="auto"):
     return qry.new_empty(qry.size(0), K, dtype=torch.int32), qry.new_empty(qry.size(0), dtype=torch.int32)
 
 
@@ -169,13 +170,17 @@ def _build_levels(sizes0: Sequence[int], ratios: Sequence[float], device: torch.
     return [Level(s, dev[i], int(host[i, -1]), max(s) if s else 0, devf[i]) for i, s in enumerate(all_sizes)]
 
 
-def fps(pos: torch.Tensor, src: Level, dst: Level, start: Optional[torch.Tensor] = None
+def fps(pos: torch.Tensor, src: Level, dst: Level, start: Optional[torch.Tensor] = None, *, seed: int = 0,
+        rng_state: Optional[torch.Tensor] = None, cluster: int = 0, threads: int = 0
         ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """idx [M] int64 (global), pos[idx] [M,3], batch[idx] [M] -- pointnet2_regressor.py:13,19."""
-    return torch.ops.b2pn.fps(pos, src.ptr, dst.ptr, start, src.max_n, dst.total)
+    """idx [M] int64 (global), pos[idx] [M,3], batch[idx] [M] -- pointnet2_regressor.py:13,19.
+    ``start``: explicit cloud-local start indices; else, with ``rng_state`` (int64[2] on the device, zeroed once), the
+    kernel draws torch_cluster's ``random_start`` itself from (seed, rng_state[0], cloud) and advances the counter; else
+    every cloud starts at its point 0.  ``cluster`` / ``threads``: force a kernel variant (benchmark sweeps)."""
+    return torch.ops.b2pn.fps(pos, src.ptr, dst.ptr, start, src.max_n, dst.total, int(seed), rng_state, cluster, threads)
 
 
-def ball_query(src_pos: torch.Tensor, qry_pos: torch.Tensor, src: Level, qry: Level, r: float, K: int = 64
-               ) -> Tuple[torch.Tensor, torch.Tensor]:
+def ball_query(src_pos: torch.Tensor, qry_pos: torch.Tensor, src: Level, qry: Level, r: float, K: int = 64,
+               mode: str = "auto") -> Tuple[torch.Tensor, torch.Tensor]:
     """Fixed-width neighbour slots nbr [M,K] int32 / cnt [M] -- pointnet2_regressor.py:14-16."""
-    return torch.ops.b2pn.ball_query(src_pos, qry_pos, src.ptr, qry.ptr, src.max_n, qry.max_n, float(r), K)
+    return torch.ops.b2pn.ball_query(src_pos, qry_pos, src.ptr, qry.ptr, src.max_n, qry.max_n, float(r), K, mode)

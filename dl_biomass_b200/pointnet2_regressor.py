@@ -97,14 +97,23 @@ class SAModule(torch.nn.Module):
         self.conv = PointConv(nn, add_self_loops=False)
         self.precision = "fp32"
         self.random_start = True  # torch_cluster.fps default
+        # random_start is drawn INSIDE the sampling kernel from (seed, call counter, cloud): the counter is a device
+        # scalar the kernel advances, so CUDA-graph replays draw fresh start points and no ATen kernel is involved.
+        # Plain attributes, not buffers: the module's state_dict stays exactly the reference's.
+        self._fps_seed = int(torch.initial_seed() & 0x7fffffffffffffff) ^ (hash((float(ratio), float(r))) & 0xffffffff)
+        self._fps_rng_state = None
+
+    def _rng_state(self, device):
+        st = self._fps_rng_state
+        if st is None or st.device != device:
+            st = torch.zeros(2, dtype=torch.int64, device=device)
+            self._fps_rng_state = st
+        return st
 
     def _sample(self, pos, src: ops.Level, dst: ops.Level, start=None):
         """fps + pos[idx] + batch[idx] (:13, :19): depends on the positions only, never on the weights."""
         if start is None and self.random_start and src.total > 0:
-            n = src.sizes_f32
-            if n is None:
-                n = torch.tensor(src.sizes, dtype=torch.float32).to(pos.device, non_blocking=True)
-            start = (torch.rand(len(src.sizes), device=pos.device) * n).to(torch.int64)
+            return ops.fps(pos, src, dst, None, seed=self._fps_seed, rng_state=self._rng_state(pos.device))
         return ops.fps(pos, src, dst, start)
 
     def _group(self, pos, pos_dst, src: ops.Level, dst: ops.Level, x=None, gather: bool = False):
@@ -119,17 +128,18 @@ class SAModule(torch.nn.Module):
                 l1op = sa.gather_rows(x, pos, pos_dst, self.max_num_neighbors, rowmap)
         return nbr, cnt, rowmap, l1op
 
-    def _run(self, x, pos, src: ops.Level, dst: ops.Level, start=None, sampled=None, grouped=None):
+    def _run(self, x, pos, src: ops.Level, dst: ops.Level, start=None, sampled=None, grouped=None, x_bf16=None):
+        """Returns (out, pos[idx], batch[idx], idx, bf16 copy of out or None)."""
         idx, pos_dst, batch_dst = sampled if sampled is not None else self._sample(pos, src, dst, start)
         nbr, cnt, rowmap, l1op = grouped if grouped is not None else self._group(pos, pos_dst, src, dst)
-        out, _ = sa.sa_apply(self.conv.local_nn, x, pos, pos_dst, nbr, cnt, None, seg_mode=sa.SEG_SLOTS,
-                             K=self.max_num_neighbors, n_dst=dst.total, precision=_PRECISIONS[self.precision],
-                             rowmap=rowmap, l1op=l1op)                                       # :18
-        return out, pos_dst, batch_dst, idx
+        out, _, out16 = sa.sa_apply(self.conv.local_nn, x, pos, pos_dst, nbr, cnt, None, seg_mode=sa.SEG_SLOTS,
+                                    K=self.max_num_neighbors, n_dst=dst.total, precision=_PRECISIONS[self.precision],
+                                    rowmap=rowmap, l1op=l1op, x_bf16=x_bf16, want_bf16_out=True)   # :18
+        return out, pos_dst, batch_dst, idx, out16
 
     def forward(self, x, pos, batch):
         lv = ops.build_levels(_cloud_sizes(batch), [self.ratio], pos.device)
-        out, pos_dst, batch_dst, _ = self._run(x, pos, lv[0], lv[1])
+        out, pos_dst, batch_dst, _, _ = self._run(x, pos, lv[0], lv[1])
         return out, pos_dst, batch_dst
 
 
@@ -141,9 +151,9 @@ class GlobalSAModule(torch.nn.Module):
         self.nn = nn
         self.precision = "fp32"
 
-    def _run(self, x, pos, batch, num_clouds: int):
+    def _run(self, x, pos, batch, num_clouds: int, x_bf16=None):
         out, _ = sa.sa_apply(self.nn, x, pos, None, None, None, batch, seg_mode=sa.SEG_CLOUDS, K=0,
-                             n_dst=num_clouds, precision=_PRECISIONS[self.precision])    # :29-30
+                             n_dst=num_clouds, precision=_PRECISIONS[self.precision], x_bf16=x_bf16)   # :29-30
         return out
 
     def forward(self, x, pos, batch):
@@ -224,6 +234,12 @@ class Net(torch.nn.Module):
         self._head_seed = int(torch.initial_seed() & 0x7fffffffffffffff)
         self.set_precision(precision)
 
+    def __getstate__(self):
+        # torch.save(model) of /root/reference/main.py:245 pickles the module: the optimiser's arena is not part of it
+        st = self.__dict__.copy()
+        st.pop("_b2pn_arena", None)
+        return st
+
     def set_precision(self, precision: str) -> "Net":
         if precision not in _PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
@@ -293,16 +309,16 @@ class Net(torch.nn.Module):
         s2 = None if sampling is None else sampling.level2
         g1 = None if sampling is None else self._usable(sampling.group1)
         g2 = None if sampling is None else self._usable(sampling.group2)
-        x1, pos1, _, _ = self.sa1_module._run(x, pos, lv[0], lv[1], start, s1, g1)       # :54
+        x1, pos1, _, _, x1h = self.sa1_module._run(x, pos, lv[0], lv[1], start, s1, g1)  # :54
         if before_level1_backward is not None and torch.is_grad_enabled() and x1.requires_grad:
             x1 = _CallInBackward.apply(x1, before_level1_backward)
-        x2, pos2, batch2, _ = self.sa2_module._run(x1, pos1, lv[1], lv[2], None, s2, g2)  # :55
+        x2, pos2, batch2, _, x2h = self.sa2_module._run(x1, pos1, lv[1], lv[2], None, s2, g2, x_bf16=x1h)  # :55
         if after_grouping is not None:
             if torch.is_grad_enabled() and x2.requires_grad:
                 x2 = _CallInBackward.apply(x2, after_grouping)
             else:
                 after_grouping()
-        x3 = self.sa3_module._run(x2, pos2, batch2, len(sizes))                          # :56
+        x3 = self.sa3_module._run(x2, pos2, batch2, len(sizes), x_bf16=x2h)              # :56
         if head.supported(self.mlp, x3):                                                 # :58
             if self._head_rng_counter is None or self._head_rng_counter.device != x3.device:
                 self._head_rng_counter = torch.zeros((), dtype=torch.int64, device=x3.device)

@@ -7,11 +7,14 @@
 from __future__ import annotations
 
 import ctypes
+import threading
+from contextlib import contextmanager
 from typing import List, Optional, Sequence
 
 import torch
 
 from . import _lib
+from .optim import grad_dst
 
 PREC_F32, PREC_BF16 = 0, 1
 SEG_SLOTS, SEG_CLOUDS = 0, 1
@@ -27,6 +30,44 @@ def _dp(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+# Per-call launch options of the set-abstraction kernels (b2pn_sa_args::sm_limit / ::deterministic).  They are fields of
+# every call's argument struct -- libb2pn has no process-wide state -- and on the Python side they are THREAD-local, so
+# the reference's thread-per-GPU callers (/root/reference/main.py:140) cannot disturb each other.
+_tls = threading.local()
+
+
+def launch_options():
+    """(sm_limit, deterministic) the calling thread's next set-abstraction calls are issued with."""
+    return getattr(_tls, "sm_limit", 0), getattr(_tls, "deterministic", 0)
+
+
+def set_sm_limit(n: int) -> None:
+    """Cap the persistent tensor-core kernels launched by THIS thread at ``n`` CTAs (0 = one per SM)."""
+    if n < 0:
+        raise ValueError("sm_limit must be >= 0")
+    _tls.sm_limit = int(n)
+
+
+def set_deterministic(on: bool) -> bool:
+    """Fixed-order gradient reductions for the calls of THIS thread; returns the previous setting."""
+    prev = bool(getattr(_tls, "deterministic", 0))
+    _tls.deterministic = 1 if on else 0
+    return prev
+
+
+@contextmanager
+def options(sm_limit: Optional[int] = None, deterministic: Optional[bool] = None):
+    prev = launch_options()
+    try:
+        if sm_limit is not None:
+            set_sm_limit(sm_limit)
+        if deterministic is not None:
+            set_deterministic(deterministic)
+        yield
+    finally:
+        _tls.sm_limit, _tls.deterministic = prev
+
+
 def act_code(act) -> int:
     if act is None:
         return ACT_NONE
@@ -40,8 +81,10 @@ def act_code(act) -> int:
 
 def _fill_args(a: SaArgs, *, precision, training, seg_mode, K, n_src, n_dst, c_in, x, pos_src, pos_dst, nbr, cnt,
                batch, chans, act, eps, momentum, ws, bs, gammas, betas, rmeans, rvars, nbts, out, arg, h1, h2, bn,
-               rowmap=None, acts=None):
+               rowmap=None, acts=None, out_bf16=None):
     a.precision, a.training, a.seg_mode, a.K = precision, int(training), seg_mode, K
+    a.sm_limit, a.deterministic = launch_options()
+    a.out_bf16 = _dp(out_bf16)
     a.n_src, a.n_dst, a.c_in = n_src, n_dst, c_in
     a.x_dtype = 1 if (x is not None and x.dtype == torch.bfloat16) else 0
     a.x, a.pos_src, a.pos_dst = _dp(x), _dp(pos_src), _dp(pos_dst)
@@ -92,14 +135,37 @@ def pack_rows(nbr: torch.Tensor, cnt: torch.Tensor, K: int):
     return rgrp, row_src, num_rows, cap, row_valid
 
 
-def _l1_input(x: Optional[torch.Tensor]):
+def _l1_input(x: Optional[torch.Tensor], x_bf16: Optional[torch.Tensor] = None):
     """How the kernels take the level's input features: (tensor or None, c_in, image columns).  Raw low-dimensional
     inputs (e.g. lidar intensity) stay fp32 -- the kernels feed them to the tensor cores as bf16 hi+lo column pairs --
-    wide feature maps from the previous level go in as bf16."""
+    wide feature maps from the previous level go in as bf16 (``x_bf16``: the copy the previous level's epilogue wrote,
+    if there is one)."""
     c_in = 0 if x is None else x.shape[1]
     split = x is not None and x.dtype == torch.float32 and c_in <= 16
-    xs = None if x is None else x.detach().to(torch.float32 if split else torch.bfloat16).contiguous()
+    if x is None:
+        xs = None
+    elif not split and x_bf16 is not None and x_bf16.shape == x.shape and x_bf16.dtype == torch.bfloat16:
+        xs = x_bf16.contiguous()
+    else:
+        xs = x.detach().to(torch.float32 if split else torch.bfloat16).contiguous()
     return xs, c_in, (2 * c_in if split else c_in) + 6
+
+
+_RV_CACHE: dict = {}
+
+
+def _row_valid_clouds(ld: int, n_src: int, dev) -> torch.Tensor:
+    """bf16 [ld]: 1 on the n_src real rows of a CLOUDS level (the "ones" operand line of its dW GEMMs).  Read-only and
+    a function of two integers: built once per shape."""
+    key = (int(ld), int(n_src), str(dev))
+    rv = _RV_CACHE.get(key)
+    if rv is None:
+        if len(_RV_CACHE) >= 64:
+            _RV_CACHE.pop(next(iter(_RV_CACHE)))
+        rv = torch.zeros(ld, dtype=torch.bfloat16, device=dev)
+        rv[:n_src] = 1
+        _RV_CACHE[key] = rv
+    return rv
 
 
 def gather_rows(x: Optional[torch.Tensor], pos_src: torch.Tensor, pos_dst: torch.Tensor, K: int, rowmap):
@@ -132,9 +198,11 @@ class _SAFunction(torch.autograd.Function):
     """forward/backward of one set-abstraction level through libb2pn."""
 
     @staticmethod
-    def forward(ctx, cfg, rowmap_in, l1op_in, x, pos_src, pos_dst, nbr, cnt, batch, w1, b1, g1, be1, w2, b2, g2, be2, w3, b3,
-                rm1, rv1, nbt1, rm2, rv2, nbt2):
+    def forward(ctx, cfg, rowmap_in, l1op_in, extra, x, pos_src, pos_dst, nbr, cnt, batch, w1, b1, g1, be1, w2, b2, g2, be2,
+                w3, b3, rm1, rv1, nbt1, rm2, rv2, nbt2):
         lib = _lib.lib()
+        ctx.set_materialize_grads(False)  # no zero-filled gradient tensors for the index / bf16 side outputs
+        grad_dsts, x_bf16, want_bf16_out = extra
         dev = pos_src.device
         if not pos_src.is_cuda:
             raise RuntimeError("b2pn set abstraction runs on a B200 only: there is no CPU fallback")
@@ -157,21 +225,21 @@ class _SAFunction(torch.autograd.Function):
             rows = rowmap[3]
         out = torch.empty(n_dst, chans[3], dtype=f32, device=dev)
         arg = torch.empty(n_dst, chans[3], dtype=torch.int32, device=dev)
+        out_bf16 = (torch.empty(n_dst, chans[3], dtype=torch.bfloat16, device=dev)
+                    if (want_bf16_out and prec == PREC_BF16) else None)
         acts = None
         if prec == PREC_F32:   # row-major fp32 activations [rows, c]
             xs = None if x is None else x.detach().to(f32).contiguous()
             h1 = torch.empty(rows, chans[1], dtype=f32, device=dev)
             h2 = torch.empty(rows, chans[2], dtype=f32, device=dev)
         else:                  # feature-major bf16 activations [c, ld], ld = rows rounded up to whole 128-row tiles
-            xs, _, k_img = _l1_input(x)
+            xs, _, k_img = _l1_input(x, x_bf16)
             ld = (rows + 127) // 128 * 128
             h1 = torch.empty(chans[1], ld, dtype=torch.bfloat16, device=dev)
             h2 = torch.empty(chans[2], ld, dtype=torch.bfloat16, device=dev)
             acts = [torch.empty_like(h1), torch.empty_like(h2)]  # post-activation copies (TMA operands)
             if seg_mode == SEG_CLOUDS:   # the "ones" operand line of the dW GEMMs: 1 on every real row
-                rv = torch.zeros(ld, dtype=torch.bfloat16, device=dev)
-                rv[:n_src] = 1
-                rowmap = (None, None, None, 0, rv)
+                rowmap = (None, None, None, 0, _row_valid_clouds(ld, n_src, dev))
             if seg_mode == SEG_SLOTS and k_img + 16 <= 256:   # gathered layer-1 operand incl. its ones line
                 if l1op_in is not None and tuple(l1op_in.shape) != (k_img + 1, ld):
                     raise ValueError("l1op does not belong to these rows / features")
@@ -187,7 +255,7 @@ class _SAFunction(torch.autograd.Function):
                    x=xs, pos_src=pos_src, pos_dst=pos_dst, nbr=nbr, cnt=cnt, batch=batch, chans=chans, act=act,
                    eps=eps, momentum=momentum, ws=ws, bs=bs, gammas=gs, betas=bes, rmeans=(rm1, rm2),
                    rvars=(rv1, rv2), nbts=(nbt1, nbt2), out=out, arg=arg, h1=h1, h2=h2, bn=bn, rowmap=rowmap,
-                   acts=acts)
+                   acts=acts, out_bf16=out_bf16)
         a.g1_ready = 1 if (prec == PREC_BF16 and l1op_in is not None) else 0
         nbytes = lib.b2pn_sa_workspace_bytes(ctypes.byref(a), 0)
         if nbytes < 0:
@@ -203,16 +271,20 @@ class _SAFunction(torch.autograd.Function):
         ctx.has_x = x is not None
         ctx.x_needs_grad = x is not None and x.requires_grad
         ctx.row_capacity = None if rowmap is None else rowmap[3]
+        ctx.grad_dsts = grad_dsts
         rmt = (None, None, None, None) if rowmap is None else (rowmap[0], rowmap[1], rowmap[2], rowmap[4])
         at = (None, None, None) if acts is None else (acts + (None,))[:3]
         ctx.save_for_backward(xs, pos_src, pos_dst, nbr, cnt, batch, *ws, *bs, *gs, *bes, rm1, rv1, rm2, rv2,
                               arg, h1, h2, bn, *rmt, *at)
-        ctx.mark_non_differentiable(arg)
-        return out, arg
+        if out_bf16 is None:
+            ctx.mark_non_differentiable(arg)
+            return out, arg, None
+        ctx.mark_non_differentiable(arg, out_bf16)
+        return out, arg, out_bf16
 
     @staticmethod
     @torch.autograd.function.once_differentiable
-    def backward(ctx, grad_out, _grad_arg):
+    def backward(ctx, grad_out, _grad_arg=None, _grad_bf16=None):
         lib = _lib.lib()
         (xs, pos_src, pos_dst, nbr, cnt, batch, w1, w2, w3, b1, b2, b3, g1, g2, be1, be2, rm1, rv1, rm2, rv2,
          arg, h1, h2, bn, rgrp, row_src, num_rows, row_valid, a1, a2, l1op) = ctx.saved_tensors
@@ -223,10 +295,13 @@ class _SAFunction(torch.autograd.Function):
         chans = ctx.chans
         f32 = torch.float32
         grad_out = grad_out.to(f32).contiguous()
-        gw = [torch.empty_like(w) for w in (w1, w2, w3)]
-        gb = [torch.empty_like(b) for b in (b1, b2, b3)]
-        gg = [torch.empty_like(g) for g in (g1, g2)]
-        gbe = [torch.empty_like(b) for b in (be1, be2)]
+        # gradients land where the parameter arena wants them (optim.ParamArena) or in fresh tensors
+        d = ctx.grad_dsts if ctx.grad_dsts is not None else (None,) * 10
+        fresh = lambda dst, like: dst if dst is not None else torch.empty_like(like)  # noqa: E731
+        gw = [fresh(d[0], w1), fresh(d[4], w2), fresh(d[8], w3)]
+        gb = [fresh(d[1], b1), fresh(d[5], b2), fresh(d[9], b3)]
+        gg = [fresh(d[2], g1), fresh(d[6], g2)]
+        gbe = [fresh(d[3], be1), fresh(d[7], be2)]
         gx = torch.zeros(xs.shape, dtype=f32, device=dev) if ctx.x_needs_grad else None
         a = SaArgs()
         _fill_args(a, precision=prec, training=training, seg_mode=seg_mode, K=K, n_src=pos_src.shape[0], n_dst=n_dst,
@@ -249,15 +324,17 @@ class _SAFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             rc = lib.b2pn_sa_backward(ctypes.byref(a), ctypes.byref(g), torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, "b2pn_sa_backward")
-        return (None, None, None, gx, None, None, None, None, None, gw[0], gb[0], gg[0], gbe[0], gw[1], gb[1], gg[1], gbe[1],
-                gw[2], gb[2], None, None, None, None, None, None)
+        return (None, None, None, None, gx, None, None, None, None, None, gw[0], gb[0], gg[0], gbe[0], gw[1], gb[1], gg[1],
+                gbe[1], gw[2], gb[2], None, None, None, None, None, None)
 
 
 def sa_apply(mlp, x, pos_src, pos_dst, nbr, cnt, batch, *, seg_mode: int, K: int, n_dst: int, precision: int,
-             rowmap=None, l1op=None):
+             rowmap=None, l1op=None, x_bf16=None, want_bf16_out: bool = False):
     """Run one set-abstraction level with the parameters of ``mlp`` (a b2pn ``MLP`` of three Linear layers).
     ``rowmap`` / ``l1op``: the results of ``pack_rows(nbr, cnt, K)`` and ``gather_rows(x, ...)`` if the caller already
-    has them (bf16 path; ``l1op`` must have been built from this very ``x``)."""
+    has them (bf16 path; ``l1op`` must have been built from this very ``x``).  ``x_bf16``: a bf16 copy of ``x`` the
+    previous level's epilogue already wrote (saves the cast); ``want_bf16_out``: have this level write one too.
+    Returns (out, arg), or (out, arg, out_bf16 or None) with ``want_bf16_out``."""
     if len(mlp.lins) != 3 or len(mlp.norms) != 2:
         raise NotImplementedError("set-abstraction kernels are built for the reference's 3-layer MLPs with BatchNorm")
     if mlp.dropout != 0.0 and mlp.training:
@@ -266,11 +343,15 @@ def sa_apply(mlp, x, pos_src, pos_dst, nbr, cnt, batch, *, seg_mode: int, K: int
     cfg = (precision, bool(mlp.training), seg_mode, K, n_dst, act_code(mlp.act_name), float(n0.eps),
            float(n0.momentum if n0.momentum is not None else 0.1))
     l0, l1, l2 = mlp.lins
-    out, arg = _SAFunction.apply(cfg, rowmap, l1op if rowmap is not None else None, x, pos_src, pos_dst, nbr, cnt, batch,
-                                 l0.weight, l0.bias, n0.weight, n0.bias, l1.weight, l1.bias, n1.weight, n1.bias,
-                                 l2.weight, l2.bias, n0.running_mean, n0.running_var, n0.num_batches_tracked,
-                                 n1.running_mean, n1.running_var, n1.num_batches_tracked)
-    return out, arg
+    params = (l0.weight, l0.bias, n0.weight, n0.bias, l1.weight, l1.bias, n1.weight, n1.bias, l2.weight, l2.bias)
+    dsts = tuple(grad_dst(p) for p in params) if torch.is_grad_enabled() else None
+    if dsts is not None and all(t is None for t in dsts):
+        dsts = None
+    extra = (dsts, x_bf16, bool(want_bf16_out))
+    res = _SAFunction.apply(cfg, rowmap, l1op if rowmap is not None else None, extra, x, pos_src, pos_dst, nbr, cnt, batch,
+                            *params, n0.running_mean, n0.running_var, n0.num_batches_tracked,
+                            n1.running_mean, n1.running_var, n1.num_batches_tracked)
+    return res if want_bf16_out else res[:2]
 
 
 def bf16_available() -> bool:

@@ -13,7 +13,11 @@
  *   - `ptr` arrays are CSR-style cloud offsets (int64, B+1 entries), as torch_cluster takes.
  *   - return value: 0 = ok, <0 = B2PN_E* argument error (nothing enqueued), >0 = cudaError_t
  *     reported by the launch.  b2pn_error_string() renders either.
- *   - re-entrant: no global mutable state besides one-time per-device kernel attributes.
+ *   - re-entrant: there is NO process-wide setting.  Every option that shapes a launch (SM cap, deterministic
+ *     reductions, kernel variant, random-number state) is a field of the call's argument struct, so the reference's
+ *     thread-per-GPU callers (torch_geometric.nn.DataParallel, /root/reference/main.py:140) can drive several
+ *     devices from several host threads.  The only static data are per-device caches of immutable facts (SM count,
+ *     "dynamic shared memory attribute already raised") and the launch counter below (atomic).
  */
 #ifndef B2PN_H_
 #define B2PN_H_
@@ -24,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B2PN_ABI_VERSION 5
+#define B2PN_ABI_VERSION 6
 #define B2PN_OK 0
 #define B2PN_EINVAL (-1)   /* null pointer / negative size / bad flag            */
 #define B2PN_ENOTSUP (-2)  /* shape outside what the sm_100a kernels are built for */
@@ -35,25 +39,6 @@ int b2pn_abi_version(void);
 const char *b2pn_error_string(int code);
 /* kernels enqueued by this library so far in this process (bench.py's gpu_launches) */
 int64_t b2pn_launch_count(void);
-
-/*
- * Cap the grid of the persistent tensor-core kernels at n CTAs (0 = one per SM, the default).  Used when
- * the grouping kernels of the NEXT batch run on a second stream: farthest-point sampling occupies one SM per
- * cloud for its whole (latency-bound) duration, and a persistent kernel must not wait for those SMs.
- * Process-wide setting; change it only between steps.
- */
-int b2pn_set_sm_limit(int32_t n);
-
-/*
- * Weight-gradient summation of the bf16 set-abstraction backward.  0 (default): the row splits of a dW GEMM add their
- * partial sums into one buffer with fp32 atomics (red.global.add.v4.f32) -- fastest, but the order of the additions,
- * hence the last bits of the gradients, varies from run to run (as it does in the reference's scatter / cuBLAS
- * kernels).  1: every split keeps its own partial and a reduction kernel adds them in a fixed order: bit-reproducible
- * dW sums for ~1 % of the step time.  (The scatter-add of a level's feature gradient into its source points stays
- * atomic in both modes, as in torch_scatter: weight gradients of levels BELOW such a scatter inherit its rounding
- * order.)  Process-wide; returns the previous setting.
- */
-int b2pn_set_deterministic(int32_t on);
 
 /* samples per cloud: ceil(float32(n) * float32(ratio)) -- torch_cluster.fps sizing
  * (reached from /root/reference/pointnet2_regressor.py:13).  Host-side helper. */
@@ -70,11 +55,22 @@ int64_t b2pn_fps_num_samples(int64_t n, float ratio);
  *   out_idx  [M]   i64 GLOBAL point indices, per cloud in selection order (first = start)
  *   out_pos  [M,3] f32 pos[out_idx]   (optional, may be NULL; fuses pointnet2_regressor.py:19)
  *   out_batch[M]   i64 cloud id       (optional, may be NULL; fuses batch[idx] of :19)
+ *   opts     host struct or NULL (defaults): kernel variant and the in-kernel random start (below)
  * Distances are ((dx*dx+dy*dy)+dz*dz) in separately rounded fp32; ties -> lowest index.
  */
+typedef struct b2pn_fps_options {
+    int32_t cluster;             /* CTAs per cloud: 0 = auto, 1/2/4/8/16; -1 / -2 = the pruned / Morton-sorted variants */
+    int32_t threads;             /* threads per CTA: 0 = auto, 256/512/1024 (640/768 for the sorted variant)           */
+    uint64_t seed;               /* random_start=True of torch_cluster.fps (the PyG default the reference runs with,    */
+    int64_t *rng_state;          /* SURVEY.md A.1): with start == NULL and rng_state != NULL (DEVICE, 2 x i64, zeroed   */
+                                 /* once by the caller) cloud b starts at b2pn_fps_random_start(seed, rng_state[0], b,  */
+                                 /* n_b); the kernel advances rng_state[0] by one per call (graph replays included)     */
+} b2pn_fps_options;
 int b2pn_fps_f32(const float *pos, const int64_t *ptr, const int64_t *out_ptr, const int64_t *start,
                  int32_t B, int64_t max_n, int64_t *out_idx, float *out_pos, int64_t *out_batch,
-                 b2pn_stream_t stream);
+                 const b2pn_fps_options *opts, b2pn_stream_t stream);
+/* host-side restatement of the kernel's start draw: floor(u * n), u in [0,1) a hash of (seed, call, cloud) */
+int64_t b2pn_fps_random_start(uint64_t seed, int64_t call, int32_t cloud, int64_t n);
 
 /*
  * Farthest-point sampling in float64: the offline resampler that prepares the training clouds.  Replaces the numpy
@@ -86,9 +82,6 @@ int b2pn_fps_f32(const float *pos, const int64_t *ptr, const int64_t *out_ptr, c
  */
 int b2pn_fps_f64(const double *pos, const int64_t *ptr, const int64_t *out_ptr, const int64_t *start, int32_t B,
                  int64_t *out_idx, double *dist_workspace, b2pn_stream_t stream);
-
-/* Force a kernel variant (benchmark sweeps): cluster size (1,2,4,8,16), threads per CTA; 0 = auto. */
-int b2pn_fps_set_variant(int32_t cluster, int32_t threads);
 
 /*
  * Segmented radius ball query with a neighbour cap.  Replaces
@@ -209,6 +202,18 @@ typedef struct b2pn_sa_args {
      * b2pn_sa_gather_rows: set g1_ready = 1 and forward skips the gather), read by backward.                    */
     void *g1;
     int32_t g1_ready;
+    /* per-call launch options (there is no process-wide state)                                              */
+    int32_t sm_limit;            /* > 0: the persistent tensor-core kernels of THIS call take at most this many CTAs
+                                    (0 = one per SM).  Used while the grouping kernels of the next batch run on a second
+                                    stream: farthest-point sampling holds one SM per cloud for its whole latency-bound
+                                    duration and a persistent kernel must not wait for those SMs                      */
+    int32_t deterministic;       /* PREC_BF16 backward.  0: the row splits of a dW GEMM add their partial sums into one
+                                    buffer with fp32 atomics (red.global.add.v4.f32): fastest, last bits vary from run to
+                                    run (as in the reference's scatter / cuBLAS kernels).  1: per-split partials summed
+                                    in a fixed order and the grad_x scatter done by one owner per source row: bit-
+                                    reproducible gradients                                                            */
+    void *out_bf16;              /* PREC_BF16, optional: a bf16 copy of `out` [n_dst, c3] written by the same epilogue --
+                                    the next level's gather reads it (half the bytes, no separate cast kernel)         */
 } b2pn_sa_args;
 
 typedef struct b2pn_sa_grads {
@@ -271,6 +276,15 @@ int b2pn_head_backward(const b2pn_head_args *args, const b2pn_head_grads *grads,
  * its gradient grad[b,c] = 2 w[c] (pred - y) / B (grad may be NULL).  fp32, fixed summation order. */
 int b2pn_weighted_mse(const float *pred, const float *y, const float *w, int32_t B, int32_t C, float *loss,
                       float *grad, b2pn_stream_t stream);
+
+/* The optimiser step of /root/reference/main.py:84,172 -- torch.optim.Adam(params, lr, weight_decay): L2 penalty added
+ * to the gradient, bias-corrected first / second moments, no amsgrad -- as ONE launch over a flat arena holding every
+ * parameter (dl_biomass_b200/optim.py): param, grad, exp_avg, exp_avg_sq are parallel fp32 buffers of n elements
+ * (n % 4 == 0, 16-byte aligned).  grad is multiplied by grad_scale first (1/world_size after a SUM all-reduce).
+ * state: DEVICE, 2 x i64 zero-initialised: [0] steps taken so far (the kernel uses state[0] + 1 in the bias corrections
+ * and advances it, so a CUDA-graph replay is a real optimiser step), [1] scratch. */
+int b2pn_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, float grad_scale, int64_t *state, b2pn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Training-time augmentation on the device: point_removal -> random_noise -> rotate_points of

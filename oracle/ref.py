@@ -34,6 +34,18 @@ _LIB_PATH = os.path.join(_HERE, "libb2pn_oracle.so")
 _lib = None
 
 
+
+def ptr_from_batch(batch: torch.Tensor, num_clouds=None) -> torch.Tensor:
+    """``ptr`` from a sorted ``batch`` vector, as PyG's fps wrapper derives it (scatter_add of ones,
+    cumsum).  The oracle's own copy: nothing under oracle/ imports the product package."""
+    if num_clouds is None:
+        num_clouds = int(batch.max().item()) + 1 if batch.numel() else 0
+    counts = torch.bincount(batch, minlength=num_clouds)
+    ptr = torch.zeros(num_clouds + 1, dtype=torch.int64)
+    ptr[1:] = torch.cumsum(counts, 0)
+    return ptr
+
+
 def build_oracle(force: bool = False) -> str:
     src = os.path.join(_HERE, "b2pn_oracle.c")
     if force or not os.path.exists(_LIB_PATH) or (
@@ -245,7 +257,6 @@ class SAModuleRef(torch.nn.Module):
         self.conv.local_nn = nn  # same state_dict keys as PointNetConv: conv.local_nn.*
 
     def forward(self, x, pos, batch, ptr=None, start=None):
-        from dl_biomass_b200.data import ptr_from_batch
         if ptr is None:
             ptr = ptr_from_batch(batch)
         idx = fps_ref(pos, ptr, self.ratio, start)                              # :13
@@ -286,7 +297,6 @@ class NetRef(torch.nn.Module):
         self.mlp = MLPRef([1024 * nm, 128 * nm, 128 * nm, 4], act=None, dropout=dropout_probability)
 
     def forward(self, data, start=None):
-        from dl_biomass_b200.data import ptr_from_batch
         ptr = getattr(data, "ptr", None)
         if ptr is None:
             ptr = ptr_from_batch(data.batch)

@@ -38,8 +38,15 @@ def test_header_symbols_exported_and_bound(built_lib):
 
 def test_argument_errors_need_no_gpu(built_lib):
     h = built_lib.lib()
-    assert h.b2pn_fps_f32(None, None, None, None, 2, 10, None, None, None, None) == -1
-    assert h.b2pn_fps_f32(None, None, None, None, 0, 0, None, None, None, None) == 0
+    assert h.b2pn_fps_f32(None, None, None, None, 2, 10, None, None, None, None, None) == -1
+    assert h.b2pn_fps_f32(None, None, None, None, 0, 0, None, None, None, None, None) == 0
+    import ctypes
+    bad = built_lib.FpsOptions(3, 0, 0, None)                 # no such cluster size
+    assert h.b2pn_fps_f32(None, None, None, None, 0, 0, None, None, None, ctypes.byref(bad), None) == -1
+    assert 0 <= h.b2pn_fps_random_start(7, 0, 3, 1000) < 1000 and h.b2pn_fps_random_start(7, 0, 3, 0) == -1
+    assert h.b2pn_adam_step(None, None, None, None, 8, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0, None, None) == -1
+    assert h.b2pn_adam_step(None, None, None, None, 6, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0, None, None) == -1   # n % 4
+    assert h.b2pn_adam_step(None, None, None, None, 0, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0, None, None) == 0
     assert h.b2pn_ball_query_f32(None, None, None, None, 1, 5, 5, 2.0, 64, None, None, None) == -1
     assert h.b2pn_ball_query_f32(None, None, None, None, 1, 5, 5, 2.0, 0, None, None, None) == -1
 
@@ -52,6 +59,15 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
                 assert "libb2pn_oracle" not in txt, f
+
+
+def test_oracle_never_imports_product():
+    """The oracle is an independent restatement: oracle/ref.py and oracle/augment_ref.py must not lean on the package they
+    check (the golden-vector generator scripts may use its synthetic-cloud helper)."""
+    for f in ("ref.py", "augment_ref.py", "b2pn_oracle.c"):
+        txt = open(os.path.join(ROOT, "oracle", f)).read()
+        assert not re.search(r"^\s*(from|import)\s+dl_biomass_b200\b", txt, flags=re.M), f
+        assert "libb2pn.so" not in txt, f
 
 
 def test_cpu_tensors_fail_loudly(built_lib):
@@ -94,8 +110,11 @@ def test_host_side_sizing_helpers(built_lib):
     assert h.b2pn_pack_rows_workspace_bytes(24000) >= 24000 * 4
     assert h.b2pn_ball_query_workspace_bytes(12, 120000) >= 120000 * 4 + 12 * 8192 * 4
     assert h.b2pn_ball_query_workspace_bytes(-1, 10) == -1
-    assert h.b2pn_set_sm_limit(-3) == -1 and h.b2pn_set_sm_limit(0) == 0
-    assert h.b2pn_set_deterministic(1) == 0 and h.b2pn_set_deterministic(0) == 1 and h.b2pn_set_deterministic(0) == 0
+    neg = built_lib.SaArgs()                                  # launch options are per-call fields, checked per call
+    neg.precision, neg.sm_limit = 1, -3
+    assert h.b2pn_sa_forward(ctypes.byref(neg), None) == -1 and h.b2pn_sa_workspace_bytes(ctypes.byref(neg), 0) == -1
+    nm = subprocess.run(["nm", "-D", "--defined-only", built_lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "b2pn_set_" not in nm and "set_variant" not in nm   # no process-wide setters left in the ABI
     assert h.b2pn_head_forward(None, None) == -1 and h.b2pn_head_backward(None, None, None) == -1
     assert h.b2pn_sa_gather_rows(None, None) == -1
     sa_args = built_lib.SaArgs()                              # fp32 levels gather inside their loaders

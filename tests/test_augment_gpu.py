@@ -87,3 +87,19 @@ def test_many_clouds_and_training_on_augmented_batches(cuda_device):
         bt = cache.batch([1, 7, 9, 30], rng, seed=13, epoch=ep)
         losses.append(float(train_step(net, opt, bt)))
     assert all(np.isfinite(losses))
+
+
+def test_copies_of_a_cloud_in_one_epoch_are_augmented_independently(cuda_device):
+    """The reference's training set holds every cloud 1 + num_augs times per epoch, each copy augmented on its own
+    (/root/reference/main.py:100-112): two records of the SAME cloud in the same epoch must get different per-point
+    streams (different permutations / duplicated points), not just different scalar draws."""
+    clouds = _clouds([800], 1, seed=5)
+    cache = CloudCache(clouds, cuda_device)
+    rng = random.Random(3)
+    plan = cache.plan([0, 0, 0], rng, epoch=1)
+    assert len({r[6] for r in plan}) == 3                     # three distinct generator streams
+    b = cache.batch(None, seed=9, plan=plan, return_source=True)
+    src = b.source_index.cpu().numpy()
+    off = np.cumsum([0] + b.cloud_sizes)
+    firsts = [tuple(src[off[i]:off[i] + 32].tolist()) for i in range(3)]
+    assert len(set(firsts)) == 3                              # different point orders, not nested prefixes of one

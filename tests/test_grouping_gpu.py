@@ -13,19 +13,19 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def _run_level(pos_cpu, sizes, ratio, r, dev, start=None, K=64):
+def _run_level(pos_cpu, sizes, ratio, r, dev, start=None, K=64, variant=(0, 0)):
     lv = ops.build_levels(sizes, [ratio], dev)
     pos = pos_cpu.to(dev)
     st = None if start is None else start.to(dev)
-    idx, pos_out, batch_out = ops.fps(pos, lv[0], lv[1], st)
+    idx, pos_out, batch_out = ops.fps(pos, lv[0], lv[1], st, cluster=variant[0], threads=variant[1])
     nbr, cnt = ops.ball_query(pos, pos_out, lv[0], lv[1], r, K)
     torch.cuda.synchronize()
     return lv, idx.cpu(), pos_out.cpu(), batch_out.cpu(), nbr.cpu(), cnt.cpu()
 
 
-def _check_level(pos_cpu, ptr, ratio, r, dev, start=None, K=64):
+def _check_level(pos_cpu, ptr, ratio, r, dev, start=None, K=64, variant=(0, 0)):
     sizes = (ptr[1:] - ptr[:-1]).tolist()
-    lv, idx, pos_out, batch_out, nbr, cnt = _run_level(pos_cpu, sizes, ratio, r, dev, start, K)
+    lv, idx, pos_out, batch_out, nbr, cnt = _run_level(pos_cpu, sizes, ratio, r, dev, start, K, variant)
     want_idx = ref.fps_ref(pos_cpu, ptr, ratio, start)
     assert torch.equal(idx, want_idx), f"fps mismatch at {int((idx != want_idx).nonzero()[0])}"
     assert torch.equal(pos_out, pos_cpu[want_idx])
@@ -69,12 +69,8 @@ def test_ties_and_duplicates_all_variants(cuda_device, cluster, threads):
     pts = torch.from_numpy(rng.integers(-16, 16, size=(4000, 3)).astype(np.float32) / 2.0)
     pts = torch.cat([pts, pts[:700]], 0)  # duplicates
     ptr = torch.tensor([0, 1700, 4700])
-    try:
-        _lib.check(_lib.lib().b2pn_fps_set_variant(cluster, threads), "set_variant")
-        _check_level(pts, ptr, 0.3, 2.0, cuda_device)
-        _check_level(pts, ptr, 0.95, 1.0, cuda_device)
-    finally:
-        _lib.lib().b2pn_fps_set_variant(0, 0)
+    _check_level(pts, ptr, 0.3, 2.0, cuda_device, variant=(cluster, threads))   # the variant is a per-call option
+    _check_level(pts, ptr, 0.95, 1.0, cuda_device, variant=(cluster, threads))
 
 
 @pytest.mark.parametrize("n,r,K", [(3000, 2.0, 64), (3000, 0.3, 64), (3000, 9.0, 64), (3000, 40.0, 64), (5000, 2.0, 8),
@@ -92,15 +88,12 @@ def test_grid_ball_query_equals_scan(cuda_device, n, r, K):
     _, qpos, _ = ops.fps(pos, lv[0], lv[1])
     old = ops.GRID_MIN_SOURCES
     try:
-        ops.set_ball_query_mode("scan")
-        nbr0, cnt0 = ops.ball_query(pos, qpos, lv[0], lv[1], r, K)
-        ops.set_ball_query_mode("auto")
+        nbr0, cnt0 = ops.ball_query(pos, qpos, lv[0], lv[1], r, K, mode="scan")
         ops.GRID_MIN_SOURCES = 0
-        nbr1, cnt1 = ops.ball_query(pos, qpos, lv[0], lv[1], r, K)
+        nbr1, cnt1 = ops.ball_query(pos, qpos, lv[0], lv[1], r, K, mode="auto")
         torch.cuda.synchronize()
     finally:
         ops.GRID_MIN_SOURCES = old
-        ops.set_ball_query_mode("auto")
     assert torch.equal(cnt0, cnt1)
     assert torch.equal(nbr0, nbr1)
     # and the scan itself against the oracle
@@ -146,13 +139,49 @@ def test_fps_variants_agree(cuda_device, cluster, threads):
     b = Batch.from_data_list(synthetic_clouds(77, 5, 6000, 1, True))
     want = ref.fps_ref(b.pos, b.ptr, 0.2)
     lv = ops.build_levels((b.ptr[1:] - b.ptr[:-1]).tolist(), [0.2], cuda_device)
-    try:
-        _lib.check(_lib.lib().b2pn_fps_set_variant(cluster, threads), "set_variant")
-        idx, _, _ = ops.fps(b.pos.to(cuda_device), lv[0], lv[1])
-        torch.cuda.synchronize()
-    finally:
-        _lib.lib().b2pn_fps_set_variant(0, 0)
+    idx, _, _ = ops.fps(b.pos.to(cuda_device), lv[0], lv[1], cluster=cluster, threads=threads)
+    torch.cuda.synchronize()
     assert torch.equal(idx.cpu(), want)
+
+
+def test_random_start_is_drawn_in_the_kernel_and_advances(cuda_device):
+    """random_start=True of torch_cluster.fps: with an rng_state the kernel draws floor(u*n) per cloud
+    from (seed, call counter, cloud), bumps the counter once per launch (so CUDA-graph replays draw fresh starts), and
+    the result equals FPS from that explicit start."""
+    b = Batch.from_data_list(synthetic_clouds(91, 4, 900, 1, True))
+    sizes = b.cloud_sizes
+    lv = ops.build_levels(sizes, [0.2], cuda_device)
+    pos = b.pos.to(cuda_device)
+    state = torch.zeros(2, dtype=torch.int64, device=cuda_device)
+    seed = 123456789
+    lib = _lib.lib()
+    seen = []
+    for call in range(3):
+        idx, _, _ = ops.fps(pos, lv[0], lv[1], None, seed=seed, rng_state=state)
+        torch.cuda.synchronize()
+        assert state.tolist() == [call + 1, 0]
+        start = torch.tensor([lib.b2pn_fps_random_start(seed, call, c, n) for c, n in enumerate(sizes)])
+        assert all(0 <= int(s) < n for s, n in zip(start, sizes))
+        first = idx.cpu()[lv[1].ptr.cpu()[:-1]] - b.ptr[:-1]
+        assert torch.equal(first, start)
+        assert torch.equal(idx.cpu(), ref.fps_ref(b.pos, b.ptr, 0.2, start))
+        seen.append(tuple(start.tolist()))
+    assert len(set(seen)) == 3          # fresh starts every call
+    # CUDA-graph replays advance the counter too
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream(cuda_device)
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        ops.fps(pos, lv[0], lv[1], None, seed=seed, rng_state=state)
+    torch.cuda.current_stream().wait_stream(s)
+    with torch.cuda.graph(g):
+        gidx, _, _ = ops.fps(pos, lv[0], lv[1], None, seed=seed, rng_state=state)
+    firsts = []
+    for _ in range(2):
+        g.replay()
+        torch.cuda.synchronize()
+        firsts.append(tuple((gidx.cpu()[lv[1].ptr.cpu()[:-1]] - b.ptr[:-1]).tolist()))
+    assert state.tolist() == [6, 0] and firsts[0] != firsts[1]
 
 
 def test_dense_cloud_properties(cuda_device):

@@ -1,0 +1,97 @@
+"""GPU parity of the WHOLE network (forward + backward of /root/reference/pointnet2_regressor.py:52-58 under the loss of
+main.py:157-169) on the HEADLINE shape of BASELINE.json configs[1]: 12 clouds x 10 000 points, fixed and ragged.
+
+Truth is the CPU oracle evaluated in float64.  Tolerances (north_star): fp32 mode 1e-4 relative on outputs and gradients,
+bf16 mode 2e-2 on the regression outputs.  A gradient tensor is held to 1e-4 unless the oracle's OWN float32 evaluation
+(the precision the reference runs in) is further than that from the float64 truth: such a tensor is ill-conditioned at
+float32 in ANY implementation, and it is then held to twice the float32 oracle's error instead (printed)."""
+import pytest
+import torch
+
+from oracle import ref
+from dl_biomass_b200.data import Batch, synthetic_clouds
+from dl_biomass_b200.pointnet2_regressor import Net
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(got, want):
+    got, want = got.detach().double().cpu(), want.detach().double().cpu()
+    return float((got - want).abs().max() / want.abs().max().clamp_min(1e-300))
+
+
+def _oracle(b, dtype):
+    net = ref.seeded_init_(ref.NetRef(1, "ReLU", 0, 0.0), seed=7).to(dtype)
+    net.train()
+    data = type("D", (), {})()
+    data.x, data.pos, data.batch, data.ptr = b.x.to(dtype), b.pos.to(dtype), b.batch, b.ptr
+    out = net(data)
+    loss = ref.weighted_mse(out, b.y.to(dtype))
+    loss.backward()
+    return net, out.detach(), {k: p.grad.detach() for k, p in net.named_parameters()}
+
+
+@pytest.fixture(scope="module", params=[False, True], ids=["fixed", "ragged"])
+def headline(request):
+    b = Batch.from_data_list(synthetic_clouds(1234, 12, 10000, 1, request.param))
+    n64, out64, g64 = _oracle(b, torch.float64)
+    n32, out32, g32 = _oracle(b, torch.float32)
+    return b, n32, out64, g64, out32, g32
+
+
+def _gpu(b, net32, precision, dev):
+    net = Net(1, "ReLU", 0, 0.0, precision=precision)
+    net.load_state_dict(net32.state_dict())
+    net = net.to(dev).set_random_start(False)
+    net.train()
+    out = net(b.to(dev))
+    loss = ref.weighted_mse(out, b.y.to(dev))
+    loss.backward()
+    torch.cuda.synchronize()
+    return net, out.detach(), {k: p.grad.detach() for k, p in net.named_parameters()}
+
+
+@pytest.mark.timeout(900)
+def test_net_fp32_headline_shape(cuda_device, headline):
+    b, n32, out64, g64, out32, g32 = headline
+    net, out, g = _gpu(b, n32, "fp32", cuda_device)
+    e_out = rel_err(out, out64)
+    print(f"fp32 12x10000 out rel err vs f64 oracle: {e_out:.3e} (f32 oracle: {rel_err(out32, out64):.3e})")
+    assert e_out < 1e-4
+    scale = max(float(v.abs().max()) for v in g64.values())
+    worst, relaxed = 0.0, []
+    for k, want in g64.items():
+        if float(want.abs().max()) < 1e-7 * scale:   # biases in front of a BatchNorm: exactly 0 in theory
+            continue
+        e, e_ref = rel_err(g[k], want), rel_err(g32[k], want)
+        bound = 1e-4 if e_ref <= 1e-4 else 2.0 * e_ref
+        if e_ref > 1e-4:
+            relaxed.append((k, e, e_ref))
+        worst = max(worst, e)
+        assert e <= bound, (k, e, e_ref)
+    print(f"fp32 12x10000 worst grad rel err vs f64 oracle: {worst:.3e}; tensors ill-conditioned at f32 "
+          f"(f32 oracle itself > 1e-4): {[(k, f'{e:.2e}', f'{r:.2e}') for k, e, r in relaxed]}")
+    for (k, v), (_, vr) in zip(net.named_buffers(), n32.named_buffers()):
+        assert rel_err(v.float(), vr.float()) < 1e-4, k
+
+
+@pytest.mark.timeout(900)
+def test_net_bf16_headline_shape(cuda_device, headline):
+    b, n32, out64, g64, out32, g32 = headline
+    net, out, g = _gpu(b, n32, "bf16", cuda_device)
+    e_out = rel_err(out, out64)
+    print(f"bf16 12x10000 out rel err vs f64 oracle: {e_out:.3e}  (bound 2e-2, margin {2e-2 / max(e_out, 1e-30):.2f}x)")
+    assert e_out < 2e-2
+    cos, rels = [], {}
+    for k, want in g64.items():
+        a, r = g[k].double().cpu().flatten(), want.flatten()
+        assert torch.isfinite(a).all(), k
+        if float(r.abs().max()) < 1e-7 * max(float(v.abs().max()) for v in g64.values()):
+            continue
+        cos.append(float((a @ r) / (a.norm() * r.norm()).clamp_min(1e-300)))
+        rels[k] = float((a - r).norm() / r.norm())
+    worst = max(rels, key=rels.get)
+    print(f"bf16 12x10000 grads vs f64 oracle: cosine min {min(cos):.4f} mean {sum(cos) / len(cos):.4f}; "
+          f"worst relative L2 error {rels[worst]:.3e} ({worst})")
+    # bf16 activations flip ReLU masks / arg-max winners of near-ties, so gradients agree in direction, not to 2e-2
+    assert min(cos) > 0.9 and sum(cos) / len(cos) > 0.98, (min(cos), rels)

@@ -12,6 +12,9 @@ from dl_biomass_b200.pointnet2_regressor import MLP, Net
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
+# run-to-run spread allowed on the bf16 level-1 weight gradients in the DEFAULT (atomic) mode, relative to the largest
+# level-1 gradient: measured over 20 runs in profiles/r02_grad_spread.md; the deterministic mode is held to bit-equality
+SA1_SPREAD_BOUND = 2e-2
 
 
 def rel_err(got, want):
@@ -381,24 +384,29 @@ def test_net_train_step_bf16_vs_oracle(cuda_device):
     assert min(cos) > 0.7 and sum(cos) / len(cos) > 0.95, cos
 
 
-def test_graphed_train_step_matches_eager(cuda_device):
-    """train.GraphedTrainStep (one CUDA-graph replay per iteration) walks the same trajectory as eager launches."""
-    from dl_biomass_b200.train import GraphedTrainStep, make_optimizer, train_step
+def _make_opt(kind, net, graph):
+    from dl_biomass_b200.train import make_optimizer
+    # "flat": optim.FlatAdam over the parameter arena (one libb2pn launch); "torch": ATen's fused Adam
+    return make_optimizer(net) if kind == "flat" else make_optimizer(net.parameters(), capturable=graph)
+
+
+@pytest.mark.parametrize("opt_kind", ["flat", "torch"])
+def test_graphed_train_step_matches_eager(cuda_device, opt_kind):
+    """train.GraphedTrainStep (one CUDA-graph replay per iteration) walks the same trajectory as eager launches, and
+    BUILDING it does not train: warm-up and capture leave weights, BatchNorm buffers and optimiser state untouched."""
+    from dl_biomass_b200.train import GraphedTrainStep, train_step
     batches = [Batch.from_data_list(synthetic_clouds(900 + 7 * i, 4, 512, 1, False)).to(cuda_device) for i in range(3)]
     losses = {}
     for mode in ("eager", "graph"):
         torch.manual_seed(3)
         net = Net(1, "ReLU", 0, 0.0, precision="bf16").to(cuda_device).set_random_start(False)
         net.train()
-        opt = make_optimizer(net.parameters(), capturable=(mode == "graph"))
+        opt = _make_opt(opt_kind, net, mode == "graph")
         if mode == "graph":
             state = {k: v.clone() for k, v in net.state_dict().items()}
-            step = GraphedTrainStep(net, opt, batches[0], warmup=1)   # warm-up + capture already trained a little:
-            net.load_state_dict(state)                                # rewind the weights and the optimiser state
-            for st in opt.state.values():
-                for v in st.values():
-                    if torch.is_tensor(v):
-                        v.zero_()
+            step = GraphedTrainStep(net, opt, batches[0], warmup=2)
+            for k, v in net.state_dict().items():
+                assert torch.equal(v, state[k]), f"building the stepper changed {k}"
             assert step.launches_per_replay > 20
             losses[mode] = [float(step(b)) for b in batches]
         else:
@@ -408,12 +416,13 @@ def test_graphed_train_step_matches_eager(cuda_device):
         assert abs(a - b) <= 2e-3 * max(abs(a), 1e-6)
 
 
-@pytest.mark.parametrize("graph", [False, True])
-def test_pipelined_train_step_matches_eager(cuda_device, graph):
+@pytest.mark.parametrize("graph,opt_kind", [(False, "flat"), (True, "flat"), (True, "torch")])
+def test_pipelined_train_step_matches_eager(cuda_device, graph, opt_kind):
     """train.PipelinedTrainStep (FPS of the next batch on a second stream, optionally one CUDA graph per step)
-    trains exactly like the plain loop, one call later."""
-    from dl_biomass_b200 import _lib
-    from dl_biomass_b200.train import PipelinedTrainStep, make_optimizer, train_step
+    trains exactly like the plain loop, one call later; building it does not train; flush() trains the last batch, so
+    every batch is trained on exactly once (/root/reference/main.py:150-172)."""
+    from dl_biomass_b200 import sa
+    from dl_biomass_b200.train import PipelinedTrainStep, train_step
     batches = [Batch.from_data_list(synthetic_clouds(500 + 11 * i, 4, 512, 1, False)).to(cuda_device) for i in range(4)]
 
     def fresh():
@@ -423,28 +432,31 @@ def test_pipelined_train_step_matches_eager(cuda_device, graph):
         return net
 
     net = fresh()
-    opt = make_optimizer(net.parameters())
-    want = [float(train_step(net, opt, b)) for b in batches[:3]]
+    opt = _make_opt(opt_kind, net, False)
+    want = [float(train_step(net, opt, b)) for b in batches]
+    want_state = {k: v.clone() for k, v in net.state_dict().items()}
 
     net = fresh()
-    opt = make_optimizer(net.parameters(), capturable=graph)
+    opt = _make_opt(opt_kind, net, graph)
     state = {k: v.clone() for k, v in net.state_dict().items()}
     stepper = PipelinedTrainStep(net, opt, batches[0], graph=graph, warmup=1)
     try:
-        if graph:  # warm-up and capture trained a little: rewind weights and optimiser state
-            net.load_state_dict(state)
-            for st in opt.state.values():
-                for v in st.values():
-                    if torch.is_tensor(v):
-                        v.zero_()
+        for k, v in net.state_dict().items():
+            assert torch.equal(v, state[k]), f"building the stepper changed {k}"
         got = [float(stepper.step(b)) for b in batches[1:4]]
         assert stepper.launches_per_step > 20
+        got.append(float(stepper.flush()))
+        with pytest.raises(RuntimeError):
+            stepper.step(batches[0])
     finally:
         stepper.close()
     print(want, got)
     for a, b in zip(want, got):
         assert abs(a - b) <= 2e-3 * max(abs(a), 1e-6)
-    assert _lib.lib().b2pn_set_sm_limit(0) == 0
+    for k, v in net.state_dict().items():     # same trajectory: BatchNorm step counters agree exactly, weights closely
+        if "num_batches_tracked" in k:
+            assert torch.equal(v, want_state[k]), k
+    assert sa.launch_options()[0] == 0
 
 
 def test_pipelined_eager_step_takes_ragged_batches(cuda_device):
@@ -501,18 +513,18 @@ def test_precomputed_grouping_gives_identical_results(cuda_device, precision):
         # level 2's atomic scatter-add, and its BatchNorm backward (differences of nearly equal sums) amplifies that
         # rounding freedom (bf16 path; the fp32 path keeps the tight bound)
         if precision == "bf16" and n.startswith("sa1_module"):
-            assert float((ga - gb).abs().max()) <= 2e-2 * scale1, n
+            assert float((ga - gb).abs().max()) <= SA1_SPREAD_BOUND * scale1, n
         else:
             assert float((ga - gb).abs().max()) <= 1e-4 * float(ga.abs().max()) + 1e-6 * scale, n
 
 
-def test_deterministic_mode_gives_bit_identical_weight_gradients(cuda_device):
-    """b2pn_set_deterministic(1): the dW split partials are summed in a fixed order -> bit-identical weight gradients
-    from run to run wherever no scatter-add sits upstream (levels 2, 3 and the head; level 1 receives the feature
-    gradient that level 2 scatter-adds into the source points with atomics, like torch_scatter does); the default
-    (fp32 atomics for the dW sums too) agrees to rounding."""
-    from dl_biomass_b200 import _lib
-    lib = _lib.lib()
+def test_deterministic_mode_gives_bit_identical_gradients(cuda_device):
+    """b2pn_sa_args::deterministic: the dW split partials are summed in a fixed order and the feature gradient a level
+    scatters into its source points is accumulated in 64-bit fixed point (integer atomics are order-independent), so
+    EVERY gradient of the network is bit-identical from run to run -- level 1 included, which sits below level 2's
+    scatter.  The default mode (fp32 atomics) agrees with it to rounding; its measured run-to-run spread is in
+    profiles/r02_grad_spread.md."""
+    from dl_biomass_b200 import sa
     b = Batch.from_data_list(synthetic_clouds(77, 3, 1024, 1, False)).to(cuda_device)
     torch.manual_seed(2)
     net = Net(1, "ReLU", 0, 0.0, precision="bf16").to(cuda_device).set_random_start(False)
@@ -526,20 +538,16 @@ def test_deterministic_mode_gives_bit_identical_weight_gradients(cuda_device):
         net(b).square().sum().backward()
         return [p.grad.detach().clone() for p in net.parameters()]
 
-    try:
-        assert lib.b2pn_set_deterministic(1) == 0
-        g1, g2 = grads(), grads()
-    finally:
-        lib.b2pn_set_deterministic(0)
+    with sa.options(deterministic=True):
+        g1, g2, g2b = grads(), grads(), grads()
+    assert sa.launch_options() == (0, 0)
     g3 = grads()
     scale = max(float(g.abs().max()) for g in g1)
     scale1 = max(float(g.abs().max()) for n, g in zip(names, g1) if n.startswith("sa1_module"))
-    for n, a, c, e in zip(names, g1, g2, g3):
+    for n, a, c, c2, e in zip(names, g1, g2, g2b, g3):
+        assert torch.equal(a, c) and torch.equal(a, c2), n
         if n.startswith("sa1_module"):
-            # downstream of level 2's atomic scatter-add: equal up to the rounding order of those atomics, which the
-            # BatchNorm backward of level 1 (differences of nearly equal sums) amplifies
-            for other in (c, e):
-                assert float((a - other).abs().max()) <= 2e-2 * scale1, n
+            # default mode: level 1 sits downstream of level 2's fp32 atomic scatter-add (see the spread table)
+            assert float((a - e).abs().max()) <= SA1_SPREAD_BOUND * scale1, n
         else:
-            assert torch.equal(a, c), n
             assert float((a - e).abs().max()) <= 1e-4 * float(a.abs().max()) + 1e-6 * scale, n

@@ -16,7 +16,7 @@ a = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.manual_seed(7)
 net = Net(1, "ReLU", 0, 0.5, precision=a.precision).to(dev)
-opt = make_optimizer(net.parameters())
+opt = make_optimizer(net)   # FlatAdam over the parameter arena
 b = Batch.from_data_list(synthetic_clouds(1234, a.batch, a.points, 1, False)).to(dev)
 def step():
     if a.eval:

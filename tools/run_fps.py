@@ -6,7 +6,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
-from dl_biomass_b200 import _lib, ops  # noqa: E402
+from dl_biomass_b200 import ops  # noqa: E402
 from dl_biomass_b200.data import Batch, synthetic_clouds  # noqa: E402
 
 cluster = int(sys.argv[1]) if len(sys.argv) > 1 else 0
@@ -17,8 +17,7 @@ dev = torch.device("cuda:0")
 b = Batch.from_data_list(synthetic_clouds(1234, 12, n, 1, False))
 pos = b.pos.to(dev)
 lv = ops.build_levels([n] * 12, [ratio], dev)
-_lib.check(_lib.lib().b2pn_fps_set_variant(cluster, threads), "set_variant")
 for _ in range(3):
-    idx, _, _ = ops.fps(pos, lv[0], lv[1])
+    idx, _, _ = ops.fps(pos, lv[0], lv[1], cluster=cluster, threads=threads)   # the variant is a per-call option
 torch.cuda.synchronize()
 print("ok", idx[:4].tolist())

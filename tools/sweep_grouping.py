@@ -41,9 +41,8 @@ def main():
         ref_idx = None
         for cluster in ((1, -2) if quick else (1, -2, -1, 2, 4, 8, 16)):
             for threads in ((256, 512, 640, 768, 1024) if cluster == -2 else (256, 512, 1024)):
-                rc = _lib.lib().b2pn_fps_set_variant(cluster, threads)
                 try:
-                    idx, _, _ = ops.fps(pos, lv[0], lv[1])
+                    idx, _, _ = ops.fps(pos, lv[0], lv[1], cluster=cluster, threads=threads)
                     torch.cuda.synchronize()
                 except RuntimeError as e:
                     out["fps"].append({"cfg": tag, "cluster": cluster, "threads": threads, "error": str(e)[:80]})
@@ -51,14 +50,13 @@ def main():
                 if ref_idx is None:
                     ref_idx = idx.clone()
                 same = bool(torch.equal(idx, ref_idx))
-                ms = timeit(lambda: ops.fps(pos, lv[0], lv[1]), iters=3 if n > 20000 else 7)
+                ms = timeit(lambda: ops.fps(pos, lv[0], lv[1], cluster=cluster, threads=threads), iters=3 if n > 20000 else 7)
                 scan_gb = B * m * n * 16 / 1e9
                 rec = {"cfg": tag, "cluster": cluster, "threads": threads, "ms": round(ms, 4),
                        "us_per_iter": round(ms * 1e3 / m, 4), "scan_GBps": round(scan_gb / (ms * 1e-3), 1),
                        "same_as_first": same}
                 print(rec, flush=True)
                 out["fps"].append(rec)
-        _lib.lib().b2pn_fps_set_variant(0, 0)
         ms = timeit(lambda: ops.fps(pos, lv[0], lv[1]))
         out["fps"].append({"cfg": tag, "cluster": "auto", "ms": round(ms, 4)})
         print(out["fps"][-1], flush=True)
