@@ -80,7 +80,8 @@ class CloudCache:
             # uid = the per-point random stream of THIS sample: fresh 64 bits per record.  The reference puts every cloud
             # into an epoch 1 + num_augs times, each copy augmented independently (/root/reference/main.py:100-112); a uid
             # derived from (epoch, cloud id) alone would give all those copies the same permutation and the same noise.
-            uid = rng.getrandbits(64) if augment else (int(epoch) * len(self.sizes) + int(cid))
+            uid = ((rng.getrandbits(64) ^ (int(epoch) * 0x9E3779B97F4A7C15)) & 0xFFFFFFFFFFFFFFFF) if augment \
+                else (int(epoch) * len(self.sizes) + int(cid))
             recs.append((int(cid), n, n_keep, n_dup, sd, angle, uid))
         return recs
 
@@ -89,7 +90,7 @@ class CloudCache:
         """An (augmented) training batch of the given clouds, assembled on the device in one launch per 64 clouds.
         ``augment=False`` copies the clouds unchanged except for their point ORDER, which is still shuffled (use
         ``Batch.from_data_list`` for evaluation batches that must keep the stored order)."""
-        recs = plan if plan is not None else self.plan(cloud_ids, rng or random.Random(seed), epoch, augment)
+        recs = plan if plan is not None else self.plan(cloud_ids, rng or random.Random((int(seed) << 24) ^ int(epoch)), epoch, augment)
         if len(recs) == 0:
             raise ValueError("no cloud of this batch has enough points")
         B = len(recs)

@@ -146,10 +146,11 @@ __global__ void pack_rows_fill_kernel(const int32_t *cnt, const int32_t *nbr, in
     int4 *dst = reinterpret_cast<int4 *>(row_src + r0);
     dst[0] = make_int4(v[0], v[1], v[2], v[3]);
     dst[1] = make_int4(v[4], v[5], v[6], v[7]);
-    if (row_valid) {  // bf16 1.0 = 0x3F80 for valid rows: the "ones" line of the dW GEMMs (bias gradients)
+    if (row_valid) {  // fp16 1.0 = 0x3C00 for valid rows: the "ones" line of the dW GEMMs (bias gradients); it rides with
+                      // the stored activations, i.e. in the forward-domain format (tc_common.cuh)
         unsigned w[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) w[q] = (2 * q < nv ? 0x3F80u : 0u) | (2 * q + 1 < nv ? 0x3F800000u : 0u);
+        for (int q = 0; q < 4; ++q) w[q] = (2 * q < nv ? 0x3C00u : 0u) | (2 * q + 1 < nv ? 0x3C000000u : 0u);
         *reinterpret_cast<uint4 *>(row_valid + r0) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }

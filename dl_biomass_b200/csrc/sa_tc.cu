@@ -149,7 +149,8 @@ int make_tma_row_valid(TmaMap *out, const void *base, int64_t ld)
 }
 
 struct GemmParams {
-    const uint8_t *a_packed;  // [m_group][k_chunk][MT*128 lines][128 B], swizzled bf16
+    const uint8_t *a_packed;  // [m_group][k_chunk][MT*128 lines][128 B], swizzled 16-bit (a_fmt)
+    int a_fmt, b_fmt;         // FMT_F16 / FMT_BF16 of the weight image and of the B operand tiles
     int num_kc;
     int64_t rows;             // host value (CLOUDS, self-test) ...
     const int64_t *rows_dev;  // ... or the device scalar of the compacted SLOTS layout (wins when non-NULL)
@@ -176,6 +177,46 @@ struct InCols {
 };
 
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16(v)); }
+// forward-domain values are fp16 (tc_common.cuh): the hi part of an fp32 input and what is left of it
+__device__ __forceinline__ float f16_round(float v) { return __half2float(__float2half_rn(v)); }
+
+// fp16 twins (forward-domain tensors: zhat, activation operands, level outputs handed to the next level)
+__device__ __forceinline__ void unpack8h(const uint4 &raw, float (&f)[8])
+{
+    const float2 a = unpack_f16x2(raw.x), b = unpack_f16x2(raw.y), c = unpack_f16x2(raw.z), d = unpack_f16x2(raw.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8h(const float (&f)[8])
+{
+    uint4 o;
+    o.x = pack_f16x2(f[0], f[1]);
+    o.y = pack_f16x2(f[2], f[3]);
+    o.z = pack_f16x2(f[4], f[5]);
+    o.w = pack_f16x2(f[6], f[7]);
+    return o;
+}
+__device__ __forceinline__ void unpack8(const uint4 &raw, float (&f)[8])
+{
+    f[0] = bf16_lo(raw.x); f[1] = bf16_hi(raw.x); f[2] = bf16_lo(raw.y); f[3] = bf16_hi(raw.y);
+    f[4] = bf16_lo(raw.z); f[5] = bf16_hi(raw.z); f[6] = bf16_lo(raw.w); f[7] = bf16_hi(raw.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8])
+{
+    uint4 o;
+    o.x = pack_bf16x2(f[0], f[1]);
+    o.y = pack_bf16x2(f[2], f[3]);
+    o.z = pack_bf16x2(f[4], f[5]);
+    o.w = pack_bf16x2(f[6], f[7]);
+    return o;
+}
+
+// eight fp16 values -> eight bf16 values (exact range, 10 -> 7 mantissa bits): stored activations meeting bf16 gradients
+__device__ __forceinline__ uint4 f16_to_bf16_chunk(const uint4 &raw)
+{
+    float f[8];
+    unpack8h(raw, f);
+    return pack8(f);
+}
 
 // =================================================================================================
 //  B-tile loaders for the rows GEMM (128 threads).  produce() fills one 16 KB chunk for K chunk kc.
@@ -185,11 +226,12 @@ struct GatherLoaderTC {  // K-major B: line = row of the tile, 64 k per line
     static constexpr bool USES_TMA = false;
     static constexpr bool WIDE = false;
     RowMapTC rm;
-    const void *x;  // [n_src, c_in] row-major, fp32 (cols.x_f32) or bf16
+    const void *x;  // [n_src, c_in] row-major, fp32 (cols.x_f32) or fp16
     InCols cols;
     const float *pos_src;
     const float *pos_dst;
     int ones_col;  // image column that carries 1 for valid rows (dW bias column), -1: none
+    int out_fmt;   // FMT_F16: forward operand / materialised g1; FMT_BF16: X side of a dW GEMM (meets bf16 gradients)
     // per-thread state for the current row
     bool ok;
     int64_t src;
@@ -226,30 +268,32 @@ struct GatherLoaderTC {  // K-major B: line = row of the tile, 64 k per line
         const int c_in = cols.c_in, nx = cols.nx();
         if (k < c_in) {
             return cols.x_f32 ? reinterpret_cast<const float *>(x)[src * c_in + k]
-                              : __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(x)[src * c_in + k]);
+                              : __half2float(reinterpret_cast<const __half *>(x)[src * c_in + k]);
         }
         if (k < nx) {
             const float v = reinterpret_cast<const float *>(x)[src * c_in + (k - c_in)];
-            return v - bf16_round(v);
+            return v - (out_fmt == FMT_F16 ? f16_round(v) : bf16_round(v));
         }
         const int j = k - nx;
         if (j >= 6) return 0.f;
         const int a = j < 3 ? j : j - 3;
         const float v = a == 0 ? d0 : (a == 1 ? d1 : d2);
-        return j < 3 ? v : v - bf16_round(v);
+        return j < 3 ? v : v - (out_fmt == FMT_F16 ? f16_round(v) : bf16_round(v));
     }
     // 16-byte chunk holding image columns kk .. kk+7 of the current row
     __device__ __forceinline__ uint4 chunk(int kk) const
     {
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if (!ok) return v;
-        if (!cols.x_f32 && (cols.c_in & 7) == 0 && kk + 8 <= cols.c_in)
-            return __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(x) + src * cols.c_in + kk));
+        if (!cols.x_f32 && (cols.c_in & 7) == 0 && kk + 8 <= cols.c_in) {
+            v = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(x) + src * cols.c_in + kk));
+            return out_fmt == FMT_F16 ? v : f16_to_bf16_chunk(v);
+        }
         if (kk < cols.k_img() + (ones_col >= 0 ? 1 : 0)) {
-            v.x = pack_bf16x2(elem(kk + 0), elem(kk + 1));
-            v.y = pack_bf16x2(elem(kk + 2), elem(kk + 3));
-            v.z = pack_bf16x2(elem(kk + 4), elem(kk + 5));
-            v.w = pack_bf16x2(elem(kk + 6), elem(kk + 7));
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = elem(kk + e);
+            v = out_fmt == FMT_F16 ? pack8h(f) : pack8(f);
         }
         return v;
     }
@@ -293,21 +337,6 @@ __global__ void __launch_bounds__(256) gather_l1_tc_kernel(GatherLoaderTC gl, co
     }
 }
 
-__device__ __forceinline__ void unpack8(const uint4 &raw, float (&f)[8])
-{
-    f[0] = bf16_lo(raw.x); f[1] = bf16_hi(raw.x); f[2] = bf16_lo(raw.y); f[3] = bf16_hi(raw.y);
-    f[4] = bf16_lo(raw.z); f[5] = bf16_hi(raw.z); f[6] = bf16_lo(raw.w); f[7] = bf16_hi(raw.w);
-}
-__device__ __forceinline__ uint4 pack8(const float (&f)[8])
-{
-    uint4 o;
-    o.x = pack_bf16x2(f[0], f[1]);
-    o.y = pack_bf16x2(f[2], f[3]);
-    o.z = pack_bf16x2(f[4], f[5]);
-    o.w = pack_bf16x2(f[6], f[7]);
-    return o;
-}
-
 // 8 consecutive rows (r8 .. r8+7) of channel ch of a feature-major tensor, as the B/A operand wants them:
 //   MODE 0: plain, invalid rows -> 0      MODE 1: affine + activation on load, invalid rows -> 0
 // `inf` is the group descriptor RowMapTC::info(r8) (the caller caches it per tile).
@@ -323,6 +352,8 @@ struct FeatSource {
     int ones_line;  // channel index that carries 1 for valid rows (dW bias column), -1: none
     const float *gamma;
     const float *beta;
+    int out_fmt;    // FMT_F16: forward operand; FMT_BF16: X side of a dW GEMM (meets bf16 gradients)
+    __device__ __forceinline__ uint4 pack_out(const float (&f)[8]) const { return out_fmt == FMT_F16 ? pack8h(f) : pack8(f); }
     __device__ __forceinline__ void resolve(int64_t r) { rm.resolve(r); }
     __device__ __forceinline__ uint4 chunk_i(int ch, int64_t r8, unsigned inf) const
     {
@@ -331,14 +362,14 @@ struct FeatSource {
         if (ch == ones_line) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = e < nv ? 1.f : 0.f;
-            return pack8(f);
+            return pack_out(f);
         }
         const bool live = ch < C && nv > 0;
         uint4 raw = make_uint4(0u, 0u, 0u, 0u);
         if (!live) return raw;
         raw = __ldg(reinterpret_cast<const uint4 *>(t + (int64_t)ch * ld + r8));
-        if (MODE == 0 && nv == 8) return raw;
-        unpack8(raw, f);
+        if (MODE == 0 && nv == 8 && out_fmt == FMT_F16) return raw;
+        unpack8h(raw, f);
         float ga = 1.f, be = 0.f;
         if (MODE != 0) {
             ga = gamma[ch];
@@ -353,7 +384,7 @@ struct FeatSource {
             }
             f[e] = e < nv ? v : 0.f;
         }
-        return pack8(f);
+        return pack_out(f);
     }
 };
 
@@ -586,8 +617,8 @@ struct StatsEpTC {  // pass A of a BatchNorm layer: per-channel sum and sum of s
     }
 };
 
-struct NormStoreEpTC {  // pass B: zT[ch][row] = bf16((acc + bias - mean) * rstd), the NORMALISED value zhat (what backward
-                        // needs), and aT[ch][row] = bf16(act(gamma*zhat + beta)) with invalid rows zeroed: the operand
+struct NormStoreEpTC {  // pass B: zT[ch][row] = fp16((acc + bias - mean) * rstd), the NORMALISED value zhat (what backward
+                        // needs), and aT[ch][row] = fp16(act(gamma*zhat + beta)) with invalid rows zeroed: the operand
                         // of the next layer and of the dW GEMMs, stored so that they can take it through the TMA unit
     static constexpr bool STAGED = true;
     // zT and aT leave through the warp's staging tiles and two TMA stores (EpCtx::m0 = map of z, m1 = map of a)
@@ -626,8 +657,8 @@ struct NormStoreEpTC {  // pass B: zT[ch][row] = bf16((acc + bias - mean) * rstd
                 float f[8], g[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] = fmaf(v[8 * j + e], sc, sh);
-                const uint4 zp = pack8(f);
-                unpack8(zp, f);  // the activation is defined on the STORED (bf16) zhat, as backward recomputes it
+                const uint4 zp = pack8h(f);
+                unpack8h(zp, f);  // the activation is defined on the STORED (fp16) zhat, as backward recomputes it
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     float y = fmaf(f[e], ga, be);
@@ -636,7 +667,7 @@ struct NormStoreEpTC {  // pass B: zT[ch][row] = bf16((acc + bias - mean) * rstd
                 }
                 const int gidx = (cc - half * 2) * 4 + j;  // 16-byte chunk of my 128-byte line (64 rows of this half)
                 stage_chunk(zt, lane, gidx, zp);
-                stage_chunk(at, lane, gidx, pack8(g));
+                stage_chunk(at, lane, gidx, pack8h(g));
             }
         }
         fence_proxy_async_smem();
@@ -663,7 +694,7 @@ struct SlotMaxEpTC {  // out[m][ch] = max over the valid rows of centroid m, arg
     const float *bias;
     const uint32_t *rgrp;
     int64_t rows;
-    __nv_bfloat16 *out16;  // optional bf16 copy of out (the next level's gather operand)
+    __half *out16;  // optional fp16 copy of out (the next level's gather operand)
     __device__ __forceinline__ void resolve(int64_t r) { rows = r; }
     __device__ __forceinline__ void begin() {}
     __device__ __forceinline__ void tile_mt(uint32_t taddr, int64_t tile, int ch, int mt, int half, const EpCtx &cx)
@@ -699,7 +730,7 @@ struct SlotMaxEpTC {  // out[m][ch] = max over the valid rows of centroid m, arg
                     const float o = bk >= 0 ? best : 0.f;
                     out[m * C + ch] = o;
                     arg[m * C + ch] = bk;
-                    if (out16) out16[m * C + ch] = __float2bfloat16(o);
+                    if (out16) out16[m * C + ch] = __float2half_rn(o);
                 }
             }
         }
@@ -810,7 +841,7 @@ struct MaskSumsStoreEpTC {  // backward through activation + sums for the BatchN
             for (int j = 0; j < 4; ++j) {
                 const int gidx = (cc - half * 2) * 4 + j;
                 float zf[8], o[8];
-                unpack8(unstage_chunk(zt, lane, gidx), zf);
+                unpack8h(unstage_chunk(zt, lane, gidx), zf);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     // channels past C: zero-padded weight rows give da = 0 exactly (and ga = be = 0 mask them under ReLU);
@@ -1055,7 +1086,7 @@ __global__ void __launch_bounds__(gemm_threads<BL>(), 1)
     } else if (warp == MMA_WARP) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            constexpr uint32_t IDESC = idesc_bf16(128, R, false, BL::B_MN);
+            const uint32_t IDESC = idesc_16(128, R, false, BL::B_MN, gp.a_fmt, gp.b_fmt);
             uint32_t it = 0, tl = 0;
             for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
                 const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
@@ -1177,16 +1208,28 @@ struct TmaFill {
     __device__ __forceinline__ void resolve(int64_t) {}
     __device__ __forceinline__ void fill(uint8_t *, int, int64_t, int, int, const unsigned (&)[8]) {}
     // N group ng covers lines [256 ng, 256 ng + 256) of [tensor channels | ones line | zero padding]
-    __device__ __forceinline__ void fill_tma(uint8_t *B, int64_t r0, int ng, const TmaMap *map_x, const TmaMap *map_v,
-                                             uint64_t *bar) const
+    // lines of the X tile the copies of N group ng write (whole 64-line boxes + the 16-line ones box)
+    __device__ __forceinline__ int landed_lines(int ng) const
     {
         const int ch0 = ng * 256;
         const int left = c - ch0;
         const int boxes = left <= 0 ? 0 : ((left < 256 ? left : 256) + 63) >> 6;
         const bool ones_here = ones_box && c >= ch0 && c < ch0 + 256;
-        mbar_expect_tx(bar, (unsigned)((boxes * 64 + (ones_here ? 16 : 0)) * LINE_BYTES));
+        const int tensor_lines = boxes * 64;
+        return ones_here ? max(tensor_lines, c - ch0 + 16) : tensor_lines;
+    }
+    __device__ __forceinline__ unsigned fill_tma(uint8_t *B, int64_t r0, int ng, const TmaMap *map_x, const TmaMap *map_v,
+                                                 uint64_t *bar) const
+    {
+        const int ch0 = ng * 256;
+        const int left = c - ch0;
+        const int boxes = left <= 0 ? 0 : ((left < 256 ? left : 256) + 63) >> 6;
+        const bool ones_here = ones_box && c >= ch0 && c < ch0 + 256;
+        const unsigned bytes = (unsigned)((boxes * 64 + (ones_here ? 16 : 0)) * LINE_BYTES);
+        mbar_expect_tx(bar, bytes);
         for (int blk = 0; blk < boxes; ++blk) tma_load_2d(B + blk * (64 * LINE_BYTES), map_x, (int)r0, ch0 + blk * 64, bar);
         if (ones_here) tma_load_2d(B + (c - ch0) * LINE_BYTES, map_v, (int)r0, 0, bar);
+        return bytes;
     }
     static __device__ __forceinline__ uint64_t b_desc(uint32_t b_saddr, int ks) { return smem_desc_sw128(b_saddr + ks * 32, 16, ATOM_BYTES); }
 };
@@ -1238,7 +1281,8 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + nst * sbytes);
     uint64_t *empty = full + nst;
     uint64_t *done = empty + nst;
-    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(done + 1);
+    uint64_t *xland = done + 1;  // per stage: the X tile's TMA copies have landed (it is converted fp16 -> bf16 in place)
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(xland + nst);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int split = blockIdx.x, mg = blockIdx.y, ng = blockIdx.z;
@@ -1257,6 +1301,7 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
         for (int s = 0; s < nst; ++s) {
             mbar_init(&full[s], NUM_LOAD);
             mbar_init(&empty[s], 1);
+            mbar_init(&xland[s], 1);
         }
         mbar_init(done, 1);
         fence_barrier_init();
@@ -1325,17 +1370,32 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
                 }
             }
             if constexpr (XF::USES_TMA) {
-                if (lt == 0) xf.fill_tma(B, r0, ng, &tmap_x, &tmap_v, &full[s]);
+                // the stored activations are fp16, the gradients on the Y side bf16: the group converts the landed X tile
+                // to bf16 in place (16-byte chunks, element-wise: the swizzle is untouched)
+                if (lt == 0) {
+                    const unsigned bytes = xf.fill_tma(B, r0, ng, &tmap_x, &tmap_v, &xland[s]);
+                    (void)bytes;
+                    mbar_arrive(&xland[s]);
+                }
+                mbar_wait(&xland[s], ph);
+                const int nchunk16 = xf.landed_lines(ng) * 8;
+                for (int c = lt; c < nchunk16; c += NUM_LOAD) {
+                    uint4 *q = reinterpret_cast<uint4 *>(B) + c;
+                    *q = f16_to_bf16_chunk(*q);
+                }
+                fence_proxy_async_smem();
             } else {
                 xf.fill(B, lt, r0, ng, nb_lines, inf);
+                fence_proxy_async_smem();
             }
-            if constexpr (!(YS::USES_TMA && XF::USES_TMA)) fence_proxy_async_smem();
             mbar_arrive(&full[s]);
 #pragma unroll
             for (int g = 0; g < 8; ++g) inf[g] = infn[g];
         }
     } else if (warp == MMA_WARP) {
         if (lane == 0 && nchunks > 0) {
+            // both operands are bf16 at MMA time: kind::f16 wants ONE format for A and B (a bf16 x fp16 instruction is an
+            // illegal instruction on sm_100a -- measured), so the fp16 activations are converted on their way in
             const uint32_t idesc = idesc_bf16(128, nb_lines, false, XF::B_MN);
             for (int64_t i = 0; i < nchunks; ++i) {
                 const int s = (int)(i % nst);
@@ -1412,6 +1472,7 @@ struct PackJob {
     InCols cols;
     int MT, num_mg, num_kc;
     uint8_t *img;
+    int fmt;  // FMT_F16 (forward weights) / FMT_BF16 (transposed weights that meet gradients)
 };
 struct PackJobs {
     PackJob j[3];
@@ -1439,7 +1500,7 @@ __global__ void pack_weights_kernel(const PackJobs jobs)
             f[e] = (m < jb.M && col >= 0) ? jb.w[(int64_t)m * jb.sm + (int64_t)col * jb.sk] : 0.f;
         }
         uint8_t *dst = jb.img + (((int64_t)mgi * jb.num_kc + kc) * lines) * LINE_BYTES + line_chunk_off(line, c);
-        *reinterpret_cast<uint4 *>(dst) = pack8(f);
+        *reinterpret_cast<uint4 *>(dst) = jb.fmt == FMT_F16 ? pack8h(f) : pack8(f);
     }
 }
 
@@ -1449,10 +1510,12 @@ struct Packed {
     uint8_t *img;
     int MT, num_mg, num_kc;
     int64_t bytes;
+    int fmt;
 };
-static Packed plan_pack(int M, int Kimg)
+static Packed plan_pack(int M, int Kimg, int fmt)
 {
     Packed p;
+    p.fmt = fmt;
     const int mpad = (int)align_up(M, 128);
     p.MT = mpad >= 256 ? 2 : 1;
     p.num_mg = (mpad + p.MT * 128 - 1) / (p.MT * 128);
@@ -1463,7 +1526,7 @@ static Packed plan_pack(int M, int Kimg)
 }
 static PackJob pack_job(const float *w, int M, int Kimg, int64_t sm, int64_t sk, const InCols *map, const Packed &p)
 {
-    PackJob j = {w, M, Kimg, sm, sk, map ? 1 : 0, map ? *map : InCols{0, 0}, p.MT, p.num_mg, p.num_kc, p.img};
+    PackJob j = {w, M, Kimg, sm, sk, map ? 1 : 0, map ? *map : InCols{0, 0}, p.MT, p.num_mg, p.num_kc, p.img, p.fmt};
     return j;
 }
 static void launch_packs(const PackJob *jobs, int n, cudaStream_t st)
@@ -1532,7 +1595,7 @@ static int launch_gemm(const Packed &pk, const RowsArg &ra, const BL &bl, const 
     auto kern = tc_rows_gemm_kernel<MT, BL, EP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
     if (e != cudaSuccess) return (int)e;
-    GemmParams gp = {pk.img, pk.num_kc, ra.cap, ra.dev};
+    GemmParams gp = {pk.img, pk.fmt, pk.fmt, pk.num_kc, ra.cap, ra.dev};
     dim3 grid((unsigned)grid_x_for(pk, ra.tiles()), (unsigned)pk.num_mg);
     kern<<<grid, gemm_threads<BL>(), P::TOTAL, st>>>(gp, bl, ep, map, e0, e1);
     note_launch();
@@ -1711,7 +1774,7 @@ __global__ void bn_bwd_apply_tc_kernel(RowMapTC rm, const int64_t *rows_dev, __n
         }
         float d[8], zf[8];
         unpack8(*p, d);
-        unpack8(__ldg(reinterpret_cast<const uint4 *>(z + (int64_t)ch * ld + r8)), zf);
+        unpack8h(__ldg(reinterpret_cast<const uint4 *>(z + (int64_t)ch * ld + r8)), zf);
         const float sc = scale[ch];
         const float s1 = sbar[ch], s2 = sbar[C + ch];
 #pragma unroll
@@ -1873,7 +1936,10 @@ int tc_gemm_selftest(const float *w, int m_out, int k, const void *b, int mode, 
                      float *out, int64_t ld_out, void *workspace, int64_t workspace_bytes, cudaStream_t st)
 {
     if (!w || !b || !out || !workspace || !zeros3 || m_out <= 0 || k <= 0 || rows <= 0) return B2PN_EINVAL;
-    Packed pk = plan_pack(m_out, k);
+    // fp16 weights x fp16 operand: the forward configuration.  (A bf16 x fp16 kind::f16 instruction is an ILLEGAL
+    // INSTRUCTION on sm_100a -- measured in round 2 -- which is why the dW kernel converts its fp16 X tiles to bf16.)
+    if (mode < 0 || mode > 2) return B2PN_EINVAL;
+    Packed pk = plan_pack(m_out, k, FMT_F16);
     if (workspace_bytes < pk.bytes + 1024) return B2PN_EINVAL;
     pk.img = (uint8_t *)align_up((int64_t)(uintptr_t)workspace, 1024);
     launch_pack(w, m_out, k, k, 1, nullptr, pk, st);
@@ -1882,7 +1948,7 @@ int tc_gemm_selftest(const float *w, int m_out, int k, const void *b, int mode, 
     StoreF32Ep ep = {out, m_out, ld_out};
     if (mode == 0) {
         // all k columns are bf16 features (c_in = k); the appended dpos columns multiply zero weights
-        GatherLoaderTC gl = {rm, b, InCols{k, 0}, zeros3, nullptr, -1};
+        GatherLoaderTC gl = {rm, b, InCols{k, 0}, zeros3, nullptr, -1, FMT_F16};
         return launch_by_mt(pk, ra, gl, ep, ep, st);
     }
     if (mode == 2) {  // the same feature-major operand through the TMA unit
@@ -1892,7 +1958,7 @@ int tc_gemm_selftest(const float *w, int m_out, int k, const void *b, int mode, 
         TmaFeatLoader tl;
         return launch_by_mt(pk, ra, tl, ep, ep, st, map);
     }
-    FeatLoaderTC<FeatSource<0>> fl = {{rm, (const __nv_bfloat16 *)b, k, ld, 0, -1, nullptr, nullptr}};
+    FeatLoaderTC<FeatSource<0>> fl = {{rm, (const __nv_bfloat16 *)b, k, ld, 0, -1, nullptr, nullptr, FMT_F16}};
     return launch_by_mt(pk, ra, fl, ep, ep, st);
 }
 
@@ -1994,9 +2060,9 @@ struct FwdWsTC {
 static FwdWsTC carve_fwd_tc(const b2pn_sa_args &a, const ShapesTC &s, WsTC &ws)
 {
     FwdWsTC f;
-    f.pk[0] = plan_pack(s.c1, s.k1);
-    f.pk[1] = plan_pack(s.c2, s.c1);
-    f.pk[2] = plan_pack(s.c3, s.c2);
+    f.pk[0] = plan_pack(s.c1, s.k1, FMT_F16);   // forward: fp16 weights meet fp16 activations
+    f.pk[1] = plan_pack(s.c2, s.c1, FMT_F16);
+    f.pk[2] = plan_pack(s.c3, s.c2, FMT_F16);
     for (int l = 0; l < 3; ++l) f.pk[l].img = ws.take<uint8_t>(f.pk[l].bytes);
     f.partial = ws.take<double>((int64_t)MAX_GX * 4 * 2 * s.cpad);
     f.keys = a.seg_mode == B2PN_SEG_CLOUDS ? ws.take<unsigned long long>(a.n_dst * (int64_t)s.c3) : nullptr;
@@ -2045,9 +2111,9 @@ struct BwdWsTC {
 static BwdWsTC carve_bwd_tc(const b2pn_sa_args &a, const ShapesTC &s, WsTC &ws)
 {
     BwdWsTC b;
-    b.pkT[2] = plan_pack(s.c2, s.c3);               // W3^T
-    b.pkT[1] = plan_pack(s.c1, s.c2);               // W2^T
-    b.pkT[0] = plan_pack(a.c_in > 0 ? a.c_in : 1, s.c1);  // feature rows of W1^T
+    b.pkT[2] = plan_pack(s.c2, s.c3, FMT_BF16);               // W3^T: meets gradients (bf16)
+    b.pkT[1] = plan_pack(s.c1, s.c2, FMT_BF16);               // W2^T
+    b.pkT[0] = plan_pack(a.c_in > 0 ? a.c_in : 1, s.c1, FMT_BF16);  // feature rows of W1^T
     for (int l = 0; l < 3; ++l) b.pkT[l].img = ws.take<uint8_t>(b.pkT[l].bytes);
     b.partial = ws.take<double>((int64_t)MAX_GX * 4 * 2 * s.cpad);
     b.dz1 = ws.take<__nv_bfloat16>((int64_t)s.c1 * s.ld);
@@ -2081,7 +2147,7 @@ static void launch_gather_l1(const b2pn_sa_args &a, const ShapesTC &s, cudaStrea
 {
     const RowMapTC rm = rowmap_tc(a, s);
     const RowsArg ra = rowsarg_tc(a, s);
-    GatherLoaderTC gg = {rm, a.x, s.cols, a.pos_src, a.pos_dst, s.k1};  // column k1 = ones (dW1 bias line)
+    GatherLoaderTC gg = {rm, a.x, s.cols, a.pos_src, a.pos_dst, s.k1, FMT_F16};  // column k1 = ones (dW1 bias line)
     const int kg = s.k1 + 1, kg8 = (kg + 7) & ~7;
     gather_l1_tc_kernel<<<(unsigned)(s.ld / GATHER_ROWS), 256, kg8 * GATHER_ROWS * 2, st>>>(gg, ra.dev, kg, s.ld,
                                                                                              (__nv_bfloat16 *)a.g1);
@@ -2130,7 +2196,7 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
     const CountArg count = {a.seg_mode == B2PN_SEG_SLOTS ? a.num_rows + 1 : nullptr, (double)s.rows};
 
     // ---- layer 1: gather + concat + Linear; pass A = batch statistics, pass B = normalise + store z1
-    GatherLoaderTC gl = {rm, a.x, s.cols, a.pos_src, a.pos_dst, -1};
+    GatherLoaderTC gl = {rm, a.x, s.cols, a.pos_src, a.pos_dst, -1, FMT_F16};
     const bool use_g1 = l1_materialised(a, s);
     TmaMap map_g1 = kNoMap;
     TmaFeatLoader tl1;
@@ -2183,7 +2249,7 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
     }
     // ---- layer 3 + max aggregation
     if (a.seg_mode == B2PN_SEG_SLOTS) {
-        SlotMaxEpTC e = {a.out, a.arg, s.c3, a.mlp.b[2], a.rgrp, s.rows, (__nv_bfloat16 *)a.out_bf16};
+        SlotMaxEpTC e = {a.out, a.arg, s.c3, a.mlp.b[2], a.rgrp, s.rows, (__half *)a.out_bf16};
         if ((rc = launch_by_mt(f.pk[2], ra, l3, e, e, st, map_a2))) return rc;
     } else {
         const int64_t n = a.n_dst * (int64_t)s.c3;
@@ -2301,7 +2367,7 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
     TmaMap mdz2, mz2;  // epilogue maps (32-channel boxes): dz2 out, zhat2 in
     if ((rc = make_tma_feature_major(&mdz2, b.dz2, s.c2, s.ld, 32))) return rc;
     if ((rc = make_tma_feature_major(&mz2, z2, s.c2, s.ld, 32))) return rc;
-    LineFillK<FeatSource<1>> xa2 = {{rm, z2, s.c2, s.ld, a.mlp.act, s.c2, a.mlp.gamma[1], a.mlp.beta[1]}};
+    LineFillK<FeatSource<1>> xa2 = {{rm, z2, s.c2, s.ld, a.mlp.act, s.c2, a.mlp.gamma[1], a.mlp.beta[1], FMT_BF16}};
     // X sides through TMA: stored activations + the row-valid "ones" line (64-channel boxes, so c % 64 == 0)
     TmaMap map_v = kNoMap, map_a1 = kNoMap, map_a2 = kNoMap;
     const bool tma_x = a.row_valid != nullptr;
@@ -2366,7 +2432,7 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
             TmaFill xt = {s.c1, 1};
             rc = launch_dw(y2, xt, s.c2, s.c1 + 1, s, ra, b.dwp[1], st, map2, map_a1, map_v);
         } else {
-            LineFillK<FeatSource<1>> xa1 = {{rm, z1, s.c1, s.ld, a.mlp.act, s.c1, a.mlp.gamma[0], a.mlp.beta[0]}};
+            LineFillK<FeatSource<1>> xa1 = {{rm, z1, s.c1, s.ld, a.mlp.act, s.c1, a.mlp.gamma[0], a.mlp.beta[0], FMT_BF16}};
             rc = launch_dw(y2, xa1, s.c2, s.c1 + 1, s, ra, b.dwp[1], st, map2);
         }
         if (rc) return rc;
@@ -2387,7 +2453,7 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
             TmaFill xt = {s.k1 + 1, 0};
             rc = launch_dw(y1, xt, s.c1, s.k1 + 1, s, ra, b.dwp[0], st, map1, map_g1, kNoMap);
         } else {
-            LineFillGather xg = {{rm, a.x, s.cols, a.pos_src, a.pos_dst, s.k1}};
+            LineFillGather xg = {{rm, a.x, s.cols, a.pos_src, a.pos_dst, s.k1, FMT_BF16}};  // X side of dW1: meets bf16 gradients
             rc = launch_dw(y1, xg, s.c1, s.k1 + 1, s, ra, b.dwp[0], st, map1);
         }
         if (rc) return rc;

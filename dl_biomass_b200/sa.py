@@ -17,6 +17,10 @@ from . import _lib
 from .optim import grad_dst
 
 PREC_F32, PREC_BF16 = 0, 1
+# storage format of the FORWARD-domain 16-bit tensors of the tensor-core mode (weights, normalised activations, level
+# outputs handed to the next level): fp16 -- 8x finer than bf16 on O(1) values, which the 2e-2 output tolerance needs at
+# the reference's batch shape (tools/bf16_attribution.py); gradients stay bf16 inside libb2pn
+H16 = torch.float16
 SEG_SLOTS, SEG_CLOUDS = 0, 1
 ACT_NONE, ACT_RELU = 0, 1
 
@@ -31,41 +35,64 @@ def _dp(t: Optional[torch.Tensor]):
 
 
 # Per-call launch options of the set-abstraction kernels (b2pn_sa_args::sm_limit / ::deterministic).  They are fields of
-# every call's argument struct -- libb2pn has no process-wide state -- and on the Python side they are THREAD-local, so
-# the reference's thread-per-GPU callers (/root/reference/main.py:140) cannot disturb each other.
+# every call's argument struct -- libb2pn has no process-wide state.  On the Python side they live in a small holder
+# object; every host thread has its own current holder, so the reference's thread-per-GPU callers
+# (/root/reference/main.py:140) cannot disturb each other.  A forward call remembers the holder it ran under and its
+# backward -- which autograd runs on ITS OWN thread -- reads the same holder at backward time, so a training loop can
+# change an option between forward and backward, or in the middle of the backward pass (train.PipelinedTrainStep lifts
+# the SM cap before the level-1 backward).
+class LaunchOptions:
+    __slots__ = ("sm_limit", "deterministic")
+
+    def __init__(self, sm_limit: int = 0, deterministic: int = 0):
+        self.sm_limit, self.deterministic = int(sm_limit), int(deterministic)
+
+
 _tls = threading.local()
 
 
+def current_options() -> LaunchOptions:
+    """The holder the calling thread's next set-abstraction calls are issued with (created on first use)."""
+    h = getattr(_tls, "holder", None)
+    if h is None:
+        h = _tls.holder = LaunchOptions()
+    return h
+
+
 def launch_options():
-    """(sm_limit, deterministic) the calling thread's next set-abstraction calls are issued with."""
-    return getattr(_tls, "sm_limit", 0), getattr(_tls, "deterministic", 0)
+    """(sm_limit, deterministic) of the calling thread's current holder."""
+    h = current_options()
+    return h.sm_limit, h.deterministic
 
 
 def set_sm_limit(n: int) -> None:
-    """Cap the persistent tensor-core kernels launched by THIS thread at ``n`` CTAs (0 = one per SM)."""
+    """Cap the persistent tensor-core kernels launched by THIS thread's calls at ``n`` CTAs (0 = one per SM)."""
     if n < 0:
         raise ValueError("sm_limit must be >= 0")
-    _tls.sm_limit = int(n)
+    current_options().sm_limit = int(n)
 
 
 def set_deterministic(on: bool) -> bool:
-    """Fixed-order gradient reductions for the calls of THIS thread; returns the previous setting."""
-    prev = bool(getattr(_tls, "deterministic", 0))
-    _tls.deterministic = 1 if on else 0
+    """Fixed-order gradient reductions for the calls of THIS thread (forward AND their backward); returns the
+    previous setting."""
+    h = current_options()
+    prev = bool(h.deterministic)
+    h.deterministic = 1 if on else 0
     return prev
 
 
 @contextmanager
 def options(sm_limit: Optional[int] = None, deterministic: Optional[bool] = None):
-    prev = launch_options()
+    h = current_options()
+    prev = (h.sm_limit, h.deterministic)
     try:
         if sm_limit is not None:
             set_sm_limit(sm_limit)
         if deterministic is not None:
             set_deterministic(deterministic)
-        yield
+        yield h
     finally:
-        _tls.sm_limit, _tls.deterministic = prev
+        h.sm_limit, h.deterministic = prev
 
 
 def act_code(act) -> int:
@@ -81,12 +108,13 @@ def act_code(act) -> int:
 
 def _fill_args(a: SaArgs, *, precision, training, seg_mode, K, n_src, n_dst, c_in, x, pos_src, pos_dst, nbr, cnt,
                batch, chans, act, eps, momentum, ws, bs, gammas, betas, rmeans, rvars, nbts, out, arg, h1, h2, bn,
-               rowmap=None, acts=None, out_bf16=None):
+               rowmap=None, acts=None, out_bf16=None, holder=None):
     a.precision, a.training, a.seg_mode, a.K = precision, int(training), seg_mode, K
-    a.sm_limit, a.deterministic = launch_options()
+    h = holder if holder is not None else current_options()
+    a.sm_limit, a.deterministic = h.sm_limit, h.deterministic
     a.out_bf16 = _dp(out_bf16)
     a.n_src, a.n_dst, a.c_in = n_src, n_dst, c_in
-    a.x_dtype = 1 if (x is not None and x.dtype == torch.bfloat16) else 0
+    a.x_dtype = 1 if (x is not None and x.dtype == H16) else 0
     a.x, a.pos_src, a.pos_dst = _dp(x), _dp(pos_src), _dp(pos_dst)
     a.nbr, a.cnt, a.batch = _dp(nbr), _dp(cnt), _dp(batch)
     m = a.mlp
@@ -125,7 +153,7 @@ def pack_rows(nbr: torch.Tensor, cnt: torch.Tensor, K: int):
     rgrp = torch.empty(cap // 8, dtype=torch.int32, device=dev)
     row_src = torch.empty(cap, dtype=torch.int32, device=dev)
     num_rows = torch.empty(2, dtype=torch.int64, device=dev)
-    row_valid = torch.empty(cap, dtype=torch.bfloat16, device=dev)
+    row_valid = torch.empty(cap, dtype=torch.float16, device=dev)
     wsb = torch.empty(int(lib.b2pn_pack_rows_workspace_bytes(n_dst)), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         rc = lib.b2pn_pack_rows(cnt.data_ptr(), nbr.data_ptr(), n_dst, K, rgrp.data_ptr(), row_src.data_ptr(),
@@ -138,16 +166,16 @@ def pack_rows(nbr: torch.Tensor, cnt: torch.Tensor, K: int):
 def _l1_input(x: Optional[torch.Tensor], x_bf16: Optional[torch.Tensor] = None):
     """How the kernels take the level's input features: (tensor or None, c_in, image columns).  Raw low-dimensional
     inputs (e.g. lidar intensity) stay fp32 -- the kernels feed them to the tensor cores as bf16 hi+lo column pairs --
-    wide feature maps from the previous level go in as bf16 (``x_bf16``: the copy the previous level's epilogue wrote,
-    if there is one)."""
+    wide feature maps from the previous level go in as fp16, the forward-domain operand format (``x_bf16``: the 16-bit
+    copy the previous level's epilogue wrote, if there is one)."""
     c_in = 0 if x is None else x.shape[1]
     split = x is not None and x.dtype == torch.float32 and c_in <= 16
     if x is None:
         xs = None
-    elif not split and x_bf16 is not None and x_bf16.shape == x.shape and x_bf16.dtype == torch.bfloat16:
+    elif not split and x_bf16 is not None and x_bf16.shape == x.shape and x_bf16.dtype == H16:
         xs = x_bf16.contiguous()
     else:
-        xs = x.detach().to(torch.float32 if split else torch.bfloat16).contiguous()
+        xs = x.detach().to(torch.float32 if split else H16).contiguous()
     return xs, c_in, (2 * c_in if split else c_in) + 6
 
 
@@ -162,7 +190,7 @@ def _row_valid_clouds(ld: int, n_src: int, dev) -> torch.Tensor:
     if rv is None:
         if len(_RV_CACHE) >= 64:
             _RV_CACHE.pop(next(iter(_RV_CACHE)))
-        rv = torch.zeros(ld, dtype=torch.bfloat16, device=dev)
+        rv = torch.zeros(ld, dtype=H16, device=dev)
         rv[:n_src] = 1
         _RV_CACHE[key] = rv
     return rv
@@ -179,11 +207,11 @@ def gather_rows(x: Optional[torch.Tensor], pos_src: torch.Tensor, pos_dst: torch
     rgrp, row_src, num_rows, cap, row_valid = rowmap
     ld = (cap + 127) // 128 * 128
     dev = pos_src.device
-    g = torch.empty(k_img + 1, ld, dtype=torch.bfloat16, device=dev)
+    g = torch.empty(k_img + 1, ld, dtype=H16, device=dev)
     a = SaArgs()
     a.precision, a.seg_mode, a.K = PREC_BF16, SEG_SLOTS, K
     a.n_src, a.n_dst, a.c_in = pos_src.shape[0], pos_dst.shape[0], c_in
-    a.x_dtype = 1 if (xs is not None and xs.dtype == torch.bfloat16) else 0
+    a.x_dtype = 1 if (xs is not None and xs.dtype == H16) else 0
     a.x, a.pos_src, a.pos_dst = _dp(xs), _dp(pos_src.contiguous()), _dp(pos_dst)
     a.mlp.c[0] = c_in + 3
     a.rgrp, a.row_src, a.num_rows, a.row_capacity = _dp(rgrp), _dp(row_src), _dp(num_rows), cap
@@ -225,7 +253,7 @@ class _SAFunction(torch.autograd.Function):
             rows = rowmap[3]
         out = torch.empty(n_dst, chans[3], dtype=f32, device=dev)
         arg = torch.empty(n_dst, chans[3], dtype=torch.int32, device=dev)
-        out_bf16 = (torch.empty(n_dst, chans[3], dtype=torch.bfloat16, device=dev)
+        out_bf16 = (torch.empty(n_dst, chans[3], dtype=H16, device=dev)
                     if (want_bf16_out and prec == PREC_BF16) else None)
         acts = None
         if prec == PREC_F32:   # row-major fp32 activations [rows, c]
@@ -235,8 +263,8 @@ class _SAFunction(torch.autograd.Function):
         else:                  # feature-major bf16 activations [c, ld], ld = rows rounded up to whole 128-row tiles
             xs, _, k_img = _l1_input(x, x_bf16)
             ld = (rows + 127) // 128 * 128
-            h1 = torch.empty(chans[1], ld, dtype=torch.bfloat16, device=dev)
-            h2 = torch.empty(chans[2], ld, dtype=torch.bfloat16, device=dev)
+            h1 = torch.empty(chans[1], ld, dtype=H16, device=dev)
+            h2 = torch.empty(chans[2], ld, dtype=H16, device=dev)
             acts = [torch.empty_like(h1), torch.empty_like(h2)]  # post-activation copies (TMA operands)
             if seg_mode == SEG_CLOUDS:   # the "ones" operand line of the dW GEMMs: 1 on every real row
                 rowmap = (None, None, None, 0, _row_valid_clouds(ld, n_src, dev))
@@ -244,7 +272,7 @@ class _SAFunction(torch.autograd.Function):
                 if l1op_in is not None and tuple(l1op_in.shape) != (k_img + 1, ld):
                     raise ValueError("l1op does not belong to these rows / features")
                 acts.append(l1op_in if l1op_in is not None else
-                            torch.empty(k_img + 1, ld, dtype=torch.bfloat16, device=dev))
+                            torch.empty(k_img + 1, ld, dtype=H16, device=dev))
             else:
                 l1op_in = None
             acts = tuple(acts)
@@ -272,6 +300,7 @@ class _SAFunction(torch.autograd.Function):
         ctx.x_needs_grad = x is not None and x.requires_grad
         ctx.row_capacity = None if rowmap is None else rowmap[3]
         ctx.grad_dsts = grad_dsts
+        ctx.holder = current_options()   # backward runs on autograd's thread: it reads THIS holder, at backward time
         rmt = (None, None, None, None) if rowmap is None else (rowmap[0], rowmap[1], rowmap[2], rowmap[4])
         at = (None, None, None) if acts is None else (acts + (None,))[:3]
         ctx.save_for_backward(xs, pos_src, pos_dst, nbr, cnt, batch, *ws, *bs, *gs, *bes, rm1, rv1, rm2, rv2,
@@ -308,7 +337,7 @@ class _SAFunction(torch.autograd.Function):
                    c_in=ctx.c_in, x=xs, pos_src=pos_src, pos_dst=pos_dst, nbr=nbr, cnt=cnt, batch=batch, chans=chans,
                    act=act, eps=eps, momentum=momentum, ws=(w1, w2, w3), bs=(b1, b2, b3), gammas=(g1, g2),
                    betas=(be1, be2), rmeans=(rm1, rm2), rvars=(rv1, rv2), nbts=(None, None), out=grad_out, arg=arg,
-                   h1=h1, h2=h2, bn=bn, rowmap=rowmap, acts=acts)
+                   h1=h1, h2=h2, bn=bn, rowmap=rowmap, acts=acts, holder=ctx.holder)
         nbytes = lib.b2pn_sa_workspace_bytes(ctypes.byref(a), 1)
         if nbytes < 0:
             _lib.check(int(nbytes), "b2pn_sa_workspace_bytes")

@@ -317,17 +317,22 @@ class PipelinedTrainStep:
         # flight they are launched with a capped grid.  join="end": the whole step runs capped and waits for the
         # branch after the optimiser (the HBM-bound kernels lose little on 136 of 148 SMs; 2.59 vs 2.93 ms/step).
         # join="backward": the wait sits in the backward pass right before the level-2 backward and lifts the cap.
-        sa = self._sa
-        sa.set_sm_limit(self.sm_limit if sample_next else 0)
+        # the options holder of THIS thread: forward remembers it, backward (autograd's thread) reads it when it runs,
+        # so the closures below change the cap for the kernels launched after them, whichever thread launches them
+        opts = self._sa.current_options()
+        opts.sm_limit = self.sm_limit if sample_next else 0
+
+        def set_cap(n):
+            opts.sm_limit = n
 
         def join():
             if sample_next:
                 main.wait_stream(self.side)
-            sa.set_sm_limit(0)
+            set_cap(0)
 
         step = forward_backward if self.split else train_step
         early = self.join_at == "backward"
-        uncap = (lambda: sa.set_sm_limit(0)) if (self.uncap_l1 and not early) else None
+        uncap = (lambda: set_cap(0)) if (self.uncap_l1 and not early) else None
         loss = step(self.model, self.optimizer, cur, self.reducer, sampling=cur_sampling,
                     after_grouping=join if early else None, before_level1_backward=uncap)
         if not early:

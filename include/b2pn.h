@@ -118,7 +118,7 @@ int b2pn_ball_query_grid_f32(const float *src_pos, const float *qry_pos, const i
  *   rgrp    [capacity/8] u32      one descriptor per 8-row group: bits 0..23 centroid (0xFFFFFF none),
  *                                 24..26 first slot/8, 27..30 valid rows, 31 last group of the centroid
  *   row_src [capacity]   i32      gathered source point of the row, -1 = padding
- *   row_valid [capacity] bf16     1.0 for valid rows, 0 elsewhere (optional, may be NULL): the "ones" operand
+ *   row_valid [capacity] fp16     1.0 for valid rows, 0 elsewhere (optional, may be NULL): the "ones" operand
  *                                 line that yields the bias gradients in the dW GEMMs
  *   num_rows [2]         i64      [0] rows in use (multiple of 64), [1] valid rows = edges (sum of cnt)
  * Centroid m owns max(8, round_up(cnt[m], 8)) consecutive rows that never cross a 64-row boundary.
@@ -140,11 +140,12 @@ int b2pn_pack_rows(const int32_t *cnt, const int32_t *nbr, int64_t n_dst, int32_
  * layers with BatchNorm1d + activation after the first two.
  * ---------------------------------------------------------------------------------------------- */
 #define B2PN_PREC_F32 0   /* fp32 FMA on CUDA cores: the 1e-4 parity mode                      */
-#define B2PN_PREC_BF16 1  /* bf16 tcgen05 tensor-core tiles, fp32 accumulation in TMEM          */
+#define B2PN_PREC_BF16 1  /* 16-bit tcgen05 tensor-core tiles, fp32 accumulation in TMEM: forward-domain operands
+                             (weights, normalised activations) in fp16, gradients in bf16 -- see DESIGN.md section 3 */
 #define B2PN_SEG_SLOTS 0  /* SAModule: targets own K fixed-width neighbour slots (nbr/cnt)      */
 #define B2PN_SEG_CLOUDS 1 /* GlobalSAModule: every source row belongs to cloud batch[row]       */
 #define B2PN_X_F32 0
-#define B2PN_X_BF16 1
+#define B2PN_X_BF16 1     /* 16-bit features (fp16: the out_bf16 side output of the previous level)            */
 #define B2PN_ACT_NONE 0
 #define B2PN_ACT_RELU 1
 
@@ -168,7 +169,7 @@ typedef struct b2pn_sa_args {
     int32_t K;                   /* slots per target (SLOTS); PREC_BF16: K <= 64                      */
     int64_t n_src, n_dst;        /* source points; targets (centroids or clouds)                      */
     int32_t c_in;                /* feature channels of x (0: no features, pointnet2_regressor.py:17) */
-    int32_t x_dtype;             /* B2PN_X_F32 / B2PN_X_BF16 (bf16 only with B2PN_PREC_BF16)          */
+    int32_t x_dtype;             /* B2PN_X_F32 / B2PN_X_BF16 (16-bit = fp16, only with B2PN_PREC_BF16) */
     const void *x;               /* [n_src, c_in] row-major or NULL                                   */
     const float *pos_src;        /* [n_src, 3]                                                        */
     const float *pos_dst;        /* [n_dst, 3] (SLOTS) / NULL (CLOUDS: centre is the origin)          */
@@ -180,7 +181,7 @@ typedef struct b2pn_sa_args {
     int32_t *arg;                /* [n_dst, c3] arg-max slot (SLOTS) or source row (CLOUDS); -1 none  */
     void *h1, *h2;               /* saved activations of the two hidden layers.
                                     PREC_F32: pre-BN values, f32 row-major [rows, c], rows = n_dst*K (SLOTS) or
-                                    n_src (CLOUDS).  PREC_BF16: normalised values (h-mean)*rstd, bf16
+                                    n_src (CLOUDS).  PREC_BF16: normalised values (h-mean)*rstd, fp16
                                     FEATURE-major [c, ld], ld = row_capacity (SLOTS) or n_src rounded up to a
                                     multiple of 128 (CLOUDS)                                            */
     float *bn;                   /* [2][4][cmax] per BN layer: mean, rstd, scale, shift; cmax=max(c1,c2) */
@@ -191,13 +192,13 @@ typedef struct b2pn_sa_args {
     const int32_t *row_src;
     const int64_t *num_rows;
     int64_t row_capacity;        /* b2pn_pack_rows_capacity(n_dst, K)                                   */
-    const void *row_valid;       /* bf16 [row_capacity] from b2pn_pack_rows, or NULL                    */
-    /* PREC_BF16: activations of the two hidden layers AFTER BatchNorm affine + activation, bf16 feature-major
+    const void *row_valid;       /* fp16 [row_capacity] from b2pn_pack_rows, or NULL                    */
+    /* PREC_BF16: activations of the two hidden layers AFTER BatchNorm affine + activation, fp16 feature-major
      * [c, ld] like h1/h2, invalid rows zero.  Written by forward, read by backward: stored next to the
      * normalised values so that every later consumer is a plain tensor-map (TMA) copy.                  */
     void *a1, *a2;
     /* PREC_BF16 + SEG_SLOTS, optional (NULL = gather in the loader warps): the gathered + concatenated layer-1
-     * operand, bf16 feature-major [c_img + 1, ld] with c_img = (x fp32 ? 2 : 1) * c_in + 6 image columns
+     * operand, fp16 feature-major [c_img + 1, ld] with c_img = (x fp32 ? 2 : 1) * c_in + 6 image columns
      * [x | x_lo | dpos_hi | dpos_lo] and a last line of ones on valid rows.  Written by forward (or ahead of it by
      * b2pn_sa_gather_rows: set g1_ready = 1 and forward skips the gather), read by backward.                    */
     void *g1;
@@ -212,7 +213,7 @@ typedef struct b2pn_sa_args {
                                     run (as in the reference's scatter / cuBLAS kernels).  1: per-split partials summed
                                     in a fixed order and the grad_x scatter done by one owner per source row: bit-
                                     reproducible gradients                                                            */
-    void *out_bf16;              /* PREC_BF16, optional: a bf16 copy of `out` [n_dst, c3] written by the same epilogue --
+    void *out_bf16;              /* PREC_BF16, optional: a 16-bit (fp16) copy of `out` [n_dst, c3] written by the same epilogue --
                                     the next level's gather reads it (half the bytes, no separate cast kernel)         */
 } b2pn_sa_args;
 
@@ -319,7 +320,7 @@ int32_t b2pn_augment_max_points(void);
 /*
  * Hardware self-test of the tcgen05 GEMM pipeline (debug aid used by tests/test_tc_gpu.py; not part of
  * the reference's surface).  out[m][row] (fp32, leading dimension ld_out) = sum_k w[m][k] * b(row, k) with
- * b in bf16, row-major [rows][k] (mode 0: K-major B tiles) or feature-major [k][ld] (mode 1: MN-major B
+ * b in fp16, row-major [rows][k] (mode 0: K-major B tiles) or feature-major [k][ld] (mode 1: MN-major B
  * tiles; mode 2: the same operand fetched by TMA tensor-map copies).  zeros3: [rows,3] fp32 zeros.  workspace >= packed weight image + 1 KB.
  */
 int b2pn_tc_gemm_selftest(const float *w, int32_t m_out, int32_t k, const void *b_bf16, int32_t mode, int64_t rows,

@@ -166,11 +166,15 @@ def _resolve_act(act):
 
 
 class _RoundBF16(torch.autograd.Function):
-    """Round to bf16 in forward, identity in backward (models where the B200 bf16 mode rounds)."""
+    """Round to the 16-bit operand format in forward, identity in backward (models where the B200 tensor-core mode
+    rounds).  ``fmt``: class attribute; the kernels keep forward-domain operands in fp16 (torch.bfloat16 reproduces the
+    round-1 behaviour for error-attribution experiments)."""
+
+    fmt = torch.float16
 
     @staticmethod
     def forward(ctx, x):
-        return x.to(torch.bfloat16).to(x.dtype)
+        return x.to(_RoundBF16.fmt).to(x.dtype)
 
     @staticmethod
     def backward(ctx, g):
@@ -180,11 +184,15 @@ class _RoundBF16(torch.autograd.Function):
 class MLPRef(torch.nn.Module):
     """PyG ``MLP(channel_list, act=..., dropout=..., batch_norm=True)``.
 
-    ``emulate_bf16 = True`` rounds weights and the post-BatchNorm values to bf16 exactly where the bf16
+    ``emulate_bf16 = True`` rounds weights and the post-BatchNorm values to the 16-bit operand format exactly where the
     tensor-core mode does (fp32 accumulation and statistics), so tests can separate kernel bugs from the
-    arg-max / ReLU-mask flips that bf16 rounding legitimately causes in the gradients."""
+    arg-max / ReLU-mask flips that 16-bit rounding legitimately causes in the gradients."""
 
     emulate_bf16 = False
+    # which of the bf16 mode's roundings the emulation applies (error attribution, tools/bf16_attribution.py):
+    # W weights, X the MLP's input (a previous level's output arrives as bf16), Z the stored normalised value,
+    # A the activation operand of the next GEMM
+    emulate_parts = "WXZA"
 
     def __init__(self, channel_list: Sequence[int], act="relu", dropout: float = 0.0):
         super().__init__()
@@ -197,18 +205,25 @@ class MLPRef(torch.nn.Module):
 
     def forward(self, x):
         if self.emulate_bf16:
-            q = _RoundBF16.apply
-            x = F.linear(x, q(self.lins[0].weight), self.lins[0].bias)
+            parts = self.emulate_parts
+            rnd = _RoundBF16.apply
+            ident = lambda t: t  # noqa: E731
+            q = rnd if "A" in parts else ident
+            qz = rnd if "Z" in parts else ident
+            qw = rnd if "W" in parts else ident
+            if "X" in parts and x.size(1) > 16:   # wide feature maps go in as bf16; raw inputs as hi+lo pairs (~fp32)
+                x = torch.cat([rnd(x[:, :-3]), x[:, -3:]], 1)
+            x = F.linear(x, qw(self.lins[0].weight), self.lins[0].bias)
             for lin, norm in zip(self.lins[1:], self.norms):
                 # the kernels store the NORMALISED value in bf16 and apply gamma/beta afterwards
                 xhat = F.batch_norm(x, norm.running_mean, norm.running_var, None, None, self.training, norm.momentum,
                                     norm.eps)
                 if self.training and norm.num_batches_tracked is not None:
                     norm.num_batches_tracked += 1
-                x = q(q(xhat) * norm.weight + norm.bias)   # second rounding: the MMA operand itself is bf16
+                x = q(qz(xhat) * norm.weight + norm.bias)   # second rounding: the MMA operand itself is bf16
                 if self.act is not None:
                     x = self.act(x)
-                x = F.linear(x, q(lin.weight), lin.bias)
+                x = F.linear(x, qw(lin.weight), lin.bias)
             return x
         x = self.lins[0](x)
         for lin, norm in zip(self.lins[1:], self.norms):

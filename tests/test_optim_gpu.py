@@ -18,7 +18,9 @@ def test_flat_adam_matches_torch_adam(cuda_device):
 
     def make():
         torch.manual_seed(1)
-        m = torch.nn.Sequential(torch.nn.Linear(37, 53), torch.nn.BatchNorm1d(53), torch.nn.Linear(53, 4)).to(cuda_device)
+        # (no BatchNorm here: a bias in front of one has a zero gradient in theory and rounding noise in practice, which
+        #  Adam's normalisation turns into O(lr) parameter differences between ANY two implementations)
+        m = torch.nn.Sequential(torch.nn.Linear(37, 53), torch.nn.Tanh(), torch.nn.Linear(53, 4)).to(cuda_device)
         return m
 
     a, b = make(), make()
@@ -34,13 +36,14 @@ def test_flat_adam_matches_torch_adam(cuda_device):
             m(x).square().mean().backward()
             o.step()
         for (k, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
-            err = float((p - q).abs().max() / p.abs().max())
+            err = float((p.detach() - q.detach()).abs().max() / p.detach().abs().max())
             assert err < 2e-6 * (step + 1), (step, k, err)
     assert opt.steps_taken == 12
     sd = opt.state_dict()
     assert sd["step"] == 12 and set(sd["state"]) == {n for n, _ in b.named_parameters()}
     st = ref_opt.state[list(a.parameters())[0]]
-    assert float((st["exp_avg_sq"] - sd["state"]["0.weight"]["exp_avg_sq"]).abs().max()) < 1e-6 * float(st["exp_avg_sq"].abs().max()) + 1e-12
+    torch.testing.assert_close(sd["state"]["0.weight"]["exp_avg_sq"], st["exp_avg_sq"], rtol=1e-4, atol=1e-12)
+    torch.testing.assert_close(sd["state"]["0.weight"]["exp_avg"], st["exp_avg"], rtol=1e-4, atol=1e-9)
     # a CUDA-graph replay is a real optimiser step (the step counter lives on the device)
     opt2 = FlatAdam(ParamArena(make()), lr=ADAM_LR)
     opt2.arena.flat_grads.fill_(0.5)

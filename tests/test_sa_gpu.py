@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 # run-to-run spread allowed on the bf16 level-1 weight gradients in the DEFAULT (atomic) mode, relative to the largest
 # level-1 gradient: measured over 20 runs in profiles/r02_grad_spread.md; the deterministic mode is held to bit-equality
-SA1_SPREAD_BOUND = 2e-2
+SA1_SPREAD_BOUND = 5e-3   # measured worst over 20 runs: 9.2e-4 (3 x 640 points), 2.8e-4 (12 x 10 000 points)
 
 
 def rel_err(got, want):
@@ -307,7 +307,7 @@ def test_sa_slots_level_bf16_backward(cuda_device, c_in, chans, K):
     b = Batch.from_data_list(synthetic_clouds(21, 3, 600, max(c_in, 1), True))
     x = None if c_in == 0 else (torch.randn(b.pos.size(0), c_in, generator=torch.Generator().manual_seed(1)))
     if x is not None and c_in > 16:
-        x = x.to(torch.bfloat16).float()   # wide feature maps enter the kernel as bf16
+        x = x.to(torch.float16).float()   # wide feature maps enter the kernel as fp16 (forward-domain operand format)
     idx = ref.fps_ref(b.pos, b.ptr, 0.2)
     qptr = ref.sample_ptr(b.ptr, 0.2)
     nbr, cnt = ref.ball_query_ref(b.pos, b.pos[idx], b.ptr, qptr, 2.5, K)
@@ -338,7 +338,7 @@ def test_global_sa_level_bf16_backward(cuda_device):
     g = torch.Generator().manual_seed(5)
     sizes = [130, 257, 64]
     n = sum(sizes)
-    x = (torch.randn(n, 32, generator=g)).to(torch.bfloat16).float()
+    x = (torch.randn(n, 32, generator=g)).to(torch.float16).float()
     pos = torch.randn(n, 3, generator=g) * 3
     batch = torch.repeat_interleave(torch.arange(3), torch.tensor(sizes))
     for chans in ([35, 64, 96, 200], [35, 256, 512, 1024]):
