@@ -1328,6 +1328,31 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
         };
         unsigned inf[8], infn[8];
         if (grp < nchunks) load_inf(inf, (c_beg + grp) * 64);
+        // TMA copies of chunk i (one thread): the Y tile completes on full[s] directly; the X tile lands as fp16 and completes
+        // on xland[s], because the group converts it to bf16 before the MMA may read it.  The copies are issued up to
+        // AHEAD chunks of this group ahead of the conversion, so the ring stays as deep as before the conversion existed
+        // (these kernels are pure streams: they live off the bytes in flight).
+        auto issue = [&](int64_t i) {
+            const int s = (int)(i % nst);
+            const uint32_t ph = (uint32_t)(i / nst) & 1u;
+            uint8_t *A = smem + s * sbytes;
+            uint8_t *B = A + P::A_BYTES;
+            const int64_t r0 = (c_beg + i) * 64;
+            mbar_wait(&empty[s], ph ^ 1u);
+            if constexpr (YS::USES_TMA) {  // MTA*128 lines x 64 rows straight from the feature-major tensor, 64 lines per copy
+                mbar_expect_tx(&full[s], P::A_BYTES);
+#pragma unroll
+                for (int m = 0; m < MTA * 2; ++m)
+                    tma_load_2d(A + m * (64 * LINE_BYTES), &tmap_y, (int)r0, mg * (MTA * 128) + m * 64, &full[s]);
+            }
+            if constexpr (XF::USES_TMA) {
+                xf.fill_tma(B, r0, ng, &tmap_x, &tmap_v, &xland[s]);
+                mbar_arrive(&xland[s]);
+            }
+        };
+        constexpr bool ANY_TMA = YS::USES_TMA || XF::USES_TMA;
+        const int ahead = nst / LOAD_GROUPS > 1 ? nst / LOAD_GROUPS : 1;  // chunks of this group in flight
+        int64_t iss = grp;
         for (int64_t i = grp; i < nchunks; i += LOAD_GROUPS) {
             const int s = (int)(i % nst);
             const uint32_t ph = (uint32_t)(i / nst) & 1u;
@@ -1335,15 +1360,12 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
             uint8_t *B = A + P::A_BYTES;
             const int64_t r0 = (c_beg + i) * 64;
             if (i + LOAD_GROUPS < nchunks) load_inf(infn, (c_beg + i + LOAD_GROUPS) * 64);
-            if constexpr (YS::USES_TMA) {
-                mbar_wait(&empty[s], ph ^ 1u);
-                if (lt == 0) {  // MTA*128 lines x 64 rows straight from the feature-major tensor, 64 lines per copy
-                    mbar_expect_tx(&full[s], P::A_BYTES);
-#pragma unroll
-                    for (int m = 0; m < MTA * 2; ++m)
-                        tma_load_2d(A + m * (64 * LINE_BYTES), &tmap_y, (int)r0, mg * (MTA * 128) + m * 64, &full[s]);
-                }
-            } else {
+            if constexpr (ANY_TMA) {
+                // a wait in issue() depends on chunks < iss - nst + 1 <= i only, i.e. on work this group has already done
+                if (lt == 0)
+                    for (; iss < nchunks && iss < i + (int64_t)ahead * LOAD_GROUPS; iss += LOAD_GROUPS) issue(iss);
+            }
+            if constexpr (!YS::USES_TMA) {
                 if constexpr (YS::SCATTER) {
                     mbar_wait(&empty[s], ph ^ 1u);
 #pragma unroll
@@ -1372,22 +1394,17 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
             if constexpr (XF::USES_TMA) {
                 // the stored activations are fp16, the gradients on the Y side bf16: the group converts the landed X tile
                 // to bf16 in place (16-byte chunks, element-wise: the swizzle is untouched)
-                if (lt == 0) {
-                    const unsigned bytes = xf.fill_tma(B, r0, ng, &tmap_x, &tmap_v, &xland[s]);
-                    (void)bytes;
-                    mbar_arrive(&xland[s]);
-                }
                 mbar_wait(&xland[s], ph);
                 const int nchunk16 = xf.landed_lines(ng) * 8;
                 for (int c = lt; c < nchunk16; c += NUM_LOAD) {
                     uint4 *q = reinterpret_cast<uint4 *>(B) + c;
                     *q = f16_to_bf16_chunk(*q);
                 }
-                fence_proxy_async_smem();
             } else {
+                if constexpr (YS::USES_TMA) mbar_wait(&empty[s], ph ^ 1u);  // (the other Y paths have waited above)
                 xf.fill(B, lt, r0, ng, nb_lines, inf);
-                fence_proxy_async_smem();
             }
+            fence_proxy_async_smem();
             mbar_arrive(&full[s]);
 #pragma unroll
             for (int g = 0; g < 8; ++g) inf[g] = infn[g];
