@@ -54,7 +54,9 @@ def parse_args():
                          "dense: configs[3] (8 x 100k points, radii 4/16, train step)")
     ap.add_argument("--dp-mode", default="graph", choices=["graph", "split", "eager"],
                     help="N>1: all-reduce + Adam inside the step graph / eager after a forward+backward graph / no graph")
-    ap.add_argument("--dp-overlap", action="store_true", help="N>1: buckets go out on a side stream during backward")
+    ap.add_argument("--no-dp-overlap", dest="dp_overlap", action="store_false",
+                    help="N>1: all-reduce the buckets after backward on the training stream instead of on a side stream as "
+                         "backward finishes them (measured at N=2: 2.38 ms/step overlapped, 2.41 serial)")
     ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-mode sibling measurement (N=1, train config)")
     args = ap.parse_args()
     if args.config == "dense":
@@ -426,8 +428,7 @@ def run_b200(args):
                     "roofline": None, "cpu_baseline": None}
             print(json.dumps(line), flush=True)
         if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+            shutdown_dist(dist)
         return
 
     # =============================================================================================================
@@ -449,6 +450,8 @@ def run_b200(args):
             raise RuntimeError(f"data-parallel replicas diverged: max |param - rank 0's| = {spread}")
     if stepper is not None:
         stepper.close()
+        if world > 1 and use_graph:
+            stepper.release_graphs()   # graphs holding NCCL plans must die before the communicator can
 
     # ---- rooflines: each kernel timed alone with CUDA events, L2 flushed --------------------------------------------
     b0 = pool_dev[0]
@@ -519,8 +522,7 @@ def run_b200(args):
 
     if rank != 0:
         if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+            shutdown_dist(dist)
         return
 
     line = {"metric": metric_name(args), "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -549,12 +551,25 @@ def run_b200(args):
         line["allreduce_calls_per_step"] = dp["allreduce_calls_per_step"]
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        shutdown_dist(dist)
 
 
 def stepper_grouping(args):
     return not args.no_pregroup
+
+
+def shutdown_dist(dist):
+    """Leave the process group.  The JSON line is already out; a communicator that refuses to die must not turn a
+    finished measurement into a hung job, so a watchdog ends the process after 30 s."""
+    sys.stdout.flush()
+    t = threading.Timer(30.0, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    try:
+        dist.barrier()
+        dist.destroy_process_group()
+    finally:
+        t.cancel()
 
 
 def main():

@@ -295,6 +295,18 @@ class PipelinedTrainStep:
     def close(self) -> None:
         self._sa.set_sm_limit(0)
 
+    def release_graphs(self) -> None:
+        """Destroy the captured graphs.  REQUIRED before ``torch.distributed.destroy_process_group()`` when the
+        collectives were captured: NCCL keeps a communicator alive (and ``ncclCommDestroy`` waits) while a CUDA graph still
+        holds one of its persistent plans -- measured in round 2: the 2-GPU bench printed its line and then never
+        exited."""
+        import gc
+        torch.cuda.synchronize(self.dev)
+        self.graphs, self.graph, self.losses = None, None, None
+        self.pending = False
+        gc.collect()
+        torch.cuda.synchronize(self.dev)
+
     def __enter__(self):
         return self
 

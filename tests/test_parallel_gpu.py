@@ -70,6 +70,7 @@ def test_world1_graph_step_all_reduces_every_step(cuda_device, mode):
             got.append(float(stepper.flush()))
         torch.cuda.synchronize()
         assert red.replicas_identical() == 0.0
+        stepper.release_graphs()
     finally:
         dist.destroy_process_group()
     print(mode, want, got)
@@ -108,6 +109,7 @@ def _rank_worker(rank, world, port, out_dir, mode):
     spread = red.replicas_identical()
     torch.save({"reduced": reduced, "params": red.arena.flat_params.clone().cpu(), "spread": spread,
                 "per_step": stepper.allreduce_per_step}, os.path.join(out_dir, f"rank{rank}.pt"))
+    stepper.release_graphs()       # graphs holding NCCL plans must die before the communicator can
     dist.barrier()
     dist.destroy_process_group()
 
@@ -131,10 +133,13 @@ def test_world2_nccl_replicas_stay_identical(cuda_device, tmp_path, mode):
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
     ctx = mp.start_processes(_rank_worker, args=(2, _free_port(), str(tmp_path), mode), nprocs=2, join=False,
                              start_method="spawn")
-    if not ctx.join(timeout=600):
-        for p in ctx.processes:
-            p.kill()
-        pytest.fail("2-rank NCCL step did not finish in 600 s")
+    import time
+    t0 = time.time()
+    while not ctx.join(timeout=5):
+        if time.time() - t0 > 240:
+            for p in ctx.processes:
+                p.kill()
+            pytest.fail("2-rank NCCL step did not finish in 240 s")
     r0, r1 = torch.load(tmp_path / "rank0.pt"), torch.load(tmp_path / "rank1.pt")
     assert r0["spread"] == 0.0 and r1["spread"] == 0.0
     assert torch.equal(r0["params"], r1["params"])                 # bit-identical replicas after 4 graph-replayed steps
