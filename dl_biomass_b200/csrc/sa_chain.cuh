@@ -1,0 +1,331 @@
+// Kernel 3c -- a whole SLOTS set-abstraction level in ONE launch (included by sa_tc.cu).
+//
+//   gather + concat -> MMA1 -> epilogue (affine + ReLU) -> shared memory -> MMA2 -> epilogue -> shared memory -> MMA3 ->
+//   per-centroid max
+//
+// i.e. PointNetConv(local_nn) of /root/reference/pointnet2_regressor.py:18 with BatchNorm in EVALUATION mode (running
+// statistics: the reference's test-time pass, /root/reference/testing_model.py:56-64): nothing but the [n_dst, c3] output
+// ever leaves the SM.  The multi-pass kernels of sa_tc.cu stored every hidden activation twice (zhat and a) and made five
+// GEMM passes per level because train-mode BatchNorm needs batch statistics between the layers; evaluation does not.
+//
+// Work unit: a tile of 64 compacted rows (a centroid never crosses a 64-row boundary), channels on the TMEM lanes, rows
+// on the TMEM columns (UMMA M = 128, N = 64) -- the orientation of every kernel here, so the per-centroid max is again a
+// per-thread scan of accumulator columns.  A CTA keeps TWO tiles in flight (slots): each slot has its own loader warps,
+// epilogue warps, shared-memory operand buffers and TMEM columns, one thread issues the MMAs of both.  All three weight
+// images stay resident in shared memory.
+//
+//   warps  0- 7 / 8-15   epilogue group of slot 0 / 1: warp w drains TMEM lane quarter w % 4, column half (w / 4) % 2
+//   warp  16             MMA issuer (one thread) and TMEM owner
+//   warps 17-18 / 19-20  gather loaders of slot 0 / 1: one thread per row of the tile
+//
+// Shared-memory operand tiles follow tc_common.cuh: 128-byte lines, SWIZZLE_128B.  The gathered layer-1 operand is a K-major
+// B tile (line = row); the epilogues write the next layer's operand as an MN-major B tile (line = channel, 64 rows per line).
+#pragma once
+
+namespace b2pn {
+namespace tc {
+
+constexpr int CH_ROWS = 64;
+constexpr int CH_SLOTS = 2;
+constexpr int CH_EPI_WARPS = 8;                       // per slot
+constexpr int CH_EPI_THREADS = CH_EPI_WARPS * 32;     // 256
+constexpr int CH_LOAD_THREADS = 64;                   // per slot
+constexpr int CH_MMA_WARP = CH_SLOTS * CH_EPI_WARPS;  // 16
+constexpr int CH_THREADS = CH_SLOTS * CH_EPI_THREADS + 32 + CH_SLOTS * CH_LOAD_THREADS;  // 672
+constexpr int CH_CHUNK_BYTES = CH_ROWS * LINE_BYTES;  // 8 KB: 64 rows x 64 k (K-major) or 64 channel lines x 64 rows (MN-major)
+constexpr int CH_TMEM_PER_SLOT = 256;                 // D1 [0,64) D2 [64,128) D3 [128, 128 + 64 mt3)
+
+struct ChainParams {
+    const uint8_t *w_img[3];  // fp16 weight images (pack_weights_kernel), num_mg == 1
+    int w_bytes[3];
+    int k_img;                // real columns of the layer-1 operand
+    int k1c, c1c, c2c;        // K chunks (of 64) of layers 1, 2, 3
+    int c1, c2, c3;           // channels
+    int mt3;                  // M tiles of layer 3 (1: c3 <= 128, 2: c3 <= 256)
+    int64_t rows;
+    const int64_t *rows_dev;
+    // evaluation-mode BatchNorm folded into one multiply-add per element: y = act(acc * scale + shift)
+    const float *bias[3];
+    const float *gamma[2], *beta[2], *mean[2], *var[2];
+    float eps;
+    int act;
+    float *out;               // [n_dst][c3]
+    int32_t *arg;             // [n_dst][c3] arg-max slot
+    __half *out16;            // optional fp16 copy of out
+    const uint32_t *rgrp;
+};
+
+// barriers of a slot
+enum { CB_B1_FULL = 0, CB_B1_FREE, CB_D1_FULL, CB_A1_FULL, CB_D2_FULL, CB_A2_FULL, CB_D3_FULL, CB_D3_FREE, CB_PER_SLOT };
+
+__device__ __forceinline__ void chain_affine(const ChainParams &p, int layer, int ch, float &scale, float &shift)
+{
+    scale = 0.f;
+    shift = 0.f;
+    const int C = layer == 0 ? p.c1 : p.c2;
+    if (ch < C) {
+        const float rstd = 1.0f / sqrtf(p.var[layer][ch] + p.eps);
+        scale = p.gamma[layer][ch] * rstd;
+        shift = fmaf(p.bias[layer][ch] - p.mean[layer][ch], scale, p.beta[layer][ch]);
+    }
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_eval_kernel(const ChainParams p, GatherLoaderTC gl)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *W0 = smem, *W1 = W0 + p.w_bytes[0], *W2 = W1 + p.w_bytes[1];
+    uint8_t *slots = W2 + p.w_bytes[2];
+    const int b1_bytes = p.k1c * CH_CHUNK_BYTES;
+    const int x_bytes = (p.c1c > p.c2c ? p.c1c : p.c2c) * CH_CHUNK_BYTES;
+    const int slot_bytes = b1_bytes + x_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(slots + CH_SLOTS * slot_bytes);
+    uint64_t *w_full = bars + CH_SLOTS * CB_PER_SLOT;
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(w_full + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t rows = p.rows_dev ? *p.rows_dev : p.rows;
+    const int64_t num_tiles = (rows + CH_ROWS - 1) / CH_ROWS;
+    gl.resolve(rows);
+
+    if (tid == 0) {
+        for (int s = 0; s < CH_SLOTS; ++s) {
+            uint64_t *b = bars + s * CB_PER_SLOT;
+            mbar_init(&b[CB_B1_FULL], CH_LOAD_THREADS);
+            mbar_init(&b[CB_B1_FREE], 1);
+            mbar_init(&b[CB_D1_FULL], 1);
+            mbar_init(&b[CB_A1_FULL], CH_EPI_THREADS);
+            mbar_init(&b[CB_D2_FULL], 1);
+            mbar_init(&b[CB_A2_FULL], CH_EPI_THREADS);
+            mbar_init(&b[CB_D3_FULL], 1);
+            mbar_init(&b[CB_D3_FREE], CH_EPI_THREADS);
+        }
+        mbar_init(w_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == CH_MMA_WARP) tmem_alloc<512>(tmem_holder);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    // tile j of slot s in iteration it: (it * gridDim.x + blockIdx.x) * CH_SLOTS + s
+    auto tile_of = [&](int64_t it, int s) { return (it * (int64_t)gridDim.x + blockIdx.x) * CH_SLOTS + s; };
+
+    if (warp == CH_MMA_WARP) {
+        // ---------------------------------------------------------------- weights (once) + MMA issue for both slots
+        if (lane == 0) {
+            const int total = p.w_bytes[0] + p.w_bytes[1] + p.w_bytes[2];
+            mbar_expect_tx(w_full, (unsigned)total);
+            for (int l = 0; l < 3; ++l) {
+                uint8_t *dst = l == 0 ? W0 : (l == 1 ? W1 : W2);
+                for (int off = 0; off < p.w_bytes[l]; off += 16384)
+                    bulk_g2s(dst + off, p.w_img[l] + off, 16384u, w_full);
+            }
+            mbar_arrive(w_full);
+            mbar_wait(w_full, 0);
+            const uint32_t idesc_k = idesc_16(128, CH_ROWS, false, false, FMT_F16, FMT_F16);   // layer 1: K-major B
+            const uint32_t idesc_mn = idesc_16(128, CH_ROWS, false, true, FMT_F16, FMT_F16);   // layers 2, 3: MN-major B
+            int stage[CH_SLOTS] = {0, 0};
+            int64_t it[CH_SLOTS] = {0, 0};
+            bool done[CH_SLOTS];
+            for (int s = 0; s < CH_SLOTS; ++s) done[s] = tile_of(0, s) >= num_tiles;
+            while (!(done[0] && done[1])) {
+#pragma unroll
+                for (int s = 0; s < CH_SLOTS; ++s) {
+                    if (done[s]) continue;
+                    uint64_t *b = bars + s * CB_PER_SLOT;
+                    const uint32_t ph = (uint32_t)(it[s] & 1);
+                    uint8_t *B1 = slots + s * slot_bytes;
+                    uint8_t *X = B1 + b1_bytes;
+                    const uint32_t d1 = tmem_base + s * CH_TMEM_PER_SLOT, d2 = d1 + 64, d3 = d1 + 128;
+                    if (stage[s] == 0) {
+                        if (!mbar_try_wait(&b[CB_B1_FULL], ph)) continue;
+                        tc_fence_after();
+                        for (int kc = 0; kc < p.k1c; ++kc) {
+                            const int left = p.k_img - kc * KC;
+                            const int nks = left >= KC ? 4 : (left + 15) / 16;
+                            const uint32_t a_s = smem_u32(W0 + kc * (128 * LINE_BYTES));
+                            const uint32_t b_s = smem_u32(B1 + kc * CH_CHUNK_BYTES);
+                            for (int ks = 0; ks < nks; ++ks)
+                                umma_bf16(d1, smem_desc_sw128(a_s + ks * 32, 16, ATOM_BYTES),
+                                          smem_desc_sw128(b_s + ks * 32, 16, ATOM_BYTES), idesc_k, (kc | ks) != 0);
+                        }
+                        umma_commit(&b[CB_B1_FREE]);
+                        umma_commit(&b[CB_D1_FULL]);
+                        stage[s] = 1;
+                    } else if (stage[s] == 1) {
+                        if (!mbar_try_wait(&b[CB_A1_FULL], ph)) continue;
+                        tc_fence_after();
+                        for (int kc = 0; kc < p.c1c; ++kc) {
+                            const uint32_t a_s = smem_u32(W1 + kc * (128 * LINE_BYTES));
+                            const uint32_t b_s = smem_u32(X + kc * CH_CHUNK_BYTES);
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                umma_bf16(d2, smem_desc_sw128(a_s + ks * 32, 16, ATOM_BYTES),
+                                          smem_desc_sw128(b_s + ks * (16 * LINE_BYTES), 64 * LINE_BYTES, ATOM_BYTES), idesc_mn,
+                                          (kc | ks) != 0);
+                        }
+                        umma_commit(&b[CB_D2_FULL]);
+                        stage[s] = 2;
+                    } else {
+                        if (!mbar_try_wait(&b[CB_A2_FULL], ph)) continue;
+                        if (!mbar_try_wait(&b[CB_D3_FREE], ph ^ 1u)) continue;   // the previous tile's max has left D3
+                        tc_fence_after();
+                        for (int mt = 0; mt < p.mt3; ++mt) {
+                            for (int kc = 0; kc < p.c2c; ++kc) {
+                                const uint32_t a_s = smem_u32(W2 + (kc * p.mt3 + mt) * (128 * LINE_BYTES));
+                                const uint32_t b_s = smem_u32(X + kc * CH_CHUNK_BYTES);
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)
+                                    umma_bf16(d3 + mt * 64, smem_desc_sw128(a_s + ks * 32, 16, ATOM_BYTES),
+                                              smem_desc_sw128(b_s + ks * (16 * LINE_BYTES), 64 * LINE_BYTES, ATOM_BYTES),
+                                              idesc_mn, (kc | ks) != 0);
+                            }
+                        }
+                        umma_commit(&b[CB_D3_FULL]);
+                        stage[s] = 0;
+                        ++it[s];
+                        done[s] = tile_of(it[s], s) >= num_tiles;
+                    }
+                }
+            }
+        }
+    } else if (warp > CH_MMA_WARP) {
+        // ---------------------------------------------------------------- gather loaders: thread = row of the tile
+        const int lt0 = tid - (CH_MMA_WARP + 1) * 32;
+        const int s = lt0 / CH_LOAD_THREADS, lt = lt0 % CH_LOAD_THREADS;
+        uint64_t *b = bars + s * CB_PER_SLOT;
+        uint8_t *B1 = slots + s * slot_bytes;
+        for (int64_t it = 0;; ++it) {
+            const int64_t tile = tile_of(it, s);
+            if (tile >= num_tiles) break;
+            gl.set_row(tile * CH_ROWS + lt);
+            mbar_wait(&b[CB_B1_FREE], (uint32_t)(it & 1) ^ 1u);
+            for (int kc = 0; kc < p.k1c; ++kc) gl.produce(B1 + kc * CH_CHUNK_BYTES, kc, lt);
+            fence_proxy_async_smem();
+            mbar_arrive(&b[CB_B1_FULL]);
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue group of slot s
+        const int s = warp / CH_EPI_WARPS, w8 = warp % CH_EPI_WARPS;
+        const int q = w8 & 3, half = w8 >> 2;
+        uint64_t *b = bars + s * CB_PER_SLOT;
+        uint8_t *X = slots + s * slot_bytes + b1_bytes;
+        const int ch = q * 32 + lane;                                  // my channel within a 128-lane M tile
+        const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
+        const uint32_t d1 = tmem_base + lane_addr + s * CH_TMEM_PER_SLOT, d2 = d1 + 64, d3 = d1 + 128;
+        float sc1, sh1, sc2, sh2;
+        chain_affine(p, 0, ch, sc1, sh1);
+        chain_affine(p, 1, ch, sc2, sh2);
+        const bool relu = p.act == B2PN_ACT_RELU;
+        // layer 3: with two M tiles the column halves become M tiles (every thread scans all 64 rows of its channel)
+        const int ch3 = (p.mt3 == 2 ? half * 128 : 0) + ch;
+        const bool ep3 = p.mt3 == 2 || half == 0;
+        const float b3 = (ep3 && ch3 < p.c3) ? p.bias[2][ch3] : 0.f;
+        // my 32 rows of the tile as four 16-byte groups of my channel's line in the MN-major operand tile
+        uint8_t *xline = X + (ch >> 6) * CH_CHUNK_BYTES + (ch & 63) * LINE_BYTES;
+        const int sw = ch & 7;
+
+        auto hidden = [&](uint32_t dcol, float sc, float sh, int C, uint64_t *full, uint64_t *ready, uint32_t ph) {
+            mbar_wait(full, ph);
+            tc_fence_after();
+            if (ch - lane < C) {   // a warp whose 32 channels are all padding has nothing to drain
+                float v[32];
+                tmem_ld32(dcol + half * 32, v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        float y = fmaf(v[8 * j + e], sc, sh);
+                        f[e] = relu ? fmaxf(y, 0.f) : y;
+                    }
+                    *reinterpret_cast<uint4 *>(xline + (((half * 4 + j) ^ sw) << 4)) = pack8h(f);
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(ready);
+        };
+
+        for (int64_t it = 0;; ++it) {
+            const int64_t tile = tile_of(it, s);
+            if (tile >= num_tiles) break;
+            const uint32_t ph = (uint32_t)(it & 1);
+            hidden(d1, sc1, sh1, p.c1, &b[CB_D1_FULL], &b[CB_A1_FULL], ph);
+            hidden(d2, sc2, sh2, p.c2, &b[CB_D2_FULL], &b[CB_A2_FULL], ph);
+            // ---- layer 3 + max over the rows of every centroid of the tile
+            mbar_wait(&b[CB_D3_FULL], ph);
+            tc_fence_after();
+            if (ep3 && ch3 - lane < p.c3) {
+                const uint32_t dcol = d3 + (p.mt3 == 2 ? half * 64 : 0);
+                float best = -INFINITY;
+                int bk = -1;
+#pragma unroll 1
+                for (int cc = 0; cc < 2; ++cc) {
+                    float v[32];
+                    tmem_ld32(dcol + cc * 32, v);
+                    const int64_t g0 = tile * (CH_ROWS / 8) + cc * 4;
+#pragma unroll
+                    for (int gg = 0; gg < 4; ++gg) {
+                        unsigned inf = GI_NONE;
+                        if ((g0 + gg) * 8 < rows) inf = __ldg(p.rgrp + g0 + gg);  // warp-uniform
+                        if (gi_none(inf)) continue;
+                        const int s0 = gi_slot0(inf), nv = gi_nv(inf);
+                        if (s0 == 0) {
+                            best = -INFINITY;
+                            bk = -1;
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float x = v[gg * 8 + e] + b3;
+                            if (e < nv && x > best) {
+                                best = x;
+                                bk = s0 + e;
+                            }
+                        }
+                        if (gi_last(inf) && ch3 < p.c3) {
+                            const int64_t m = gi_seg(inf);
+                            const float o = bk >= 0 ? best : 0.f;
+                            p.out[m * p.c3 + ch3] = o;
+                            if (p.arg) p.arg[m * p.c3 + ch3] = bk;
+                            if (p.out16) p.out16[m * p.c3 + ch3] = __float2half_rn(o);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&b[CB_D3_FREE]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == CH_MMA_WARP) tmem_dealloc<512>(tmem_base);
+}
+
+// shapes the chained kernel covers: hidden widths of whole 64-channel chunks up to 128, output up to 256 channels, a
+// layer-1 operand of at most three 64-column chunks (the reference's levels 1 and 2 with neuron_multiplier 1)
+static bool chain_shapes_ok(const b2pn_sa_args &a, int k_img, int c1, int c2, int c3)
+{
+    if (a.seg_mode != B2PN_SEG_SLOTS || a.training) return false;
+    if (c1 % 64 || c2 % 64 || c1 > 128 || c2 > 128 || c3 > 256 || k_img > 3 * KC) return false;
+    return true;
+}
+// the caller opts in by passing h1 == NULL ("I do not want the hidden activations": no backward pass will follow)
+static bool chain_eligible(const b2pn_sa_args &a, int k_img, int c1, int c2, int c3)
+{
+    if (a.h1 != nullptr) return false;
+    if (a.seg_mode != B2PN_SEG_SLOTS || a.training) return false;
+    if (c1 % 64 || c2 % 64 || c1 > 128 || c2 > 128 || c3 > 256 || k_img > 3 * KC) return false;
+    return true;
+}
+
+static int chain_smem_bytes(const ChainParams &p)
+{
+    const int x_bytes = (p.c1c > p.c2c ? p.c1c : p.c2c) * CH_CHUNK_BYTES;
+    return p.w_bytes[0] + p.w_bytes[1] + p.w_bytes[2] + CH_SLOTS * (p.k1c * CH_CHUNK_BYTES + x_bytes) + 256 + 1024;
+}
+
+}  // namespace tc
+}  // namespace b2pn

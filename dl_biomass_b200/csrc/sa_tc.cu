@@ -1568,6 +1568,12 @@ static void launch_pack(const float *w, int M, int Kimg, int64_t sm, int64_t sk,
     launch_packs(&j, 1, st);
 }
 
+}  // namespace tc
+}  // namespace b2pn
+#include "sa_chain.cuh"
+namespace b2pn {
+namespace tc {
+
 static int sm_count()
 {
     static int sms_of[64] = {};  // per device; a racing first call writes the same value twice
@@ -2048,8 +2054,19 @@ static int check_args_tc(const b2pn_sa_args &a)
         if (!a.mlp.w[l] || !a.mlp.b[l]) return B2PN_EINVAL;
     for (int l = 0; l < 2; ++l)
         if (!a.mlp.gamma[l] || !a.mlp.beta[l] || !a.mlp.running_mean[l] || !a.mlp.running_var[l]) return B2PN_EINVAL;
-    if (!a.out || !a.arg || !a.h1 || !a.h2 || !a.bn || !a.a1 || !a.a2) return B2PN_EINVAL;
+    if (!a.out || !a.arg) return B2PN_EINVAL;
+    // the hidden-activation buffers are only touched by the multi-pass (training / wide-level) kernels
+    const ShapesTC sh = shapes_tc(a);
+    if (!chain_eligible(a, sh.k1, sh.c1, sh.c2, sh.c3) && (!a.h1 || !a.h2 || !a.bn || !a.a1 || !a.a2)) return B2PN_EINVAL;
     return B2PN_OK;
+}
+
+// 1 when b2pn_sa_forward runs these arguments through the single-launch evaluation kernel (no hidden activations stored)
+int sa_eval_fused_bf16(const b2pn_sa_args &a)
+{
+    if (a.mlp.c[0] != a.c_in + 3) return 0;
+    const ShapesTC s = shapes_tc(a);
+    return chain_shapes_ok(a, s.k1, s.c1, s.c2, s.c3) ? 1 : 0;
 }
 
 static RowMapTC rowmap_tc(const b2pn_sa_args &a, const ShapesTC &s)
@@ -2209,6 +2226,49 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
                                  pack_job(a.mlp.w[1], s.c2, s.c1, s.c1, 1, nullptr, f.pk[1]),
                                  pack_job(a.mlp.w[2], s.c3, s.c2, s.c2, 1, nullptr, f.pk[2])};
         launch_packs(jobs, 3, st);
+    }
+    if (chain_eligible(a, s.k1, s.c1, s.c2, s.c3)) {
+        // evaluation mode: the whole level in one launch, nothing but `out` written (sa_chain.cuh)
+        if (s.rows == 0) return B2PN_OK;
+        ChainParams cp = {};
+        for (int l = 0; l < 3; ++l) {
+            cp.w_img[l] = f.pk[l].img;
+            cp.w_bytes[l] = (int)f.pk[l].bytes;
+            cp.bias[l] = a.mlp.b[l];
+        }
+        for (int l = 0; l < 2; ++l) {
+            cp.gamma[l] = a.mlp.gamma[l];
+            cp.beta[l] = a.mlp.beta[l];
+            cp.mean[l] = a.mlp.running_mean[l];
+            cp.var[l] = a.mlp.running_var[l];
+        }
+        cp.k_img = s.k1;
+        cp.k1c = f.pk[0].num_kc;
+        cp.c1c = f.pk[1].num_kc;
+        cp.c2c = f.pk[2].num_kc;
+        cp.c1 = s.c1;
+        cp.c2 = s.c2;
+        cp.c3 = s.c3;
+        cp.mt3 = f.pk[2].MT;
+        cp.rows = ra.cap;
+        cp.rows_dev = ra.dev;
+        cp.eps = a.mlp.eps;
+        cp.act = a.mlp.act;
+        cp.out = a.out;
+        cp.arg = a.arg;
+        cp.out16 = (__half *)a.out_bf16;
+        cp.rgrp = a.rgrp;
+        GatherLoaderTC cg = {rm, a.x, s.cols, a.pos_src, a.pos_dst, -1, FMT_F16};
+        const int smem = chain_smem_bytes(cp);
+        cudaError_t e = cudaFuncSetAttribute(tc_chain_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        const int64_t tiles64 = (ra.cap + CH_ROWS - 1) / CH_ROWS;
+        int gx = sm_count();
+        if ((int64_t)gx * CH_SLOTS > tiles64) gx = (int)((tiles64 + CH_SLOTS - 1) / CH_SLOTS);
+        tc_chain_eval_kernel<<<gx, CH_THREADS, smem, st>>>(cp, cg);
+        note_launch();
+        B2PN_LAUNCH_CHECK();
+        return B2PN_OK;
     }
     const CountArg count = {a.seg_mode == B2PN_SEG_SLOTS ? a.num_rows + 1 : nullptr, (double)s.rows};
 

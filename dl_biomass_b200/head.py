@@ -21,7 +21,11 @@ def supported(mlp, x: torch.Tensor) -> bool:
     if len(mlp.lins) != 3 or len(mlp.norms) != 2 or mlp.act_name is not None:
         return False
     c = mlp.channel_list
-    return 0 < x.size(0) <= MAX_ROWS and c[1] <= MAX_HIDDEN and c[2] <= MAX_HIDDEN and c[3] <= MAX_OUT
+    # evaluation mode normalises with the running statistics, i.e. row by row: any number of clouds goes through in
+    # chunks of MAX_ROWS (the reference evaluates its whole test set as one batch, testing_model.py:56); training mode
+    # needs the batch statistics of all rows in one CTA
+    rows_ok = 0 < x.size(0) <= MAX_ROWS or (x.size(0) > 0 and not mlp.training)
+    return rows_ok and c[1] <= MAX_HIDDEN and c[2] <= MAX_HIDDEN and c[3] <= MAX_OUT
 
 
 def _fill(a, x, mlp, training, p, out, saved, seed, counter):
@@ -109,6 +113,11 @@ def head_apply(mlp, x: torch.Tensor, counter: torch.Tensor, seed: int) -> torch.
     bumped by every training forward); ``seed``: per-model constant."""
     l0, l1, l2 = mlp.lins
     n0, n1 = mlp.norms
-    return _HeadFunction.apply(mlp, bool(mlp.training), float(mlp.dropout), int(seed), counter, x,
-                               l0.weight, l0.bias, n0.weight, n0.bias, l1.weight, l1.bias, n1.weight, n1.bias,
-                               l2.weight, l2.bias)
+    params = (l0.weight, l0.bias, n0.weight, n0.bias, l1.weight, l1.bias, n1.weight, n1.bias, l2.weight, l2.bias)
+    if x.size(0) > MAX_ROWS:
+        if mlp.training:
+            raise ValueError(f"the fused head trains on at most {MAX_ROWS} clouds per batch")
+        outs = [_HeadFunction.apply(mlp, False, 0.0, int(seed), counter, x[i:i + MAX_ROWS], *params)
+                for i in range(0, x.size(0), MAX_ROWS)]
+        return torch.cat(outs, 0)
+    return _HeadFunction.apply(mlp, bool(mlp.training), float(mlp.dropout), int(seed), counter, x, *params)

@@ -230,7 +230,7 @@ class _SAFunction(torch.autograd.Function):
                 w3, b3, rm1, rv1, nbt1, rm2, rv2, nbt2):
         lib = _lib.lib()
         ctx.set_materialize_grads(False)  # no zero-filled gradient tensors for the index / bf16 side outputs
-        grad_dsts, x_bf16, want_bf16_out = extra
+        grad_dsts, x_bf16, want_bf16_out, needs_bwd = extra
         dev = pos_src.device
         if not pos_src.is_cuda:
             raise RuntimeError("b2pn set abstraction runs on a B200 only: there is no CPU fallback")
@@ -256,7 +256,19 @@ class _SAFunction(torch.autograd.Function):
         out_bf16 = (torch.empty(n_dst, chans[3], dtype=H16, device=dev)
                     if (want_bf16_out and prec == PREC_BF16) else None)
         acts = None
-        if prec == PREC_F32:   # row-major fp32 activations [rows, c]
+        # evaluation without a backward pass to follow: one launch per level, no hidden activation stored (sa_chain.cuh)
+        fused_eval = False
+        if prec == PREC_BF16 and seg_mode == SEG_SLOTS and not training and not needs_bwd:
+            probe = SaArgs()
+            probe.precision, probe.training, probe.seg_mode, probe.K, probe.c_in = prec, 0, seg_mode, K, c_in
+            probe.x_dtype = 0 if (x is not None and x.dtype == f32 and c_in <= 16) else 1
+            for i in range(4):
+                probe.mlp.c[i] = chans[i]
+            fused_eval = lib.b2pn_sa_eval_fused(ctypes.byref(probe)) == 1
+        if fused_eval:
+            xs, _, _ = _l1_input(x, x_bf16)
+            h1 = h2 = None
+        elif prec == PREC_F32:   # row-major fp32 activations [rows, c]
             xs = None if x is None else x.detach().to(f32).contiguous()
             h1 = torch.empty(rows, chans[1], dtype=f32, device=dev)
             h2 = torch.empty(rows, chans[2], dtype=f32, device=dev)
@@ -277,7 +289,7 @@ class _SAFunction(torch.autograd.Function):
                 l1op_in = None
             acts = tuple(acts)
         cmax = max(chans[1], chans[2])
-        bn = torch.empty(2, 4, cmax, dtype=f32, device=dev)
+        bn = None if fused_eval else torch.empty(2, 4, cmax, dtype=f32, device=dev)
         a = SaArgs()
         _fill_args(a, precision=prec, training=training, seg_mode=seg_mode, K=K, n_src=n_src, n_dst=n_dst, c_in=c_in,
                    x=xs, pos_src=pos_src, pos_dst=pos_dst, nbr=nbr, cnt=cnt, batch=batch, chans=chans, act=act,
@@ -376,7 +388,9 @@ def sa_apply(mlp, x, pos_src, pos_dst, nbr, cnt, batch, *, seg_mode: int, K: int
     dsts = tuple(grad_dst(p) for p in params) if torch.is_grad_enabled() else None
     if dsts is not None and all(t is None for t in dsts):
         dsts = None
-    extra = (dsts, x_bf16, bool(want_bf16_out))
+    # (inside Function.forward grad mode is always off and needs_input_grad ignores it: decide here)
+    needs_bwd = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or (x is not None and x.requires_grad))
+    extra = (dsts, x_bf16, bool(want_bf16_out), needs_bwd)
     res = _SAFunction.apply(cfg, rowmap, l1op if rowmap is not None else None, extra, x, pos_src, pos_dst, nbr, cnt, batch,
                             *params, n0.running_mean, n0.running_var, n0.num_batches_tracked,
                             n1.running_mean, n1.running_var, n1.num_batches_tracked)

@@ -551,3 +551,40 @@ def test_deterministic_mode_gives_bit_identical_gradients(cuda_device):
             assert float((a - e).abs().max()) <= SA1_SPREAD_BOUND * scale1, n
         else:
             assert float((a - e).abs().max()) <= 1e-4 * float(a.abs().max()) + 1e-6 * scale, n
+
+
+@pytest.mark.parametrize("B,n", [(5, 700), (40, 1500)])
+def test_eval_mode_single_launch_levels_vs_oracle(cuda_device, B, n):
+    """Evaluation (BatchNorm on running statistics, no grad: /root/reference/testing_model.py:56-64): every SLOTS level
+    is ONE launch (csrc/sa_chain.cuh: gather -> MMA1 -> MMA2 -> MMA3 -> max, no hidden activation stored) and the head
+    takes any number of clouds.  Outputs within 2e-2 of the fp32 oracle (measured ~2e-3), equal to the multi-pass
+    kernels' to 16-bit rounding, and the launch count per level drops from 7 to 2 (weight packing + the level)."""
+    from dl_biomass_b200 import _lib
+    b = Batch.from_data_list(synthetic_clouds(99, B, n, 1, True))
+    netr, net = _net_pair(cuda_device, "bf16", False)
+    # give the running statistics something non-trivial: a few training steps' worth of updates on the oracle
+    netr.train()
+    with torch.no_grad():
+        for i in range(2):
+            netr(Batch.from_data_list(synthetic_clouds(500 + i, 4, 600, 1, True)))
+    netr.eval()
+    net.load_state_dict(netr.state_dict())
+    net.eval()
+    with torch.no_grad():
+        want = netr(b)
+        bg = b.to(cuda_device)
+        l0 = _lib.lib().b2pn_launch_count()
+        out = net(bg)
+        fused_launches = _lib.lib().b2pn_launch_count() - l0
+    with torch.enable_grad():      # the multi-pass kernels (hidden activations stored): same numbers to rounding
+        l0 = _lib.lib().b2pn_launch_count()
+        bg2 = b.to(cuda_device)
+        bg2.x = bg2.x.clone().requires_grad_(True)
+        out2 = net(bg2)
+        multi_launches = _lib.lib().b2pn_launch_count() - l0
+    torch.cuda.synchronize()
+    err = rel_err(out, want)
+    print("eval fused rel err", err, "vs multi-pass", rel_err(out, out2), "launches", fused_launches, multi_launches)
+    assert err < 2e-2
+    assert rel_err(out, out2) < 5e-3
+    assert fused_launches <= multi_launches - 10
