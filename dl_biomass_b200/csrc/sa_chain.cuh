@@ -16,7 +16,9 @@
 //
 //   warps  0- 7 / 8-15   epilogue group of slot 0 / 1: warp w drains TMEM lane quarter w % 4, column half (w / 4) % 2
 //   warp  16             MMA issuer (one thread) and TMEM owner
-//   warps 17-18 / 19-20  gather loaders of slot 0 / 1: one thread per row of the tile
+//   warps 17-20 / 21-24  gather loaders of slot 0 / 1: two threads per row of the tile; the row indices of the NEXT tile are
+//                        prefetched and all loads of a row are in flight together (the gather is a chain of dependent
+//                        L2 round trips: row -> source index -> feature row)
 //
 // Shared-memory operand tiles follow tc_common.cuh: 128-byte lines, SWIZZLE_128B.  The gathered layer-1 operand is a K-major
 // B tile (line = row); the epilogues write the next layer's operand as an MN-major B tile (line = channel, 64 rows per line).
@@ -29,9 +31,9 @@ constexpr int CH_ROWS = 64;
 constexpr int CH_SLOTS = 2;
 constexpr int CH_EPI_WARPS = 8;                       // per slot
 constexpr int CH_EPI_THREADS = CH_EPI_WARPS * 32;     // 256
-constexpr int CH_LOAD_THREADS = 64;                   // per slot
+constexpr int CH_LOAD_THREADS = 128;                  // per slot: two threads per row of the tile
 constexpr int CH_MMA_WARP = CH_SLOTS * CH_EPI_WARPS;  // 16
-constexpr int CH_THREADS = CH_SLOTS * CH_EPI_THREADS + 32 + CH_SLOTS * CH_LOAD_THREADS;  // 672
+constexpr int CH_THREADS = CH_SLOTS * CH_EPI_THREADS + 32 + CH_SLOTS * CH_LOAD_THREADS;  // 800
 constexpr int CH_CHUNK_BYTES = CH_ROWS * LINE_BYTES;  // 8 KB: 64 rows x 64 k (K-major) or 64 channel lines x 64 rows (MN-major)
 constexpr int CH_TMEM_PER_SLOT = 256;                 // D1 [0,64) D2 [64,128) D3 [128, 128 + 64 mt3)
 
@@ -70,14 +72,24 @@ __device__ __forceinline__ void chain_affine(const ChainParams &p, int layer, in
     }
 }
 
+// Shape parameters as template arguments (-1: take the run-time value of ChainParams).  The MMA issuer is ONE thread: with
+// run-time loop bounds its descriptor arithmetic is a dependent instruction stream of ~20 instructions per tcgen05.mma at
+// 4-6 cycles each, which made every MMA hop of the chain ~2000 cycles long (ncu, round 2: the epilogue warps spent 55 % of
+// their time waiting for D2 / D3); fully unrolled, a tcgen05.mma costs two 64-bit adds.
+template <int K1C_, int NKS_LAST_, int C1C_, int C2C_, int MT3_>
 __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_eval_kernel(const ChainParams p, GatherLoaderTC gl)
 {
+    const int k1c = K1C_ >= 0 ? K1C_ : p.k1c;
+    const int c1c = C1C_ >= 0 ? C1C_ : p.c1c;
+    const int c2c = C2C_ >= 0 ? C2C_ : p.c2c;
+    const int mt3 = MT3_ >= 0 ? MT3_ : p.mt3;
+    const int nks_last = NKS_LAST_ >= 0 ? NKS_LAST_ : ((p.k_img - (p.k1c - 1) * KC) >= KC ? 4 : (p.k_img - (p.k1c - 1) * KC + 15) / 16);
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *W0 = smem, *W1 = W0 + p.w_bytes[0], *W2 = W1 + p.w_bytes[1];
     uint8_t *slots = W2 + p.w_bytes[2];
-    const int b1_bytes = p.k1c * CH_CHUNK_BYTES;
-    const int x_bytes = (p.c1c > p.c2c ? p.c1c : p.c2c) * CH_CHUNK_BYTES;
+    const int b1_bytes = k1c * CH_CHUNK_BYTES;
+    const int x_bytes = (c1c > c2c ? c1c : c2c) * CH_CHUNK_BYTES;
     const int slot_bytes = b1_bytes + x_bytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(slots + CH_SLOTS * slot_bytes);
     uint64_t *w_full = bars + CH_SLOTS * CB_PER_SLOT;
@@ -91,14 +103,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_eval_kernel(const Chai
     if (tid == 0) {
         for (int s = 0; s < CH_SLOTS; ++s) {
             uint64_t *b = bars + s * CB_PER_SLOT;
-            mbar_init(&b[CB_B1_FULL], CH_LOAD_THREADS);
+            // one arrival per WARP (its lanes fence their own writes, __syncwarp, lane 0 arrives): 256 arrivals on one
+            // shared-memory word would serialise for ~250 cycles per barrier
+            mbar_init(&b[CB_B1_FULL], CH_LOAD_THREADS / 32);
             mbar_init(&b[CB_B1_FREE], 1);
             mbar_init(&b[CB_D1_FULL], 1);
-            mbar_init(&b[CB_A1_FULL], CH_EPI_THREADS);
+            mbar_init(&b[CB_A1_FULL], CH_EPI_WARPS);
             mbar_init(&b[CB_D2_FULL], 1);
-            mbar_init(&b[CB_A2_FULL], CH_EPI_THREADS);
+            mbar_init(&b[CB_A2_FULL], CH_EPI_WARPS);
             mbar_init(&b[CB_D3_FULL], 1);
-            mbar_init(&b[CB_D3_FREE], CH_EPI_THREADS);
+            mbar_init(&b[CB_D3_FREE], CH_EPI_WARPS);
         }
         mbar_init(w_full, 1);
         fence_barrier_init();
@@ -126,6 +140,22 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_eval_kernel(const Chai
             mbar_wait(w_full, 0);
             const uint32_t idesc_k = idesc_16(128, CH_ROWS, false, false, FMT_F16, FMT_F16);   // layer 1: K-major B
             const uint32_t idesc_mn = idesc_16(128, CH_ROWS, false, true, FMT_F16, FMT_F16);   // layers 2, 3: MN-major B
+            // per slot: the five operand base descriptors (loop-invariant: every tile of a slot uses the same buffers)
+            uint64_t da1[CH_SLOTS], db1[CH_SLOTS], db2[CH_SLOTS];
+            const uint64_t dw0 = smem_desc_sw128(smem_u32(W0), 16, ATOM_BYTES);
+            const uint64_t dw1 = smem_desc_sw128(smem_u32(W1), 16, ATOM_BYTES);
+            const uint64_t dw2 = smem_desc_sw128(smem_u32(W2), 16, ATOM_BYTES);
+#pragma unroll
+            for (int s = 0; s < CH_SLOTS; ++s) {
+                uint8_t *B1 = slots + s * slot_bytes;
+                da1[s] = 0;
+                db1[s] = smem_desc_sw128(smem_u32(B1), 16, ATOM_BYTES);                        // K-major gathered rows
+                db2[s] = smem_desc_sw128(smem_u32(B1 + b1_bytes), 64 * LINE_BYTES, ATOM_BYTES);  // MN-major activations
+            }
+            (void)da1;
+            // descriptor address field is in 16-byte units: advancing an operand by `bytes` adds bytes >> 4
+            constexpr uint64_t A_KS = 32 >> 4, A_CHUNK = (128 * LINE_BYTES) >> 4, B_KS_K = 32 >> 4,
+                               B_KS_MN = (16 * LINE_BYTES) >> 4, B_CHUNK = CH_CHUNK_BYTES >> 4;
             int stage[CH_SLOTS] = {0, 0};
             int64_t it[CH_SLOTS] = {0, 0};
             bool done[CH_SLOTS];
@@ -136,51 +166,53 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_eval_kernel(const Chai
                     if (done[s]) continue;
                     uint64_t *b = bars + s * CB_PER_SLOT;
                     const uint32_t ph = (uint32_t)(it[s] & 1);
-                    uint8_t *B1 = slots + s * slot_bytes;
-                    uint8_t *X = B1 + b1_bytes;
                     const uint32_t d1 = tmem_base + s * CH_TMEM_PER_SLOT, d2 = d1 + 64, d3 = d1 + 128;
                     if (stage[s] == 0) {
-                        if (!mbar_try_wait(&b[CB_B1_FULL], ph)) continue;
+                        if (!mbar_test_wait(&b[CB_B1_FULL], ph)) continue;
                         tc_fence_after();
-                        for (int kc = 0; kc < p.k1c; ++kc) {
-                            const int left = p.k_img - kc * KC;
-                            const int nks = left >= KC ? 4 : (left + 15) / 16;
-                            const uint32_t a_s = smem_u32(W0 + kc * (128 * LINE_BYTES));
-                            const uint32_t b_s = smem_u32(B1 + kc * CH_CHUNK_BYTES);
-                            for (int ks = 0; ks < nks; ++ks)
-                                umma_bf16(d1, smem_desc_sw128(a_s + ks * 32, 16, ATOM_BYTES),
-                                          smem_desc_sw128(b_s + ks * 32, 16, ATOM_BYTES), idesc_k, (kc | ks) != 0);
+#pragma unroll
+                        for (int kc = 0; kc < (K1C_ >= 0 ? K1C_ : 3); ++kc) {
+                            if (kc < k1c) {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)
+                                    if (kc + 1 < k1c || ks < nks_last)
+                                        umma_bf16(d1, dw0 + kc * A_CHUNK + ks * A_KS, db1[s] + kc * B_CHUNK + ks * B_KS_K, idesc_k,
+                                                  (kc | ks) != 0);
+                            }
                         }
                         umma_commit(&b[CB_B1_FREE]);
                         umma_commit(&b[CB_D1_FULL]);
                         stage[s] = 1;
                     } else if (stage[s] == 1) {
-                        if (!mbar_try_wait(&b[CB_A1_FULL], ph)) continue;
+                        if (!mbar_test_wait(&b[CB_A1_FULL], ph)) continue;
                         tc_fence_after();
-                        for (int kc = 0; kc < p.c1c; ++kc) {
-                            const uint32_t a_s = smem_u32(W1 + kc * (128 * LINE_BYTES));
-                            const uint32_t b_s = smem_u32(X + kc * CH_CHUNK_BYTES);
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)
-                                umma_bf16(d2, smem_desc_sw128(a_s + ks * 32, 16, ATOM_BYTES),
-                                          smem_desc_sw128(b_s + ks * (16 * LINE_BYTES), 64 * LINE_BYTES, ATOM_BYTES), idesc_mn,
-                                          (kc | ks) != 0);
+                        for (int kc = 0; kc < (C1C_ >= 0 ? C1C_ : 2); ++kc) {
+                            if (kc < c1c) {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)
+                                    umma_bf16(d2, dw1 + kc * A_CHUNK + ks * A_KS, db2[s] + kc * B_CHUNK + ks * B_KS_MN, idesc_mn,
+                                              (kc | ks) != 0);
+                            }
                         }
                         umma_commit(&b[CB_D2_FULL]);
                         stage[s] = 2;
                     } else {
-                        if (!mbar_try_wait(&b[CB_A2_FULL], ph)) continue;
-                        if (!mbar_try_wait(&b[CB_D3_FREE], ph ^ 1u)) continue;   // the previous tile's max has left D3
+                        if (!mbar_test_wait(&b[CB_A2_FULL], ph)) continue;
+                        if (!mbar_test_wait(&b[CB_D3_FREE], ph ^ 1u)) continue;   // the previous tile's max has left D3
                         tc_fence_after();
-                        for (int mt = 0; mt < p.mt3; ++mt) {
-                            for (int kc = 0; kc < p.c2c; ++kc) {
-                                const uint32_t a_s = smem_u32(W2 + (kc * p.mt3 + mt) * (128 * LINE_BYTES));
-                                const uint32_t b_s = smem_u32(X + kc * CH_CHUNK_BYTES);
 #pragma unroll
-                                for (int ks = 0; ks < 4; ++ks)
-                                    umma_bf16(d3 + mt * 64, smem_desc_sw128(a_s + ks * 32, 16, ATOM_BYTES),
-                                              smem_desc_sw128(b_s + ks * (16 * LINE_BYTES), 64 * LINE_BYTES, ATOM_BYTES),
-                                              idesc_mn, (kc | ks) != 0);
+                        for (int mt = 0; mt < (MT3_ >= 0 ? MT3_ : 2); ++mt) {
+                            if (mt < mt3) {
+#pragma unroll
+                                for (int kc = 0; kc < (C2C_ >= 0 ? C2C_ : 2); ++kc) {
+                                    if (kc < c2c) {
+#pragma unroll
+                                        for (int ks = 0; ks < 4; ++ks)
+                                            umma_bf16(d3 + mt * 64, dw2 + (uint64_t)(kc * mt3 + mt) * A_CHUNK + ks * A_KS,
+                                                      db2[s] + kc * B_CHUNK + ks * B_KS_MN, idesc_mn, (kc | ks) != 0);
+                                    }
+                                }
                             }
                         }
                         umma_commit(&b[CB_D3_FULL]);
@@ -192,19 +224,48 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_eval_kernel(const Chai
             }
         }
     } else if (warp > CH_MMA_WARP) {
-        // ---------------------------------------------------------------- gather loaders: thread = row of the tile
+        // ---------------------------------------------------------------- gather loaders: two threads per row of the tile
         const int lt0 = tid - (CH_MMA_WARP + 1) * 32;
         const int s = lt0 / CH_LOAD_THREADS, lt = lt0 % CH_LOAD_THREADS;
+        const int r = lt >> 1, part = lt & 1;   // my row of the tile; my half of every 128-byte line (chunks 4 part .. 4 part + 3)
         uint64_t *b = bars + s * CB_PER_SLOT;
         uint8_t *B1 = slots + s * slot_bytes;
+        // (source index, centroid) of my row in a tile: the head of the dependent chain, fetched one tile ahead
+        auto fetch_idx = [&](int64_t tile, int &sidx, int &m) {
+            sidx = -1;
+            m = 0;
+            const int64_t row = tile * CH_ROWS + r;
+            if (tile < num_tiles && row < rows) {
+                sidx = __ldg(gl.rm.row_src + row);
+                m = gi_seg(__ldg(gl.rm.rgrp + (row >> 3)));
+            }
+        };
+        int sidx, m;
+        fetch_idx(tile_of(0, s), sidx, m);
         for (int64_t it = 0;; ++it) {
             const int64_t tile = tile_of(it, s);
             if (tile >= num_tiles) break;
-            gl.set_row(tile * CH_ROWS + lt);
+            gl.set_row_idx(sidx, m);                  // position loads of my row
+            uint4 v[3][4];                            // my chunks of the (at most three) K chunks
+#pragma unroll
+            for (int kc = 0; kc < 3; ++kc)
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    v[kc][c] = (kc < k1c && kc * KC + (part * 4 + c) * 8 < p.k_img) ? gl.chunk(kc * KC + (part * 4 + c) * 8)
+                                                                         : make_uint4(0u, 0u, 0u, 0u);
+            fetch_idx(tile_of(it + 1, s), sidx, m);   // next tile's indices: in flight while this tile is stored
             mbar_wait(&b[CB_B1_FREE], (uint32_t)(it & 1) ^ 1u);
-            for (int kc = 0; kc < p.k1c; ++kc) gl.produce(B1 + kc * CH_CHUNK_BYTES, kc, lt);
+#pragma unroll
+            for (int kc = 0; kc < 3; ++kc) {
+                if (kc < k1c) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        *reinterpret_cast<uint4 *>(B1 + kc * CH_CHUNK_BYTES + line_chunk_off(r, part * 4 + c)) = v[kc][c];
+                }
+            }
             fence_proxy_async_smem();
-            mbar_arrive(&b[CB_B1_FULL]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&b[CB_B1_FULL]);
         }
     } else {
         // ---------------------------------------------------------------- epilogue group of slot s
@@ -220,8 +281,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_eval_kernel(const Chai
         chain_affine(p, 1, ch, sc2, sh2);
         const bool relu = p.act == B2PN_ACT_RELU;
         // layer 3: with two M tiles the column halves become M tiles (every thread scans all 64 rows of its channel)
-        const int ch3 = (p.mt3 == 2 ? half * 128 : 0) + ch;
-        const bool ep3 = p.mt3 == 2 || half == 0;
+        const int ch3 = (mt3 == 2 ? half * 128 : 0) + ch;
+        const bool ep3 = mt3 == 2 || half == 0;
+        const bool want_arg = p.arg != nullptr;
         const float b3 = (ep3 && ch3 < p.c3) ? p.bias[2][ch3] : 0.f;
         // my 32 rows of the tile as four 16-byte groups of my channel's line in the MN-major operand tile
         uint8_t *xline = X + (ch >> 6) * CH_CHUNK_BYTES + (ch & 63) * LINE_BYTES;
@@ -246,57 +308,71 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_eval_kernel(const Chai
             }
             fence_proxy_async_smem();
             tc_fence_before();
-            mbar_arrive(ready);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ready);
         };
 
         for (int64_t it = 0;; ++it) {
             const int64_t tile = tile_of(it, s);
             if (tile >= num_tiles) break;
             const uint32_t ph = (uint32_t)(it & 1);
+            // the tile's eight group descriptors (warp-uniform): requested now, needed after two more layers
+            unsigned dsc[8];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const int64_t gi = tile * (CH_ROWS / 8) + g;
+                dsc[g] = (ep3 && gi * 8 < rows) ? __ldg(p.rgrp + gi) : GI_NONE;
+            }
             hidden(d1, sc1, sh1, p.c1, &b[CB_D1_FULL], &b[CB_A1_FULL], ph);
             hidden(d2, sc2, sh2, p.c2, &b[CB_D2_FULL], &b[CB_A2_FULL], ph);
             // ---- layer 3 + max over the rows of every centroid of the tile
             mbar_wait(&b[CB_D3_FULL], ph);
             tc_fence_after();
             if (ep3 && ch3 - lane < p.c3) {
-                const uint32_t dcol = d3 + (p.mt3 == 2 ? half * 64 : 0);
+                const uint32_t dcol = d3 + (mt3 == 2 ? half * 64 : 0);
                 float best = -INFINITY;
                 int bk = -1;
 #pragma unroll 1
                 for (int cc = 0; cc < 2; ++cc) {
                     float v[32];
                     tmem_ld32(dcol + cc * 32, v);
-                    const int64_t g0 = tile * (CH_ROWS / 8) + cc * 4;
 #pragma unroll
                     for (int gg = 0; gg < 4; ++gg) {
-                        unsigned inf = GI_NONE;
-                        if ((g0 + gg) * 8 < rows) inf = __ldg(p.rgrp + g0 + gg);  // warp-uniform
+                        const unsigned inf = cc == 0 ? dsc[gg] : dsc[4 + gg];  // warp-uniform
                         if (gi_none(inf)) continue;
                         const int s0 = gi_slot0(inf), nv = gi_nv(inf);
                         if (s0 == 0) {
                             best = -INFINITY;
                             bk = -1;
                         }
+                        if (want_arg) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float x = v[gg * 8 + e] + b3;
-                            if (e < nv && x > best) {
-                                best = x;
-                                bk = s0 + e;
+                            for (int e = 0; e < 8; ++e) {
+                                const float x = v[gg * 8 + e] + b3;
+                                if (e < nv && x > best) {
+                                    best = x;
+                                    bk = s0 + e;
+                                }
                             }
+                        } else {   // evaluation: the value alone (bias added once per centroid below)
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (e < nv) best = fmaxf(best, v[gg * 8 + e]);
+                            bk = 0;
                         }
                         if (gi_last(inf) && ch3 < p.c3) {
                             const int64_t m = gi_seg(inf);
-                            const float o = bk >= 0 ? best : 0.f;
+                            const float o = bk >= 0 ? (want_arg ? best : best + b3) : 0.f;
                             p.out[m * p.c3 + ch3] = o;
-                            if (p.arg) p.arg[m * p.c3 + ch3] = bk;
+                            if (want_arg) p.arg[m * p.c3 + ch3] = bk;
                             if (p.out16) p.out16[m * p.c3 + ch3] = __float2half_rn(o);
                         }
                     }
                 }
             }
             tc_fence_before();
-            mbar_arrive(&b[CB_D3_FREE]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&b[CB_D3_FREE]);
         }
     }
     tc_fence_before();

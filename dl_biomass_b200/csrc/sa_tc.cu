@@ -261,6 +261,18 @@ struct GatherLoaderTC {  // K-major B: line = row of the tile, 64 k per line
             }
         }
     }
+    // SLOTS rows whose (source index, centroid) the caller has already fetched (sidx < 0: padding row)
+    __device__ __forceinline__ void set_row_idx(int sidx, int m)
+    {
+        ok = sidx >= 0;
+        src = ok ? sidx : 0;
+        d0 = d1 = d2 = 0.f;
+        if (ok) {
+            d0 = __fsub_rn(__ldg(pos_src + 3 * src + 0), __ldg(pos_dst + 3 * (int64_t)m + 0));
+            d1 = __fsub_rn(__ldg(pos_src + 3 * src + 1), __ldg(pos_dst + 3 * (int64_t)m + 1));
+            d2 = __fsub_rn(__ldg(pos_src + 3 * src + 2), __ldg(pos_dst + 3 * (int64_t)m + 2));
+        }
+    }
     __device__ __forceinline__ void begin_tile(int64_t tile, int lt) { set_row(tile * R + lt); }
     __device__ __forceinline__ float elem(int k) const
     {
@@ -2054,10 +2066,10 @@ static int check_args_tc(const b2pn_sa_args &a)
         if (!a.mlp.w[l] || !a.mlp.b[l]) return B2PN_EINVAL;
     for (int l = 0; l < 2; ++l)
         if (!a.mlp.gamma[l] || !a.mlp.beta[l] || !a.mlp.running_mean[l] || !a.mlp.running_var[l]) return B2PN_EINVAL;
-    if (!a.out || !a.arg) return B2PN_EINVAL;
-    // the hidden-activation buffers are only touched by the multi-pass (training / wide-level) kernels
+    if (!a.out) return B2PN_EINVAL;
+    // the arg-max slots and the hidden-activation buffers are only touched by the multi-pass (training / wide-level) kernels
     const ShapesTC sh = shapes_tc(a);
-    if (!chain_eligible(a, sh.k1, sh.c1, sh.c2, sh.c3) && (!a.h1 || !a.h2 || !a.bn || !a.a1 || !a.a2)) return B2PN_EINVAL;
+    if (!chain_eligible(a, sh.k1, sh.c1, sh.c2, sh.c3) && (!a.arg || !a.h1 || !a.h2 || !a.bn || !a.a1 || !a.a2)) return B2PN_EINVAL;
     return B2PN_OK;
 }
 
@@ -2255,17 +2267,26 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
         cp.eps = a.mlp.eps;
         cp.act = a.mlp.act;
         cp.out = a.out;
-        cp.arg = a.arg;
+        cp.arg = nullptr;   // the evaluation path never differentiates through the max: the arg-max slots are not written
         cp.out16 = (__half *)a.out_bf16;
         cp.rgrp = a.rgrp;
         GatherLoaderTC cg = {rm, a.x, s.cols, a.pos_src, a.pos_dst, -1, FMT_F16};
         const int smem = chain_smem_bytes(cp);
-        cudaError_t e = cudaFuncSetAttribute(tc_chain_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
         const int64_t tiles64 = (ra.cap + CH_ROWS - 1) / CH_ROWS;
         int gx = sm_count();
         if ((int64_t)gx * CH_SLOTS > tiles64) gx = (int)((tiles64 + CH_SLOTS - 1) / CH_SLOTS);
-        tc_chain_eval_kernel<<<gx, CH_THREADS, smem, st>>>(cp, cg);
+        const int nks_last = (s.k1 - (cp.k1c - 1) * KC) >= KC ? 4 : (s.k1 - (cp.k1c - 1) * KC + 15) / 16;
+        auto launch = [&](auto kern) -> int {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return (int)e;
+            kern<<<gx, CH_THREADS, smem, st>>>(cp, cg);
+            return 0;
+        };
+        // the reference's two levels get fully unrolled MMA issue code; anything else the run-time-shaped instance
+        if (cp.k1c == 1 && nks_last == 1 && cp.c1c == 1 && cp.c2c == 1 && cp.mt3 == 1) rc = launch(tc_chain_eval_kernel<1, 1, 1, 1, 1>);
+        else if (cp.k1c == 3 && nks_last == 1 && cp.c1c == 2 && cp.c2c == 2 && cp.mt3 == 2) rc = launch(tc_chain_eval_kernel<3, 1, 2, 2, 2>);
+        else rc = launch(tc_chain_eval_kernel<-1, -1, -1, -1, -1>);
+        if (rc) return rc;
         note_launch();
         B2PN_LAUNCH_CHECK();
         return B2PN_OK;

@@ -46,6 +46,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity)
         : "memory");
     return ok != 0;
 }
+// non-blocking probe: try_wait may SUSPEND the thread for a system-defined time when the phase is not complete, which is
+// what a thread polling several barriers must not do
+__device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
 {
     while (!mbar_try_wait(bar, parity)) {

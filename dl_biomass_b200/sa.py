@@ -268,6 +268,7 @@ class _SAFunction(torch.autograd.Function):
         if fused_eval:
             xs, _, _ = _l1_input(x, x_bf16)
             h1 = h2 = None
+            arg = torch.empty(0, dtype=torch.int32, device=dev)   # no backward will follow: arg-max slots not recorded
         elif prec == PREC_F32:   # row-major fp32 activations [rows, c]
             xs = None if x is None else x.detach().to(f32).contiguous()
             h1 = torch.empty(rows, chans[1], dtype=f32, device=dev)
@@ -294,8 +295,8 @@ class _SAFunction(torch.autograd.Function):
         _fill_args(a, precision=prec, training=training, seg_mode=seg_mode, K=K, n_src=n_src, n_dst=n_dst, c_in=c_in,
                    x=xs, pos_src=pos_src, pos_dst=pos_dst, nbr=nbr, cnt=cnt, batch=batch, chans=chans, act=act,
                    eps=eps, momentum=momentum, ws=ws, bs=bs, gammas=gs, betas=bes, rmeans=(rm1, rm2),
-                   rvars=(rv1, rv2), nbts=(nbt1, nbt2), out=out, arg=arg, h1=h1, h2=h2, bn=bn, rowmap=rowmap,
-                   acts=acts, out_bf16=out_bf16)
+                   rvars=(rv1, rv2), nbts=(nbt1, nbt2), out=out, arg=None if fused_eval else arg, h1=h1, h2=h2, bn=bn,
+                   rowmap=rowmap, acts=acts, out_bf16=out_bf16)
         a.g1_ready = 1 if (prec == PREC_BF16 and l1op_in is not None) else 0
         nbytes = lib.b2pn_sa_workspace_bytes(ctypes.byref(a), 0)
         if nbytes < 0:

@@ -228,8 +228,9 @@ typedef struct b2pn_sa_grads {
 int64_t b2pn_sa_workspace_bytes(const b2pn_sa_args *args, int32_t backward);
 int b2pn_sa_forward(const b2pn_sa_args *args, b2pn_stream_t stream);
 /* 1 if b2pn_sa_forward would run these arguments (shapes, precision, training flag) through the single-launch evaluation
- * kernel, which stores no hidden activation.  The caller opts in by passing h1 == NULL (then h2, a1, a2, bn, g1 are not
- * touched either and no backward pass can follow); with h1 != NULL the multi-pass kernels run and fill them.  0 otherwise. */
+ * kernel, which stores no hidden activation.  The caller opts in by passing h1 == NULL (then h2, a1, a2, bn, g1 and arg
+ * are not touched either -- arg may be NULL -- and no backward pass can follow); with h1 != NULL the multi-pass kernels run
+ * and fill them.  0 otherwise. */
 int b2pn_sa_eval_fused(const b2pn_sa_args *args);
 /* PREC_BF16 + SEG_SLOTS: only the gather + concat of /root/reference/pointnet2_regressor.py:17-18's message inputs
  * ([x_j | pos_j - pos_i]) into args->g1.  Needs x, pos_src, pos_dst, the compacted rows and c_in / mlp.c[0..1]; no
