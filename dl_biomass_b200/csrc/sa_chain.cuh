@@ -15,8 +15,11 @@
 // images stay resident in shared memory.
 //
 //   warps  0- 7 / 8-15   epilogue group of slot 0 / 1: warp w drains TMEM lane quarter w % 4, column half (w / 4) % 2
-//   warp  16             MMA issuer (one thread) and TMEM owner
-//   warps 17-20 / 21-24  gather loaders of slot 0 / 1: two threads per row of the tile; the row indices of the NEXT tile are
+//   warps 16 / 17        MMA issuer of slot 0 / 1 (warp 16 owns the TMEM allocation).  The WHOLE warp runs the issue loop and
+//                        one elected lane executes the tcgen05 instructions: under a divergent `if (lane == 0)` every
+//                        operand descriptor went through R2UR moves (4-5 per tcgen05.mma, ncu round 2); warp-uniform code
+//                        keeps them in uniform registers
+//   warps 18-21 / 22-25  gather loaders of slot 0 / 1: two threads per row of the tile; the row indices of the NEXT tile are
 //                        prefetched and all loads of a row are in flight together (the gather is a chain of dependent
 //                        L2 round trips: row -> source index -> feature row)
 //
@@ -32,8 +35,8 @@ constexpr int CH_SLOTS = 2;
 constexpr int CH_EPI_WARPS = 8;                       // per slot
 constexpr int CH_EPI_THREADS = CH_EPI_WARPS * 32;     // 256
 constexpr int CH_LOAD_THREADS = 128;                  // per slot: two threads per row of the tile
-constexpr int CH_MMA_WARP = CH_SLOTS * CH_EPI_WARPS;  // 16
-constexpr int CH_THREADS = CH_SLOTS * CH_EPI_THREADS + 32 + CH_SLOTS * CH_LOAD_THREADS;  // 800
+constexpr int CH_MMA_WARP = CH_SLOTS * CH_EPI_WARPS;  // 16, 17: one MMA issuer warp per slot
+constexpr int CH_THREADS = CH_SLOTS * CH_EPI_THREADS + CH_SLOTS * 32 + CH_SLOTS * CH_LOAD_THREADS;  // 832
 constexpr int CH_CHUNK_BYTES = CH_ROWS * LINE_BYTES;  // 8 KB: 64 rows x 64 k (K-major) or 64 channel lines x 64 rows (MN-major)
 constexpr int CH_TMEM_PER_SLOT = 256;                 // D1 [0,64) D2 [64,128) D3 [128, 128 + 64 mt3)
 
@@ -126,106 +129,96 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_eval_kernel(const Chai
     // tile j of slot s in iteration it: (it * gridDim.x + blockIdx.x) * CH_SLOTS + s
     auto tile_of = [&](int64_t it, int s) { return (it * (int64_t)gridDim.x + blockIdx.x) * CH_SLOTS + s; };
 
-    if (warp == CH_MMA_WARP) {
-        // ---------------------------------------------------------------- weights (once) + MMA issue for both slots
-        if (lane == 0) {
+    if (warp >= CH_MMA_WARP && warp < CH_MMA_WARP + CH_SLOTS) {
+        // ---------------------------------------------------------------- MMA issuer of slot s (whole warp, one elected lane)
+        const int s = warp - CH_MMA_WARP;
+        unsigned leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+        if (s == 0 && leader) {   // the weight images, once
             const int total = p.w_bytes[0] + p.w_bytes[1] + p.w_bytes[2];
             mbar_expect_tx(w_full, (unsigned)total);
             for (int l = 0; l < 3; ++l) {
                 uint8_t *dst = l == 0 ? W0 : (l == 1 ? W1 : W2);
-                for (int off = 0; off < p.w_bytes[l]; off += 16384)
-                    bulk_g2s(dst + off, p.w_img[l] + off, 16384u, w_full);
+                for (int off = 0; off < p.w_bytes[l]; off += 16384) bulk_g2s(dst + off, p.w_img[l] + off, 16384u, w_full);
             }
             mbar_arrive(w_full);
-            mbar_wait(w_full, 0);
-            const uint32_t idesc_k = idesc_16(128, CH_ROWS, false, false, FMT_F16, FMT_F16);   // layer 1: K-major B
-            const uint32_t idesc_mn = idesc_16(128, CH_ROWS, false, true, FMT_F16, FMT_F16);   // layers 2, 3: MN-major B
-            // per slot: the five operand base descriptors (loop-invariant: every tile of a slot uses the same buffers)
-            uint64_t da1[CH_SLOTS], db1[CH_SLOTS], db2[CH_SLOTS];
-            const uint64_t dw0 = smem_desc_sw128(smem_u32(W0), 16, ATOM_BYTES);
-            const uint64_t dw1 = smem_desc_sw128(smem_u32(W1), 16, ATOM_BYTES);
-            const uint64_t dw2 = smem_desc_sw128(smem_u32(W2), 16, ATOM_BYTES);
+        }
+        __syncwarp();
+        mbar_wait(w_full, 0);
+        const uint32_t idesc_k = idesc_16(128, CH_ROWS, false, false, FMT_F16, FMT_F16);   // layer 1: K-major B
+        const uint32_t idesc_mn = idesc_16(128, CH_ROWS, false, true, FMT_F16, FMT_F16);   // layers 2, 3: MN-major B
+        uint64_t *b = bars + s * CB_PER_SLOT;
+        uint8_t *B1 = slots + s * slot_bytes;
+        const uint64_t dw0 = smem_desc_sw128(smem_u32(W0), 16, ATOM_BYTES);
+        const uint64_t dw1 = smem_desc_sw128(smem_u32(W1), 16, ATOM_BYTES);
+        const uint64_t dw2 = smem_desc_sw128(smem_u32(W2), 16, ATOM_BYTES);
+        const uint64_t db1 = smem_desc_sw128(smem_u32(B1), 16, ATOM_BYTES);                        // K-major gathered rows
+        const uint64_t db2 = smem_desc_sw128(smem_u32(B1 + b1_bytes), 64 * LINE_BYTES, ATOM_BYTES);  // MN-major activations
+        // descriptor address field is in 16-byte units: advancing an operand by `bytes` adds bytes >> 4
+        constexpr uint64_t A_KS = 32 >> 4, A_CHUNK = (128 * LINE_BYTES) >> 4, B_KS_K = 32 >> 4,
+                           B_KS_MN = (16 * LINE_BYTES) >> 4, B_CHUNK = CH_CHUNK_BYTES >> 4;
+        const uint32_t d1 = tmem_base + s * CH_TMEM_PER_SLOT, d2 = d1 + 64, d3 = d1 + 128;
+        for (int64_t it = 0;; ++it) {
+            if (tile_of(it, s) >= num_tiles) break;
+            const uint32_t ph = (uint32_t)(it & 1);
+            // ---- layer 1
+            mbar_wait(&b[CB_B1_FULL], ph);
+            tc_fence_after();
+            if (leader) {
 #pragma unroll
-            for (int s = 0; s < CH_SLOTS; ++s) {
-                uint8_t *B1 = slots + s * slot_bytes;
-                da1[s] = 0;
-                db1[s] = smem_desc_sw128(smem_u32(B1), 16, ATOM_BYTES);                        // K-major gathered rows
-                db2[s] = smem_desc_sw128(smem_u32(B1 + b1_bytes), 64 * LINE_BYTES, ATOM_BYTES);  // MN-major activations
-            }
-            (void)da1;
-            // descriptor address field is in 16-byte units: advancing an operand by `bytes` adds bytes >> 4
-            constexpr uint64_t A_KS = 32 >> 4, A_CHUNK = (128 * LINE_BYTES) >> 4, B_KS_K = 32 >> 4,
-                               B_KS_MN = (16 * LINE_BYTES) >> 4, B_CHUNK = CH_CHUNK_BYTES >> 4;
-            int stage[CH_SLOTS] = {0, 0};
-            int64_t it[CH_SLOTS] = {0, 0};
-            bool done[CH_SLOTS];
-            for (int s = 0; s < CH_SLOTS; ++s) done[s] = tile_of(0, s) >= num_tiles;
-            while (!(done[0] && done[1])) {
+                for (int kc = 0; kc < (K1C_ >= 0 ? K1C_ : 3); ++kc) {
+                    if (kc < k1c) {
 #pragma unroll
-                for (int s = 0; s < CH_SLOTS; ++s) {
-                    if (done[s]) continue;
-                    uint64_t *b = bars + s * CB_PER_SLOT;
-                    const uint32_t ph = (uint32_t)(it[s] & 1);
-                    const uint32_t d1 = tmem_base + s * CH_TMEM_PER_SLOT, d2 = d1 + 64, d3 = d1 + 128;
-                    if (stage[s] == 0) {
-                        if (!mbar_test_wait(&b[CB_B1_FULL], ph)) continue;
-                        tc_fence_after();
-#pragma unroll
-                        for (int kc = 0; kc < (K1C_ >= 0 ? K1C_ : 3); ++kc) {
-                            if (kc < k1c) {
-#pragma unroll
-                                for (int ks = 0; ks < 4; ++ks)
-                                    if (kc + 1 < k1c || ks < nks_last)
-                                        umma_bf16(d1, dw0 + kc * A_CHUNK + ks * A_KS, db1[s] + kc * B_CHUNK + ks * B_KS_K, idesc_k,
-                                                  (kc | ks) != 0);
-                            }
-                        }
-                        umma_commit(&b[CB_B1_FREE]);
-                        umma_commit(&b[CB_D1_FULL]);
-                        stage[s] = 1;
-                    } else if (stage[s] == 1) {
-                        if (!mbar_test_wait(&b[CB_A1_FULL], ph)) continue;
-                        tc_fence_after();
-#pragma unroll
-                        for (int kc = 0; kc < (C1C_ >= 0 ? C1C_ : 2); ++kc) {
-                            if (kc < c1c) {
-#pragma unroll
-                                for (int ks = 0; ks < 4; ++ks)
-                                    umma_bf16(d2, dw1 + kc * A_CHUNK + ks * A_KS, db2[s] + kc * B_CHUNK + ks * B_KS_MN, idesc_mn,
-                                              (kc | ks) != 0);
-                            }
-                        }
-                        umma_commit(&b[CB_D2_FULL]);
-                        stage[s] = 2;
-                    } else {
-                        if (!mbar_test_wait(&b[CB_A2_FULL], ph)) continue;
-                        if (!mbar_test_wait(&b[CB_D3_FREE], ph ^ 1u)) continue;   // the previous tile's max has left D3
-                        tc_fence_after();
-#pragma unroll
-                        for (int mt = 0; mt < (MT3_ >= 0 ? MT3_ : 2); ++mt) {
-                            if (mt < mt3) {
-#pragma unroll
-                                for (int kc = 0; kc < (C2C_ >= 0 ? C2C_ : 2); ++kc) {
-                                    if (kc < c2c) {
-#pragma unroll
-                                        for (int ks = 0; ks < 4; ++ks)
-                                            umma_bf16(d3 + mt * 64, dw2 + (uint64_t)(kc * mt3 + mt) * A_CHUNK + ks * A_KS,
-                                                      db2[s] + kc * B_CHUNK + ks * B_KS_MN, idesc_mn, (kc | ks) != 0);
-                                    }
-                                }
-                            }
-                        }
-                        umma_commit(&b[CB_D3_FULL]);
-                        stage[s] = 0;
-                        ++it[s];
-                        done[s] = tile_of(it[s], s) >= num_tiles;
+                        for (int ks = 0; ks < 4; ++ks)
+                            if (kc + 1 < k1c || ks < nks_last)
+                                umma_bf16(d1, dw0 + kc * A_CHUNK + ks * A_KS, db1 + kc * B_CHUNK + ks * B_KS_K, idesc_k, (kc | ks) != 0);
                     }
                 }
+                umma_commit(&b[CB_B1_FREE]);
+                umma_commit(&b[CB_D1_FULL]);
             }
+            __syncwarp();
+            // ---- layer 2
+            mbar_wait(&b[CB_A1_FULL], ph);
+            tc_fence_after();
+            if (leader) {
+#pragma unroll
+                for (int kc = 0; kc < (C1C_ >= 0 ? C1C_ : 2); ++kc) {
+                    if (kc < c1c) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_bf16(d2, dw1 + kc * A_CHUNK + ks * A_KS, db2 + kc * B_CHUNK + ks * B_KS_MN, idesc_mn, (kc | ks) != 0);
+                    }
+                }
+                umma_commit(&b[CB_D2_FULL]);
+            }
+            __syncwarp();
+            // ---- layer 3 (its accumulator must have been drained by the previous tile's max)
+            mbar_wait(&b[CB_A2_FULL], ph);
+            mbar_wait(&b[CB_D3_FREE], ph ^ 1u);
+            tc_fence_after();
+            if (leader) {
+#pragma unroll
+                for (int mt = 0; mt < (MT3_ >= 0 ? MT3_ : 2); ++mt) {
+                    if (mt < mt3) {
+#pragma unroll
+                        for (int kc = 0; kc < (C2C_ >= 0 ? C2C_ : 2); ++kc) {
+                            if (kc < c2c) {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)
+                                    umma_bf16(d3 + mt * 64, dw2 + (uint64_t)(kc * mt3 + mt) * A_CHUNK + ks * A_KS,
+                                              db2 + kc * B_CHUNK + ks * B_KS_MN, idesc_mn, (kc | ks) != 0);
+                            }
+                        }
+                    }
+                }
+                umma_commit(&b[CB_D3_FULL]);
+            }
+            __syncwarp();
         }
-    } else if (warp > CH_MMA_WARP) {
+    } else if (warp >= CH_MMA_WARP + CH_SLOTS) {
         // ---------------------------------------------------------------- gather loaders: two threads per row of the tile
-        const int lt0 = tid - (CH_MMA_WARP + 1) * 32;
+        const int lt0 = tid - (CH_MMA_WARP + CH_SLOTS) * 32;
         const int s = lt0 / CH_LOAD_THREADS, lt = lt0 % CH_LOAD_THREADS;
         const int r = lt >> 1, part = lt & 1;   // my row of the tile; my half of every 128-byte line (chunks 4 part .. 4 part + 3)
         uint64_t *b = bars + s * CB_PER_SLOT;
