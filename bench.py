@@ -328,7 +328,10 @@ def run_b200(args):
         return float(t.item())
 
     use_graph = not args.no_graph and not (world > 1 and args.dp_mode == "eager")
-    pipeline = not args.no_pipeline and args.config != "eval"
+    # dense clouds (100k points): farthest-point sampling runs one 16-CTA cluster per cloud -- 128 of the 148 SMs for
+    # ~46 ms, 0.85 of the HBM roofline in scan-equivalent bytes -- so there is no idle machine to overlap the training
+    # kernels with: the step is one graph, sampling first
+    pipeline = not args.no_pipeline and args.config == "train"
 
     def build_training(prec):
         """model + optimiser + reducer + stepper for one precision mode"""

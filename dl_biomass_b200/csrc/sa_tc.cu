@@ -1405,7 +1405,10 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
             }
             if constexpr (XF::USES_TMA) {
                 // the stored activations are fp16, the gradients on the Y side bf16: the group converts the landed X tile
-                // to bf16 in place (16-byte chunks, element-wise: the swizzle is untouched)
+                // to bf16 in place (16-byte chunks, element-wise: the swizzle is untouched).  Every thread first makes sure
+                // the stage's PREVIOUS use has been consumed (with an odd number of stages the two groups alternate on a
+                // stage, and a parity wait on xland alone could be satisfied by the use before the previous one)
+                mbar_wait(&empty[s], ph ^ 1u);
                 mbar_wait(&xland[s], ph);
                 const int nchunk16 = xf.landed_lines(ng) * 8;
                 for (int c = lt; c < nchunk16; c += NUM_LOAD) {

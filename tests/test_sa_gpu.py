@@ -184,11 +184,13 @@ def test_sa_slots_level_bf16_forward(cuda_device, c_in, chans, K, train):
     err = rel_err(out, want)
     print("bf16 SA level rel err", err)
     assert err < 2e-2
-    a = arg.cpu().long()
-    assert int(a.min()) >= 0 and bool((a < cnt.long()[:, None]).all())
     if train:
+        a = arg.cpu().long()
+        assert int(a.min()) >= 0 and bool((a < cnt.long()[:, None]).all())
         for (k, v), (_, vr) in zip(m.named_buffers(), mref.named_buffers()):
             assert rel_err(v.float(), vr.float()) < 2e-2, k
+    else:   # evaluation without grad: the single-launch kernel, which records no arg-max slots (no backward can follow)
+        assert arg.numel() == 0
 
 
 @pytest.mark.parametrize("K,n,r", [(64, 600, 2.5), (64, 3000, 1.0), (40, 600, 2.5), (8, 600, 9.0), (16, 50, 0.01)])
