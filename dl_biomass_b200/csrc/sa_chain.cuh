@@ -373,6 +373,332 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_eval_kernel(const Chai
     if (warp == CH_MMA_WARP) tmem_dealloc<512>(tmem_base);
 }
 
+// =====================================================================================================================
+//  Training passes.  Train-mode BatchNorm needs the batch statistics of a layer before its output can be normalised, so a
+//  level cannot be one launch; but two consecutive layers CAN share one: the pass that normalises layer l also runs layer
+//  l + 1 on the freshly normalised tile while it is still in shared memory.  The forward pass of a level becomes
+//      A1  statistics of layer 1                                   (tc_rows_gemm_kernel<StatsEpTC>, sa_tc.cu)
+//      P2  layer 1 -> normalise, store zhat1 / a1 -> layer 2 -> statistics of layer 2          (this kernel, PASS 2)
+//      P3  a1 -> layer 2 -> normalise, store zhat2 / a2 -> layer 3 -> max + arg-max            (this kernel, PASS 3)
+//  three GEMM passes instead of five, and a1 / a2 are read back once instead of twice (round-1 verdict: 31-38x the
+//  compulsory bytes).  The input tile (g1 for P2, a1 for P3) is a stored feature-major tensor: one thread fetches it with
+//  TMA tensor-map copies straight into the MN-major operand layout.
+//
+//   warps  0- 7 / 8-15   epilogue group of slot 0 / 1
+//   warps 16 / 17        MMA issuer of slot 0 / 1 (whole warp, one elected lane; warp 16 owns the TMEM allocation)
+//   warps 18 / 19        TMA producer of slot 0 / 1 (one elected lane)
+// =====================================================================================================================
+constexpr int CT_THREADS = CH_SLOTS * CH_EPI_THREADS + CH_SLOTS * 32 + CH_SLOTS * 32;  // 640
+enum { TB_IN_FULL = 0, TB_IN_FREE, TB_DA_FULL, TB_XA_FULL, TB_DB_FULL, TB_DB_FREE, TB_PER_SLOT };
+
+struct ChainTrainParams {
+    const uint8_t *w_img[2];  // P2: layers 1, 2; P3: layers 2, 3 (fp16 images, num_mg == 1)
+    int w_bytes[2];
+    int k_in;                 // real K of the first GEMM (P2: image columns of g1; P3: c1)
+    int kc_in, kc_mid;        // K chunks of the first / second GEMM
+    int c_a, c_b;             // output channels of the first / second GEMM
+    int mt_b;                 // M tiles of the second GEMM
+    int64_t rows;
+    const int64_t *rows_dev;
+    int64_t ld;
+    // first GEMM: zhat = (acc + bias - mean) * rstd; a = act(gamma * zhat + beta), invalid rows 0; both stored [c_a][ld]
+    const float *bias_a, *mean_a, *rstd_a, *gamma_a, *beta_a;
+    int act;
+    __half *z_out, *a_out;
+    // second GEMM: PASS 2 -> per-channel sum / sum of squares of the bias-free accumulators, per CTA and writer group:
+    // partial[(blockIdx.x * 4 + slot * 2 + half)][2][cpad]; PASS 3 -> per-centroid max (+ bias) and arg-max slot
+    double *partial;
+    int cpad;
+    const float *bias_b;
+    float *out;
+    int32_t *arg;
+    __half *out16;
+    const uint32_t *rgrp;
+};
+
+template <int PASS, int KCI_, int NKSL_, int KCM_, int MTB_>
+__global__ void __launch_bounds__(CT_THREADS, 1)
+    tc_chain_train_kernel(const ChainTrainParams p, const __grid_constant__ TmaMap map_in, const __grid_constant__ TmaMap map_z,
+                          const __grid_constant__ TmaMap map_a)
+{
+    static_assert(PASS == 2 || PASS == 3, "PASS 2: layer 1 + statistics of layer 2; PASS 3: layer 2 + layer 3 + max");
+    const int kc_in = KCI_ >= 0 ? KCI_ : p.kc_in;
+    const int kc_mid = KCM_ >= 0 ? KCM_ : p.kc_mid;
+    const int mt_b = MTB_ >= 0 ? MTB_ : p.mt_b;
+    const int nks_last = NKSL_ >= 0 ? NKSL_ : ((p.k_in - (p.kc_in - 1) * KC) >= KC ? 4 : (p.k_in - (p.kc_in - 1) * KC + 15) / 16);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *Wa = smem, *Wb = Wa + p.w_bytes[0];
+    uint8_t *slots = Wb + p.w_bytes[1];
+    // per slot: IN (the fetched input tile), X (a: operand of the second GEMM AND source of its TMA store), Z (zhat staging)
+    const int in_bytes = kc_in * CH_CHUNK_BYTES, x_bytes = kc_mid * CH_CHUNK_BYTES;
+    const int slot_bytes = in_bytes + 2 * x_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(slots + CH_SLOTS * slot_bytes);
+    uint64_t *w_full = bars + CH_SLOTS * TB_PER_SLOT;
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(w_full + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t rows = p.rows_dev ? *p.rows_dev : p.rows;
+    // whole 128-row tiles, like every other consumer of the stored tensors: the pad rows of the last one get a = 0
+    const int64_t num_tiles = ((rows + 127) / 128) * 2;
+
+    if (tid == 0) {
+        for (int s = 0; s < CH_SLOTS; ++s) {
+            uint64_t *b = bars + s * TB_PER_SLOT;
+            mbar_init(&b[TB_IN_FULL], 1);
+            mbar_init(&b[TB_IN_FREE], 1);
+            mbar_init(&b[TB_DA_FULL], 1);
+            mbar_init(&b[TB_XA_FULL], 1);
+            mbar_init(&b[TB_DB_FULL], 1);
+            mbar_init(&b[TB_DB_FREE], CH_EPI_WARPS);
+        }
+        mbar_init(w_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == CH_MMA_WARP) tmem_alloc<512>(tmem_holder);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    auto tile_of = [&](int64_t it, int s) { return (it * (int64_t)gridDim.x + blockIdx.x) * CH_SLOTS + s; };
+    unsigned leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+
+    if (warp >= CH_MMA_WARP + CH_SLOTS) {
+        // ---------------------------------------------------------------- TMA producer of slot s
+        const int s = warp - (CH_MMA_WARP + CH_SLOTS);
+        if (s < CH_SLOTS && leader) {
+            uint64_t *b = bars + s * TB_PER_SLOT;
+            uint8_t *IN = slots + s * slot_bytes;
+            for (int64_t it = 0;; ++it) {
+                const int64_t tile = tile_of(it, s);
+                if (tile >= num_tiles) break;
+                mbar_wait(&b[TB_IN_FREE], (uint32_t)(it & 1) ^ 1u);
+                mbar_expect_tx(&b[TB_IN_FULL], (unsigned)in_bytes);
+                for (int kc = 0; kc < kc_in; ++kc)
+                    tma_load_2d(IN + kc * CH_CHUNK_BYTES, &map_in, (int)(tile * CH_ROWS), kc * KC, &b[TB_IN_FULL]);
+                mbar_arrive(&b[TB_IN_FULL]);
+            }
+        }
+    } else if (warp >= CH_MMA_WARP) {
+        // ---------------------------------------------------------------- MMA issuer of slot s
+        const int s = warp - CH_MMA_WARP;
+        if (s == 0 && leader) {
+            mbar_expect_tx(w_full, (unsigned)(p.w_bytes[0] + p.w_bytes[1]));
+            for (int l = 0; l < 2; ++l) {
+                uint8_t *dst = l == 0 ? Wa : Wb;
+                for (int off = 0; off < p.w_bytes[l]; off += 16384) bulk_g2s(dst + off, p.w_img[l] + off, 16384u, w_full);
+            }
+            mbar_arrive(w_full);
+        }
+        __syncwarp();
+        mbar_wait(w_full, 0);
+        const uint32_t idesc_mn = idesc_16(128, CH_ROWS, false, true, FMT_F16, FMT_F16);
+        uint64_t *b = bars + s * TB_PER_SLOT;
+        uint8_t *IN = slots + s * slot_bytes;
+        const uint64_t dwa = smem_desc_sw128(smem_u32(Wa), 16, ATOM_BYTES);
+        const uint64_t dwb = smem_desc_sw128(smem_u32(Wb), 16, ATOM_BYTES);
+        const uint64_t din = smem_desc_sw128(smem_u32(IN), 64 * LINE_BYTES, ATOM_BYTES);
+        const uint64_t dx = smem_desc_sw128(smem_u32(IN + in_bytes), 64 * LINE_BYTES, ATOM_BYTES);
+        constexpr uint64_t A_KS = 32 >> 4, A_CHUNK = (128 * LINE_BYTES) >> 4, B_KS_MN = (16 * LINE_BYTES) >> 4,
+                           B_CHUNK = CH_CHUNK_BYTES >> 4;
+        const uint32_t da = tmem_base + s * CH_TMEM_PER_SLOT, db = da + 64;
+        for (int64_t it = 0;; ++it) {
+            if (tile_of(it, s) >= num_tiles) break;
+            const uint32_t ph = (uint32_t)(it & 1);
+            mbar_wait(&b[TB_IN_FULL], ph);
+            tc_fence_after();
+            if (leader) {
+#pragma unroll
+                for (int kc = 0; kc < (KCI_ >= 0 ? KCI_ : 3); ++kc) {
+                    if (kc < kc_in) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            if (kc + 1 < kc_in || ks < nks_last)
+                                umma_bf16(da, dwa + kc * A_CHUNK + ks * A_KS, din + kc * B_CHUNK + ks * B_KS_MN, idesc_mn, (kc | ks) != 0);
+                    }
+                }
+                umma_commit(&b[TB_IN_FREE]);
+                umma_commit(&b[TB_DA_FULL]);
+            }
+            __syncwarp();
+            mbar_wait(&b[TB_XA_FULL], ph);
+            mbar_wait(&b[TB_DB_FREE], ph ^ 1u);
+            tc_fence_after();
+            if (leader) {
+#pragma unroll
+                for (int mt = 0; mt < (MTB_ >= 0 ? MTB_ : 2); ++mt) {
+                    if (mt < mt_b) {
+#pragma unroll
+                        for (int kc = 0; kc < (KCM_ >= 0 ? KCM_ : 2); ++kc) {
+                            if (kc < kc_mid) {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)
+                                    umma_bf16(db + mt * 64, dwb + (uint64_t)(kc * mt_b + mt) * A_CHUNK + ks * A_KS,
+                                              dx + kc * B_CHUNK + ks * B_KS_MN, idesc_mn, (kc | ks) != 0);
+                            }
+                        }
+                    }
+                }
+                umma_commit(&b[TB_DB_FULL]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue group of slot s
+        const int s = warp / CH_EPI_WARPS, w8 = warp % CH_EPI_WARPS;
+        const int q = w8 & 3, half = w8 >> 2;
+        uint64_t *b = bars + s * TB_PER_SLOT;
+        uint8_t *X = slots + s * slot_bytes + in_bytes;
+        const int ch = q * 32 + lane;
+        const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
+        const uint32_t da = tmem_base + lane_addr + s * CH_TMEM_PER_SLOT, db = da + 64;
+        float sc = 0.f, sh = 0.f, ga = 0.f, be = 0.f;
+        if (ch < p.c_a) {
+            sc = p.rstd_a[ch];
+            sh = (p.bias_a[ch] - p.mean_a[ch]) * sc;
+            ga = p.gamma_a[ch];
+            be = p.beta_a[ch];
+        }
+        const bool relu = p.act == B2PN_ACT_RELU;
+        const int chb = (PASS == 3 && mt_b == 2 ? half * 128 : 0) + ch;   // my channel of the second GEMM
+        const bool epb = PASS == 2 || mt_b == 2 || half == 0;
+        const float bb = (PASS == 3 && epb && chb < p.c_b) ? p.bias_b[chb] : 0.f;
+        uint8_t *xline = X + (ch >> 6) * CH_CHUNK_BYTES + (ch & 63) * LINE_BYTES;
+        const int sw = ch & 7;
+        double S = 0.0, Q = 0.0;   // PASS 2: statistics of my channel over all my tiles
+        for (int64_t it = 0;; ++it) {
+            const int64_t tile = tile_of(it, s);
+            if (tile >= num_tiles) break;
+            const uint32_t ph = (uint32_t)(it & 1);
+            const int64_t row0 = tile * CH_ROWS;
+            unsigned dsc[8];   // the tile's eight group descriptors (warp-uniform)
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const int64_t gi = tile * (CH_ROWS / 8) + g;
+                dsc[g] = (gi * 8 < rows) ? __ldg(p.rgrp + gi) : GI_NONE;
+                if (gi_none(dsc[g])) dsc[g] = GI_NONE;
+            }
+            // ---- first GEMM: normalise; zhat and a leave through shared-memory tiles and TMA stores (16-byte global stores
+            // 2*ld bytes apart per lane made this epilogue 3x slower, as they had in round 1); a is also the operand of
+            // the second GEMM, read in place
+            mbar_wait(&b[TB_DA_FULL], ph);
+            tc_fence_after();
+            if (w8 == 0 && lane == 0) bulk_wait_read_all();      // the previous tile's stores have read X and Z
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + s), "n"(CH_EPI_THREADS) : "memory");
+            if (ch - lane < p.c_a) {
+                float v[32];
+                tmem_ld32(da + half * 32, v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int nv = gi_nv(half == 0 ? dsc[j] : dsc[4 + j]);
+                    float f[8], g[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = fmaf(v[8 * j + e], sc, sh);
+                    const uint4 zq = pack8h(f);
+                    unpack8h(zq, f);   // the activation is defined on the STORED (fp16) zhat, as backward recomputes it
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        float y = fmaf(f[e], ga, be);
+                        if (relu) y = fmaxf(y, 0.f);
+                        g[e] = e < nv ? y : 0.f;
+                    }
+                    const int off = ((half * 4 + j) ^ sw) << 4;
+                    *reinterpret_cast<uint4 *>(xline + x_bytes + off) = zq;        // Z tile (behind X)
+                    *reinterpret_cast<uint4 *>(xline + off) = pack8h(g);           // X tile
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + s), "n"(CH_EPI_THREADS) : "memory");
+            if (w8 == 0 && lane == 0) {
+                for (int kc = 0; kc < kc_mid; ++kc) {   // channels past c_a are clipped by the tensor maps
+                    tma_store_2d(&map_z, X + x_bytes + kc * CH_CHUNK_BYTES, (int)row0, kc * KC);
+                    tma_store_2d(&map_a, X + kc * CH_CHUNK_BYTES, (int)row0, kc * KC);
+                }
+                bulk_commit_group();
+                mbar_arrive(&b[TB_XA_FULL]);
+            }
+            // ---- second GEMM
+            mbar_wait(&b[TB_DB_FULL], ph);
+            tc_fence_after();
+            if (PASS == 2) {
+                if (ch - lane < p.c_b) {
+                    float v[32];
+                    tmem_ld32(db + half * 32, v);
+                    float sm = 0.f, qm = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        sm += v[j];
+                        qm = fmaf(v[j], v[j], qm);
+                    }
+                    S += (double)sm;
+                    Q += (double)qm;
+                }
+            } else if (epb && chb - lane < p.c_b) {
+                const uint32_t dcol = db + (mt_b == 2 ? half * 64 : 0);
+                float best = -INFINITY;
+                int bk = -1;
+#pragma unroll 1
+                for (int cc = 0; cc < 2; ++cc) {
+                    float v[32];
+                    tmem_ld32(dcol + cc * 32, v);
+#pragma unroll
+                    for (int gg = 0; gg < 4; ++gg) {
+                        const unsigned inf = cc == 0 ? dsc[gg] : dsc[4 + gg];
+                        if (gi_none(inf)) continue;
+                        const int s0 = gi_slot0(inf), nv = gi_nv(inf);
+                        if (s0 == 0) {
+                            best = -INFINITY;
+                            bk = -1;
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float x = v[gg * 8 + e] + bb;
+                            if (e < nv && x > best) {
+                                best = x;
+                                bk = s0 + e;
+                            }
+                        }
+                        if (gi_last(inf) && chb < p.c_b) {
+                            const int64_t m = gi_seg(inf);
+                            const float o = bk >= 0 ? best : 0.f;
+                            p.out[m * p.c_b + chb] = o;
+                            p.arg[m * p.c_b + chb] = bk;
+                            if (p.out16) p.out16[m * p.c_b + chb] = __float2half_rn(o);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&b[TB_DB_FREE]);
+        }
+        if (w8 == 0 && lane == 0) bulk_wait_all();
+        if (PASS == 2 && ch < p.c_b) {   // every (CTA, writer group) writes its slice, tiles or not: the finalize sums them all
+            double *pt = p.partial + ((int64_t)blockIdx.x * 4 + s * 2 + half) * 2 * p.cpad;
+            pt[ch] = S;
+            pt[p.cpad + ch] = Q;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == CH_MMA_WARP) tmem_dealloc<512>(tmem_base);
+}
+
+// shapes the chained training passes cover (the reference's levels 1 and 2 with neuron_multiplier 1)
+static bool chain_train_ok(const b2pn_sa_args &a, int k_img, int c1, int c2, int c3)
+{
+    if (a.seg_mode != B2PN_SEG_SLOTS || !a.training) return false;
+    if (c1 % 64 || c2 % 64 || c1 > 128 || c2 > 128 || c3 > 256 || k_img + 1 > 3 * KC) return false;
+    return true;
+}
+
+static int chain_train_smem_bytes(const ChainTrainParams &p)
+{
+    return p.w_bytes[0] + p.w_bytes[1] + CH_SLOTS * (p.kc_in + 2 * p.kc_mid) * CH_CHUNK_BYTES + 256 + 1024;
+}
+
 // shapes the chained kernel covers: hidden widths of whole 64-channel chunks up to 128, output up to 256 channels, a
 // layer-1 operand of at most three 64-column chunks (the reference's levels 1 and 2 with neuron_multiplier 1)
 static bool chain_shapes_ok(const b2pn_sa_args &a, int k_img, int c1, int c2, int c3)

@@ -2317,6 +2317,61 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
                                                                  a.mlp.running_var[0], a.mlp.num_batches_tracked[0], a.mlp.eps,
                                                                  a.mlp.momentum, bn1, s.cmax);
     note_launch();
+    if (train && s.rows > 0 && use_g1 && chain_train_ok(a, s.k1, s.c1, s.c2, s.c3)) {
+        // ---- layers 1-3 in TWO chained launches (sa_chain.cuh): P2 normalises layer 1 and takes the statistics of layer 2
+        // from the tile while it is in shared memory, P3 re-runs layer 2 on the stored a1, normalises, and runs layer 3 + max
+        const int64_t tiles64 = ((ra.cap + 127) / 128) * 2;
+        int gx = sm_count();
+        if ((int64_t)gx * CH_SLOTS > tiles64) gx = (int)((tiles64 + CH_SLOTS - 1) / CH_SLOTS);
+        auto launch = [&](auto kern, const ChainTrainParams &cp, const TmaMap &map) -> int {
+            const int smem = chain_train_smem_bytes(cp);
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return (int)e;
+            TmaMap mz, ma;   // output maps: boxes of 64 rows x 64 channels, the layout of the shared-memory tiles
+            int r2 = make_tma_feature_major(&mz, cp.z_out, cp.c_a, cp.ld);
+            if (r2) return r2;
+            if ((r2 = make_tma_feature_major(&ma, cp.a_out, cp.c_a, cp.ld))) return r2;
+            kern<<<gx, CT_THREADS, smem, st>>>(cp, map, mz, ma);
+            note_launch();
+            e = cudaPeekAtLastError();
+            return e == cudaSuccess ? 0 : (int)e;
+        };
+        ChainTrainParams p2 = {};
+        p2.w_img[0] = f.pk[0].img; p2.w_bytes[0] = (int)f.pk[0].bytes;
+        p2.w_img[1] = f.pk[1].img; p2.w_bytes[1] = (int)f.pk[1].bytes;
+        p2.k_in = s.k1; p2.kc_in = f.pk[0].num_kc; p2.kc_mid = f.pk[1].num_kc;
+        p2.c_a = s.c1; p2.c_b = s.c2; p2.mt_b = 1;
+        p2.rows = ra.cap; p2.rows_dev = ra.dev; p2.ld = s.ld;
+        p2.bias_a = a.mlp.b[0]; p2.mean_a = bn1; p2.rstd_a = bn1 + s.cmax; p2.gamma_a = a.mlp.gamma[0]; p2.beta_a = a.mlp.beta[0];
+        p2.act = a.mlp.act; p2.z_out = (__half *)z1; p2.a_out = (__half *)a.a1;
+        p2.partial = f.partial; p2.cpad = s.cpad; p2.rgrp = a.rgrp;
+        const int nks1 = (s.k1 - (p2.kc_in - 1) * KC) >= KC ? 4 : (s.k1 - (p2.kc_in - 1) * KC + 15) / 16;
+        if (p2.kc_in == 1 && nks1 == 1 && p2.kc_mid == 1) rc = launch(tc_chain_train_kernel<2, 1, 1, 1, 1>, p2, map_g1);
+        else if (p2.kc_in == 3 && nks1 == 1 && p2.kc_mid == 2) rc = launch(tc_chain_train_kernel<2, 3, 1, 2, 1>, p2, map_g1);
+        else rc = launch(tc_chain_train_kernel<2, -1, -1, -1, -1>, p2, map_g1);
+        if (rc) return rc;
+        bn_fwd_finalize_tc_kernel<<<(s.c2 + 3) / 4, 128, 0, st>>>(f.partial, 4 * gx, s.c2, s.cpad, count, train, a.mlp.b[1], a.mlp.gamma[1],
+                                                                     a.mlp.beta[1], a.mlp.running_mean[1], a.mlp.running_var[1],
+                                                                     a.mlp.num_batches_tracked[1], a.mlp.eps, a.mlp.momentum, bn2, s.cmax);
+        note_launch();
+        TmaMap map_in3;
+        if ((rc = make_tma_feature_major(&map_in3, a.a1, s.c1, s.ld))) return rc;
+        ChainTrainParams p3 = {};
+        p3.w_img[0] = f.pk[1].img; p3.w_bytes[0] = (int)f.pk[1].bytes;
+        p3.w_img[1] = f.pk[2].img; p3.w_bytes[1] = (int)f.pk[2].bytes;
+        p3.k_in = s.c1; p3.kc_in = f.pk[1].num_kc; p3.kc_mid = f.pk[2].num_kc;
+        p3.c_a = s.c2; p3.c_b = s.c3; p3.mt_b = f.pk[2].MT;
+        p3.rows = ra.cap; p3.rows_dev = ra.dev; p3.ld = s.ld;
+        p3.bias_a = a.mlp.b[1]; p3.mean_a = bn2; p3.rstd_a = bn2 + s.cmax; p3.gamma_a = a.mlp.gamma[1]; p3.beta_a = a.mlp.beta[1];
+        p3.act = a.mlp.act; p3.z_out = (__half *)z2; p3.a_out = (__half *)a.a2;
+        p3.bias_b = a.mlp.b[2]; p3.out = a.out; p3.arg = a.arg; p3.out16 = (__half *)a.out_bf16; p3.rgrp = a.rgrp;
+        if (p3.kc_in == 1 && p3.kc_mid == 1 && p3.mt_b == 1) rc = launch(tc_chain_train_kernel<3, 1, 4, 1, 1>, p3, map_in3);
+        else if (p3.kc_in == 2 && p3.kc_mid == 2 && p3.mt_b == 2) rc = launch(tc_chain_train_kernel<3, 2, 4, 2, 2>, p3, map_in3);
+        else rc = launch(tc_chain_train_kernel<3, -1, -1, -1, -1>, p3, map_in3);
+        if (rc) return rc;
+        B2PN_LAUNCH_CHECK();
+        return B2PN_OK;
+    }
     if (s.rows > 0) {
         NormStoreEpTC e = {s.c1, a.mlp.b[0], bn1, bn1 + s.cmax, a.mlp.gamma[0], a.mlp.beta[0], a.mlp.act, rm};
         TmaMap mz, ma;  // 32-channel boxes: one per epilogue warp
