@@ -2621,7 +2621,9 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
     if (need_dx) {
         TmaFeatLoader bl;
         const int64_t nx = a.n_src * (int64_t)a.c_in;
+        // the scatter-add target starts from zero (SLOTS levels; CLOUDS levels store every row exactly once)
         if (b.dxi) B2PN_CUDA(cudaMemsetAsync(b.dxi, 0, (size_t)nx * sizeof(long long), st));
+        else if (a.seg_mode == B2PN_SEG_SLOTS) B2PN_CUDA(cudaMemsetAsync(g.grad_x, 0, (size_t)nx * sizeof(float), st));
         ScatterEpTC e = {rm, g.grad_x, a.c_in, b.dxi};
         if ((rc = launch_by_mt(b.pkT[0], ra, bl, e, e, st, map1))) return rc;
         if (b.dxi) {

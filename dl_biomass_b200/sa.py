@@ -344,7 +344,9 @@ class _SAFunction(torch.autograd.Function):
         gb = [fresh(d[1], b1), fresh(d[5], b2), fresh(d[9], b3)]
         gg = [fresh(d[2], g1), fresh(d[6], g2)]
         gbe = [fresh(d[3], be1), fresh(d[7], be2)]
-        gx = torch.zeros(xs.shape, dtype=f32, device=dev) if ctx.x_needs_grad else None
+        # (the tensor-core path clears its scatter-add target itself: a memset node, not an ATen kernel)
+        gx = ((torch.empty if prec == PREC_BF16 else torch.zeros)(xs.shape, dtype=f32, device=dev)
+              if ctx.x_needs_grad else None)
         a = SaArgs()
         _fill_args(a, precision=prec, training=training, seg_mode=seg_mode, K=K, n_src=pos_src.shape[0], n_dst=n_dst,
                    c_in=ctx.c_in, x=xs, pos_src=pos_src, pos_dst=pos_dst, nbr=nbr, cnt=cnt, batch=batch, chans=chans,

@@ -221,7 +221,8 @@ typedef struct b2pn_sa_grads {
     const float *grad_out;       /* [n_dst, c3]                                                       */
     float *grad_w[3], *grad_b[3];/* overwritten                                                       */
     float *grad_gamma[2], *grad_beta[2];
-    float *grad_x;               /* [n_src, c_in], ZERO-INITIALISED by the caller (scatter-add); NULL = skip */
+    float *grad_x;               /* [n_src, c_in], overwritten (PREC_BF16: the library clears it before its scatter-add;
+                                    PREC_F32: the caller passes it ZERO-INITIALISED); NULL = skip */
 } b2pn_sa_grads;
 
 /* scratch bytes needed by forward (backward=0) or backward (backward=1) for these shapes */
