@@ -110,3 +110,45 @@ def test_net_bf16_headline_shape(cuda_device, headline):
             f"worst relative L2 error {rels[worst]:.3e} ({worst})")
     # bf16 activations flip ReLU masks / arg-max winners of near-ties, so gradients agree in direction, not to 2e-2
     assert min(cos) > 0.9 and sum(cos) / len(cos) > 0.98, (min(cos), rels)
+
+
+def test_reference_spelled_checkpoint_and_evaluation_on_the_device(cuda_device):
+    """SURVEY 8(f) rows f3 / f4 on the GPU: a state_dict in the reference's spelling (`module.` prefix of its DataParallel
+    wrapper, PyG >= 2.1 `norms.i.module.*`; /root/reference/main.py:140,245, testing_model.py:30-37) loads into the B200
+    Net on the device and reproduces the oracle's evaluation-mode outputs; `metrics.evaluate` over device batches gives
+    the oracle's metric table, whether the test set goes through as one batch or in chunks."""
+    from dl_biomass_b200 import checkpoint, metrics
+    netr = ref.seeded_init_(ref.NetRef(1, "ReLU", 0, 0.5), seed=3)
+    netr.train()
+    with torch.no_grad():   # non-trivial running statistics
+        for i in range(2):
+            netr(Batch.from_data_list(synthetic_clouds(300 + i, 5, 700, 1, True)))
+    netr.eval()
+    sd = {}
+    for k, v in netr.state_dict().items():
+        k = checkpoint._NORM_PLAIN.sub(r"\1.module.\2", "." + k)[1:]
+        sd["module." + k] = v.clone()
+    assert any(".norms.0.module.running_mean" in k for k in sd) and all(k.startswith("module.") for k in sd)
+    clouds = synthetic_clouds(777, 9, 900, 1, True)
+    whole = Batch.from_data_list(clouds)
+    with torch.no_grad():
+        want = netr(whole)
+    want_table = metrics.regression_metrics(whole.y.reshape(-1, 4), want)
+    for precision, tol in (("fp32", 1e-4), ("bf16", 2e-2)):
+        net = Net(1, "ReLU", 0, 0.5, precision=precision).to(cuda_device).set_random_start(False)
+        res = checkpoint.load_reference_state_dict(net, sd)
+        assert not res.missing_keys and not res.unexpected_keys
+        chunks = [Batch.from_data_list(clouds[:4]).to(cuda_device), Batch.from_data_list(clouds[4:]).to(cuda_device)]
+        table, (obs, pred) = metrics.evaluate(net, chunks, return_predictions=True)
+        assert pred.is_cuda and not net.training
+        e = rel_err(pred, want)
+        _record(f"{precision} eval through a reference-spelled checkpoint, 9 clouds in 2 chunks: out rel err {e:.3e}")
+        assert e < tol
+        one, _ = metrics.evaluate(net, [whole.to(cuda_device)], return_predictions=True)
+        for name in want_table:
+            for m in ("r2", "rmse", "mape"):
+                assert abs(table[name][m] - want_table[name][m]) <= 5e-2 * max(1.0, abs(want_table[name][m])), (name, m)
+                assert abs(one[name][m] - table[name][m]) <= 1e-3 * max(1.0, abs(table[name][m])), (name, m)
+        # and back out in the reference's spelling
+        back = checkpoint.reference_state_dict(net, pyg_norm_wrapper=True, data_parallel=True)
+        assert set(back) == set(sd) and all(torch.equal(back[k].cpu(), sd[k]) for k in sd)
