@@ -58,6 +58,7 @@ int64_t sa_workspace_bytes_bf16(const b2pn_sa_args &a, int backward);
 int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st);
 int sa_gather_rows_bf16(const b2pn_sa_args &a, cudaStream_t st);
 int sa_eval_fused_bf16(const b2pn_sa_args &a);
+int sa_train_chained_bf16(const b2pn_sa_args &a);
 int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t st);
 }  // namespace tc
 }  // namespace b2pn
@@ -87,6 +88,13 @@ extern "C" int b2pn_sa_eval_fused(const b2pn_sa_args *args)
     if (!args) return B2PN_EINVAL;
     if (args->precision != B2PN_PREC_BF16) return 0;
     return b2pn::tc::sa_eval_fused_bf16(*args);
+}
+
+extern "C" int b2pn_sa_train_chained(const b2pn_sa_args *args)
+{
+    if (!args) return B2PN_EINVAL;
+    if (args->precision != B2PN_PREC_BF16) return 0;
+    return b2pn::tc::sa_train_chained_bf16(*args);
 }
 
 extern "C" int b2pn_sa_gather_rows(const b2pn_sa_args *args, b2pn_stream_t stream)

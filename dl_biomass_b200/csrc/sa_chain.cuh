@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_eval_kernel(const Chai
 //   warps 18 / 19        TMA producer of slot 0 / 1 (one elected lane)
 // =====================================================================================================================
 constexpr int CT_THREADS = CH_SLOTS * CH_EPI_THREADS + CH_SLOTS * 32 + CH_SLOTS * 32;  // 640
-enum { TB_IN_FULL = 0, TB_IN_FREE, TB_DA_FULL, TB_XA_FULL, TB_DB_FULL, TB_DB_FREE, TB_PER_SLOT };
+enum { TB_IN_FULL = 0, TB_IN_FREE, TB_DA_FULL, TB_XA_FULL, TB_DB_FULL, TB_DB_FREE, TB_IN_LAND, TB_PER_SLOT };
 
 struct ChainTrainParams {
     const uint8_t *w_img[2];  // P2: layers 1, 2; P3: layers 2, 3 (fp16 images, num_mg == 1)
@@ -404,7 +404,10 @@ struct ChainTrainParams {
     // first GEMM: zhat = (acc + bias - mean) * rstd; a = act(gamma * zhat + beta), invalid rows 0; both stored [c_a][ld]
     const float *bias_a, *mean_a, *rstd_a, *gamma_a, *beta_a;
     int act;
-    __half *z_out, *a_out;
+    __half *z_out, *a_out;    // a_out NULL: only zhat is stored (one tensor per hidden layer); consumers rebuild a from it
+    // non-NULL: the fetched input tile holds zhat of the PREVIOUS layer (its a was not stored): the epilogue group turns
+    // it into a = act(gamma * zhat + beta), invalid rows 0, in shared memory before the first GEMM reads it
+    const float *fix_gamma, *fix_beta;
     // second GEMM: PASS 2 -> per-channel sum / sum of squares of the bias-free accumulators, per CTA and writer group:
     // partial[(blockIdx.x * 4 + slot * 2 + half)][2][cpad]; PASS 3 -> per-centroid max (+ bias) and arg-max slot
     double *partial;
@@ -451,10 +454,12 @@ __global__ void __launch_bounds__(CT_THREADS, 1)
             mbar_init(&b[TB_XA_FULL], 1);
             mbar_init(&b[TB_DB_FULL], 1);
             mbar_init(&b[TB_DB_FREE], CH_EPI_WARPS);
+            mbar_init(&b[TB_IN_LAND], 1);
         }
         mbar_init(w_full, 1);
         fence_barrier_init();
     }
+    const bool fix_in = p.fix_gamma != nullptr;
     if (warp == CH_MMA_WARP) tmem_alloc<512>(tmem_holder);
     tc_fence_before();
     __syncthreads();
@@ -474,10 +479,11 @@ __global__ void __launch_bounds__(CT_THREADS, 1)
                 const int64_t tile = tile_of(it, s);
                 if (tile >= num_tiles) break;
                 mbar_wait(&b[TB_IN_FREE], (uint32_t)(it & 1) ^ 1u);
-                mbar_expect_tx(&b[TB_IN_FULL], (unsigned)in_bytes);
+                uint64_t *land = fix_in ? &b[TB_IN_LAND] : &b[TB_IN_FULL];   // a fetched zhat tile is fixed up before the MMA
+                mbar_expect_tx(land, (unsigned)in_bytes);
                 for (int kc = 0; kc < kc_in; ++kc)
-                    tma_load_2d(IN + kc * CH_CHUNK_BYTES, &map_in, (int)(tile * CH_ROWS), kc * KC, &b[TB_IN_FULL]);
-                mbar_arrive(&b[TB_IN_FULL]);
+                    tma_load_2d(IN + kc * CH_CHUNK_BYTES, &map_in, (int)(tile * CH_ROWS), kc * KC, land);
+                mbar_arrive(land);
             }
         }
     } else if (warp >= CH_MMA_WARP) {
@@ -579,6 +585,35 @@ __global__ void __launch_bounds__(CT_THREADS, 1)
                 dsc[g] = (gi * 8 < rows) ? __ldg(p.rgrp + gi) : GI_NONE;
                 if (gi_none(dsc[g])) dsc[g] = GI_NONE;
             }
+            if (fix_in) {
+                // ---- the fetched tile is zhat of the previous layer: a = act(gamma * zhat + beta), invalid rows 0, in place
+                unsigned nvp = 0u;   // valid rows of the tile's eight 8-row groups, 4 bits each
+#pragma unroll
+                for (int g = 0; g < 8; ++g) nvp |= (unsigned)gi_nv(dsc[g]) << (4 * g);
+                uint8_t *IN = slots + s * slot_bytes;
+                mbar_wait(&b[TB_IN_LAND], ph);
+                const int t = w8 * 32 + lane;
+                for (int c = t; c < kc_in * 512; c += CH_EPI_THREADS) {
+                    const int line = (c >> 3) & 63, kc = c >> 9;
+                    const int g = (c & 7) ^ (line & 7);               // row group held by this physical 16-byte chunk
+                    const int nv = (int)((nvp >> (4 * g)) & 15u);
+                    const int chn = kc * KC + line;
+                    const float fg = __ldg(p.fix_gamma + chn), fb = __ldg(p.fix_beta + chn);
+                    uint4 *q = reinterpret_cast<uint4 *>(IN) + c;
+                    float f[8];
+                    unpack8h(*q, f);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        float y = fmaf(f[e], fg, fb);
+                        if (relu) y = fmaxf(y, 0.f);
+                        f[e] = e < nv ? y : 0.f;
+                    }
+                    *q = pack8h(f);
+                }
+                fence_proxy_async_smem();
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + s), "n"(CH_EPI_THREADS) : "memory");
+                if (w8 == 0 && lane == 0) mbar_arrive(&b[TB_IN_FULL]);
+            }
             // ---- first GEMM: normalise; zhat and a leave through shared-memory tiles and TMA stores (16-byte global stores
             // 2*ld bytes apart per lane made this epilogue 3x slower, as they had in round 1); a is also the operand of
             // the second GEMM, read in place
@@ -614,7 +649,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1)
             if (w8 == 0 && lane == 0) {
                 for (int kc = 0; kc < kc_mid; ++kc) {   // channels past c_a are clipped by the tensor maps
                     tma_store_2d(&map_z, X + x_bytes + kc * CH_CHUNK_BYTES, (int)row0, kc * KC);
-                    tma_store_2d(&map_a, X + kc * CH_CHUNK_BYTES, (int)row0, kc * KC);
+                    if (p.a_out) tma_store_2d(&map_a, X + kc * CH_CHUNK_BYTES, (int)row0, kc * KC);
                 }
                 bulk_commit_group();
                 mbar_arrive(&b[TB_XA_FULL]);

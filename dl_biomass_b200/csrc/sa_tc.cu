@@ -1215,6 +1215,26 @@ struct TmaFill {
     static constexpr bool USES_TMA = true;
     int c;         // channels of the tensor; with the ones box: a multiple of 64 with (c % 256) + 16 <= 256
     int ones_box;  // 1: append the row-valid box at line c; 0: the tensor carries its own ones line (layer-1 operand)
+    // non-NULL: the tensor holds the NORMALISED values zhat and the operand wanted is the activation a = act(gamma*zhat+beta),
+    // rebuilt per channel line while the tile is converted to bf16 (only zhat is stored per hidden layer)
+    const float *fix_gamma;
+    const float *fix_beta;
+    int fix_act;
+    // 16-byte chunk c16 of the landed tile of N group ng, converted (and fixed up) in place
+    __device__ __forceinline__ uint4 convert(const uint4 &raw, int c16, int ng) const
+    {
+        const int ch = ng * 256 + (c16 >> 3);
+        if (fix_gamma == nullptr || ch >= c) return f16_to_bf16_chunk(raw);   // plain tensor / the ones box
+        const float ga = __ldg(fix_gamma + ch), be = __ldg(fix_beta + ch);
+        float f[8];
+        unpack8h(raw, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            f[e] = fmaf(f[e], ga, be);
+            if (fix_act == B2PN_ACT_RELU) f[e] = fmaxf(f[e], 0.f);
+        }
+        return pack8(f);
+    }
     // the copies come in whole 64-line boxes: the tile must hold them even when fewer lines are used
     static __host__ __device__ int bytes(int nb_lines) { return ((nb_lines + 63) / 64) * 64 * LINE_BYTES; }
     __device__ __forceinline__ void resolve(int64_t) {}
@@ -1413,7 +1433,7 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
                 const int nchunk16 = xf.landed_lines(ng) * 8;
                 for (int c = lt; c < nchunk16; c += NUM_LOAD) {
                     uint4 *q = reinterpret_cast<uint4 *>(B) + c;
-                    *q = f16_to_bf16_chunk(*q);
+                    *q = xf.convert(*q, c, ng);
                 }
             } else {
                 if constexpr (YS::USES_TMA) mbar_wait(&empty[s], ph ^ 1u);  // (the other Y paths have waited above)
@@ -2072,8 +2092,21 @@ static int check_args_tc(const b2pn_sa_args &a)
     if (!a.out) return B2PN_EINVAL;
     // the arg-max slots and the hidden-activation buffers are only touched by the multi-pass (training / wide-level) kernels
     const ShapesTC sh = shapes_tc(a);
-    if (!chain_eligible(a, sh.k1, sh.c1, sh.c2, sh.c3) && (!a.arg || !a.h1 || !a.h2 || !a.bn || !a.a1 || !a.a2)) return B2PN_EINVAL;
+    if (!chain_eligible(a, sh.k1, sh.c1, sh.c2, sh.c3)) {
+        if (!a.arg || !a.h1 || !a.h2 || !a.bn) return B2PN_EINVAL;
+        // the activation copies a1 / a2 are optional where the chained training kernels run (they rebuild a from zhat)
+        const bool zonly_ok = chain_train_ok(a, sh.k1, sh.c1, sh.c2, sh.c3) && a.g1 != nullptr && a.row_valid != nullptr;
+        if ((!a.a1 || !a.a2) && !(zonly_ok && !a.a1 && !a.a2)) return B2PN_EINVAL;
+    }
     return B2PN_OK;
+}
+
+// 1 when the chained TRAINING kernels cover these shapes: only zhat is stored per hidden layer, a1 / a2 may be NULL
+int sa_train_chained_bf16(const b2pn_sa_args &a)
+{
+    if (a.mlp.c[0] != a.c_in + 3) return 0;
+    const ShapesTC s = shapes_tc(a);
+    return (chain_train_ok(a, s.k1, s.c1, s.c2, s.c3) && s.k1 + 1 + 15 <= 256) ? 1 : 0;
 }
 
 // 1 when b2pn_sa_forward runs these arguments through the single-launch evaluation kernel (no hidden activations stored)
@@ -2327,10 +2360,10 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
             const int smem = chain_train_smem_bytes(cp);
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return (int)e;
-            TmaMap mz, ma;   // output maps: boxes of 64 rows x 64 channels, the layout of the shared-memory tiles
+            TmaMap mz, ma = kNoMap;   // output maps: boxes of 64 rows x 64 channels, the layout of the shared-memory tiles
             int r2 = make_tma_feature_major(&mz, cp.z_out, cp.c_a, cp.ld);
             if (r2) return r2;
-            if ((r2 = make_tma_feature_major(&ma, cp.a_out, cp.c_a, cp.ld))) return r2;
+            if (cp.a_out && (r2 = make_tma_feature_major(&ma, cp.a_out, cp.c_a, cp.ld))) return r2;
             kern<<<gx, CT_THREADS, smem, st>>>(cp, map, mz, ma);
             note_launch();
             e = cudaPeekAtLastError();
@@ -2343,7 +2376,7 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
         p2.c_a = s.c1; p2.c_b = s.c2; p2.mt_b = 1;
         p2.rows = ra.cap; p2.rows_dev = ra.dev; p2.ld = s.ld;
         p2.bias_a = a.mlp.b[0]; p2.mean_a = bn1; p2.rstd_a = bn1 + s.cmax; p2.gamma_a = a.mlp.gamma[0]; p2.beta_a = a.mlp.beta[0];
-        p2.act = a.mlp.act; p2.z_out = (__half *)z1; p2.a_out = (__half *)a.a1;
+        p2.act = a.mlp.act; p2.z_out = (__half *)z1; p2.a_out = (__half *)a.a1;   // a_out NULL: zhat alone is stored
         p2.partial = f.partial; p2.cpad = s.cpad; p2.rgrp = a.rgrp;
         const int nks1 = (s.k1 - (p2.kc_in - 1) * KC) >= KC ? 4 : (s.k1 - (p2.kc_in - 1) * KC + 15) / 16;
         if (p2.kc_in == 1 && nks1 == 1 && p2.kc_mid == 1) rc = launch(tc_chain_train_kernel<2, 1, 1, 1, 1>, p2, map_g1);
@@ -2354,8 +2387,8 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
                                                                      a.mlp.beta[1], a.mlp.running_mean[1], a.mlp.running_var[1],
                                                                      a.mlp.num_batches_tracked[1], a.mlp.eps, a.mlp.momentum, bn2, s.cmax);
         note_launch();
-        TmaMap map_in3;
-        if ((rc = make_tma_feature_major(&map_in3, a.a1, s.c1, s.ld))) return rc;
+        TmaMap map_in3;   // P3 reads a1, or -- when only zhat1 is stored -- zhat1 and rebuilds a1 in shared memory
+        if ((rc = make_tma_feature_major(&map_in3, a.a1 ? a.a1 : (const void *)z1, s.c1, s.ld))) return rc;
         ChainTrainParams p3 = {};
         p3.w_img[0] = f.pk[1].img; p3.w_bytes[0] = (int)f.pk[1].bytes;
         p3.w_img[1] = f.pk[2].img; p3.w_bytes[1] = (int)f.pk[2].bytes;
@@ -2364,6 +2397,10 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
         p3.rows = ra.cap; p3.rows_dev = ra.dev; p3.ld = s.ld;
         p3.bias_a = a.mlp.b[1]; p3.mean_a = bn2; p3.rstd_a = bn2 + s.cmax; p3.gamma_a = a.mlp.gamma[1]; p3.beta_a = a.mlp.beta[1];
         p3.act = a.mlp.act; p3.z_out = (__half *)z2; p3.a_out = (__half *)a.a2;
+        if (!a.a1) {
+            p3.fix_gamma = a.mlp.gamma[0];
+            p3.fix_beta = a.mlp.beta[0];
+        }
         p3.bias_b = a.mlp.b[2]; p3.out = a.out; p3.arg = a.arg; p3.out16 = (__half *)a.out_bf16; p3.rgrp = a.rgrp;
         if (p3.kc_in == 1 && p3.kc_mid == 1 && p3.mt_b == 1) rc = launch(tc_chain_train_kernel<3, 1, 4, 1, 1>, p3, map_in3);
         else if (p3.kc_in == 2 && p3.kc_mid == 2 && p3.mt_b == 2) rc = launch(tc_chain_train_kernel<3, 2, 4, 2, 2>, p3, map_in3);
@@ -2531,8 +2568,11 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
     if (tma_x2 || tma_x1) {
         if ((rc = make_tma_row_valid(&map_v, a.row_valid, s.ld))) return rc;
     }
-    if (tma_x2 && (rc = make_tma_feature_major(&map_a2, a.a2, s.c2, s.ld))) return rc;
-    if (tma_x1 && (rc = make_tma_feature_major(&map_a1, a.a1, s.c1, s.ld))) return rc;
+    // only zhat stored (a1 == NULL, chained training path): the X sides read zhat and rebuild a in shared memory
+    const bool x_from_z = a.a1 == nullptr;
+    if (x_from_z && !(tma_x1 && tma_x2 && a.seg_mode == B2PN_SEG_SLOTS)) return B2PN_EINVAL;
+    if (tma_x2 && (rc = make_tma_feature_major(&map_a2, x_from_z ? (const void *)z2 : a.a2, s.c2, s.ld))) return rc;
+    if (tma_x1 && (rc = make_tma_feature_major(&map_a1, x_from_z ? (const void *)z1 : a.a1, s.c1, s.ld))) return rc;
     if (a.seg_mode == B2PN_SEG_CLOUDS) {
         // global level (few rows): materialise dh3 once, then both consumers read it through TMA
         route_grad_tc_kernel<true><<<apply_grid(s.ld, s.c3), 256, 0, st>>>(rm, ra.dev, g.grad_out, a.arg, s.c3, s.ld, b.dh3);
@@ -2543,7 +2583,7 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
         if ((rc = launch_by_mt(b.pkT[2], ra, bl, e31, e32, st, map3, mdz2, mz2))) return rc;          // da2 = W3^T dh3
         TmaSource y3 = {rm};
         if (tma_x2) {
-            TmaFill xt = {s.c2, 1};
+            TmaFill xt = {s.c2, 1, nullptr, nullptr, 0};
             rc = launch_dw(y3, xt, s.c3, s.c2 + 1, s, ra, b.dwp[2], st, map3, map_a2, map_v);   // dW3 = dh3^T a2
         } else {
             rc = launch_dw(y3, xa2, s.c3, s.c2 + 1, s, ra, b.dwp[2], st, map3);
@@ -2556,7 +2596,7 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
         FeatLoaderTC<RouteSource, true> bl = {rs};
         if ((rc = launch_by_mt(b.pkT[2], ra, bl, e31, e32, st, kNoMap, mdz2, mz2))) return rc;        // da2 = W3^T dh3
         if (tma_x2) {
-            TmaFill xt = {s.c2, 1};
+            TmaFill xt = {s.c2, 1, x_from_z ? a.mlp.gamma[1] : nullptr, a.mlp.beta[1], a.mlp.act};
             rc = launch_dw(rs, xt, s.c3, s.c2 + 1, s, ra, b.dwp[2], st, kNoMap, map_a2, map_v);  // dW3 = dh3^T a2
         } else {
             rc = launch_dw(rs, xa2, s.c3, s.c2 + 1, s, ra, b.dwp[2], st);
@@ -2585,7 +2625,7 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
         if ((rc = make_tma_feature_major(&mz1, z1, s.c1, s.ld, 32))) return rc;
         if ((rc = launch_by_mt(b.pkT[1], ra, bl, e1, e2, st, map2, mdz1, mz1))) return rc;
         if (tma_x1) {
-            TmaFill xt = {s.c1, 1};
+            TmaFill xt = {s.c1, 1, x_from_z ? a.mlp.gamma[0] : nullptr, a.mlp.beta[0], a.mlp.act};
             rc = launch_dw(y2, xt, s.c2, s.c1 + 1, s, ra, b.dwp[1], st, map2, map_a1, map_v);
         } else {
             LineFillK<FeatSource<1>> xa1 = {{rm, z1, s.c1, s.ld, a.mlp.act, s.c1, a.mlp.gamma[0], a.mlp.beta[0], FMT_BF16}};
@@ -2606,7 +2646,7 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
         if (l1_materialised(a, s)) {
             TmaMap map_g1;
             if ((rc = make_tma_feature_major(&map_g1, a.g1, s.k1 + 1, s.ld))) return rc;
-            TmaFill xt = {s.k1 + 1, 0};
+            TmaFill xt = {s.k1 + 1, 0, nullptr, nullptr, 0};
             rc = launch_dw(y1, xt, s.c1, s.k1 + 1, s, ra, b.dwp[0], st, map1, map_g1, kNoMap);
         } else {
             LineFillGather xg = {{rm, a.x, s.cols, a.pos_src, a.pos_dst, s.k1, FMT_BF16}};  // X side of dW1: meets bf16 gradients

@@ -140,7 +140,7 @@ def test_reference_spelled_checkpoint_and_evaluation_on_the_device(cuda_device):
         assert not res.missing_keys and not res.unexpected_keys
         chunks = [Batch.from_data_list(clouds[:4]).to(cuda_device), Batch.from_data_list(clouds[4:]).to(cuda_device)]
         table, (obs, pred) = metrics.evaluate(net, chunks, return_predictions=True)
-        assert pred.is_cuda and not net.training
+        assert pred.is_cuda and net.training          # evaluate() ran in eval mode and restored the training flag
         e = rel_err(pred, want)
         _record(f"{precision} eval through a reference-spelled checkpoint, 9 clouds in 2 chunks: out rel err {e:.3e}")
         assert e < tol
