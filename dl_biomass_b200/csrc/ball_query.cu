@@ -211,6 +211,8 @@ struct BqGridParams {
     GridInfo *info;         // [B]
     int32_t *cell_start;    // [B][GRID_MAX_CELLS + 1]
     int32_t *cell_pts;      // [N] cloud-local source indices grouped by cell
+    float4 *cell_rec;       // [N] the same points as records {x, y, z, bits of the cloud-local index}, in cell order: a
+                            // query streams its candidates with ONE coalesced load each instead of index -> position gathers
 };
 
 __device__ __forceinline__ int grid_cell_of(const GridInfo &g, float x, float y, float z)
@@ -330,9 +332,13 @@ __global__ void __launch_bounds__(1024) bq_grid_build_kernel(const BqGridParams 
     if (tid == 0) cs[ncell] = n;
     __syncthreads();
     int32_t *pts = p.cell_pts + s0;
+    float4 *rec = p.cell_rec + s0;
     for (int i = tid; i < n; i += 1024) {
-        const int c = grid_cell_of(gi, __ldg(g + 3 * i), __ldg(g + 3 * i + 1), __ldg(g + 3 * i + 2));
-        pts[atomicAdd(&s_cnt[c], 1)] = i;  // order inside a cell is arbitrary: the query sorts its hits
+        const float x = __ldg(g + 3 * i), y = __ldg(g + 3 * i + 1), z = __ldg(g + 3 * i + 2);
+        const int c = grid_cell_of(gi, x, y, z);
+        const int slot = atomicAdd(&s_cnt[c], 1);  // order inside a cell is arbitrary: the query sorts its hits
+        pts[slot] = i;
+        rec[slot] = make_float4(x, y, z, __int_as_float(i));
     }
 }
 
@@ -352,7 +358,6 @@ __global__ void __launch_bounds__(WARPS * 32) bq_grid_query_kernel(const BqGridP
     const GridInfo gi = p.info[b];
     const float *gsrc = p.src + 3 * s0;
     const int32_t *cs = p.cell_start + (int64_t)b * (GRID_MAX_CELLS + 1);
-    const int32_t *pts = p.cell_pts + s0;
     const float qx = __ldg(p.qry + 3 * (q0 + ql)), qy = __ldg(p.qry + 3 * (q0 + ql) + 1), qz = __ldg(p.qry + 3 * (q0 + ql) + 2);
     const unsigned lt_mask = (1u << lane) - 1u;
     int *list = s_list[warp];
@@ -364,66 +369,77 @@ __global__ void __launch_bounds__(WARPS * 32) bq_grid_query_kernel(const BqGridP
         cx = min(max(cx, 0), gi.n[0] - 1);
         cy = min(max(cy, 0), gi.n[1] - 1);
         cz = min(max(cz, 0), gi.n[2] - 1);
-        // Dense neighbourhood?  The ball holds ~15 % of the 27 cells' points; once that is several times K the
-        // ascending scan finds its K hits after a short prefix of the cloud and beats collecting + sorting them all.
-        {
-            int cand = 0;
-            if (lane < 9) {
-                const int z = cz + lane / 3 - 1, y = cy + lane % 3 - 1;
-                if (z >= 0 && z < gi.n[2] && y >= 0 && y < gi.n[1]) {
-                    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, gi.n[0] - 1);
-                    const int c_lo = (z * gi.n[1] + y) * gi.n[0] + x0;
-                    cand = cs[c_lo + (x1 - x0) + 1] - cs[c_lo];
-                }
-            }
-            cand = __reduce_add_sync(0xffffffffu, cand);
-            overflow = cand > 13 * K;
-        }
-        for (int dz = -1; dz <= 1 && !overflow; ++dz) {
-            const int z = cz + dz;
-            if (z < 0 || z >= gi.n[2]) continue;
-            for (int dy = -1; dy <= 1 && !overflow; ++dy) {
-                const int y = cy + dy;
-                if (y < 0 || y >= gi.n[1]) continue;
-                // the three x-neighbours are consecutive cells: one contiguous range of cell_pts
+        // The nine (z, y) cell rows around the query are nine contiguous ranges of the cell-ordered records (the three
+        // x-neighbours are consecutive cells).  Lanes 0..8 hold one range each; the warp then walks the CONCATENATION of
+        // the ranges 32 candidates at a time, so a query costs ceil(candidates / 32) coalesced record loads instead of
+        // nine (or more) rounds of two dependent gathers (index, then position).
+        int beg = 0, len = 0;
+        if (lane < 9) {
+            const int z = cz + lane / 3 - 1, y = cy + lane % 3 - 1;
+            if (z >= 0 && z < gi.n[2] && y >= 0 && y < gi.n[1]) {
                 const int x0 = max(cx - 1, 0), x1 = min(cx + 1, gi.n[0] - 1);
                 const int c_lo = (z * gi.n[1] + y) * gi.n[0] + x0;
-                const int beg = cs[c_lo], end = cs[c_lo + (x1 - x0) + 1];
-                for (int j0 = beg; j0 < end; j0 += 32) {
-                    const int j = j0 + lane;
-                    int idx = -1;
-                    bool hit = false;
-                    if (j < end) {
-                        idx = __ldg(pts + j);
-                        const float d = dist2_scalar(__ldg(gsrc + 3 * idx), __ldg(gsrc + 3 * idx + 1), __ldg(gsrc + 3 * idx + 2), qx, qy, qz);
-                        hit = d < p.r2;
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, hit);
-                    if (m != 0u) {
-                        const int pos = h + __popc(m & lt_mask);
-                        if (hit && pos < GRID_LIST_CAP) list[pos] = idx;
-                        h += __popc(m);
-                        if (h > GRID_LIST_CAP) {
-                            overflow = true;
-                            break;
-                        }
-                    }
-                }
+                beg = cs[c_lo];
+                len = cs[c_lo + (x1 - x0) + 1] - beg;
+            }
+        }
+        int pre = len;   // inclusive prefix of the range lengths over lanes 0..8
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, pre, o);
+            if (lane >= o) pre += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, pre, 8);
+        // Dense neighbourhood?  The ball holds ~15 % of the 27 cells' points; once that is several times K the
+        // ascending scan finds its K hits after a short prefix of the cloud and beats collecting + sorting them all.
+        overflow = total > 13 * K;
+        const float4 *rec = p.cell_rec + s0;
+        for (int t0 = 0; t0 < total && !overflow; t0 += 32) {
+            const int t = t0 + lane;
+            int j = -1;
+#pragma unroll
+            for (int rr = 0; rr < 9; ++rr) {   // the range candidate t falls into
+                const int hi = __shfl_sync(0xffffffffu, pre, rr), ln = __shfl_sync(0xffffffffu, len, rr),
+                          bg = __shfl_sync(0xffffffffu, beg, rr);
+                if (j < 0 && t < hi) j = bg + (t - (hi - ln));
+            }
+            int idx = -1;
+            bool hit = false;
+            if (t < total) {
+                const float4 q = __ldg(rec + j);
+                idx = __float_as_int(q.w);
+                hit = dist2_scalar(q.x, q.y, q.z, qx, qy, qz) < p.r2;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m != 0u) {
+                const int pos = h + __popc(m & lt_mask);
+                if (hit && pos < GRID_LIST_CAP) list[pos] = idx;
+                h += __popc(m);
+                if (h > GRID_LIST_CAP) overflow = true;
             }
         }
     }
     int32_t *row = p.nbr + (q0 + ql) * (int64_t)K;
     if (overflow) {
         // (rare) more hits than the list holds: plain ascending scan with early exit, like Kernel 2
+        // four batches of 32 points per round: their loads are in flight together (the early-exit test made every round
+        // of the plain loop wait for its own L2 round trip), the ballots keep the ascending order
         int c = 0;
-        for (int j0 = 0; j0 < n && c < K; j0 += 32) {
-            const int j = j0 + lane;
-            bool hit = false;
-            if (j < n) hit = dist2_scalar(__ldg(gsrc + 3 * j), __ldg(gsrc + 3 * j + 1), __ldg(gsrc + 3 * j + 2), qx, qy, qz) < p.r2;
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            const int slot = c + __popc(m & lt_mask);
-            if (hit && slot < K) row[slot] = (int)(s0 + j);
-            c += __popc(m);
+        for (int j0 = 0; j0 < n && c < K; j0 += 128) {
+            bool hit[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u * 32 + lane;
+                hit[u] = false;
+                if (j < n) hit[u] = dist2_scalar(__ldg(gsrc + 3 * j), __ldg(gsrc + 3 * j + 1), __ldg(gsrc + 3 * j + 2), qx, qy, qz) < p.r2;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned m = __ballot_sync(0xffffffffu, hit[u]);
+                const int slot = c + __popc(m & lt_mask);
+                if (hit[u] && slot < K) row[slot] = (int)(s0 + j0 + u * 32 + lane);
+                c += __popc(m);
+            }
         }
         c = min(c, K);
         for (int s = c + lane; s < K; s += 32) row[s] = -1;
@@ -461,7 +477,8 @@ __global__ void __launch_bounds__(WARPS * 32) bq_grid_query_kernel(const BqGridP
 extern "C" int64_t b2pn_ball_query_workspace_bytes(int32_t B, int64_t n_src_total)
 {
     if (B < 0 || n_src_total < 0) return B2PN_EINVAL;
-    return (int64_t)B * (sizeof(b2pn::GridInfo) + (b2pn::GRID_MAX_CELLS + 1) * sizeof(int32_t)) + n_src_total * sizeof(int32_t) + 1024;
+    return (int64_t)B * (sizeof(b2pn::GridInfo) + (b2pn::GRID_MAX_CELLS + 1) * sizeof(int32_t)) +
+           n_src_total * (int64_t)(sizeof(int32_t) + sizeof(float4)) + 2048;
 }
 
 extern "C" int b2pn_ball_query_grid_f32(const float *src_pos, const float *qry_pos, const int64_t *src_ptr,
@@ -478,9 +495,11 @@ extern "C" int b2pn_ball_query_grid_f32(const float *src_pos, const float *qry_p
     GridInfo *info = (GridInfo *)w;
     w += ((int64_t)B * sizeof(GridInfo) + 255) / 256 * 256;
     int32_t *cell_start = (int32_t *)w;
-    w += (int64_t)B * (GRID_MAX_CELLS + 1) * sizeof(int32_t);
+    w += ((int64_t)B * (GRID_MAX_CELLS + 1) * sizeof(int32_t) + 255) / 256 * 256;
     int32_t *cell_pts = (int32_t *)w;
-    BqGridParams p = {src_pos, qry_pos, src_ptr, qry_ptr, nbr, cnt, (float)r, (float)(r * r), K, info, cell_start, cell_pts};
+    w += (n_src_total * (int64_t)sizeof(int32_t) + 255) / 256 * 256;
+    float4 *cell_rec = (float4 *)w;
+    BqGridParams p = {src_pos, qry_pos, src_ptr, qry_ptr, nbr, cnt, (float)r, (float)(r * r), K, info, cell_start, cell_pts, cell_rec};
     cudaStream_t st = (cudaStream_t)stream;
     bq_grid_build_kernel<<<(unsigned)B, 1024, 0, st>>>(p);
     note_launch();
