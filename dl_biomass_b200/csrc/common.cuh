@@ -32,6 +32,24 @@ extern long long g_launches;
 // reference's thread-per-GPU DataParallel, /root/reference/main.py:140) never see each other's settings
 extern thread_local int t_sm_limit;       // upper bound on the CTAs of the persistent tcgen05 kernels (0 = every SM)
 extern thread_local int t_deterministic;  // 1: fixed-order reduction of the dW split partials (bit-reproducible)
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-(kernel, device) property: raise it once, not on every launch
+// (invisible under CUDA graphs, but ~1 us of host time per launch in the eager, ragged-batch training loop).
+// `slot`: one static per call site (per kernel instantiation): the largest size set so far per device.
+struct SmemAttrSlot {
+    int bytes[64];
+};
+template <class K>
+static inline cudaError_t ensure_dynamic_smem(K kern, int bytes, SmemAttrSlot &slot)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && slot.bytes[dev] >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) slot.bytes[dev] = bytes;   // a racing first call sets the same value twice
+    return e;
+}
+
 static inline void note_launch(int n = 1) { __atomic_fetch_add(&g_launches, (long long)n, __ATOMIC_RELAXED); }
 
 // ---- packed fp32x2 arithmetic (Blackwell FADD2/FMUL2), each half rounded separately ----------

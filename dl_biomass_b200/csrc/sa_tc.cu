@@ -1651,7 +1651,8 @@ static int launch_gemm(const Packed &pk, const RowsArg &ra, const BL &bl, const 
 {
     using P = SmemPlan<MT, EP::STAGED, BL::WIDE>;
     auto kern = tc_rows_gemm_kernel<MT, BL, EP>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
+    static SmemAttrSlot slot = {};
+    cudaError_t e = ensure_dynamic_smem(kern, P::TOTAL, slot);
     if (e != cudaSuccess) return (int)e;
     GemmParams gp = {pk.img, pk.fmt, pk.fmt, pk.num_kc, ra.cap, ra.dev};
     dim3 grid((unsigned)grid_x_for(pk, ra.tiles()), (unsigned)pk.num_mg);
@@ -2482,13 +2483,15 @@ static int launch_dw(const YS &ys, const XF &xf, int n_out, int k_total, const S
     if (d.MTA == 1) {
         auto kern = tc_dw_kernel<1, YS, XF>;
         const int smem = plan(DwPlan<1>::A_BYTES);
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        static SmemAttrSlot slot = {};
+        e = ensure_dynamic_smem(kern, smem, slot);
         if (e != cudaSuccess) return (int)e;
         kern<<<grid, NT, smem, st>>>(p, ys, xf, map_y, map_x, map_v);
     } else {
         auto kern = tc_dw_kernel<2, YS, XF>;
         const int smem = plan(DwPlan<2>::A_BYTES);
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        static SmemAttrSlot slot = {};
+        e = ensure_dynamic_smem(kern, smem, slot);
         if (e != cudaSuccess) return (int)e;
         kern<<<grid, NT, smem, st>>>(p, ys, xf, map_y, map_x, map_v);
     }

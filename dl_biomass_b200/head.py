@@ -9,7 +9,7 @@ import ctypes
 import torch
 
 from . import _lib
-from .optim import grad_dst
+from .optim import fresh_alias, grad_dst
 
 MAX_ROWS, MAX_HIDDEN, MAX_OUT = 32, 256, 8
 
@@ -92,7 +92,7 @@ class _HeadFunction(torch.autograd.Function):
         # parameter order of forward: w0 b0 g0 be0 w1 b1 g1 be1 w2 b2; gradients land in the parameter arena when
         # there is one (optim.ParamArena), else in fresh tensors
         d = ctx.grad_dsts
-        fresh = lambda dst, like: dst if dst is not None else torch.empty_like(like)  # noqa: E731
+        fresh = lambda dst, like: fresh_alias(dst) if dst is not None else torch.empty_like(like)  # noqa: E731
         gw = [fresh(d[0], mlp.lins[0].weight), fresh(d[4], mlp.lins[1].weight), fresh(d[8], mlp.lins[2].weight)]
         gb = [fresh(d[1], mlp.lins[0].bias), fresh(d[5], mlp.lins[1].bias), fresh(d[9], mlp.lins[2].bias)]
         gg = [fresh(d[2], mlp.norms[0].weight), fresh(d[6], mlp.norms[1].weight)]

@@ -162,9 +162,11 @@ def _build_levels(sizes0: Sequence[int], ratios: Sequence[float], device: torch.
         host[i, 1:] = torch.cumsum(torch.tensor(s, dtype=torch.int64), 0)
     hostf = torch.tensor(all_sizes, dtype=torch.float32).reshape(len(all_sizes), B)
     if device.type == "cuda":
+        # asynchronous: torch's pinned-memory allocator keeps a staging buffer alive until the copy that reads it has
+        # run, so no synchronisation is needed here.  (A host-side wait at this point made every step of a RAGGED
+        # training loop -- a new layout per batch -- wait for the GPU to drain before the next launch could be queued.)
         dev = host.pin_memory().to(device, non_blocking=True)
         devf = hostf.pin_memory().to(device, non_blocking=True)
-        torch.cuda.current_stream(device).synchronize()  # the pinned staging buffers die here; cached result is final
     else:
         dev, devf = host, hostf
     return [Level(s, dev[i], int(host[i, -1]), max(s) if s else 0, devf[i]) for i, s in enumerate(all_sizes)]

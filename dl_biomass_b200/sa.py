@@ -14,7 +14,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from .optim import grad_dst
+from .optim import fresh_alias, grad_dst
 
 PREC_F32, PREC_BF16 = 0, 1
 # True: the chained training kernels keep ONE tensor per hidden layer (zhat) and rebuild the activation a = act(gamma*zhat
@@ -355,7 +355,7 @@ class _SAFunction(torch.autograd.Function):
         grad_out = grad_out.to(f32).contiguous()
         # gradients land where the parameter arena wants them (optim.ParamArena) or in fresh tensors
         d = ctx.grad_dsts if ctx.grad_dsts is not None else (None,) * 10
-        fresh = lambda dst, like: dst if dst is not None else torch.empty_like(like)  # noqa: E731
+        fresh = lambda dst, like: fresh_alias(dst) if dst is not None else torch.empty_like(like)  # noqa: E731
         gw = [fresh(d[0], w1), fresh(d[4], w2), fresh(d[8], w3)]
         gb = [fresh(d[1], b1), fresh(d[5], b2), fresh(d[9], b3)]
         gg = [fresh(d[2], g1), fresh(d[6], g2)]

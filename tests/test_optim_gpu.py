@@ -96,3 +96,24 @@ def test_sa_calls_are_reentrant_across_threads(cuda_device):
     assert caps == [40, 100] and sa.launch_options()[0] == 0      # per-thread options, the main thread's untouched
     for g, w in zip(got, want):
         assert torch.equal(g, w)
+
+
+def test_backward_kernels_write_straight_into_the_parameter_arena(cuda_device):
+    """With a ParamArena (make_optimizer(model)) every parameter gradient of the network lands in the flat gradient buffer
+    directly: after backward ``p.grad`` IS a view of the arena (autograd took the returned alias over without a copy), so
+    the optimiser step and the data-parallel all-reduce need no flattening copies."""
+    from dl_biomass_b200.optim import ParamArena
+    from dl_biomass_b200.pointnet2_regressor import Net
+    from dl_biomass_b200.train import forward_backward, make_optimizer
+    torch.manual_seed(3)
+    net = Net(1, "ReLU", 0, 0.5, precision="bf16").to(cuda_device).set_random_start(False)
+    net.train()
+    opt = make_optimizer(net)
+    arena = ParamArena.of(net)
+    b = Batch.from_data_list(synthetic_clouds(5, 4, 600, 1, True)).to(cuda_device)
+    forward_backward(net, opt, b)
+    torch.cuda.synchronize()
+    for n, p in net.named_parameters():
+        assert p.grad is not None, n
+        assert p.grad.data_ptr() == arena.grad_views[p].data_ptr(), f"{n}: gradient was copied instead of written in place"
+    assert float(arena.flat_grads.abs().max()) > 0

@@ -55,7 +55,7 @@ out["numpy_oracle_clouds_per_s"] = round(B / cpu, 1)
 torch.manual_seed(0)
 net = Net(1, "ReLU", 0, 0.5, precision="bf16").to(dev)
 net.train()
-opt = make_optimizer(net.parameters())
+opt = make_optimizer(net)   # FlatAdam over the parameter arena
 nb = lambda i: cache.batch(ids[i % len(ids)], rng, seed=2, epoch=i)
 with PipelinedTrainStep(net, opt, nb(0), graph=False) as stepper:
     for i in range(1, 8):
