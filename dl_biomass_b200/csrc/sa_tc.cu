@@ -423,35 +423,59 @@ struct RouteSource {
     int C;
     __device__ __forceinline__ void resolve(int64_t r) { rm.resolve(r); }
     static constexpr bool SCATTER = true;
-    // One 128-byte line = 64 rows of channel ch, built as: zero the line, then drop the gradient of every centroid
-    // that STARTS in these 64 rows (a centroid never crosses a 64-row boundary) at its arg-max row.  `line` is the
-    // shared-memory address of the line (128-byte aligned inside a 1024-byte swizzle atom), `sw` = (line index & 7) << 4
-    // its swizzle.  Branch-free: the eight (arg, dout) pairs are in flight together, the 2-byte stores are predicated.
-    __device__ __forceinline__ void fill_line(int ch, const unsigned (&inf)[8], uint32_t line, uint32_t sw) const
+    // The tile is zeros except for one element per (centroid that starts in it, channel): a centroid never crosses a
+    // 64-row boundary, so its arg-max row is g*8 + arg inside the 64-row block its first row group g lies in.
+    // Cooperative form (what the kernels use): a loader group zeroes the tile with 16-byte stores, meets at a named
+    // barrier, then every thread drops QUADS -- 4 consecutive channels of one centroid, one 16-byte load of arg and one of
+    // dout -- at their arg-max rows.  An item costs a thread ~100 instructions instead of the ~650 of a per-line fill
+    // (ncu, round 2: with one loader warp per scheduler the routed kernels were bound by the loaders' dependent issue
+    // latency, ~1.5 us per item, while the epilogue warps sat at their barrier 80 % of the time).
+    // Needs C % 4 == 0 and 16-byte aligned arg / dout rows (`vec`, checked on the host); else four scalar loads.
+    int vec;
+    struct Quad {
+        int4 a;
+        float4 d;
+    };
+    __device__ __forceinline__ bool starts(unsigned inf, int ch4) const { return ch4 < C && gi_nv(inf) > 0 && gi_slot0(inf) == 0; }
+    __device__ __forceinline__ void load_quad(unsigned inf, int ch4, Quad &q) const
     {
-        int a[8];
-        float d[8];
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            const bool first = ch < C && gi_nv(inf[g]) > 0 && gi_slot0(inf[g]) == 0;
-            const int64_t idx = first ? (int64_t)gi_seg(inf[g]) * C + ch : 0;
-            a[g] = __ldg(arg + idx);
-            d[g] = __ldg(dout + idx);
-            if (!first) a[g] = -1;
+        const bool first = starts(inf, ch4);
+        const int64_t idx = first ? (int64_t)gi_seg(inf) * C + ch4 : 0;
+        if (vec) {
+            q.a = __ldg(reinterpret_cast<const int4 *>(arg + idx));
+            q.d = __ldg(reinterpret_cast<const float4 *>(dout + idx));
+        } else {
+            const int64_t last = (first ? (int64_t)gi_seg(inf) * C : 0) + C - 1;  // clamp inside the centroid's row
+            q.a = make_int4(__ldg(arg + idx), __ldg(arg + min(idx + 1, last)), __ldg(arg + min(idx + 2, last)), __ldg(arg + min(idx + 3, last)));
+            q.d = make_float4(__ldg(dout + idx), __ldg(dout + min(idx + 1, last)), __ldg(dout + min(idx + 2, last)),
+                              __ldg(dout + min(idx + 3, last)));
         }
+    }
+    // lines l0 .. l0+3 (channels ch4 .. ch4+3) of the 64-row block at shared address `blk` (1024-byte aligned), row group g
+    __device__ __forceinline__ void store_quad(const Quad &q, bool first, int ch4, int g, uint32_t blk, int l0) const
+    {
+        const int a[4] = {q.a.x, q.a.y, q.a.z, q.a.w};
+        const float d[4] = {q.d.x, q.d.y, q.d.z, q.d.w};
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(line + (((uint32_t)g << 4) ^ sw)), "r"(0u) : "memory");
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            const unsigned row = (unsigned)(g * 8 + a[g]);  // a = -1 (no centroid starts here) -> row >= 64 or wraps
-            const unsigned ok = (a[g] >= 0 && row < 64u) ? 1u : 0u;
-            const uint32_t addr = line + ((((row >> 3) & 7u) << 4) ^ sw) + ((row & 7u) << 1);
-            const unsigned short gb = __bfloat16_as_ushort(__float2bfloat16(d[g]));
+        for (int e = 0; e < 4; ++e) {
+            const unsigned row = (unsigned)(g * 8 + a[e]);
+            const unsigned ok = (first && ch4 + e < C && a[e] >= 0 && row < 64u) ? 1u : 0u;
+            const uint32_t line = (uint32_t)(l0 + e);
+            const uint32_t addr = blk + line * LINE_BYTES + ((((row >> 3) & 7u) ^ (line & 7u)) << 4) + ((row & 7u) << 1);
+            const unsigned short gb = __bfloat16_as_ushort(__float2bfloat16(d[e]));
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.b16 [%0], %1;\n\t}" ::"r"(addr), "h"(gb), "r"(ok)
                          : "memory");
         }
     }
+    // my share of zeroing `bytes` (a multiple of 2048) at `base`: conflict-free 16-byte stores
+    template <int NTHR = NUM_LOAD>
+    static __device__ __forceinline__ void zero_tile(uint32_t base, int bytes, int lt)
+    {
+        for (int o = lt * 16; o < bytes; o += NTHR * 16)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + (uint32_t)o), "r"(0u) : "memory");
+    }
+    template <int NTHR = NUM_LOAD>
+    static __device__ __forceinline__ void group_barrier(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NTHR) : "memory"); }
     // 8 rows of channel ch as one 16-byte chunk; no branch around the loads: a thread's eight (arg, dout) pairs are in
     // flight together
     __device__ __forceinline__ uint4 chunk_i(int ch, int64_t, unsigned inf) const
@@ -481,10 +505,61 @@ struct FeatLoaderTC {
     static constexpr bool B_MN = true;
     static constexpr bool USES_TMA = false;
     static constexpr bool WIDE = WIDE_;
+    // SCATTER sources (the routed gradient): the kernel runs the loader group as a software pipeline over quads (see
+    // RouteSource) -- thread lt owns channel quad (lt & 15) of the 64-channel chunk and row group (lt >> 4) of both 64-row
+    // blocks; descriptors are fetched one tile ahead, the (arg, dout) quads one item ahead of the shared-memory stores
+    static constexpr bool PIPELINED = SRC::SCATTER;
     SRC src;
     int64_t row0;
     unsigned inf[8];  // descriptors of the 8 row groups of my row block
+    // PIPELINED: 256 loader threads (8 warps: the per-item work is a dependent chain, so two warps per scheduler hide each
+    // other's issue latency); thread lt owns row block lt >> 7, row group (lt >> 4) & 7 and channel quad lt & 15.
+    // Descriptor of my row group -- this tile (normalised), the next and the one after (RAW table words + a "past the
+    // end" flag: normalising would wait for the load right where it is issued)
+    static constexpr int LOADERS = PIPELINED ? 256 : NUM_LOAD;
+    unsigned qinf, qraw1, qraw2, qdead1, qdead2;
+    struct Item {
+        typename SRC::Quad q;
+        unsigned first;  // a centroid starts in my row group (known without waiting for the loads)
+    };
     __device__ __forceinline__ void resolve(int64_t r) { src.resolve(r); }
+    // request the descriptors of `tile` (SLOTS levels only: routed gradients exist nowhere else)
+    __device__ __forceinline__ void fetch_tile(int64_t tile, int lt)
+    {
+        const int64_t r8 = tile * R + (lt >> 7) * 64 + ((lt >> 4) & 7) * 8;
+        qraw2 = __ldg(src.rm.rgrp + (r8 >> 3));
+        qdead2 = r8 >= src.rm.rows ? 1u : 0u;
+    }
+    __device__ __forceinline__ void no_tile() { qraw2 = GI_NONE, qdead2 = 1u; }
+    // the tile after next becomes the next one
+    __device__ __forceinline__ void shift_tiles() { qraw1 = qraw2, qdead1 = qdead2; }
+    // the next tile becomes the current one
+    __device__ __forceinline__ void advance_tile() { qinf = (qdead1 || gi_none(qraw1)) ? GI_NONE : qraw1; }
+    // pull the (arg, dout) rows the NEXT tile will read into L2 (each is read exactly once: a compulsory DRAM miss that a
+    // one-item-ahead register prefetch cannot cover); two threads per 256 bytes of a chunk issue the prefetches
+    __device__ __forceinline__ void prefetch_next_rows(int lt, int num_kc) const
+    {
+        const unsigned w = qraw1;
+        if ((lt & 7) != 0 || qdead1 || gi_none(w) || gi_nv(w) == 0 || gi_slot0(w) != 0) return;
+        const int64_t base = (int64_t)gi_seg(w) * src.C + (lt & 15) * 4;
+        for (int kc = 0; kc < num_kc; ++kc) {
+            if (kc * KC + (lt & 15) * 4 >= src.C) break;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(src.arg + base + kc * KC));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(src.dout + base + kc * KC));
+        }
+    }
+    __device__ __forceinline__ void load(int kc, int lt, Item &it) const
+    {
+        const int ch4 = kc * KC + (lt & 15) * 4;
+        src.load_quad(qinf, ch4, it.q);
+        it.first = src.starts(qinf, ch4) ? 1u : 0u;
+    }
+    // after the group has zeroed the tile and met at its barrier
+    __device__ __forceinline__ void store(uint8_t *B, int kc, int lt, const Item &it) const
+    {
+        const int ch4 = kc * KC + (lt & 15) * 4;
+        src.store_quad(it.q, it.first != 0u, ch4, (lt >> 4) & 7, smem_u32(B) + (lt >> 7) * (64 * LINE_BYTES), (lt & 15) * 4);
+    }
     __device__ __forceinline__ void begin_tile(int64_t tile, int lt)
     {
         row0 = tile * R + (lt & 1) * 64;
@@ -501,15 +576,11 @@ struct FeatLoaderTC {
         const int cl = lt >> 1, nb = lt & 1;
         uint8_t *dst = B + nb * (64 * LINE_BYTES);
         const int ch = kc * KC + cl;
-        if constexpr (SRC::SCATTER) {
-            src.fill_line(ch, inf, smem_u32(dst) + cl * LINE_BYTES, (uint32_t)(cl & 7) << 4);
-        } else {
-            uint4 v[8];
+        uint4 v[8];
 #pragma unroll
-            for (int g = 0; g < 8; ++g) v[g] = src.chunk_i(ch, row0 + g * 8, inf[g]);
+        for (int g = 0; g < 8; ++g) v[g] = src.chunk_i(ch, row0 + g * 8, inf[g]);
 #pragma unroll
-            for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4 *>(dst + line_chunk_off(cl, g)) = v[g];
-        }
+        for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4 *>(dst + line_chunk_off(cl, g)) = v[g];
     }
     // MN-major: 16 k lines per step; LBO = stride between the two 64-row blocks, SBO = 8 lines
     static __device__ __forceinline__ uint64_t b_desc(uint32_t b_saddr, int ks)
@@ -991,8 +1062,19 @@ struct SmemPlan {
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + alignment slack
 };
 
+template <class BL, class = void>
+struct LoaderPipelined { static constexpr bool value = false; };
 template <class BL>
-constexpr int gemm_threads() { return BL::USES_TMA ? NT_TMA : (BL::WIDE ? NT_WIDE : NT); }
+struct LoaderPipelined<BL, decltype((void)BL::PIPELINED)> { static constexpr bool value = BL::PIPELINED; };
+template <class BL>
+constexpr bool loader_pipelined() { return LoaderPipelined<BL>::value; }
+
+template <class BL, class = void>
+struct LoaderThreads { static constexpr int value = NUM_LOAD; };
+template <class BL>
+struct LoaderThreads<BL, decltype((void)BL::LOADERS)> { static constexpr int value = BL::LOADERS; };
+template <class BL>
+constexpr int gemm_threads() { return BL::USES_TMA ? NT_TMA : (BL::WIDE ? NT_WIDE - NUM_LOAD + LoaderThreads<BL>::value : NT); }
 
 template <int MT, class BL, class EP>
 __global__ void __launch_bounds__(gemm_threads<BL>(), 1)
@@ -1007,6 +1089,7 @@ __global__ void __launch_bounds__(gemm_threads<BL>(), 1)
     // SIMT loaders: two groups in warps 8-15 (narrow layout) or one group in warps 17-20 (wide layout)
     constexpr int LGROUPS = WIDE ? 1 : LOAD_GROUPS;
     constexpr int LOAD_T0 = WIDE ? (MMA_WARP + 1) * 32 : NUM_EPI;
+    constexpr int NLOAD = LoaderThreads<BL>::value;  // threads of a SIMT loader group
     using P = SmemPlan<MT, EP::STAGED, WIDE>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -1027,7 +1110,7 @@ __global__ void __launch_bounds__(gemm_threads<BL>(), 1)
 
     if (tid == 0) {
         for (int s = 0; s < P::STAGES; ++s) {
-            mbar_init(&full[s], TMA ? 1 : NUM_LOAD);
+            mbar_init(&full[s], TMA ? 1 : NLOAD);
             mbar_init(&empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -1063,13 +1146,80 @@ __global__ void __launch_bounds__(gemm_threads<BL>(), 1)
                 }
             }
         }
-    } else if (!TMA && tid >= LOAD_T0 && tid < LOAD_T0 + LGROUPS * NUM_LOAD) {
+    } else if (!TMA && tid >= LOAD_T0 && tid < LOAD_T0 + LGROUPS * NLOAD) {
         // ------------------------------------------------------------------ SIMT loaders: group g takes every
         // LGROUPS-th (tile, k-chunk) item, so the groups' global-load latencies overlap
         if constexpr (!TMA) {
-            const int g = (tid - LOAD_T0) / NUM_LOAD;
-            const int lt = (tid - LOAD_T0) % NUM_LOAD;
-            {
+            const int g = (tid - LOAD_T0) / NLOAD;
+            const int lt = (tid - LOAD_T0) % NLOAD;
+            if constexpr (LoaderPipelined<BL>::value) {
+                static_assert(LGROUPS == 1, "the pipelined loader is one group");
+                typename BL::Item cur, nxt;
+                int64_t tile = blockIdx.x;
+                if (tile < num_tiles) {
+                    // descriptor pipeline: this tile / next / the one after
+                    bl.fetch_tile(tile, lt);
+                    bl.shift_tiles();
+                    bl.advance_tile();
+                    bl.load(0, lt, cur);
+                    int64_t ntile = tile + gridDim.x;
+                    if (ntile < num_tiles) bl.fetch_tile(ntile, lt);
+                    else bl.no_tile();
+                    bl.shift_tiles();
+                    bl.prefetch_next_rows(lt, gp.num_kc);
+                    if (ntile + gridDim.x < num_tiles) bl.fetch_tile(ntile + gridDim.x, lt);
+                    else bl.no_tile();
+                    int kc = 0;
+                    uint32_t it = 0;
+                    // one item: `c` holds its quads (requested one item ago), `n` receives the next item's.  Called with the
+                    // two register sets swapped every other item -- a `cur = nxt` copy would wait for the loads in flight
+                    auto item = [&](typename BL::Item &c, typename BL::Item &n) -> bool {
+                        int nkc = kc + 1;
+                        bool has_next = true;
+                        if (nkc == gp.num_kc) {
+                            nkc = 0;
+                            tile = ntile;
+                            has_next = tile < num_tiles;
+                            if (has_next) {
+                                bl.advance_tile();
+                                ntile = tile + gridDim.x;
+                            }
+                        }
+                        if (has_next) bl.load(nkc, lt, n);
+                        if (has_next && nkc == 0) {
+                            // entered a new tile: its successor's descriptors have landed -> pull its rows into L2, and
+                            // request the descriptors of the tile after that
+                            bl.shift_tiles();
+                            bl.prefetch_next_rows(lt, gp.num_kc);
+                            if (ntile + gridDim.x < num_tiles) bl.fetch_tile(ntile + gridDim.x, lt);
+                            else bl.no_tile();
+                        }
+                        const int s = it % P::STAGES;
+                        const uint32_t ph = (it / P::STAGES) & 1u;
+                        mbar_wait(&empty[s], ph ^ 1u);
+                        uint8_t *A = smem + s * P::STAGE_BYTES;
+                        uint8_t *B = A + P::A_BYTES;
+                        if (lt == 0) {
+                            mbar_expect_tx(&full[s], P::A_BYTES);
+                            bulk_g2s(A, gp.a_packed + ((int64_t)mg * gp.num_kc + kc) * P::A_BYTES, P::A_BYTES, &full[s]);
+                        }
+#ifndef ROUTE_EXP_NOZERO
+                        RouteSource::zero_tile<NLOAD>(smem_u32(B), B_BYTES, lt);
+                        RouteSource::group_barrier<NLOAD>(1);
+#endif
+#ifndef ROUTE_EXP_NOSTORE
+                        bl.store(B, kc, lt, c);
+#endif
+                        fence_proxy_async_smem();
+                        mbar_arrive(&full[s]);
+                        kc = nkc;
+                        ++it;
+                        return has_next;
+                    };
+                    while (item(cur, nxt) && item(nxt, cur)) {
+                    }
+                }
+            } else {
                 uint32_t it = 0;
                 int64_t cur_tile = -1;
                 for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -1360,6 +1510,65 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
         };
         unsigned inf[8], infn[8];
         if (grp < nchunks) load_inf(inf, (c_beg + grp) * 64);
+        // Routed-gradient Y side (SCATTER): the group zeroes the tile, meets at its named barrier and drops quads (see
+        // RouteSource).  Work item k of thread lt: channel quad (lt + 128 k) % NQ, row group (lt + 128 k) / NQ.  A three-deep
+        // software pipeline per thread: descriptors two chunks ahead, (arg, dout) quads one chunk ahead, the stores of the
+        // current chunk.
+        constexpr int NQ = MTA * 32, NI = MTA * 2;
+        [[maybe_unused]] RouteSource::Quad qd[NI];
+        // descriptors: qi = this chunk (normalised); r1 / r2 / r3 = the group's next three chunks as RAW table words + a
+        // "past the end" mask (normalising a word where it is requested would wait for the load on the spot)
+        [[maybe_unused]] unsigned qi[NI], r1[NI], r2[NI], r3[NI], d1 = 0u, d2 = 0u, d3 = 0u;
+        [[maybe_unused]] auto q_fetch = [&](unsigned (&w)[NI], unsigned &dead, int64_t i) {
+            dead = 0u;
+#pragma unroll
+            for (int k = 0; k < NI; ++k) {
+                if (i < nchunks) {
+                    const int64_t r8 = (c_beg + i) * 64 + ((lt + NUM_LOAD * k) / NQ) * 8;
+                    w[k] = __ldg(ys.rm.rgrp + (r8 >> 3));
+                    dead |= (r8 >= ys.rm.rows ? 1u : 0u) << k;
+                } else {
+                    w[k] = GI_NONE;
+                    dead |= 1u << k;
+                }
+            }
+        };
+        [[maybe_unused]] auto q_norm = [&](const unsigned (&w)[NI], unsigned dead) {
+#pragma unroll
+            for (int k = 0; k < NI; ++k) qi[k] = (((dead >> k) & 1u) || gi_none(w[k])) ? GI_NONE : w[k];
+        };
+        [[maybe_unused]] auto q_load = [&]() {
+#pragma unroll
+            for (int k = 0; k < NI; ++k) {
+                if constexpr (YS::SCATTER) ys.load_quad(qi[k], mg * (MTA * 128) + ((lt + NUM_LOAD * k) % NQ) * 4, qd[k]);
+            }
+        };
+        // pull the (arg, dout) rows of a chunk two steps ahead into L2: every one of them is read exactly once (a compulsory
+        // DRAM miss that the one-chunk-ahead register prefetch cannot cover); one thread per 128 bytes
+        [[maybe_unused]] auto q_prefetch = [&](const unsigned (&w)[NI], unsigned dead) {
+            if constexpr (YS::SCATTER) {
+#pragma unroll
+                for (int k = 0; k < NI; ++k) {
+                    const int q = (lt + NUM_LOAD * k) % NQ;
+                    const int ch4 = mg * (MTA * 128) + q * 4;
+                    if ((q & 7) != 0 || ((dead >> k) & 1u) || gi_none(w[k]) || gi_nv(w[k]) == 0 || gi_slot0(w[k]) != 0 || ch4 >= ys.C) continue;
+                    const int64_t idx = (int64_t)gi_seg(w[k]) * ys.C + ch4;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ys.arg + idx));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ys.dout + idx));
+                }
+            }
+        };
+        if constexpr (YS::SCATTER) {
+#pragma unroll
+            for (int k = 0; k < NI; ++k) qi[k] = r1[k] = r2[k] = r3[k] = GI_NONE;
+            if (grp < nchunks) {
+                q_fetch(r1, d1, grp);
+                q_norm(r1, d1);
+                q_load();
+                q_fetch(r1, d1, grp + LOAD_GROUPS);
+                q_fetch(r2, d2, grp + 2 * LOAD_GROUPS);
+            }
+        }
         // TMA copies of chunk i (one thread): the Y tile completes on full[s] directly; the X tile lands as fp16 and completes
         // on xland[s], because the group converts it to bf16 before the MMA may read it.  The copies are issued up to
         // AHEAD chunks of this group ahead of the conversion, so the ring stays as deep as before the conversion existed
@@ -1392,6 +1601,10 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
             uint8_t *B = A + P::A_BYTES;
             const int64_t r0 = (c_beg + i) * 64;
             if (i + LOAD_GROUPS < nchunks) load_inf(infn, (c_beg + i + LOAD_GROUPS) * 64);
+            if constexpr (YS::SCATTER) {
+                q_fetch(r3, d3, i + 3 * LOAD_GROUPS);
+                q_prefetch(r2, d2);
+            }
             if constexpr (ANY_TMA) {
                 // a wait in issue() depends on chunks < iss - nst + 1 <= i only, i.e. on work this group has already done
                 if (lt == 0)
@@ -1400,10 +1613,18 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
             if constexpr (!YS::USES_TMA) {
                 if constexpr (YS::SCATTER) {
                     mbar_wait(&empty[s], ph ^ 1u);
+                    RouteSource::zero_tile(smem_u32(A), P::A_BYTES, lt);
+                    RouteSource::group_barrier(1 + grp);
 #pragma unroll
-                    for (int m = 0; m < MTA; ++m) {
-                        const int line = m * 128 + lt;
-                        ys.fill_line(mg * (MTA * 128) + line, inf, smem_u32(A) + line * LINE_BYTES, (uint32_t)(line & 7) << 4);
+                    for (int k = 0; k < NI; ++k) {
+                        const int l0 = ((lt + NUM_LOAD * k) % NQ) * 4, g = (lt + NUM_LOAD * k) / NQ;
+                        const int ch4 = mg * (MTA * 128) + l0;
+                        ys.store_quad(qd[k], ys.starts(qi[k], ch4), ch4, g, smem_u32(A), l0);
+                    }
+                    // the quads of this group's next chunk travel while the X tile is converted and the next slot is awaited
+                    if (i + LOAD_GROUPS < nchunks) {
+                        q_norm(r1, d1);
+                        q_load();
                     }
                 } else {
                     // the operand loads go out before the wait for the slot: their latency overlaps it
@@ -1443,6 +1664,14 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
             mbar_arrive(&full[s]);
 #pragma unroll
             for (int g = 0; g < 8; ++g) inf[g] = infn[g];
+            if constexpr (YS::SCATTER) {
+#pragma unroll
+                for (int k = 0; k < NI; ++k) {
+                    r1[k] = r2[k];
+                    r2[k] = r3[k];
+                }
+                d1 = d2, d2 = d3;
+            }
         }
     } else if (warp == MMA_WARP) {
         if (lane == 0 && nchunks > 0) {
@@ -2595,7 +2824,8 @@ int sa_backward_bf16(const b2pn_sa_args &a, const b2pn_sa_grads &g, cudaStream_t
     } else {
         // SLOTS levels: dh3 is one value per (centroid, channel) -- both consumers generate their operand tiles from
         // (arg, grad_out) in their loader warps instead of streaming a dense [c3][rows] tensor
-        RouteSource rs = {rm, g.grad_out, a.arg, s.c3};
+        const int vec = (s.c3 % 4 == 0 && ((uintptr_t)g.grad_out | (uintptr_t)a.arg) % 16 == 0) ? 1 : 0;
+        RouteSource rs = {rm, g.grad_out, a.arg, s.c3, vec};
         FeatLoaderTC<RouteSource, true> bl = {rs};
         if ((rc = launch_by_mt(b.pkT[2], ra, bl, e31, e32, st, kNoMap, mdz2, mz2))) return rc;        // da2 = W3^T dh3
         if (tma_x2) {
