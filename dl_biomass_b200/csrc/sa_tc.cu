@@ -512,53 +512,79 @@ struct FeatLoaderTC {
     SRC src;
     int64_t row0;
     unsigned inf[8];  // descriptors of the 8 row groups of my row block
-    // PIPELINED: 256 loader threads (8 warps: the per-item work is a dependent chain, so two warps per scheduler hide each
-    // other's issue latency); thread lt owns row block lt >> 7, row group (lt >> 4) & 7 and channel quad lt & 15.
-    // Descriptor of my row group -- this tile (normalised), the next and the one after (RAW table words + a "past the
-    // end" flag: normalising would wait for the load right where it is issued)
-    static constexpr int LOADERS = PIPELINED ? 256 : NUM_LOAD;
-    unsigned qinf, qraw1, qraw2, qdead1, qdead2;
+    // PIPELINED: TWO loader groups of 128 threads (8 warps) that take alternate items -- an item is a dependent chain
+    // (descriptor -> quad loads -> zero fill -> group barrier -> scatter stores -> arrive), so one group alone leaves the
+    // MMA and epilogue warps waiting however few instructions the chain has; two chains in flight halve the item period.
+    // Thread lt of a group owns channel quad lt & 15 and row group lt >> 4 of both 64-row blocks.
+    // Descriptors of my row group -- this tile (normalised), the next and the one after (RAW table words + a "past the
+    // end" mask: normalising would wait for the load right where it is issued)
+    static constexpr int PIPE_GROUPS = 2;
+    unsigned qinf[2], qraw1[2], qraw2[2], qdead1, qdead2;
     struct Item {
-        typename SRC::Quad q;
-        unsigned first;  // a centroid starts in my row group (known without waiting for the loads)
+        typename SRC::Quad q[2];
+        unsigned first;  // bit b: a centroid starts in my row group of row block b (known without waiting for the loads)
     };
     __device__ __forceinline__ void resolve(int64_t r) { src.resolve(r); }
     // request the descriptors of `tile` (SLOTS levels only: routed gradients exist nowhere else)
     __device__ __forceinline__ void fetch_tile(int64_t tile, int lt)
     {
-        const int64_t r8 = tile * R + (lt >> 7) * 64 + ((lt >> 4) & 7) * 8;
-        qraw2 = __ldg(src.rm.rgrp + (r8 >> 3));
-        qdead2 = r8 >= src.rm.rows ? 1u : 0u;
+        const int64_t r0 = tile * R + (lt >> 4) * 8;
+        qdead2 = 0u;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int64_t r8 = r0 + b * 64;
+            qraw2[b] = __ldg(src.rm.rgrp + (r8 >> 3));
+            qdead2 |= (r8 >= src.rm.rows ? 1u : 0u) << b;
+        }
     }
-    __device__ __forceinline__ void no_tile() { qraw2 = GI_NONE, qdead2 = 1u; }
+    __device__ __forceinline__ void no_tile() { qraw2[0] = qraw2[1] = GI_NONE, qdead2 = 3u; }
     // the tile after next becomes the next one
-    __device__ __forceinline__ void shift_tiles() { qraw1 = qraw2, qdead1 = qdead2; }
+    __device__ __forceinline__ void shift_tiles()
+    {
+#pragma unroll
+        for (int b = 0; b < 2; ++b) qraw1[b] = qraw2[b];
+        qdead1 = qdead2;
+    }
     // the next tile becomes the current one
-    __device__ __forceinline__ void advance_tile() { qinf = (qdead1 || gi_none(qraw1)) ? GI_NONE : qraw1; }
+    __device__ __forceinline__ void advance_tile()
+    {
+#pragma unroll
+        for (int b = 0; b < 2; ++b) qinf[b] = (((qdead1 >> b) & 1u) || gi_none(qraw1[b])) ? GI_NONE : qraw1[b];
+    }
     // pull the (arg, dout) rows the NEXT tile will read into L2 (each is read exactly once: a compulsory DRAM miss that a
     // one-item-ahead register prefetch cannot cover); two threads per 256 bytes of a chunk issue the prefetches
-    __device__ __forceinline__ void prefetch_next_rows(int lt, int num_kc) const
+    __device__ __forceinline__ void prefetch_next_rows(int lt, int kc0, int kstep, int num_kc) const
     {
-        const unsigned w = qraw1;
-        if ((lt & 7) != 0 || qdead1 || gi_none(w) || gi_nv(w) == 0 || gi_slot0(w) != 0) return;
-        const int64_t base = (int64_t)gi_seg(w) * src.C + (lt & 15) * 4;
-        for (int kc = 0; kc < num_kc; ++kc) {
-            if (kc * KC + (lt & 15) * 4 >= src.C) break;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(src.arg + base + kc * KC));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(src.dout + base + kc * KC));
+        if ((lt & 7) != 0) return;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const unsigned w = qraw1[b];
+            if (((qdead1 >> b) & 1u) || gi_none(w) || gi_nv(w) == 0 || gi_slot0(w) != 0) continue;
+            const int64_t base = (int64_t)gi_seg(w) * src.C + (lt & 15) * 4;
+            for (int kc = kc0; kc < num_kc; kc += kstep) {
+                if (kc * KC + (lt & 15) * 4 >= src.C) break;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(src.arg + base + kc * KC));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(src.dout + base + kc * KC));
+            }
         }
     }
     __device__ __forceinline__ void load(int kc, int lt, Item &it) const
     {
         const int ch4 = kc * KC + (lt & 15) * 4;
-        src.load_quad(qinf, ch4, it.q);
-        it.first = src.starts(qinf, ch4) ? 1u : 0u;
+        it.first = 0u;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            src.load_quad(qinf[b], ch4, it.q[b]);
+            it.first |= (src.starts(qinf[b], ch4) ? 1u : 0u) << b;
+        }
     }
     // after the group has zeroed the tile and met at its barrier
     __device__ __forceinline__ void store(uint8_t *B, int kc, int lt, const Item &it) const
     {
         const int ch4 = kc * KC + (lt & 15) * 4;
-        src.store_quad(it.q, it.first != 0u, ch4, (lt >> 4) & 7, smem_u32(B) + (lt >> 7) * (64 * LINE_BYTES), (lt & 15) * 4);
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+            src.store_quad(it.q[b], (it.first >> b) & 1u, ch4, lt >> 4, smem_u32(B) + b * (64 * LINE_BYTES), (lt & 15) * 4);
     }
     __device__ __forceinline__ void begin_tile(int64_t tile, int lt)
     {
@@ -1070,11 +1096,11 @@ template <class BL>
 constexpr bool loader_pipelined() { return LoaderPipelined<BL>::value; }
 
 template <class BL, class = void>
-struct LoaderThreads { static constexpr int value = NUM_LOAD; };
+struct LoaderGroupsWide { static constexpr int value = 1; };   // loader groups under the wide layout
 template <class BL>
-struct LoaderThreads<BL, decltype((void)BL::LOADERS)> { static constexpr int value = BL::LOADERS; };
+struct LoaderGroupsWide<BL, decltype((void)BL::PIPE_GROUPS)> { static constexpr int value = BL::PIPELINED ? BL::PIPE_GROUPS : 1; };
 template <class BL>
-constexpr int gemm_threads() { return BL::USES_TMA ? NT_TMA : (BL::WIDE ? NT_WIDE - NUM_LOAD + LoaderThreads<BL>::value : NT); }
+constexpr int gemm_threads() { return BL::USES_TMA ? NT_TMA : (BL::WIDE ? NT_WIDE + (LoaderGroupsWide<BL>::value - 1) * NUM_LOAD : NT); }
 
 template <int MT, class BL, class EP>
 __global__ void __launch_bounds__(gemm_threads<BL>(), 1)
@@ -1087,9 +1113,9 @@ __global__ void __launch_bounds__(gemm_threads<BL>(), 1)
     constexpr int EPI_GROUPS = WIDE ? 2 : 1;
     constexpr int EPI_WARPS = EPI_GROUPS * (NUM_EPI / 32);
     // SIMT loaders: two groups in warps 8-15 (narrow layout) or one group in warps 17-20 (wide layout)
-    constexpr int LGROUPS = WIDE ? 1 : LOAD_GROUPS;
+    constexpr int LGROUPS = WIDE ? LoaderGroupsWide<BL>::value : LOAD_GROUPS;
     constexpr int LOAD_T0 = WIDE ? (MMA_WARP + 1) * 32 : NUM_EPI;
-    constexpr int NLOAD = LoaderThreads<BL>::value;  // threads of a SIMT loader group
+    constexpr int NLOAD = NUM_LOAD;  // threads of a SIMT loader group
     using P = SmemPlan<MT, EP::STAGED, WIDE>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -1153,67 +1179,71 @@ __global__ void __launch_bounds__(gemm_threads<BL>(), 1)
             const int g = (tid - LOAD_T0) / NLOAD;
             const int lt = (tid - LOAD_T0) % NLOAD;
             if constexpr (LoaderPipelined<BL>::value) {
-                static_assert(LGROUPS == 1, "the pipelined loader is one group");
+                // group g takes items g, g + LGROUPS, ... of this CTA's (tile, k-chunk) sequence
                 typename BL::Item cur, nxt;
-                int64_t tile = blockIdx.x;
-                if (tile < num_tiles) {
+                const int num_kc = gp.num_kc;
+                const int64_t my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+                const int64_t items = my_tiles * num_kc;
+                const int tstep = num_kc >= LGROUPS ? 1 : LGROUPS / num_kc;  // my tile sequence: every tile, or every tstep-th
+                auto tile_of = [&](int64_t tl) { return (int64_t)blockIdx.x + tl * gridDim.x; };
+                auto fetch_or_none = [&](int64_t tl) {
+                    if (tl < my_tiles) bl.fetch_tile(tile_of(tl), lt);
+                    else bl.no_tile();
+                };
+                int64_t i = g;
+                if (i < items) {
+                    int64_t tl = i / num_kc;
+                    int kc = (int)(i % num_kc);
+                    const int kc0 = LGROUPS % num_kc == 0 ? kc : 0, kstep = LGROUPS % num_kc == 0 ? num_kc : 1;  // my chunks of a tile
                     // descriptor pipeline: this tile / next / the one after
-                    bl.fetch_tile(tile, lt);
+                    bl.fetch_tile(tile_of(tl), lt);
                     bl.shift_tiles();
                     bl.advance_tile();
-                    bl.load(0, lt, cur);
-                    int64_t ntile = tile + gridDim.x;
-                    if (ntile < num_tiles) bl.fetch_tile(ntile, lt);
-                    else bl.no_tile();
+                    bl.load(kc, lt, cur);
+                    fetch_or_none(tl + tstep);
                     bl.shift_tiles();
-                    bl.prefetch_next_rows(lt, gp.num_kc);
-                    if (ntile + gridDim.x < num_tiles) bl.fetch_tile(ntile + gridDim.x, lt);
-                    else bl.no_tile();
-                    int kc = 0;
-                    uint32_t it = 0;
+                    bl.prefetch_next_rows(lt, num_kc % LGROUPS == 0 ? g : 0, num_kc % LGROUPS == 0 ? LGROUPS : 1, num_kc);
+                    fetch_or_none(tl + 2 * tstep);
+                    (void)kc0, (void)kstep;
                     // one item: `c` holds its quads (requested one item ago), `n` receives the next item's.  Called with the
                     // two register sets swapped every other item -- a `cur = nxt` copy would wait for the loads in flight
                     auto item = [&](typename BL::Item &c, typename BL::Item &n) -> bool {
-                        int nkc = kc + 1;
-                        bool has_next = true;
-                        if (nkc == gp.num_kc) {
-                            nkc = 0;
-                            tile = ntile;
-                            has_next = tile < num_tiles;
-                            if (has_next) {
-                                bl.advance_tile();
-                                ntile = tile + gridDim.x;
+                        const int64_t ni = i + LGROUPS;
+                        const bool has_next = ni < items;
+                        int nkc = kc + LGROUPS;
+                        int64_t ntl = tl;
+                        while (nkc >= num_kc) {
+                            nkc -= num_kc;
+                            ++ntl;
+                        }
+                        if (has_next) {
+                            if (ntl != tl) bl.advance_tile();
+                            bl.load(nkc, lt, n);
+                            if (ntl != tl) {
+                                // entered a new tile: its successor's descriptors have landed -> pull its rows into L2, and
+                                // request the descriptors of the tile after that
+                                bl.shift_tiles();
+                                bl.prefetch_next_rows(lt, num_kc % LGROUPS == 0 ? g : 0, num_kc % LGROUPS == 0 ? LGROUPS : 1, num_kc);
+                                fetch_or_none(ntl + 2 * tstep);
                             }
                         }
-                        if (has_next) bl.load(nkc, lt, n);
-                        if (has_next && nkc == 0) {
-                            // entered a new tile: its successor's descriptors have landed -> pull its rows into L2, and
-                            // request the descriptors of the tile after that
-                            bl.shift_tiles();
-                            bl.prefetch_next_rows(lt, gp.num_kc);
-                            if (ntile + gridDim.x < num_tiles) bl.fetch_tile(ntile + gridDim.x, lt);
-                            else bl.no_tile();
-                        }
-                        const int s = it % P::STAGES;
-                        const uint32_t ph = (it / P::STAGES) & 1u;
+                        const int s = (int)(i % P::STAGES);
+                        const uint32_t ph = (uint32_t)(i / P::STAGES) & 1u;
                         mbar_wait(&empty[s], ph ^ 1u);
                         uint8_t *A = smem + s * P::STAGE_BYTES;
                         uint8_t *B = A + P::A_BYTES;
                         if (lt == 0) {
                             mbar_expect_tx(&full[s], P::A_BYTES);
-                            bulk_g2s(A, gp.a_packed + ((int64_t)mg * gp.num_kc + kc) * P::A_BYTES, P::A_BYTES, &full[s]);
+                            bulk_g2s(A, gp.a_packed + ((int64_t)mg * num_kc + kc) * P::A_BYTES, P::A_BYTES, &full[s]);
                         }
-#ifndef ROUTE_EXP_NOZERO
                         RouteSource::zero_tile<NLOAD>(smem_u32(B), B_BYTES, lt);
-                        RouteSource::group_barrier<NLOAD>(1);
-#endif
-#ifndef ROUTE_EXP_NOSTORE
+                        RouteSource::group_barrier<NLOAD>(1 + g);
                         bl.store(B, kc, lt, c);
-#endif
                         fence_proxy_async_smem();
                         mbar_arrive(&full[s]);
+                        i = ni;
                         kc = nkc;
-                        ++it;
+                        tl = ntl;
                         return has_next;
                     };
                     while (item(cur, nxt) && item(nxt, cur)) {
