@@ -46,7 +46,9 @@ def parse_args():
     ap.add_argument("--no-uncap-l1", action="store_true", help="keep the SM cap through the level-1 backward")
     ap.add_argument("--no-cap", action="store_true", help="do not cap persistent kernels while the branch runs")
     ap.add_argument("--no-pregroup", action="store_true", help="ball query / row packing inside forward")
-    ap.add_argument("--aux", action="store_true", help="third stream for the level-1 grouping")
+    ap.add_argument("--no-aux", dest="aux", action="store_false",
+                    help="level-1 grouping behind the level-2 sampling instead of beside it on a third stream")
+    ap.add_argument("--side-priority", type=int, default=0, help="CUDA priority of the sampling branch's stream (-1: high)")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="sample (FPS) every batch inside its own step instead of one step ahead on a second stream")
     ap.add_argument("--config", default="train", choices=["train", "eval", "dense"],
@@ -347,7 +349,8 @@ def run_b200(args):
             stepper = PipelinedTrainStep(net, opt, pool_dev[0], reducer, graph=use_graph, join=args.join,
                                          cap=not args.no_cap, grouping=not args.no_pregroup, aux=args.aux,
                                          uncap_level1_backward=not args.no_uncap_l1,
-                                         capture_collective=args.dp_mode == "graph", overlap_collective=args.dp_overlap)
+                                         capture_collective=args.dp_mode == "graph", overlap_collective=args.dp_overlap,
+                                         side_priority=args.side_priority)
         elif use_graph:
             graphed = GraphedTrainStep(net, opt, pool_dev[0], reducer)
 

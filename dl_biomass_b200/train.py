@@ -239,7 +239,8 @@ class PipelinedTrainStep:
     ragged batches, e.g. after the reference's point-removal / duplication augmentation).
     ``uncap_level1_backward``: with the join at the end, launch the last quarter of the step (the level-1 backward, by
     then the branch is past its farthest-point sampling) on every SM again.  ``grouping=False`` leaves ball query and row
-    compaction inside forward; ``aux=True`` runs the level-1 grouping on a third stream beside the level-2 sampling.
+    compaction inside forward; ``aux=True`` (default; 2.18 -> 2.09 ms/step, round 2) runs the level-1 grouping on a third
+    stream beside the level-2 sampling.
 
     Data parallel (``reducer``): with ``capture_collective=True`` (default) the bucketed all-reduce and the optimiser are
     part of the graph (``overlap_collective``: buckets go out on a side stream as backward finishes them; else after
@@ -256,9 +257,9 @@ class PipelinedTrainStep:
     """
 
     def __init__(self, model, optimizer, first_batch, reducer=None, graph: bool = True, warmup: int = 2,
-                 join: str = "end", cap: bool = True, grouping: bool = True, aux: bool = False,
+                 join: str = "end", cap: bool = True, grouping: bool = True, aux: bool = True,
                  uncap_level1_backward: bool = True, capture_collective: bool = True,
-                 overlap_collective: bool = False):
+                 overlap_collective: bool = False, side_priority: int = 0):
         from . import _lib, sa
         if join not in ("backward", "end"):
             raise ValueError("join must be 'backward' or 'end'")
@@ -270,7 +271,7 @@ class PipelinedTrainStep:
             raise RuntimeError("PipelinedTrainStep needs the batch on a B200")
         self.lib = _lib.lib()
         self._sa = sa
-        self.side = torch.cuda.Stream(self.dev)
+        self.side = torch.cuda.Stream(self.dev, priority=int(side_priority))   # < 0: the branch's kernels are scheduled first
         self.aux = torch.cuda.Stream(self.dev) if (aux and grouping) else None
         self.sizes = tuple(first_batch.cloud_sizes)
         sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
