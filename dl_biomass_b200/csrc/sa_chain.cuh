@@ -403,6 +403,7 @@ struct ChainTrainParams {
     int64_t ld;
     // first GEMM: zhat = (acc + bias - mean) * rstd; a = act(gamma * zhat + beta), invalid rows 0; both stored [c_a][ld]
     const float *bias_a, *mean_a, *rstd_a, *gamma_a, *beta_a;
+    int dup_a;                // c_a == 64 and the first GEMM's image repeats its rows on lines 64..127 (PackJob::dup64)
     int act;
     __half *z_out, *a_out;    // a_out NULL: only zhat is stored (one tensor per hidden layer); consumers rebuild a from it
     // non-NULL: the fetched input tile holds zhat of the PREVIOUS layer (its a was not stored): the epilogue group turns
@@ -559,19 +560,25 @@ __global__ void __launch_bounds__(CT_THREADS, 1)
         const int ch = q * 32 + lane;
         const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
         const uint32_t da = tmem_base + lane_addr + s * CH_TMEM_PER_SLOT, db = da + 64;
+        // first GEMM with 64 output channels: the weight image repeats its rows (PackJob::dup64), channel c sits on TMEM lanes
+        // c and 64 + c, and the eight warps split the tile as (32-channel half, 16-column quarter) instead of leaving the
+        // warps of lane quadrants 2 and 3 idle while the other four drain 32 columns each
+        const bool dup = (KCM_ == 1 || KCM_ < 0) && p.dup_a != 0;   // 64 channels <=> one K chunk of the second GEMM
+        const int cha = dup ? (q & 1) * 32 + lane : ch;            // my channel of the first GEMM
+        const int col16 = half * 2 + (q >> 1);                      // dup: my 16-column quarter
         float sc = 0.f, sh = 0.f, ga = 0.f, be = 0.f;
-        if (ch < p.c_a) {
-            sc = p.rstd_a[ch];
-            sh = (p.bias_a[ch] - p.mean_a[ch]) * sc;
-            ga = p.gamma_a[ch];
-            be = p.beta_a[ch];
+        if (cha < p.c_a) {
+            sc = p.rstd_a[cha];
+            sh = (p.bias_a[cha] - p.mean_a[cha]) * sc;
+            ga = p.gamma_a[cha];
+            be = p.beta_a[cha];
         }
         const bool relu = p.act == B2PN_ACT_RELU;
         const int chb = (PASS == 3 && mt_b == 2 ? half * 128 : 0) + ch;   // my channel of the second GEMM
         const bool epb = PASS == 2 || mt_b == 2 || half == 0;
         const float bb = (PASS == 3 && epb && chb < p.c_b) ? p.bias_b[chb] : 0.f;
-        uint8_t *xline = X + (ch >> 6) * CH_CHUNK_BYTES + (ch & 63) * LINE_BYTES;
-        const int sw = ch & 7;
+        uint8_t *xline = X + (cha >> 6) * CH_CHUNK_BYTES + (cha & 63) * LINE_BYTES;
+        const int sw = cha & 7;
         double S = 0.0, Q = 0.0;   // PASS 2: statistics of my channel over all my tiles
         // the eight group descriptors of a tile (warp-uniform, 32 contiguous bytes of the table) are requested one tile
         // ahead as RAW words: the load used to sit at the top of the tile and the whole group waited an L2 round trip for it
@@ -634,7 +641,32 @@ __global__ void __launch_bounds__(CT_THREADS, 1)
             tc_fence_after();
             if (w8 == 0 && lane == 0) bulk_wait_read_all();      // the previous tile's stores have read X and Z
             asm volatile("bar.sync %0, %1;" ::"r"(1 + s), "n"(CH_EPI_THREADS) : "memory");
-            if (ch - lane < p.c_a) {
+            if (dup) {
+                unsigned nv2 = 0u;   // valid rows of my two 8-row groups
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                    if ((g >> 1) == col16) nv2 |= (unsigned)gi_nv(dsc[g]) << (4 * (g & 1));
+                float v[16];
+                tmem_ld16(da + col16 * 16, v);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int nv = (int)((nv2 >> (4 * j)) & 15u);
+                    float f[8], g[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = fmaf(v[8 * j + e], sc, sh);
+                    const uint4 zq = pack8h(f);
+                    unpack8h(zq, f);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        float y = fmaf(f[e], ga, be);
+                        if (relu) y = fmaxf(y, 0.f);
+                        g[e] = e < nv ? y : 0.f;
+                    }
+                    const int off = ((col16 * 2 + j) ^ sw) << 4;
+                    *reinterpret_cast<uint4 *>(xline + x_bytes + off) = zq;
+                    *reinterpret_cast<uint4 *>(xline + off) = pack8h(g);
+                }
+            } else if (ch - lane < p.c_a) {
                 float v[32];
                 tmem_ld32(da + half * 32, v);
 #pragma unroll

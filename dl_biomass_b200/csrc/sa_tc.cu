@@ -1784,6 +1784,9 @@ struct PackJob {
     int MT, num_mg, num_kc;
     uint8_t *img;
     int fmt;  // FMT_F16 (forward weights) / FMT_BF16 (transposed weights that meet gradients)
+    // 64-row matrices only: lines 64..127 of the image repeat rows 0..63 instead of holding zeros, so the accumulator has
+    // every channel on TWO TMEM lanes (c and 64 + c) and all four lane quadrants' warps can drain it (sa_chain.cuh)
+    int dup64;
 };
 struct PackJobs {
     PackJob j[3];
@@ -1801,7 +1804,8 @@ __global__ void pack_weights_kernel(const PackJobs jobs)
         const int64_t t2 = t / lines;
         const int kc = (int)(t2 % jb.num_kc);
         const int mgi = (int)(t2 / jb.num_kc);
-        const int m = mgi * lines + line;
+        int m = mgi * lines + line;
+        if (jb.dup64 && m >= 64 && m < 128) m -= 64;
         float f[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -2529,10 +2533,16 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
     float *bn1 = a.bn, *bn2 = a.bn + 4 * s.cmax;
     const int train = a.training;
 
+    const bool train_chain = a.training && s.rows > 0 && l1_materialised(a, s) && chain_train_ok(a, s.k1, s.c1, s.c2, s.c3);
     {
-        const PackJob jobs[3] = {pack_job(a.mlp.w[0], s.c1, s.k1, s.c0, 1, &s.cols, f.pk[0]),
-                                 pack_job(a.mlp.w[1], s.c2, s.c1, s.c1, 1, nullptr, f.pk[1]),
-                                 pack_job(a.mlp.w[2], s.c3, s.c2, s.c2, 1, nullptr, f.pk[2])};
+        PackJob jobs[3] = {pack_job(a.mlp.w[0], s.c1, s.k1, s.c0, 1, &s.cols, f.pk[0]),
+                           pack_job(a.mlp.w[1], s.c2, s.c1, s.c1, 1, nullptr, f.pk[1]),
+                           pack_job(a.mlp.w[2], s.c3, s.c2, s.c2, 1, nullptr, f.pk[2])};
+        // chained training passes: a 64-channel hidden layer leaves half of the 128 accumulator lanes empty; its image
+        // repeats the 64 rows so that the normalising epilogue runs on all eight warps (every other consumer of these
+        // images ignores lanes past the layer's width)
+        jobs[0].dup64 = train_chain && s.c1 == 64;
+        jobs[1].dup64 = train_chain && s.c2 == 64;
         launch_packs(jobs, 3, st);
     }
     if (chain_eligible(a, s.k1, s.c1, s.c2, s.c3)) {
@@ -2610,7 +2620,7 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
                                                                  a.mlp.running_var[0], a.mlp.num_batches_tracked[0], a.mlp.eps,
                                                                  a.mlp.momentum, bn1, s.cmax);
     note_launch();
-    if (train && s.rows > 0 && use_g1 && chain_train_ok(a, s.k1, s.c1, s.c2, s.c3)) {
+    if (train_chain) {
         // ---- layers 1-3 in TWO chained launches (sa_chain.cuh): P2 normalises layer 1 and takes the statistics of layer 2
         // from the tile while it is in shared memory, P3 re-runs layer 2 on the stored a1, normalises, and runs layer 3 + max
         const int64_t tiles64 = ((ra.cap + 127) / 128) * 2;
@@ -2633,7 +2643,7 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
         p2.w_img[0] = f.pk[0].img; p2.w_bytes[0] = (int)f.pk[0].bytes;
         p2.w_img[1] = f.pk[1].img; p2.w_bytes[1] = (int)f.pk[1].bytes;
         p2.k_in = s.k1; p2.kc_in = f.pk[0].num_kc; p2.kc_mid = f.pk[1].num_kc;
-        p2.c_a = s.c1; p2.c_b = s.c2; p2.mt_b = 1;
+        p2.c_a = s.c1; p2.c_b = s.c2; p2.mt_b = 1; p2.dup_a = s.c1 == 64;
         p2.rows = ra.cap; p2.rows_dev = ra.dev; p2.ld = s.ld;
         p2.bias_a = a.mlp.b[0]; p2.mean_a = bn1; p2.rstd_a = bn1 + s.cmax; p2.gamma_a = a.mlp.gamma[0]; p2.beta_a = a.mlp.beta[0];
         p2.act = a.mlp.act; p2.z_out = (__half *)z1; p2.a_out = (__half *)a.a1;   // a_out NULL: zhat alone is stored
@@ -2653,7 +2663,7 @@ int sa_forward_bf16(const b2pn_sa_args &a, cudaStream_t st)
         p3.w_img[0] = f.pk[1].img; p3.w_bytes[0] = (int)f.pk[1].bytes;
         p3.w_img[1] = f.pk[2].img; p3.w_bytes[1] = (int)f.pk[2].bytes;
         p3.k_in = s.c1; p3.kc_in = f.pk[1].num_kc; p3.kc_mid = f.pk[2].num_kc;
-        p3.c_a = s.c2; p3.c_b = s.c3; p3.mt_b = f.pk[2].MT;
+        p3.c_a = s.c2; p3.c_b = s.c3; p3.mt_b = f.pk[2].MT; p3.dup_a = s.c2 == 64;
         p3.rows = ra.cap; p3.rows_dev = ra.dev; p3.ld = s.ld;
         p3.bias_a = a.mlp.b[1]; p3.mean_a = bn2; p3.rstd_a = bn2 + s.cmax; p3.gamma_a = a.mlp.gamma[1]; p3.beta_a = a.mlp.beta[1];
         p3.act = a.mlp.act; p3.z_out = (__half *)z2; p3.a_out = (__half *)a.a2;

@@ -153,6 +153,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 16 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
+{
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ---- UMMA descriptors ----------------------------------------------------------------------------------
 // shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor): start address, leading /
 // stride byte offsets in 16-byte units, version 1 (Blackwell), layout type 2.
