@@ -301,7 +301,8 @@ def _grad_errs(m, mref, skip_bn_biases=True):
 
 @pytest.mark.parametrize("c_in,chans,K", [(1, [4, 64, 64, 128], 64), (16, [19, 32, 48, 40], 16),
                                           (128, [131, 128, 128, 256], 64), (0, [3, 64, 64, 128], 32),
-                                          (8, [11, 64, 128, 256], 40)])
+                                          (8, [11, 64, 128, 256], 40),
+                                          (4, [7, 32, 32, 42], 16)])   # 42: the routed gradient's scalar (non-quad) loads
 def test_sa_slots_level_bf16_backward(cuda_device, c_in, chans, K):
     """bf16 gradients against the oracle run with bf16 rounding emulated at the same points (weights, post-BN
     values).  Against the un-rounded oracle they differ by ~10 % because rounding flips a few arg-max / ReLU
