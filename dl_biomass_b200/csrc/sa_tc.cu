@@ -1511,7 +1511,7 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
 
     if (tid == 0) {
         for (int s = 0; s < nst; ++s) {
-            mbar_init(&full[s], NUM_LOAD);
+            mbar_init(&full[s], YS::SCATTER ? 2 * NUM_LOAD : NUM_LOAD);   // converter group (+ fill group of a routed Y side)
             mbar_init(&empty[s], 1);
             mbar_init(&xland[s], 1);
         }
@@ -1540,65 +1540,6 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
         };
         unsigned inf[8], infn[8];
         if (grp < nchunks) load_inf(inf, (c_beg + grp) * 64);
-        // Routed-gradient Y side (SCATTER): the group zeroes the tile, meets at its named barrier and drops quads (see
-        // RouteSource).  Work item k of thread lt: channel quad (lt + 128 k) % NQ, row group (lt + 128 k) / NQ.  A three-deep
-        // software pipeline per thread: descriptors two chunks ahead, (arg, dout) quads one chunk ahead, the stores of the
-        // current chunk.
-        constexpr int NQ = MTA * 32, NI = MTA * 2;
-        [[maybe_unused]] RouteSource::Quad qd[NI];
-        // descriptors: qi = this chunk (normalised); r1 / r2 / r3 = the group's next three chunks as RAW table words + a
-        // "past the end" mask (normalising a word where it is requested would wait for the load on the spot)
-        [[maybe_unused]] unsigned qi[NI], r1[NI], r2[NI], r3[NI], d1 = 0u, d2 = 0u, d3 = 0u;
-        [[maybe_unused]] auto q_fetch = [&](unsigned (&w)[NI], unsigned &dead, int64_t i) {
-            dead = 0u;
-#pragma unroll
-            for (int k = 0; k < NI; ++k) {
-                if (i < nchunks) {
-                    const int64_t r8 = (c_beg + i) * 64 + ((lt + NUM_LOAD * k) / NQ) * 8;
-                    w[k] = __ldg(ys.rm.rgrp + (r8 >> 3));
-                    dead |= (r8 >= ys.rm.rows ? 1u : 0u) << k;
-                } else {
-                    w[k] = GI_NONE;
-                    dead |= 1u << k;
-                }
-            }
-        };
-        [[maybe_unused]] auto q_norm = [&](const unsigned (&w)[NI], unsigned dead) {
-#pragma unroll
-            for (int k = 0; k < NI; ++k) qi[k] = (((dead >> k) & 1u) || gi_none(w[k])) ? GI_NONE : w[k];
-        };
-        [[maybe_unused]] auto q_load = [&]() {
-#pragma unroll
-            for (int k = 0; k < NI; ++k) {
-                if constexpr (YS::SCATTER) ys.load_quad(qi[k], mg * (MTA * 128) + ((lt + NUM_LOAD * k) % NQ) * 4, qd[k]);
-            }
-        };
-        // pull the (arg, dout) rows of a chunk two steps ahead into L2: every one of them is read exactly once (a compulsory
-        // DRAM miss that the one-chunk-ahead register prefetch cannot cover); one thread per 128 bytes
-        [[maybe_unused]] auto q_prefetch = [&](const unsigned (&w)[NI], unsigned dead) {
-            if constexpr (YS::SCATTER) {
-#pragma unroll
-                for (int k = 0; k < NI; ++k) {
-                    const int q = (lt + NUM_LOAD * k) % NQ;
-                    const int ch4 = mg * (MTA * 128) + q * 4;
-                    if ((q & 7) != 0 || ((dead >> k) & 1u) || gi_none(w[k]) || gi_nv(w[k]) == 0 || gi_slot0(w[k]) != 0 || ch4 >= ys.C) continue;
-                    const int64_t idx = (int64_t)gi_seg(w[k]) * ys.C + ch4;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ys.arg + idx));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ys.dout + idx));
-                }
-            }
-        };
-        if constexpr (YS::SCATTER) {
-#pragma unroll
-            for (int k = 0; k < NI; ++k) qi[k] = r1[k] = r2[k] = r3[k] = GI_NONE;
-            if (grp < nchunks) {
-                q_fetch(r1, d1, grp);
-                q_norm(r1, d1);
-                q_load();
-                q_fetch(r1, d1, grp + LOAD_GROUPS);
-                q_fetch(r2, d2, grp + 2 * LOAD_GROUPS);
-            }
-        }
         // TMA copies of chunk i (one thread): the Y tile completes on full[s] directly; the X tile lands as fp16 and completes
         // on xland[s], because the group converts it to bf16 before the MMA may read it.  The copies are issued up to
         // AHEAD chunks of this group ahead of the conversion, so the ring stays as deep as before the conversion existed
@@ -1631,10 +1572,6 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
             uint8_t *B = A + P::A_BYTES;
             const int64_t r0 = (c_beg + i) * 64;
             if (i + LOAD_GROUPS < nchunks) load_inf(infn, (c_beg + i + LOAD_GROUPS) * 64);
-            if constexpr (YS::SCATTER) {
-                q_fetch(r3, d3, i + 3 * LOAD_GROUPS);
-                q_prefetch(r2, d2);
-            }
             if constexpr (ANY_TMA) {
                 // a wait in issue() depends on chunks < iss - nst + 1 <= i only, i.e. on work this group has already done
                 if (lt == 0)
@@ -1642,20 +1579,7 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
             }
             if constexpr (!YS::USES_TMA) {
                 if constexpr (YS::SCATTER) {
-                    mbar_wait(&empty[s], ph ^ 1u);
-                    RouteSource::zero_tile(smem_u32(A), P::A_BYTES, lt);
-                    RouteSource::group_barrier(1 + grp);
-#pragma unroll
-                    for (int k = 0; k < NI; ++k) {
-                        const int l0 = ((lt + NUM_LOAD * k) % NQ) * 4, g = (lt + NUM_LOAD * k) / NQ;
-                        const int ch4 = mg * (MTA * 128) + l0;
-                        ys.store_quad(qd[k], ys.starts(qi[k], ch4), ch4, g, smem_u32(A), l0);
-                    }
-                    // the quads of this group's next chunk travel while the X tile is converted and the next slot is awaited
-                    if (i + LOAD_GROUPS < nchunks) {
-                        q_norm(r1, d1);
-                        q_load();
-                    }
+                    // the routed Y tile is built by the fill groups (warps 0-7, below)
                 } else {
                     // the operand loads go out before the wait for the slot: their latency overlaps it
                     uint4 v[MTA][8];
@@ -1687,21 +1611,13 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
                     *q = xf.convert(*q, c, ng);
                 }
             } else {
-                if constexpr (YS::USES_TMA) mbar_wait(&empty[s], ph ^ 1u);  // (the other Y paths have waited above)
+                if constexpr (YS::USES_TMA || YS::SCATTER) mbar_wait(&empty[s], ph ^ 1u);  // (the in-thread Y paths have waited above)
                 xf.fill(B, lt, r0, ng, nb_lines, inf);
             }
             fence_proxy_async_smem();
             mbar_arrive(&full[s]);
 #pragma unroll
             for (int g = 0; g < 8; ++g) inf[g] = infn[g];
-            if constexpr (YS::SCATTER) {
-#pragma unroll
-                for (int k = 0; k < NI; ++k) {
-                    r1[k] = r2[k];
-                    r2[k] = r3[k];
-                }
-                d1 = d2, d2 = d3;
-            }
         }
     } else if (warp == MMA_WARP) {
         if (lane == 0 && nchunks > 0) {
@@ -1728,7 +1644,95 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
             }
             umma_commit(done);
         }
-    } else if (warp < 4) {
+    } else {
+        if constexpr (YS::SCATTER) {
+            // Routed-gradient Y side: warps 0-7 (idle until the final drain otherwise) form two FILL groups of 128 threads that
+            // take alternate chunks; the loader groups above only convert the X tile.  A group zeroes the Y tile, meets at its
+            // named barrier and drops quads (see RouteSource).  Work item k of thread lt: channel quad (lt + 128 k) % NQ, row
+            // group (lt + 128 k) / NQ.  A software pipeline per thread: descriptors three chunks ahead, the rows of the chunk
+            // two ahead pulled into L2, (arg, dout) quads one chunk ahead, the stores of the current chunk.
+            const int grp = tid / NUM_LOAD;
+            const int lt = tid % NUM_LOAD;
+            constexpr int NQ = MTA * 32, NI = MTA * 2;
+            RouteSource::Quad qd[NI];
+            // descriptors: qi = this chunk (normalised); r1 / r2 / r3 = the group's next three chunks as RAW table words + a
+            // "past the end" mask (normalising a word where it is requested would wait for the load on the spot)
+            unsigned qi[NI], r1[NI], r2[NI], r3[NI], d1 = 0u, d2 = 0u, d3 = 0u;
+            auto q_fetch = [&](unsigned (&w)[NI], unsigned &dead, int64_t i) {
+                dead = 0u;
+#pragma unroll
+                for (int k = 0; k < NI; ++k) {
+                    if (i < nchunks) {
+                        const int64_t r8 = (c_beg + i) * 64 + ((lt + NUM_LOAD * k) / NQ) * 8;
+                        w[k] = __ldg(ys.rm.rgrp + (r8 >> 3));
+                        dead |= (r8 >= ys.rm.rows ? 1u : 0u) << k;
+                    } else {
+                        w[k] = GI_NONE;
+                        dead |= 1u << k;
+                    }
+                }
+            };
+            auto q_norm = [&](const unsigned (&w)[NI], unsigned dead) {
+#pragma unroll
+                for (int k = 0; k < NI; ++k) qi[k] = (((dead >> k) & 1u) || gi_none(w[k])) ? GI_NONE : w[k];
+            };
+            auto q_load = [&]() {
+#pragma unroll
+                for (int k = 0; k < NI; ++k) ys.load_quad(qi[k], mg * (MTA * 128) + ((lt + NUM_LOAD * k) % NQ) * 4, qd[k]);
+            };
+            // every (arg, dout) row is read exactly once: a compulsory DRAM miss the one-chunk-ahead register prefetch cannot
+            // cover; one thread per 128 bytes pulls them into L2 two chunks ahead
+            auto q_prefetch = [&](const unsigned (&w)[NI], unsigned dead) {
+#pragma unroll
+                for (int k = 0; k < NI; ++k) {
+                    const int q = (lt + NUM_LOAD * k) % NQ;
+                    const int ch4 = mg * (MTA * 128) + q * 4;
+                    if ((q & 7) != 0 || ((dead >> k) & 1u) || gi_none(w[k]) || gi_nv(w[k]) == 0 || gi_slot0(w[k]) != 0 || ch4 >= ys.C) continue;
+                    const int64_t idx = (int64_t)gi_seg(w[k]) * ys.C + ch4;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ys.arg + idx));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ys.dout + idx));
+                }
+            };
+#pragma unroll
+            for (int k = 0; k < NI; ++k) qi[k] = r1[k] = r2[k] = r3[k] = GI_NONE;
+            if (grp < nchunks) {
+                q_fetch(r1, d1, grp);
+                q_norm(r1, d1);
+                q_load();
+                q_fetch(r1, d1, grp + LOAD_GROUPS);
+                q_fetch(r2, d2, grp + 2 * LOAD_GROUPS);
+            }
+            for (int64_t i = grp; i < nchunks; i += LOAD_GROUPS) {
+                const int s = (int)(i % nst);
+                const uint32_t ph = (uint32_t)(i / nst) & 1u;
+                uint8_t *A = smem + s * sbytes;
+                q_fetch(r3, d3, i + 3 * LOAD_GROUPS);
+                q_prefetch(r2, d2);
+                mbar_wait(&empty[s], ph ^ 1u);
+                RouteSource::zero_tile(smem_u32(A), P::A_BYTES, lt);
+                RouteSource::group_barrier(1 + grp);
+#pragma unroll
+                for (int k = 0; k < NI; ++k) {
+                    const int l0 = ((lt + NUM_LOAD * k) % NQ) * 4, g = (lt + NUM_LOAD * k) / NQ;
+                    const int ch4 = mg * (MTA * 128) + l0;
+                    ys.store_quad(qd[k], ys.starts(qi[k], ch4), ch4, g, smem_u32(A), l0);
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(&full[s]);
+                // the quads of this group's next chunk travel while the MMA and the other group work
+                if (i + LOAD_GROUPS < nchunks) {
+                    q_norm(r1, d1);
+                    q_load();
+                }
+#pragma unroll
+                for (int k = 0; k < NI; ++k) {
+                    r1[k] = r2[k];
+                    r2[k] = r3[k];
+                }
+                d1 = d2, d2 = d3;
+            }
+        }
+        if (warp < 4) {
         if (nchunks > 0) {
             mbar_wait(done, 0);
             tc_fence_after();
@@ -1762,6 +1766,7 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
                     }
                 }
             }
+        }
         }
     }
     tc_fence_before();
