@@ -1524,6 +1524,33 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
+    // Kernels whose operands all come through TMA and whose warps 0-7 have nothing else to do get a DEDICATED producer thread
+    // (warp 4, lane 0): it refills a stage the moment the MMA releases it instead of when a converter thread next comes
+    // round its loop.  Routed kernels (warps 0-7 build the Y tile) keep the issue in the converter groups.
+    constexpr bool ANY_TMA = YS::USES_TMA || XF::USES_TMA;
+    constexpr bool DEDICATED = ANY_TMA && !YS::SCATTER;
+    // TMA copies of chunk i (one thread): the Y tile completes on full[s] directly; the X tile lands as fp16 and completes
+    // on xland[s], because the group converts it to bf16 before the MMA may read it.  The copies are issued up to
+    // AHEAD chunks of this group ahead of the conversion, so the ring stays as deep as before the conversion existed
+    // (these kernels are pure streams: they live off the bytes in flight).
+    auto issue = [&](int64_t i) {
+        const int s = (int)(i % nst);
+        const uint32_t ph = (uint32_t)(i / nst) & 1u;
+        uint8_t *A = smem + s * sbytes;
+        uint8_t *B = A + P::A_BYTES;
+        const int64_t r0 = (c_beg + i) * 64;
+        mbar_wait(&empty[s], ph ^ 1u);
+        if constexpr (YS::USES_TMA) {  // MTA*128 lines x 64 rows straight from the feature-major tensor, 64 lines per copy
+            mbar_expect_tx(&full[s], P::A_BYTES);
+#pragma unroll
+            for (int m = 0; m < MTA * 2; ++m)
+                tma_load_2d(A + m * (64 * LINE_BYTES), &tmap_y, (int)r0, mg * (MTA * 128) + m * 64, &full[s]);
+        }
+        if constexpr (XF::USES_TMA) {
+            xf.fill_tma(B, r0, ng, &tmap_x, &tmap_v, &xland[s]);
+            mbar_arrive(&xland[s]);
+        }
+    };
     if (warp >= NUM_EPI / 32 && warp < MMA_WARP) {
         const int grp = (tid - NUM_EPI) / NUM_LOAD;
         const int lt = (tid - NUM_EPI) % NUM_LOAD;
@@ -1540,29 +1567,6 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
         };
         unsigned inf[8], infn[8];
         if (grp < nchunks) load_inf(inf, (c_beg + grp) * 64);
-        // TMA copies of chunk i (one thread): the Y tile completes on full[s] directly; the X tile lands as fp16 and completes
-        // on xland[s], because the group converts it to bf16 before the MMA may read it.  The copies are issued up to
-        // AHEAD chunks of this group ahead of the conversion, so the ring stays as deep as before the conversion existed
-        // (these kernels are pure streams: they live off the bytes in flight).
-        auto issue = [&](int64_t i) {
-            const int s = (int)(i % nst);
-            const uint32_t ph = (uint32_t)(i / nst) & 1u;
-            uint8_t *A = smem + s * sbytes;
-            uint8_t *B = A + P::A_BYTES;
-            const int64_t r0 = (c_beg + i) * 64;
-            mbar_wait(&empty[s], ph ^ 1u);
-            if constexpr (YS::USES_TMA) {  // MTA*128 lines x 64 rows straight from the feature-major tensor, 64 lines per copy
-                mbar_expect_tx(&full[s], P::A_BYTES);
-#pragma unroll
-                for (int m = 0; m < MTA * 2; ++m)
-                    tma_load_2d(A + m * (64 * LINE_BYTES), &tmap_y, (int)r0, mg * (MTA * 128) + m * 64, &full[s]);
-            }
-            if constexpr (XF::USES_TMA) {
-                xf.fill_tma(B, r0, ng, &tmap_x, &tmap_v, &xland[s]);
-                mbar_arrive(&xland[s]);
-            }
-        };
-        constexpr bool ANY_TMA = YS::USES_TMA || XF::USES_TMA;
         const int ahead = nst / LOAD_GROUPS > 1 ? nst / LOAD_GROUPS : 1;  // chunks of this group in flight
         int64_t iss = grp;
         for (int64_t i = grp; i < nchunks; i += LOAD_GROUPS) {
@@ -1572,7 +1576,7 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
             uint8_t *B = A + P::A_BYTES;
             const int64_t r0 = (c_beg + i) * 64;
             if (i + LOAD_GROUPS < nchunks) load_inf(infn, (c_beg + i + LOAD_GROUPS) * 64);
-            if constexpr (ANY_TMA) {
+            if constexpr (ANY_TMA && !DEDICATED) {
                 // a wait in issue() depends on chunks < iss - nst + 1 <= i only, i.e. on work this group has already done
                 if (lt == 0)
                     for (; iss < nchunks && iss < i + (int64_t)ahead * LOAD_GROUPS; iss += LOAD_GROUPS) issue(iss);
@@ -1645,6 +1649,10 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
             umma_commit(done);
         }
     } else {
+        if constexpr (DEDICATED) {
+            if (warp == 4 && lane == 0)
+                for (int64_t i = 0; i < nchunks; ++i) issue(i);
+        }
         if constexpr (YS::SCATTER) {
             // Routed-gradient Y side: warps 0-7 (idle until the final drain otherwise) form two FILL groups of 128 threads that
             // take alternate chunks; the loader groups above only convert the X tile.  A group zeroes the Y tile, meets at its
