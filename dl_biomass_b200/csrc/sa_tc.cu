@@ -1551,9 +1551,11 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
             mbar_arrive(&xland[s]);
         }
     };
-    if (warp >= NUM_EPI / 32 && warp < MMA_WARP) {
-        const int grp = (tid - NUM_EPI) / NUM_LOAD;
-        const int lt = (tid - NUM_EPI) % NUM_LOAD;
+    // converter / loader groups: warps 8-11 and 12-15; with a dedicated producer also warps 0-3 (idle until the final drain)
+    constexpr int NG = DEDICATED ? LOAD_GROUPS + 1 : LOAD_GROUPS;
+    if ((warp >= NUM_EPI / 32 && warp < MMA_WARP) || (DEDICATED && warp < 4)) {
+        const int grp = warp < 4 ? LOAD_GROUPS : (tid - NUM_EPI) / NUM_LOAD;
+        const int lt = warp < 4 ? tid : (tid - NUM_EPI) % NUM_LOAD;
         // group descriptors of the 64 rows of a chunk (unused, and dropped by the compiler, for TMA-fed operands); the ones
         // of the group's NEXT chunk are requested before the current chunk is built
         auto load_inf = [&](unsigned (&inf)[8], int64_t r0) {
@@ -1567,19 +1569,19 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
         };
         unsigned inf[8], infn[8];
         if (grp < nchunks) load_inf(inf, (c_beg + grp) * 64);
-        const int ahead = nst / LOAD_GROUPS > 1 ? nst / LOAD_GROUPS : 1;  // chunks of this group in flight
+        const int ahead = nst / NG > 1 ? nst / NG : 1;  // chunks of this group in flight
         int64_t iss = grp;
-        for (int64_t i = grp; i < nchunks; i += LOAD_GROUPS) {
+        for (int64_t i = grp; i < nchunks; i += NG) {
             const int s = (int)(i % nst);
             const uint32_t ph = (uint32_t)(i / nst) & 1u;
             uint8_t *A = smem + s * sbytes;
             uint8_t *B = A + P::A_BYTES;
             const int64_t r0 = (c_beg + i) * 64;
-            if (i + LOAD_GROUPS < nchunks) load_inf(infn, (c_beg + i + LOAD_GROUPS) * 64);
+            if (i + NG < nchunks) load_inf(infn, (c_beg + i + NG) * 64);
             if constexpr (ANY_TMA && !DEDICATED) {
                 // a wait in issue() depends on chunks < iss - nst + 1 <= i only, i.e. on work this group has already done
                 if (lt == 0)
-                    for (; iss < nchunks && iss < i + (int64_t)ahead * LOAD_GROUPS; iss += LOAD_GROUPS) issue(iss);
+                    for (; iss < nchunks && iss < i + (int64_t)ahead * NG; iss += NG) issue(iss);
             }
             if constexpr (!YS::USES_TMA) {
                 if constexpr (YS::SCATTER) {
@@ -1740,7 +1742,9 @@ __global__ void __launch_bounds__(NT, 1) tc_dw_kernel(const DwParams p, YS ys, X
                 d1 = d2, d2 = d3;
             }
         }
-        if (warp < 4) {
+    }
+    if (warp < 4) {   // the final drain of the accumulators
+        {
         if (nchunks > 0) {
             mbar_wait(done, 0);
             tc_fence_after();
