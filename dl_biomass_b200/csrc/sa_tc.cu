@@ -1092,8 +1092,6 @@ template <class BL, class = void>
 struct LoaderPipelined { static constexpr bool value = false; };
 template <class BL>
 struct LoaderPipelined<BL, decltype((void)BL::PIPELINED)> { static constexpr bool value = BL::PIPELINED; };
-template <class BL>
-constexpr bool loader_pipelined() { return LoaderPipelined<BL>::value; }
 
 template <class BL, class = void>
 struct LoaderGroupsWide { static constexpr int value = 1; };   // loader groups under the wide layout
@@ -1194,7 +1192,6 @@ __global__ void __launch_bounds__(gemm_threads<BL>(), 1)
                 if (i < items) {
                     int64_t tl = i / num_kc;
                     int kc = (int)(i % num_kc);
-                    const int kc0 = LGROUPS % num_kc == 0 ? kc : 0, kstep = LGROUPS % num_kc == 0 ? num_kc : 1;  // my chunks of a tile
                     // descriptor pipeline: this tile / next / the one after
                     bl.fetch_tile(tile_of(tl), lt);
                     bl.shift_tiles();
@@ -1204,7 +1201,6 @@ __global__ void __launch_bounds__(gemm_threads<BL>(), 1)
                     bl.shift_tiles();
                     bl.prefetch_next_rows(lt, num_kc % LGROUPS == 0 ? g : 0, num_kc % LGROUPS == 0 ? LGROUPS : 1, num_kc);
                     fetch_or_none(tl + 2 * tstep);
-                    (void)kc0, (void)kstep;
                     // one item: `c` holds its quads (requested one item ago), `n` receives the next item's.  Called with the
                     // two register sets swapped every other item -- a `cur = nxt` copy would wait for the loads in flight
                     auto item = [&](typename BL::Item &c, typename BL::Item &n) -> bool {
