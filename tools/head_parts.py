@@ -1,0 +1,58 @@
+"""The regression head + loss alone (forward, weighted MSE, backward) as one CUDA graph: what this latency-bound tail of
+the training stream costs inside the step (cold L2: flushed between replays; warm: back-to-back replays)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from dl_biomass_b200 import head  # noqa: E402
+from dl_biomass_b200.pointnet2_regressor import Net  # noqa: E402
+from dl_biomass_b200.train import loss_and_grad, make_optimizer  # noqa: E402
+
+dev = torch.device("cuda:0")
+torch.manual_seed(1)
+net = Net(1, "ReLU", 0, 0.5, precision="bf16").to(dev).train()
+opt = make_optimizer(net)
+x3 = torch.randn(12, 1024, device=dev, requires_grad=True)
+y = torch.rand(12, 4, device=dev)
+S = torch.cuda.Stream(dev)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+net._head_rng_counter = torch.zeros((), dtype=torch.int64, device=dev) if net._head_rng_counter is None else net._head_rng_counter
+
+
+def fn():
+    opt.zero_grad()
+    out = head.head_apply(net.mlp, x3, net._head_rng_counter, net._head_seed)
+    loss, grad = loss_and_grad(out, y)
+    out.backward(grad)
+
+
+S.wait_stream(torch.cuda.current_stream(dev))
+with torch.cuda.stream(S):
+    for _ in range(3):
+        fn()
+torch.cuda.current_stream(dev).wait_stream(S)
+torch.cuda.synchronize()
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g, stream=S):
+    fn()
+
+
+def timeit(cold):
+    ts = []
+    for _ in range(30):
+        if cold:
+            flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1000)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+print(f"head fwd + loss + bwd as one graph: cold L2 {timeit(True):.1f} us, warm {timeit(False):.1f} us")
