@@ -56,3 +56,44 @@ def timeit(cold):
 
 
 print(f"head fwd + loss + bwd as one graph: cold L2 {timeit(True):.1f} us, warm {timeit(False):.1f} us")
+
+# ---- the three library calls separately (each as its own graph)
+out_keep = {}
+
+
+def f_fwd():
+    out_keep["out"] = head.head_apply(net.mlp, x3, net._head_rng_counter, net._head_seed)
+
+
+def graph_of(fn):
+    S.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(S):
+        for _ in range(2):
+            fn()
+    torch.cuda.current_stream(dev).wait_stream(S)
+    torch.cuda.synchronize()
+    gg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gg, stream=S):
+        fn()
+    return gg
+
+
+g = graph_of(f_fwd)
+print(f"  forward (lin0 + rest, 2 launches): cold {timeit(True):.1f} us, warm {timeit(False):.1f} us")
+with torch.cuda.stream(S):
+    f_fwd()
+    out = out_keep["out"]
+    loss, grad = loss_and_grad(out, y)
+torch.cuda.synchronize()
+g = graph_of(lambda: loss_and_grad(out, y))
+print(f"  weighted MSE (1 launch): cold {timeit(True):.1f} us, warm {timeit(False):.1f} us")
+
+
+def f_bwd():
+    opt.zero_grad()
+    out.backward(grad, retain_graph=True)
+
+
+g = graph_of(f_bwd)
+print(f"  backward (1 launch): cold {timeit(True):.1f} us, warm {timeit(False):.1f} us")
+g = graph_of(lambda: None) if False else None
