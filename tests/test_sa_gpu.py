@@ -419,46 +419,54 @@ def test_graphed_train_step_matches_eager(cuda_device, opt_kind):
         assert abs(a - b) <= 2e-3 * max(abs(a), 1e-6)
 
 
-@pytest.mark.parametrize("graph,opt_kind", [(False, "flat"), (True, "flat"), (True, "torch")])
-def test_pipelined_train_step_matches_eager(cuda_device, graph, opt_kind):
+@pytest.mark.parametrize("graph,opt_kind,deterministic", [(False, "flat", False), (True, "flat", False), (True, "torch", False),
+                                                         (True, "flat", True)])
+def test_pipelined_train_step_matches_eager(cuda_device, graph, opt_kind, deterministic):
     """train.PipelinedTrainStep (FPS of the next batch on a second stream, optionally one CUDA graph per step)
     trains exactly like the plain loop, one call later; building it does not train; flush() trains the last batch, so
-    every batch is trained on exactly once (/root/reference/main.py:150-172)."""
+    every batch is trained on exactly once (/root/reference/main.py:150-172).
+
+    Default mode: the level gradients are summed with atomics, so two runs of the SAME loop differ by ~1e-5 after a step, and
+    this batch shape (BatchNorm over 4 rows in the head) amplifies that to <= 8e-4 of the loss one step later (measured over
+    repeated runs, profiles/r02_backward_ncu.md): steps 1-3 are held to 2e-3, step 4 to 5e-3.  Deterministic mode
+    (b2pn_sa_args::deterministic) removes the atomics: every step within 2e-4."""
     from dl_biomass_b200 import sa
     from dl_biomass_b200.train import PipelinedTrainStep, train_step
     batches = [Batch.from_data_list(synthetic_clouds(500 + 11 * i, 4, 512, 1, False)).to(cuda_device) for i in range(4)]
+    with sa.options(deterministic=deterministic):
 
-    def fresh():
-        torch.manual_seed(5)
-        net = Net(1, "ReLU", 0, 0.0, precision="bf16").to(cuda_device).set_random_start(False)
-        net.train()
-        return net
+        def fresh():
+            torch.manual_seed(5)
+            net = Net(1, "ReLU", 0, 0.0, precision="bf16").to(cuda_device).set_random_start(False)
+            net.train()
+            return net
 
-    net = fresh()
-    opt = _make_opt(opt_kind, net, False)
-    want = [float(train_step(net, opt, b)) for b in batches]
-    want_state = {k: v.clone() for k, v in net.state_dict().items()}
+        net = fresh()
+        opt = _make_opt(opt_kind, net, False)
+        want = [float(train_step(net, opt, b)) for b in batches]
+        want_state = {k: v.clone() for k, v in net.state_dict().items()}
 
-    net = fresh()
-    opt = _make_opt(opt_kind, net, graph)
-    state = {k: v.clone() for k, v in net.state_dict().items()}
-    stepper = PipelinedTrainStep(net, opt, batches[0], graph=graph, warmup=1)
-    try:
-        for k, v in net.state_dict().items():
-            assert torch.equal(v, state[k]), f"building the stepper changed {k}"
-        got = [float(stepper.step(b)) for b in batches[1:4]]
-        assert stepper.launches_per_step > 20
-        got.append(float(stepper.flush()))
-        with pytest.raises(RuntimeError):
-            stepper.step(batches[0])
-    finally:
-        stepper.close()
-    print(want, got)
-    for a, b in zip(want, got):
-        assert abs(a - b) <= 2e-3 * max(abs(a), 1e-6)
-    for k, v in net.state_dict().items():     # same trajectory: BatchNorm step counters agree exactly, weights closely
-        if "num_batches_tracked" in k:
-            assert torch.equal(v, want_state[k]), k
+        net = fresh()
+        opt = _make_opt(opt_kind, net, graph)
+        state = {k: v.clone() for k, v in net.state_dict().items()}
+        stepper = PipelinedTrainStep(net, opt, batches[0], graph=graph, warmup=1)
+        try:
+            for k, v in net.state_dict().items():
+                assert torch.equal(v, state[k]), f"building the stepper changed {k}"
+            got = [float(stepper.step(b)) for b in batches[1:4]]
+            assert stepper.launches_per_step > 20
+            got.append(float(stepper.flush()))
+            with pytest.raises(RuntimeError):
+                stepper.step(batches[0])
+        finally:
+            stepper.close()
+        print(want, got)
+        for i, (a, b) in enumerate(zip(want, got)):
+            tol = 2e-4 if deterministic else (2e-3 if i < 3 else 5e-3)
+            assert abs(a - b) <= tol * max(abs(a), 1e-6), (i, a, b)
+        for k, v in net.state_dict().items():     # same trajectory: BatchNorm step counters agree exactly, weights closely
+            if "num_batches_tracked" in k:
+                assert torch.equal(v, want_state[k]), k
     assert sa.launch_options()[0] == 0
 
 
